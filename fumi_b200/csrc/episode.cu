@@ -1,0 +1,984 @@
+// Fused episodic inner loop, query scoring and their hand-written second-order backward.
+//
+// Reference semantics: fumi/models/fumi.py:148-193 and fumi/models/maml.py:158-191 (per-task Python
+// loop: n_steps x [im_forward, cross_entropy, autograd.grad(create_graph=True), SGD update of the
+// head AND of the whole image MLP], then query forward / argmax / CE, then outer backward).
+//
+// Formulation (DESIGN.md "Gram form"): support features X are fixed during adaptation, so the
+// adapted first layer is W0_s = W0 - alpha * S_s^T X with S_s = sum_{t<s} dZ0_t  [NK x H0].  Hence
+//      Z0_s = A - alpha * G S_s + b0_s,      A = X W0^T (rows of `proj`),  G = X X^T (`gram`)
+//      Zq   = Aq - alpha * Gq S_S + b0_S     for the query rows.
+// The 2 MB per-task W0 is never materialised; per-task state is S, W1 (64 KB), b0, b1 and the head.
+//
+// One CTA (256 threads == H0 columns) walks a task; rows are processed in tiles of TR so any
+// NK <= 128 fits; W1^T lives in shared memory for the whole task, S in an L2-resident slot of the
+// workspace (ping-pong across steps).  Thread mappings:
+//   "column" ops (Z0, dZ0, S updates):  thread == hidden unit h, loop over tile rows (registers)
+//   "A" ops   (Z1 = H0 W1^T):           thread == (o = tid%64, row group = tid/64)
+//   "C" ops   (W1 -= a * dZ1^T H0):     thread == (o = tid%64, 64-wide k slab = tid/64)
+// All reductions run in a fixed order (no atomics except the scatter into d_proj) so results are
+// reproducible run to run.
+#include <cstdint>
+#include <cstring>
+
+#include "../../include/fumi_b200.h"
+#include "common.cuh"
+#include "launch.cuh"
+
+namespace {
+
+constexpr int kThreads = 256;
+constexpr int kW1S = kH1 + 1;        // padded row stride of W1^T in shared memory (bank-conflict free)
+constexpr int kGS = kMaxSupport + 4; // row stride of the Gram tile in shared memory
+constexpr int kLS = kMaxWays;        // row stride of the logits tile
+
+struct EpiParams {
+    fumi_episode_cfg cfg;
+    int64_t B;
+    const float* proj;
+    const int64_t* sup_rows;
+    const int64_t* qry_rows;
+    const int64_t* sup_y;
+    const int64_t* qry_y;
+    const float* gram;
+    const float* b0;
+    const float* w1;
+    const float* b1;
+    const float* head_table;
+    const int64_t* head_rows;
+    float* logits;
+    int64_t* preds;
+    float* task_loss;
+    float* task_acc;
+    float* stash;
+    int save;              // 1: per-task stash with step records (backward / parity dumps); 0: per-CTA scratch
+    int64_t slot_floats;
+    // backward only
+    float loss_scale;
+    float* d_proj;
+    float* d_head;
+    float* d_b0_parts;
+    float* d_w1_parts;
+    float* d_b1_parts;
+};
+
+struct Layout {
+    int64_t per_task, S0, S1, w1t, b0, b1, head, steps, per_step, oH0, oH1, oDZ1, oDL, oHP;
+};
+
+__host__ __device__ inline Layout make_layout(const fumi_episode_cfg& c) {
+    Layout L;
+    const int64_t n = c.num_support, N = c.num_ways;
+    L.S0 = 0;
+    L.S1 = n * kH0;
+    L.w1t = 2 * n * kH0;
+    L.b0 = L.w1t + int64_t(kH0) * kH1;
+    L.b1 = L.b0 + kH0;
+    L.head = L.b1 + kH1;
+    L.steps = L.head + ((N * kHD + 3) / 4) * 4;
+    L.oH0 = 0;
+    L.oH1 = n * kH0;
+    L.oDZ1 = L.oH1 + n * kH1;
+    L.oDL = L.oDZ1 + n * kH1;
+    L.oHP = L.oDL + ((n * N + 3) / 4) * 4;
+    L.per_step = L.oHP + ((N * kHD + 3) / 4) * 4;
+    L.per_task = L.steps + int64_t(c.steps) * L.per_step;
+    return L;
+}
+
+// Shared-memory carve-up (floats).  TR = rows per tile.
+template <int TR>
+struct Smem {
+    float* w1t;    // [H0][kW1S]  adapted W1^T
+    float* aw1t;   // [H0][kW1S]  (backward) adjoint of W1^T
+    float* h0t;    // [TR][H0]
+    float* tt;     // [TR][H0]    (backward) r_dH0 / r_H0 / bar_Z0
+    float* h1t;    // [TR][H1]
+    float* dz1t;   // [TR][H1]
+    float* rz1t;   // [TR][H1]    (backward) r_dZ1
+    float* rh1t;   // [TR][H1]    (backward) r_H1 / r_Z1
+    float* lt;     // [TR][kLS]   logits / dL
+    float* rlt;    // [TR][kLS]   (backward) r_dL / r_L
+    float* gt;     // [TR][kGS]   Gram tile
+    float* hp;     // [N][HD]     head (current step)
+    float* dhp;    // [N][HD]     forward: head gradient; backward: adjoint of head
+    float* rhp;    // [N][HD]     (backward) this step's contribution to the head adjoint
+    float* b1s;    // [H1]
+    float* ab1;    // [H1]        (backward)
+    float* rb1;    // [H1]        (backward)
+    float* rowv;   // [TR]        per-row scalars (loss)
+    float* rowc;   // [TR]        per-row scalars (correct)
+    long long* rows;  // [TR]     gather rows of the tile
+    int* ys;       // [TR]        labels of the tile
+};
+
+template <int TR, bool BWD>
+__host__ __device__ inline size_t smem_floats() {
+    size_t f = size_t(kH0) * kW1S + size_t(TR) * kH0 + 2 * size_t(TR) * kH1 + size_t(TR) * kLS + size_t(TR) * kGS +
+               2 * size_t(kMaxWays) * kHD + kH1 + 2 * TR + 2 * TR /*rows (8B)*/ + TR;
+    if (BWD) f += size_t(kH0) * kW1S + size_t(TR) * kH0 + 2 * size_t(TR) * kH1 + size_t(TR) * kLS +
+                  size_t(kMaxWays) * kHD + 2 * kH1;
+    return f + 16;
+}
+
+template <int TR, bool BWD>
+__device__ inline Smem<TR> carve(float* base) {
+    Smem<TR> s;
+    float* p = base;
+    s.rows = reinterpret_cast<long long*>(p); p += 2 * TR;     // 8-byte aligned: first
+    s.w1t = p; p += kH0 * kW1S;
+    // keep float4-read buffers 16-byte aligned: kH0*kW1S = 16640 floats (multiple of 4)
+    s.h0t = p; p += TR * kH0;
+    s.h1t = p; p += TR * kH1;
+    s.dz1t = p; p += TR * kH1;
+    s.lt = p; p += TR * kLS;
+    s.gt = p; p += TR * kGS;
+    s.hp = p; p += kMaxWays * kHD;
+    s.dhp = p; p += kMaxWays * kHD;
+    s.b1s = p; p += kH1;
+    s.rowv = p; p += TR;
+    s.rowc = p; p += TR;
+    s.ys = reinterpret_cast<int*>(p); p += TR;
+    if (BWD) {
+        s.tt = p; p += TR * kH0;
+        s.rz1t = p; p += TR * kH1;
+        s.rh1t = p; p += TR * kH1;
+        s.rlt = p; p += TR * kLS;
+        s.aw1t = p; p += kH0 * kW1S;
+        s.rhp = p; p += kMaxWays * kHD;
+        s.ab1 = p; p += kH1;
+        s.rb1 = p; p += kH1;
+    } else {
+        s.tt = s.rz1t = s.rh1t = s.rlt = s.aw1t = s.rhp = s.ab1 = s.rb1 = nullptr;
+    }
+    return s;
+}
+
+__device__ inline float dropout_scale(const fumi_episode_cfg& c) {
+    return c.dropout_p > 0.f ? 1.f / (1.f - c.dropout_p) : 1.f;
+}
+__device__ inline bool dropout_keep(const fumi_episode_cfg& c, int64_t task, int pass, int layer, int row, int col) {
+    if (!(c.dropout_p > 0.f)) return true;
+    const uint32_t thr = uint32_t(fminf(c.dropout_p * 4294967296.f, 4294967040.f));
+    return fumi_mask_hash(c.dropout_seed, uint64_t(task), uint32_t(pass), uint32_t(layer), uint32_t(row),
+                          uint32_t(col)) >= thr;
+}
+
+// ---- tile loaders -----------------------------------------------------------------------------
+// rows / labels / Gram rows of tile [r0, r0+tr) of the support (qry=false) or query set of task b.
+template <int TR>
+__device__ inline void load_tile_meta(const EpiParams& P, const Smem<TR>& s, int64_t b, bool qry, int r0, int tr) {
+    const int n = P.cfg.num_support, m = P.cfg.num_query;
+    const int tid = threadIdx.x;
+    if (tid < TR) {
+        long long row = 0;
+        int y = 0;
+        if (tid < tr) {
+            if (qry) { row = P.qry_rows[b * m + r0 + tid]; y = int(P.qry_y[b * m + r0 + tid]); }
+            else     { row = P.sup_rows[b * n + r0 + tid]; y = int(P.sup_y[b * n + r0 + tid]); }
+        }
+        s.rows[tid] = row;
+        s.ys[tid] = y;
+    }
+    const int n4 = (n + 3) & ~3;
+    const float* g = P.gram + (b * int64_t(n + m) + (qry ? n : 0) + r0) * n;
+    for (int idx = tid; idx < TR * n4; idx += kThreads) {
+        const int i = idx / n4, j = idx - i * n4;
+        s.gt[i * kGS + j] = (i < tr && j < n) ? g[int64_t(i) * n + j] : 0.f;
+    }
+}
+
+// (a) Z0 = A - alpha * G S + b0 -> H0 = relu(Z0) * dropout.   thread == column h.
+template <int TR>
+__device__ inline void tile_h0(const EpiParams& P, const Smem<TR>& s, int64_t task, const float* Scur, float b0h,
+                               int r0, int tr, int pass) {
+    const int h = threadIdx.x;
+    const int n = P.cfg.num_support;
+    float acc[TR];
+#pragma unroll
+    for (int i = 0; i < TR; ++i) acc[i] = 0.f;
+    if (Scur != nullptr) {
+        const int n4 = (n + 3) & ~3;
+        for (int j = 0; j < n4; j += 4) {
+            float sv[4];
+#pragma unroll
+            for (int q = 0; q < 4; ++q) sv[q] = (j + q < n) ? Scur[int64_t(j + q) * kH0 + h] : 0.f;
+#pragma unroll
+            for (int i = 0; i < TR; ++i) {
+                const float4 g = *reinterpret_cast<const float4*>(&s.gt[i * kGS + j]);
+                acc[i] = fmaf(g.x, sv[0], acc[i]);
+                acc[i] = fmaf(g.y, sv[1], acc[i]);
+                acc[i] = fmaf(g.z, sv[2], acc[i]);
+                acc[i] = fmaf(g.w, sv[3], acc[i]);
+            }
+        }
+    }
+    const float alpha = P.cfg.step_size;
+    const float sc = dropout_scale(P.cfg);
+#pragma unroll
+    for (int i = 0; i < TR; ++i) {
+        float v = 0.f;
+        if (i < tr) {
+            const float z = P.proj[s.rows[i] * kH0 + h] + b0h - alpha * acc[i];
+            if (z > 0.f && dropout_keep(P.cfg, task, pass, 0, r0 + i, h)) v = z * sc;
+        }
+        s.h0t[i * kH0 + h] = v;
+    }
+}
+
+// (b) Z1 = H0 W1^T + b1 -> H1.   thread == (o, row group).
+template <int TR>
+__device__ inline void tile_h1(const EpiParams& P, const Smem<TR>& s, int64_t task, int r0, int tr, int pass) {
+    constexpr int RPT = TR / 4;
+    const int o = threadIdx.x & 63, ig = threadIdx.x >> 6;
+    float acc[RPT];
+#pragma unroll
+    for (int ii = 0; ii < RPT; ++ii) acc[ii] = 0.f;
+    for (int k = 0; k < kH0; k += 4) {
+        const float w0 = s.w1t[(k + 0) * kW1S + o], w1 = s.w1t[(k + 1) * kW1S + o];
+        const float w2 = s.w1t[(k + 2) * kW1S + o], w3 = s.w1t[(k + 3) * kW1S + o];
+#pragma unroll
+        for (int ii = 0; ii < RPT; ++ii) {
+            const float4 hv = *reinterpret_cast<const float4*>(&s.h0t[(ig + 4 * ii) * kH0 + k]);
+            acc[ii] = fmaf(hv.x, w0, acc[ii]);
+            acc[ii] = fmaf(hv.y, w1, acc[ii]);
+            acc[ii] = fmaf(hv.z, w2, acc[ii]);
+            acc[ii] = fmaf(hv.w, w3, acc[ii]);
+        }
+    }
+    const float sc = dropout_scale(P.cfg);
+    const float b = s.b1s[o];
+#pragma unroll
+    for (int ii = 0; ii < RPT; ++ii) {
+        const int i = ig + 4 * ii;
+        float v = 0.f;
+        if (i < tr) {
+            const float z = acc[ii] + b;
+            if (z > 0.f && dropout_keep(P.cfg, task, pass, 1, r0 + i, o)) v = z * sc;
+        }
+        s.h1t[i * kH1 + o] = v;
+    }
+}
+
+// (c) logits = H1 . head[:, :64]^T + head[:, 64]
+template <int TR>
+__device__ inline void tile_logits(const EpiParams& P, const Smem<TR>& s, int tr) {
+    const int N = P.cfg.num_ways;
+    for (int idx = threadIdx.x; idx < TR * N; idx += kThreads) {
+        const int i = idx / N, c = idx - i * N;
+        float l = 0.f;
+        if (i < tr) {
+            l = s.hp[c * kHD + kH1];
+            for (int o = 0; o < kH1; ++o) l = fmaf(s.h1t[i * kH1 + o], s.hp[c * kHD + o], l);
+        }
+        s.lt[i * kLS + c] = l;
+    }
+}
+
+// softmax statistics of row i (N <= 32): returns max, sum of exp, and fills e[] with exp(l - max)
+__device__ inline void row_softmax(const float* l, int N, float& mx, float& sum) {
+    mx = l[0];
+    for (int c = 1; c < N; ++c) mx = fmaxf(mx, l[c]);
+    sum = 0.f;
+    for (int c = 0; c < N; ++c) sum += expf(l[c] - mx);
+}
+
+// "C" op:  acc[k][o] = sum_i X[i][k] * Y[i][o]  for the thread's o and its 64-wide k slab, handed
+// four k at a time to `sink(k, a0, a1, a2, a3)`.
+template <int TR, typename Sink>
+__device__ inline void outer_rows(const float* X /*[TR][H0]*/, const float* Y /*[TR][H1]*/, Sink sink) {
+    const int o = threadIdx.x & 63, kg = threadIdx.x >> 6;
+    float yr[TR];
+#pragma unroll
+    for (int i = 0; i < TR; ++i) yr[i] = Y[i * kH1 + o];
+#pragma unroll
+    for (int kk = 0; kk < 64; kk += 4) {   // fully unrolled: sinks index per-thread register arrays by kk
+        const int k = kg * 64 + kk;
+        float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+#pragma unroll
+        for (int i = 0; i < TR; ++i) {
+            const float4 xv = *reinterpret_cast<const float4*>(&X[i * kH0 + k]);
+            a0 = fmaf(xv.x, yr[i], a0);
+            a1 = fmaf(xv.y, yr[i], a1);
+            a2 = fmaf(xv.z, yr[i], a2);
+            a3 = fmaf(xv.w, yr[i], a3);
+        }
+        sink(kk, k, o, a0, a1, a2, a3);
+    }
+}
+
+// "B" op: acc[i] (+)= sum_o Y[i][o] * Wt[h][o] * wscale   thread == h.
+template <int TR>
+__device__ inline void cols_from_h1(const float* Y /*[TR][H1]*/, const float* Wt /*[H0][kW1S]*/, float wscale,
+                                    float (&acc)[TR]) {
+    const int h = threadIdx.x;
+    for (int o = 0; o < kH1; o += 4) {
+        const float w0 = Wt[h * kW1S + o] * wscale, w1 = Wt[h * kW1S + o + 1] * wscale;
+        const float w2 = Wt[h * kW1S + o + 2] * wscale, w3 = Wt[h * kW1S + o + 3] * wscale;
+#pragma unroll
+        for (int i = 0; i < TR; ++i) {
+            const float4 y = *reinterpret_cast<const float4*>(&Y[i * kH1 + o]);
+            acc[i] = fmaf(y.x, w0, acc[i]);
+            acc[i] = fmaf(y.y, w1, acc[i]);
+            acc[i] = fmaf(y.z, w2, acc[i]);
+            acc[i] = fmaf(y.w, w3, acc[i]);
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------ forward
+template <int TR, bool MULTI>
+__global__ void __launch_bounds__(kThreads, 1) episode_fwd_kernel(EpiParams P) {
+    FUMI_DYN_SMEM(float, smem_raw);
+    const Smem<TR> s = carve<TR, false>(smem_raw);
+    const fumi_episode_cfg& c = P.cfg;
+    const int tid = threadIdx.x;
+    const int n = c.num_support, m = c.num_query, N = c.num_ways, steps = c.steps;
+    const float alpha = c.step_size;
+    const Layout L = make_layout(c);
+    const int o_ = tid & 63, kg_ = tid >> 6;
+    __shared__ float task_sum[2];
+
+    for (int64_t b = blockIdx.x; b < P.B; b += gridDim.x) {
+        const int64_t task = c.task_offset + b;
+        float* slot = P.stash + (P.save ? b : int64_t(blockIdx.x)) * P.slot_floats;
+        float* Sbuf[2] = {slot + L.S0, slot + L.S1};
+        // ---- task prologue: W1^T, biases, head init
+        for (int idx = tid; idx < kH0 * kH1; idx += kThreads) {
+            const int o = idx / kH0, k = idx - o * kH0;        // w1 is [H1][H0] row-major
+            s.w1t[k * kW1S + o] = P.w1[idx];
+        }
+        float b0h = P.b0[tid];
+        if (tid < kH1) s.b1s[tid] = P.b1[tid];
+        for (int idx = tid; idx < N * kHD; idx += kThreads) {
+            const int cc = idx / kHD, o = idx - cc * kHD;
+            const int64_t r = P.head_rows ? P.head_rows[b * N + cc] : cc;
+            s.hp[idx] = P.head_table[r * kHD + o];
+        }
+        if (tid == 0) { task_sum[0] = 0.f; task_sum[1] = 0.f; }
+        __syncthreads();
+
+        int cur = 0;
+        for (int st = 0; st < steps; ++st) {
+            const float* Scur = st > 0 ? Sbuf[cur] : nullptr;       // S_0 == 0
+            float* Snext = Sbuf[cur ^ 1];
+            float* rec = P.save ? slot + L.steps + int64_t(st) * L.per_step : nullptr;
+            float db0 = 0.f, db1 = 0.f;
+            float dw1[MULTI ? 64 : 1];
+            if (MULTI) {
+#pragma unroll
+                for (int q = 0; q < (MULTI ? 64 : 1); ++q) dw1[q] = 0.f;
+            }
+            for (int idx = tid; idx < N * kHD; idx += kThreads) s.dhp[idx] = 0.f;
+            for (int r0 = 0; r0 < n; r0 += TR) {
+                const int tr = min(TR, n - r0);
+                load_tile_meta<TR>(P, s, b, false, r0, tr);
+                __syncthreads();
+                tile_h0<TR>(P, s, task, Scur, b0h, r0, tr, st);
+                __syncthreads();
+                tile_h1<TR>(P, s, task, r0, tr, st);
+                __syncthreads();
+                tile_logits<TR>(P, s, tr);
+                __syncthreads();
+                if (tid < TR) {                                    // dL = (softmax - onehot) / n
+                    float* l = &s.lt[tid * kLS];
+                    if (tid < tr) {
+                        float mx, sum;
+                        row_softmax(l, N, mx, sum);
+                        const float inv = 1.f / sum, invn = 1.f / float(n);
+                        const int y = s.ys[tid];
+                        for (int cc = 0; cc < N; ++cc) {
+                            const float p = expf(l[cc] - mx) * inv;
+                            l[cc] = (p - (cc == y ? 1.f : 0.f)) * invn;
+                        }
+                    } else {
+                        for (int cc = 0; cc < N; ++cc) l[cc] = 0.f;
+                    }
+                }
+                __syncthreads();
+                // (d) head gradient, (e) dZ1 (uses the pre-update head)
+                for (int idx = tid; idx < N * kHD; idx += kThreads) {
+                    const int cc = idx / kHD, o = idx - cc * kHD;
+                    float a = 0.f;
+                    for (int i = 0; i < tr; ++i) a = fmaf(s.lt[i * kLS + cc], o < kH1 ? s.h1t[i * kH1 + o] : 1.f, a);
+                    s.dhp[idx] += a;
+                }
+                {
+                    const float sc = dropout_scale(c);
+#pragma unroll
+                    for (int ii = 0; ii < TR / 4; ++ii) {
+                        const int i = kg_ + 4 * ii;
+                        float dz = 0.f;
+                        if (i < tr && s.h1t[i * kH1 + o_] > 0.f) {
+                            float dh = 0.f;
+                            for (int cc = 0; cc < N; ++cc) dh = fmaf(s.lt[i * kLS + cc], s.hp[cc * kHD + o_], dh);
+                            dz = dh * sc;
+                        }
+                        s.dz1t[i * kH1 + o_] = dz;
+                    }
+                }
+                __syncthreads();
+                if (tid < kH1) {
+                    float a = 0.f;
+                    for (int i = 0; i < tr; ++i) a += s.dz1t[i * kH1 + tid];
+                    db1 += a;
+                }
+                // (f) dZ0 = (dZ1 W1) * mask ; S_next = S_cur + dZ0
+                {
+                    float acc[TR];
+#pragma unroll
+                    for (int i = 0; i < TR; ++i) acc[i] = 0.f;
+                    cols_from_h1<TR>(s.dz1t, s.w1t, 1.f, acc);
+                    const float sc = dropout_scale(c);
+#pragma unroll
+                    for (int i = 0; i < TR; ++i) {
+                        if (i < tr) {
+                            const float dz0 = s.h0t[i * kH0 + tid] > 0.f ? acc[i] * sc : 0.f;
+                            const int64_t off = int64_t(r0 + i) * kH0 + tid;
+                            Snext[off] = (Scur ? Scur[off] : 0.f) + dz0;
+                            db0 += dz0;
+                        }
+                    }
+                }
+                if (rec) {                                          // records for the backward
+                    for (int i = 0; i < tr; ++i) rec[L.oH0 + int64_t(r0 + i) * kH0 + tid] = s.h0t[i * kH0 + tid];
+                    for (int idx = tid; idx < tr * kH1; idx += kThreads) {
+                        rec[L.oH1 + int64_t(r0) * kH1 + idx] = s.h1t[idx];
+                        rec[L.oDZ1 + int64_t(r0) * kH1 + idx] = s.dz1t[idx];
+                    }
+                    for (int idx = tid; idx < tr * N; idx += kThreads) {
+                        const int i = idx / N, cc = idx - i * N;
+                        rec[L.oDL + int64_t(r0) * N + idx] = s.lt[i * kLS + cc];
+                    }
+                }
+                __syncthreads();                                    // (f) done reading W1^T
+                // (g) W1 -= alpha * dZ1^T H0
+                if (MULTI) {
+                    outer_rows<TR>(s.h0t, s.dz1t, [&](int kk, int, int, float a0, float a1, float a2, float a3) {
+                        dw1[kk] += a0; dw1[kk + 1] += a1; dw1[kk + 2] += a2; dw1[kk + 3] += a3;
+                    });
+                } else {
+                    outer_rows<TR>(s.h0t, s.dz1t, [&](int, int k, int o, float a0, float a1, float a2, float a3) {
+                        s.w1t[(k + 0) * kW1S + o] -= alpha * a0;
+                        s.w1t[(k + 1) * kW1S + o] -= alpha * a1;
+                        s.w1t[(k + 2) * kW1S + o] -= alpha * a2;
+                        s.w1t[(k + 3) * kW1S + o] -= alpha * a3;
+                    });
+                }
+                __syncthreads();
+            }
+            // ---- end of step: apply the SGD update (all gradients were taken at the pre-update point)
+            if (rec) for (int idx = tid; idx < N * kHD; idx += kThreads) rec[L.oHP + idx] = s.hp[idx];
+            for (int idx = tid; idx < N * kHD; idx += kThreads) s.hp[idx] -= alpha * s.dhp[idx];
+            if (tid < kH1) s.b1s[tid] -= alpha * db1;
+            b0h -= alpha * db0;
+            if (MULTI) {
+#pragma unroll
+                for (int kk = 0; kk < (MULTI ? 64 : 1); ++kk) s.w1t[(kg_ * 64 + kk) * kW1S + o_] -= alpha * dw1[kk];
+            }
+            cur ^= 1;
+            __syncthreads();
+        }
+
+        // ---- query scoring
+        const float* Sfin = steps > 0 ? Sbuf[cur] : nullptr;
+        for (int r0 = 0; r0 < m; r0 += TR) {
+            const int tr = min(TR, m - r0);
+            load_tile_meta<TR>(P, s, b, true, r0, tr);
+            __syncthreads();
+            tile_h0<TR>(P, s, task, Sfin, b0h, r0, tr, steps);
+            __syncthreads();
+            tile_h1<TR>(P, s, task, r0, tr, steps);
+            __syncthreads();
+            tile_logits<TR>(P, s, tr);
+            __syncthreads();
+            if (tid < tr) {
+                const float* l = &s.lt[tid * kLS];
+                float mx, sum;
+                row_softmax(l, N, mx, sum);
+                int best = 0;
+                for (int cc = 1; cc < N; ++cc) if (l[cc] > l[best]) best = cc;   // first max (torch.max)
+                const int y = s.ys[tid];
+                s.rowv[tid] = (logf(sum) + mx) - l[y];
+                s.rowc[tid] = best == y ? 1.f : 0.f;
+                const int64_t q = b * m + r0 + tid;
+                P.preds[q] = best;
+                for (int cc = 0; cc < N; ++cc) P.logits[q * N + cc] = l[cc];
+            }
+            __syncthreads();
+            if (tid == 0) {
+                float a = task_sum[0], k = task_sum[1];
+                for (int i = 0; i < tr; ++i) { a += s.rowv[i]; k += s.rowc[i]; }
+                task_sum[0] = a; task_sum[1] = k;
+            }
+            __syncthreads();
+        }
+        if (tid == 0) {
+            P.task_loss[b] = task_sum[0] / float(m);
+            P.task_acc[b] = task_sum[1] / float(m);
+        }
+        if (P.save) {                                               // adapted state
+            for (int idx = tid; idx < kH0 * kH1; idx += kThreads) {
+                const int k = idx / kH1, o = idx - k * kH1;
+                slot[L.w1t + idx] = s.w1t[k * kW1S + o];
+            }
+            slot[L.b0 + tid] = b0h;
+            if (tid < kH1) slot[L.b1 + tid] = s.b1s[tid];
+            for (int idx = tid; idx < N * kHD; idx += kThreads) slot[L.head + idx] = s.hp[idx];
+        }
+        __syncthreads();
+    }
+}
+
+// ------------------------------------------------------------------------------------ backward
+// Reverse sweep through the unrolled inner loop with hand-derived Hessian-vector products
+// (oracle/episode_np.py is the line-by-line CPU statement of the same recursion).
+template <int TR>
+__global__ void __launch_bounds__(kThreads, 1) episode_bwd_kernel(EpiParams P) {
+    FUMI_DYN_SMEM(float, smem_raw);
+    const Smem<TR> s = carve<TR, true>(smem_raw);
+    const fumi_episode_cfg& c = P.cfg;
+    const int tid = threadIdx.x;
+    const int n = c.num_support, m = c.num_query, N = c.num_ways, steps = c.steps;
+    const float alpha = c.step_size;
+    const Layout L = make_layout(c);
+    const int o_ = tid & 63, kg_ = tid >> 6;
+    const float sc = dropout_scale(c);
+    constexpr int RPT = TR / 4;
+
+    for (int64_t b = blockIdx.x; b < P.B; b += gridDim.x) {
+        const int64_t task = c.task_offset + b;
+        float* slot = P.stash + b * P.slot_floats;
+        const int fin = steps & 1;
+        const float* Sfin = steps > 0 ? slot + (fin ? L.S1 : L.S0) : nullptr;
+        float* aS[2] = {slot + (fin ? L.S0 : L.S1), slot + (fin ? L.S1 : L.S0)};   // aS[1] aliases S_final
+        // ---- load the adapted state, zero the adjoints
+        for (int idx = tid; idx < kH0 * kH1; idx += kThreads) {
+            const int k = idx / kH1, o = idx - k * kH1;
+            s.w1t[k * kW1S + o] = slot[L.w1t + idx];
+            s.aw1t[k * kW1S + o] = 0.f;
+        }
+        const float b0h = slot[L.b0 + tid];
+        float ab0 = 0.f;
+        if (tid < kH1) { s.b1s[tid] = slot[L.b1 + tid]; s.ab1[tid] = 0.f; s.rb1[tid] = 0.f; }
+        for (int idx = tid; idx < N * kHD; idx += kThreads) { s.hp[idx] = slot[L.head + idx]; s.dhp[idx] = 0.f; s.rhp[idx] = 0.f; }
+        for (int j = 0; j < n; ++j) aS[0][int64_t(j) * kH0 + tid] = 0.f;
+        __syncthreads();
+
+        // ---- query pass: recompute the forward tile, then its backward
+        const float qscale = P.loss_scale / float(m);
+        for (int r0 = 0; r0 < m; r0 += TR) {
+            const int tr = min(TR, m - r0);
+            load_tile_meta<TR>(P, s, b, true, r0, tr);
+            __syncthreads();
+            tile_h0<TR>(P, s, task, Sfin, b0h, r0, tr, steps);
+            __syncthreads();
+            tile_h1<TR>(P, s, task, r0, tr, steps);
+            __syncthreads();
+            tile_logits<TR>(P, s, tr);
+            __syncthreads();
+            if (tid < TR) {
+                float* l = &s.lt[tid * kLS];
+                if (tid < tr) {
+                    float mx, sum;
+                    row_softmax(l, N, mx, sum);
+                    const float inv = 1.f / sum;
+                    const int y = s.ys[tid];
+                    for (int cc = 0; cc < N; ++cc) l[cc] = (expf(l[cc] - mx) * inv - (cc == y ? 1.f : 0.f)) * qscale;
+                } else {
+                    for (int cc = 0; cc < N; ++cc) l[cc] = 0.f;
+                }
+            }
+            __syncthreads();
+            for (int idx = tid; idx < N * kHD; idx += kThreads) {              // a_head += dLq^T [H1q | 1]
+                const int cc = idx / kHD, o = idx - cc * kHD;
+                float a = 0.f;
+                for (int i = 0; i < tr; ++i) a = fmaf(s.lt[i * kLS + cc], o < kH1 ? s.h1t[i * kH1 + o] : 1.f, a);
+                s.dhp[idx] += a;
+            }
+#pragma unroll
+            for (int ii = 0; ii < RPT; ++ii) {                                  // dZ1q
+                const int i = kg_ + 4 * ii;
+                float dz = 0.f;
+                if (i < tr && s.h1t[i * kH1 + o_] > 0.f) {
+                    float dh = 0.f;
+                    for (int cc = 0; cc < N; ++cc) dh = fmaf(s.lt[i * kLS + cc], s.hp[cc * kHD + o_], dh);
+                    dz = dh * sc;
+                }
+                s.dz1t[i * kH1 + o_] = dz;
+            }
+            __syncthreads();
+            if (tid < kH1) {
+                float a = 0.f;
+                for (int i = 0; i < tr; ++i) a += s.dz1t[i * kH1 + tid];
+                s.ab1[tid] += a;
+            }
+            outer_rows<TR>(s.h0t, s.dz1t, [&](int, int k, int o, float a0, float a1, float a2, float a3) {
+                s.aw1t[(k + 0) * kW1S + o] += a0;
+                s.aw1t[(k + 1) * kW1S + o] += a1;
+                s.aw1t[(k + 2) * kW1S + o] += a2;
+                s.aw1t[(k + 3) * kW1S + o] += a3;
+            });
+            {
+                float acc[TR];
+#pragma unroll
+                for (int i = 0; i < TR; ++i) acc[i] = 0.f;
+                cols_from_h1<TR>(s.dz1t, s.w1t, 1.f, acc);
+                float z[TR];
+#pragma unroll
+                for (int i = 0; i < TR; ++i) {
+                    z[i] = (i < tr && s.h0t[i * kH0 + tid] > 0.f) ? acc[i] * sc : 0.f;      // dZ0q
+                    if (i < tr) {
+                        ab0 += z[i];
+                        atomicAdd(&P.d_proj[s.rows[i] * kH0 + tid], z[i]);
+                    }
+                }
+                if (steps > 0) {                                                // a_S -= alpha * Gq^T dZ0q
+                    for (int j = 0; j < n; ++j) {
+                        float a = 0.f;
+#pragma unroll
+                        for (int i = 0; i < TR; ++i) a = fmaf(s.gt[i * kGS + j], z[i], a);
+                        aS[0][int64_t(j) * kH0 + tid] -= alpha * a;
+                    }
+                }
+            }
+            __syncthreads();
+        }
+
+        // ---- inner steps in reverse
+        int cur = 0;
+        if (!c.first_order) {
+            for (int st = steps - 1; st >= 0; --st) {
+                const float* rec = slot + L.steps + int64_t(st) * L.per_step;
+                // head of this step (pre-update) and W1 of this step: undo W1_{s+1} = W1_s - alpha dZ1^T H0
+                for (int idx = tid; idx < N * kHD; idx += kThreads) s.hp[idx] = rec[L.oHP + idx];
+                for (int r0 = 0; r0 < n; r0 += TR) {
+                    const int tr = min(TR, n - r0);
+                    for (int i = 0; i < TR; ++i)
+                        s.h0t[i * kH0 + tid] = i < tr ? rec[L.oH0 + int64_t(r0 + i) * kH0 + tid] : 0.f;
+                    for (int idx = tid; idx < TR * kH1; idx += kThreads)
+                        s.dz1t[idx] = idx < tr * kH1 ? rec[L.oDZ1 + int64_t(r0) * kH1 + idx] : 0.f;
+                    __syncthreads();
+                    outer_rows<TR>(s.h0t, s.dz1t, [&](int, int k, int o, float a0, float a1, float a2, float a3) {
+                        s.w1t[(k + 0) * kW1S + o] += alpha * a0;
+                        s.w1t[(k + 1) * kW1S + o] += alpha * a1;
+                        s.w1t[(k + 2) * kW1S + o] += alpha * a2;
+                        s.w1t[(k + 3) * kW1S + o] += alpha * a3;
+                    });
+                    __syncthreads();
+                }
+                const float* aScur = aS[cur];
+                float* aSnew = aS[cur ^ 1];
+                for (int j = 0; j < n; ++j) aSnew[int64_t(j) * kH0 + tid] = aScur[int64_t(j) * kH0 + tid];
+                float rb0 = 0.f;
+                float rw1[64];
+#pragma unroll
+                for (int q = 0; q < 64; ++q) rw1[q] = 0.f;
+                const float gb0 = -alpha * ab0;
+
+                for (int r0 = 0; r0 < n; r0 += TR) {
+                    const int tr = min(TR, n - r0);
+                    load_tile_meta<TR>(P, s, b, false, r0, tr);
+                    for (int i = 0; i < TR; ++i) {
+                        const float h0 = i < tr ? rec[L.oH0 + int64_t(r0 + i) * kH0 + tid] : 0.f;
+                        s.h0t[i * kH0 + tid] = h0;
+                        // (12r) r_dH0 = (a_S' + g_b0) * M0
+                        s.tt[i * kH0 + tid] = (i < tr && h0 > 0.f) ? (aScur[int64_t(r0 + i) * kH0 + tid] + gb0) * sc : 0.f;
+                    }
+                    for (int idx = tid; idx < TR * kH1; idx += kThreads) {
+                        const bool in = idx < tr * kH1;
+                        s.h1t[idx] = in ? rec[L.oH1 + int64_t(r0) * kH1 + idx] : 0.f;
+                        s.dz1t[idx] = in ? rec[L.oDZ1 + int64_t(r0) * kH1 + idx] : 0.f;
+                    }
+                    for (int idx = tid; idx < TR * kLS; idx += kThreads) {
+                        const int i = idx / kLS, cc = idx - i * kLS;
+                        s.lt[idx] = (i < tr && cc < N) ? rec[L.oDL + int64_t(r0 + i) * N + cc] : 0.f;
+                    }
+                    __syncthreads();
+                    // (11r)+(10r): r_dZ1 = r_dH0 W1^T + H0 (g_W1)^T + g_b1 ,  g_W1 = -alpha a_W1
+                    {
+                        float acc[RPT];
+#pragma unroll
+                        for (int ii = 0; ii < RPT; ++ii) acc[ii] = 0.f;
+                        for (int k = 0; k < kH0; k += 4) {
+                            float w[4], g[4];
+#pragma unroll
+                            for (int q = 0; q < 4; ++q) {
+                                w[q] = s.w1t[(k + q) * kW1S + o_];
+                                g[q] = -alpha * s.aw1t[(k + q) * kW1S + o_];
+                            }
+#pragma unroll
+                            for (int ii = 0; ii < RPT; ++ii) {
+                                const int i = kg_ + 4 * ii;
+                                const float4 t4 = *reinterpret_cast<const float4*>(&s.tt[i * kH0 + k]);
+                                const float4 h4 = *reinterpret_cast<const float4*>(&s.h0t[i * kH0 + k]);
+                                float a = acc[ii];
+                                a = fmaf(t4.x, w[0], a); a = fmaf(t4.y, w[1], a); a = fmaf(t4.z, w[2], a); a = fmaf(t4.w, w[3], a);
+                                a = fmaf(h4.x, g[0], a); a = fmaf(h4.y, g[1], a); a = fmaf(h4.z, g[2], a); a = fmaf(h4.w, g[3], a);
+                                acc[ii] = a;
+                            }
+                        }
+                        const float gb1 = -alpha * s.ab1[o_];
+#pragma unroll
+                        for (int ii = 0; ii < RPT; ++ii) {
+                            const int i = kg_ + 4 * ii;
+                            // (9r) r_dH1 = r_dZ1 * M1
+                            s.rz1t[i * kH1 + o_] = (i < tr && s.h1t[i * kH1 + o_] > 0.f) ? (acc[ii] + gb1) * sc : 0.f;
+                        }
+                    }
+                    // r_W1 += dZ1^T r_dH0   (registers)
+                    outer_rows<TR>(s.tt, s.dz1t, [&](int kk, int, int, float a0, float a1, float a2, float a3) {
+                        rw1[kk] += a0; rw1[kk + 1] += a1; rw1[kk + 2] += a2; rw1[kk + 3] += a3;
+                    });
+                    __syncthreads();
+                    // (10r) r_H0 = dZ1 g_W1  -> tt      thread == k
+                    {
+                        float acc[TR];
+#pragma unroll
+                        for (int i = 0; i < TR; ++i) acc[i] = 0.f;
+                        cols_from_h1<TR>(s.dz1t, s.aw1t, -alpha, acc);
+#pragma unroll
+                        for (int i = 0; i < TR; ++i) s.tt[i * kH0 + tid] = acc[i];
+                    }
+                    // (8r)+(7r): r_dL = r_dH1 Wh^T + H1 (g_Wh)^T + g_bh ,  g_head = -alpha a_head
+                    for (int idx = tid; idx < TR * N; idx += kThreads) {
+                        const int i = idx / N, cc = idx - i * N;
+                        float a = 0.f;
+                        if (i < tr) {
+                            a = -alpha * s.dhp[cc * kHD + kH1];
+                            for (int o = 0; o < kH1; ++o) {
+                                a = fmaf(s.rz1t[i * kH1 + o], s.hp[cc * kHD + o], a);
+                                a = fmaf(s.h1t[i * kH1 + o], -alpha * s.dhp[cc * kHD + o], a);
+                            }
+                        }
+                        s.rlt[i * kLS + cc] = a;
+                    }
+                    // r_head += dL^T r_dH1
+                    for (int idx = tid; idx < N * kH1; idx += kThreads) {
+                        const int cc = idx / kH1, o = idx - cc * kH1;
+                        float a = 0.f;
+                        for (int i = 0; i < tr; ++i) a = fmaf(s.lt[i * kLS + cc], s.rz1t[i * kH1 + o], a);
+                        s.rhp[cc * kHD + o] += a;
+                    }
+                    // (7r) r_H1 = dL g_Wh
+#pragma unroll
+                    for (int ii = 0; ii < RPT; ++ii) {
+                        const int i = kg_ + 4 * ii;
+                        float a = 0.f;
+                        if (i < tr)
+                            for (int cc = 0; cc < N; ++cc) a = fmaf(s.lt[i * kLS + cc], -alpha * s.dhp[cc * kHD + o_], a);
+                        s.rh1t[i * kH1 + o_] = a;
+                    }
+                    __syncthreads();
+                    // (6r) r_L = P * (r_dL - <P, r_dL>) / n ,  P = n dL + Y
+                    if (tid < tr) {
+                        const int y = s.ys[tid];
+                        float dot = 0.f;
+                        for (int cc = 0; cc < N; ++cc) {
+                            const float p = s.lt[tid * kLS + cc] * float(n) + (cc == y ? 1.f : 0.f);
+                            dot = fmaf(p, s.rlt[tid * kLS + cc], dot);
+                        }
+                        for (int cc = 0; cc < N; ++cc) {
+                            const float p = s.lt[tid * kLS + cc] * float(n) + (cc == y ? 1.f : 0.f);
+                            s.rlt[tid * kLS + cc] = p * (s.rlt[tid * kLS + cc] - dot) / float(n);
+                        }
+                    }
+                    __syncthreads();
+                    // (5r) r_H1 += r_L Wh ; r_head += r_L^T [H1 | 1] ; (4r) r_Z1 = r_H1 * M1
+#pragma unroll
+                    for (int ii = 0; ii < RPT; ++ii) {
+                        const int i = kg_ + 4 * ii;
+                        float a = s.rh1t[i * kH1 + o_];
+                        if (i < tr) {
+                            for (int cc = 0; cc < N; ++cc) a = fmaf(s.rlt[i * kLS + cc], s.hp[cc * kHD + o_], a);
+                        }
+                        s.rh1t[i * kH1 + o_] = (i < tr && s.h1t[i * kH1 + o_] > 0.f) ? a * sc : 0.f;
+                    }
+                    for (int idx = tid; idx < N * kHD; idx += kThreads) {
+                        const int cc = idx / kHD, o = idx - cc * kHD;
+                        float a = 0.f;
+                        for (int i = 0; i < tr; ++i) a = fmaf(s.rlt[i * kLS + cc], o < kH1 ? s.h1t[i * kH1 + o] : 1.f, a);
+                        s.rhp[idx] += a;
+                    }
+                    __syncthreads();
+                    // (3r) r_H0 += r_Z1 W1 ; r_W1 += r_Z1^T H0 ; r_b1 += sum r_Z1
+                    if (tid < kH1) {
+                        float a = 0.f;
+                        for (int i = 0; i < tr; ++i) a += s.rh1t[i * kH1 + tid];
+                        s.rb1[tid] += a;
+                    }
+                    outer_rows<TR>(s.h0t, s.rh1t, [&](int kk, int, int, float a0, float a1, float a2, float a3) {
+                        rw1[kk] += a0; rw1[kk + 1] += a1; rw1[kk + 2] += a2; rw1[kk + 3] += a3;
+                    });
+                    {
+                        float acc[TR];
+#pragma unroll
+                        for (int i = 0; i < TR; ++i) acc[i] = s.tt[i * kH0 + tid];
+                        cols_from_h1<TR>(s.rh1t, s.w1t, 1.f, acc);
+                        // (2r) bar_Z0 = r_H0 * M0 ; (1r) a_A, a_b0, a_S
+                        float z[TR];
+#pragma unroll
+                        for (int i = 0; i < TR; ++i) {
+                            z[i] = (i < tr && s.h0t[i * kH0 + tid] > 0.f) ? acc[i] * sc : 0.f;
+                            if (i < tr) {
+                                rb0 += z[i];
+                                atomicAdd(&P.d_proj[s.rows[i] * kH0 + tid], z[i]);
+                            }
+                        }
+                        for (int j = 0; j < n; ++j) {
+                            float a = 0.f;
+#pragma unroll
+                            for (int i = 0; i < TR; ++i) a = fmaf(s.gt[i * kGS + j], z[i], a);
+                            aSnew[int64_t(j) * kH0 + tid] -= alpha * a;
+                        }
+                    }
+                    __syncthreads();
+                }
+                // ---- end of reversed step: fold this step's contributions into the adjoints
+#pragma unroll
+                for (int kk = 0; kk < 64; ++kk) s.aw1t[(kg_ * 64 + kk) * kW1S + o_] += rw1[kk];
+                for (int idx = tid; idx < N * kHD; idx += kThreads) { s.dhp[idx] += s.rhp[idx]; s.rhp[idx] = 0.f; }
+                if (tid < kH1) { s.ab1[tid] += s.rb1[tid]; s.rb1[tid] = 0.f; }
+                ab0 += rb0;
+                cur ^= 1;
+                __syncthreads();
+            }
+        }
+
+        // ---- task epilogue: head gradient per task, shared-parameter gradients into this CTA's partials
+        for (int idx = tid; idx < N * kHD; idx += kThreads) P.d_head[b * N * kHD + idx] = s.dhp[idx];
+        float* pw = P.d_w1_parts + int64_t(blockIdx.x) * kH0 * kH1;
+        for (int idx = tid; idx < kH0 * kH1; idx += kThreads) {
+            const int o = idx / kH0, k = idx - o * kH0;                         // [H1][H0] like linear1.weight
+            pw[idx] += s.aw1t[k * kW1S + o];
+        }
+        P.d_b0_parts[int64_t(blockIdx.x) * kH0 + tid] += ab0;
+        if (tid < kH1) P.d_b1_parts[int64_t(blockIdx.x) * kH1 + tid] += s.ab1[tid];
+        __syncthreads();
+    }
+}
+
+int check_cfg(const fumi_episode_cfg* c) {
+    FUMI_CHECK_ARG(c != nullptr, "cfg is null");
+    if (c->hid0 != kH0 || c->hid1 != kH1) {
+        fumi_set_error("only --im_hid_dim 256 64 (the reference default) is compiled into this build");
+        return FUMI_ERR_UNSUPPORTED;
+    }
+    FUMI_CHECK_ARG(c->num_ways >= 1 && c->num_ways <= kMaxWays, "num_ways must be in [1,32]");
+    FUMI_CHECK_ARG(c->num_support >= 1 && c->num_support <= kMaxSupport, "num_support must be in [1,128]");
+    FUMI_CHECK_ARG(c->num_query >= 1, "num_query must be >= 1");
+    FUMI_CHECK_ARG(c->steps >= 0, "steps must be >= 0");
+    FUMI_CHECK_ARG(c->dropout_p >= 0.f && c->dropout_p < 1.f, "dropout_p must be in [0,1)");
+    return FUMI_OK;
+}
+
+int grid_for(int64_t B) {
+    int sms = fumi_device_sm_count();
+    if (sms <= 0) return sms;
+    return int(B < sms ? B : sms);
+}
+
+constexpr int kTRF = 32;   // forward rows per tile
+constexpr int kTRB = 16;   // backward rows per tile (two W1-sized buffers live in shared memory)
+
+}  // namespace
+
+extern "C" int64_t fumi_episode_stash_floats(const fumi_episode_cfg* cfg) {
+    if (check_cfg(cfg) != FUMI_OK) return FUMI_ERR_ARG;
+    return make_layout(*cfg).per_task;
+}
+
+extern "C" int fumi_stash_layout(const fumi_episode_cfg* cfg, fumi_stash_layout_t* out) {
+    int rc = check_cfg(cfg);
+    if (rc != FUMI_OK) return rc;
+    FUMI_CHECK_ARG(out != nullptr, "out is null");
+    const Layout L = make_layout(*cfg);
+    out->per_task = L.per_task;
+    out->S = (cfg->steps & 1) ? L.S1 : L.S0;
+    out->w1t = L.w1t;
+    out->b0 = L.b0;
+    out->b1 = L.b1;
+    out->head = L.head;
+    out->steps = L.steps;
+    out->per_step = L.per_step;
+    return FUMI_OK;
+}
+
+extern "C" int fumi_episode_bwd_parts(void) { return fumi_device_sm_count(); }
+
+extern "C" int fumi_episode_fwd(const fumi_episode_cfg* cfg, int64_t B, const float* proj, const int64_t* sup_rows,
+                                const int64_t* qry_rows, const int64_t* sup_y, const int64_t* qry_y,
+                                const float* gram, const float* b0, const float* w1, const float* b1,
+                                const float* head_table, const int64_t* head_rows, float* logits, int64_t* preds,
+                                float* task_loss, float* task_acc, float* stash, void* stream) {
+    int rc = check_cfg(cfg);
+    if (rc != FUMI_OK) return rc;
+    FUMI_CHECK_ARG(B >= 0, "B < 0");
+    if (B == 0) return FUMI_OK;
+    FUMI_CHECK_ARG(proj && sup_rows && qry_rows && sup_y && qry_y && gram && b0 && w1 && b1 && head_table &&
+                   logits && preds && task_loss && task_acc && stash, "null pointer");
+    EpiParams P;
+    std::memset(&P, 0, sizeof(P));
+    P.cfg = *cfg; P.B = B; P.proj = proj; P.sup_rows = sup_rows; P.qry_rows = qry_rows; P.sup_y = sup_y;
+    P.qry_y = qry_y; P.gram = gram; P.b0 = b0; P.w1 = w1; P.b1 = b1; P.head_table = head_table;
+    P.head_rows = head_rows; P.logits = logits; P.preds = preds; P.task_loss = task_loss; P.task_acc = task_acc;
+    P.stash = stash;
+    P.save = cfg->reserved != 0;
+    P.slot_floats = make_layout(*cfg).per_task;
+    const int grid = grid_for(B);
+    if (grid <= 0) return grid;
+    const size_t smem = smem_floats<kTRF, false>() * sizeof(float);
+#ifndef FUMI_EMU
+    static bool attr_done = false;
+    if (!attr_done) {
+        cudaError_t e = cudaFuncSetAttribute(episode_fwd_kernel<kTRF, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem));
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(episode_fwd_kernel<kTRF, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem));
+        if (e != cudaSuccess) return fumi_cuda_fail(e, "cudaFuncSetAttribute(episode_fwd)");
+        attr_done = true;
+    }
+#endif
+    if (cfg->num_support > kTRF) {
+        FUMI_LAUNCH((episode_fwd_kernel<kTRF, true>), grid, kThreads, smem, stream, P);
+    } else {
+        FUMI_LAUNCH((episode_fwd_kernel<kTRF, false>), grid, kThreads, smem, stream, P);
+    }
+    FUMI_CHECK_LAUNCH("episode_fwd_kernel");
+    return FUMI_OK;
+}
+
+extern "C" int fumi_episode_bwd(const fumi_episode_cfg* cfg, int64_t B, const float* proj, const int64_t* sup_rows,
+                                const int64_t* qry_rows, const int64_t* sup_y, const int64_t* qry_y,
+                                const float* gram, const float* stash, float loss_scale, float* d_proj,
+                                float* d_head, float* d_b0_parts, float* d_w1_parts, float* d_b1_parts,
+                                void* stream) {
+    int rc = check_cfg(cfg);
+    if (rc != FUMI_OK) return rc;
+    FUMI_CHECK_ARG(B >= 0, "B < 0");
+    if (B == 0) return FUMI_OK;
+    FUMI_CHECK_ARG(cfg->reserved != 0, "the forward pass must have run with save-for-backward (cfg.reserved = 1)");
+    FUMI_CHECK_ARG(proj && sup_rows && qry_rows && sup_y && qry_y && gram && stash && d_proj && d_head &&
+                   d_b0_parts && d_w1_parts && d_b1_parts, "null pointer");
+    EpiParams P;
+    std::memset(&P, 0, sizeof(P));
+    P.cfg = *cfg; P.B = B; P.proj = proj; P.sup_rows = sup_rows; P.qry_rows = qry_rows; P.sup_y = sup_y;
+    P.qry_y = qry_y; P.gram = gram;
+    P.stash = const_cast<float*>(stash);     // the S ping-pong slots are reused for the adjoint of S
+    P.save = 1;
+    P.slot_floats = make_layout(*cfg).per_task;
+    P.loss_scale = loss_scale; P.d_proj = d_proj; P.d_head = d_head;
+    P.d_b0_parts = d_b0_parts; P.d_w1_parts = d_w1_parts; P.d_b1_parts = d_b1_parts;
+    const int grid = grid_for(B);
+    if (grid <= 0) return grid;
+    const size_t smem = smem_floats<kTRB, true>() * sizeof(float);
+#ifndef FUMI_EMU
+    static bool attr_done = false;
+    if (!attr_done) {
+        cudaError_t e = cudaFuncSetAttribute(episode_bwd_kernel<kTRB>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem));
+        if (e != cudaSuccess) return fumi_cuda_fail(e, "cudaFuncSetAttribute(episode_bwd)");
+        attr_done = true;
+    }
+#endif
+    FUMI_LAUNCH((episode_bwd_kernel<kTRB>), grid, kThreads, smem, stream, P);
+    FUMI_CHECK_LAUNCH("episode_bwd_kernel");
+    return FUMI_OK;
+}

@@ -1,0 +1,332 @@
+"""Host orchestration of the episodic hot path over the C ABI (include/fumi_b200.h).
+
+One meta-batch of B tasks = a fixed sequence of launches on the current CUDA stream:
+
+  FuMI (fumi/models/fumi.py:115-196)                      MAML (fumi/models/maml.py:134-193)
+  1 hypernetwork over the class text rows                 (head table = lin_final [W|b])
+  2 first-layer projection of the feature rows   proj = X W0^T        (fumi_linear_fwd)
+  3 Gram blocks of every task                    G = X X^T            (fumi_gram)
+  4 fused inner loop + query scoring                                  (fumi_episode_fwd)
+  train only:
+  5 fused second-order backward                                       (fumi_episode_bwd)
+  6 dW0 = d_proj^T X, reductions of the per-CTA partials, hypernetwork backward
+  7 (multi-GPU) one all-reduce of the flat meta-gradient; the optimizer step follows in evaluate().
+
+PyTorch supplies device memory, streams and torch.distributed only; every arithmetic step is a
+kernel of libfumi_b200.so.  There is no CPU path: a non-CUDA device raises.
+"""
+import ctypes as C
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+from . import _lib
+from .data.bank import EpisodeBatch
+
+H0, H1 = 256, 64
+HD = H1 + 1
+
+
+def first_row_of_each_label(targets, num_ways):
+    """[B,N] index of the first row with label i (fumi.py:208-210: (targets==i).nonzero()[0][0])."""
+    B, n = targets.shape
+    eq = targets.unsqueeze(-1) == torch.arange(num_ways, device=targets.device).view(1, 1, -1)   # [B,n,N]
+    pos = torch.arange(n, device=targets.device).view(1, n, 1).expand(B, n, num_ways)
+    first = torch.where(eq, pos, torch.full_like(pos, n)).min(dim=1).values
+    if bool((first >= n).any()):
+        raise IndexError("index 0 is out of bounds for dimension 0 with size 0")   # label without support row
+    return first
+
+
+class EpisodeEngine:
+    def __init__(self, device, precision=0):
+        self.device = torch.device(device)
+        if self.device.type != "cuda" and not _lib.is_emulation():
+            raise _lib.FumiError(f"fumi_b200 runs on CUDA devices only (got {self.device}); there is no CPU path")
+        self.L = _lib.lib()
+        self.precision = precision       # 0: fp32 FMA dense layers, 1: tcgen05 3xTF32
+        self.launches = 0                # kernels launched through this engine (bench: gpu_launches)
+
+    # ------------------------------------------------------------------ thin wrappers over the C ABI
+    def _stream(self):
+        return _lib.stream_ptr(self.device) if self.device.type == "cuda" else None
+
+    def _new(self, *shape, dtype=torch.float32):
+        return torch.empty(*shape, dtype=dtype, device=self.device)
+
+    def linear_fwd(self, x, w, bias=None, act=0, precision=None):
+        M, K = x.shape
+        N = w.shape[0]
+        y = self._new(M, N)
+        _lib.check(self.L.fumi_linear_fwd(_lib.ptr(x), _lib.ptr(w), _lib.ptr(bias), _lib.ptr(y), M, N, K, act,
+                                          self.precision if precision is None else precision, self._stream()),
+                   "fumi_linear_fwd")
+        self.launches += 1
+        return y
+
+    def linear_wgrad(self, dy, x, dw, db=None, accumulate=False, precision=None):
+        M, N = dy.shape
+        K = x.shape[1]
+        _lib.check(self.L.fumi_linear_wgrad(_lib.ptr(dy), _lib.ptr(x), _lib.ptr(dw), _lib.ptr(db), M, N, K,
+                                            int(accumulate), self.precision if precision is None else precision,
+                                            self._stream()), "fumi_linear_wgrad")
+        self.launches += 2 + (db is not None)
+
+    def linear_dgrad(self, dy, w, gate=None):
+        M, N = dy.shape
+        K = w.shape[1]
+        dx = self._new(M, K)
+        _lib.check(self.L.fumi_linear_dgrad(_lib.ptr(dy), _lib.ptr(w), _lib.ptr(gate), _lib.ptr(dx), M, N, K,
+                                            self._stream()), "fumi_linear_dgrad")
+        self.launches += 1
+        return dx
+
+    def gram(self, feats, sup_rows, qry_rows):
+        B, NK = sup_rows.shape
+        NQ = qry_rows.shape[1]
+        g = self._new(B, NK + NQ, NK)
+        _lib.check(self.L.fumi_gram(_lib.ptr(feats), feats.shape[0], feats.shape[1], _lib.ptr(sup_rows),
+                                    _lib.ptr(qry_rows), B, NK, NQ, _lib.ptr(g), self._stream()), "fumi_gram")
+        self.launches += 1
+        return g
+
+    def make_cfg(self, N, NK, NQ, steps, step_size, dropout_p=0.0, dropout_seed=0, task_offset=0, first_order=False,
+                 save=False):
+        return _lib.EpisodeCfg(num_ways=N, num_support=NK, num_query=NQ, hid0=H0, hid1=H1, steps=steps,
+                               step_size=step_size, dropout_p=dropout_p, dropout_seed=dropout_seed,
+                               task_offset=task_offset, first_order=int(first_order), reserved=int(save))
+
+    def stash_layout(self, cfg):
+        lay = _lib.StashLayout()
+        _lib.check(self.L.fumi_stash_layout(C.byref(cfg), C.byref(lay)), "fumi_stash_layout")
+        return lay
+
+    def episode_fwd(self, cfg, proj, eb, gram, b0, w1, b1, head_table, head_rows):
+        B, NQ, N = eb.sup_rows.shape[0], cfg.num_query, cfg.num_ways
+        per = _lib.check(self.L.fumi_episode_stash_floats(C.byref(cfg)), "fumi_episode_stash_floats")
+        slots = B if cfg.reserved else min(B, max(1, _lib.check(self.L.fumi_device_sm_count(), "sm_count")))
+        out = dict(logits=self._new(B, NQ, N), preds=self._new(B, NQ, dtype=torch.int64), task_loss=self._new(B),
+                   task_acc=self._new(B), stash=self._new(slots * per), stash_per_task=per)
+        _lib.check(self.L.fumi_episode_fwd(
+            C.byref(cfg), B, _lib.ptr(proj), _lib.ptr(eb.sup_rows), _lib.ptr(eb.qry_rows), _lib.ptr(eb.sup_y),
+            _lib.ptr(eb.qry_y), _lib.ptr(gram), _lib.ptr(b0), _lib.ptr(w1), _lib.ptr(b1), _lib.ptr(head_table),
+            _lib.ptr(head_rows), _lib.ptr(out["logits"]), _lib.ptr(out["preds"]), _lib.ptr(out["task_loss"]),
+            _lib.ptr(out["task_acc"]), _lib.ptr(out["stash"]), self._stream()), "fumi_episode_fwd")
+        self.launches += 1
+        return out
+
+    def episode_bwd(self, cfg, proj, eb, gram, stash, loss_scale, d_proj):
+        B, N = eb.sup_rows.shape[0], cfg.num_ways
+        P = _lib.check(self.L.fumi_episode_bwd_parts(), "fumi_episode_bwd_parts")
+        parts = torch.zeros(P * (H0 + H0 * H1 + H1), dtype=torch.float32, device=self.device)
+        pb0, pw1, pb1 = parts[:P * H0], parts[P * H0:P * (H0 + H0 * H1)], parts[P * (H0 + H0 * H1):]
+        d_head = self._new(B, N, HD)
+        _lib.check(self.L.fumi_episode_bwd(
+            C.byref(cfg), B, _lib.ptr(proj), _lib.ptr(eb.sup_rows), _lib.ptr(eb.qry_rows), _lib.ptr(eb.sup_y),
+            _lib.ptr(eb.qry_y), _lib.ptr(gram), _lib.ptr(stash), float(loss_scale), _lib.ptr(d_proj), _lib.ptr(d_head),
+            _lib.ptr(pb0), _lib.ptr(pw1), _lib.ptr(pb1), self._stream()), "fumi_episode_bwd")
+        self.launches += 2
+        return d_head, (pb0, pw1, pb1, P)
+
+    def reduce_parts(self, parts, P, out):
+        n = out.numel()
+        _lib.check(self.L.fumi_reduce_parts(_lib.ptr(parts), P, n, _lib.ptr(out), 0, self._stream()), "fumi_reduce_parts")
+        self.launches += 1
+
+    def loss_acc(self, task_loss, task_acc):
+        out = self._new(2)
+        _lib.check(self.L.fumi_reduce_loss_acc(_lib.ptr(task_loss), _lib.ptr(task_acc), task_loss.numel(),
+                                               _lib.ptr(out), self._stream()), "fumi_reduce_loss_acc")
+        self.launches += 1
+        return out
+
+    # ------------------------------------------------------------------ batch plumbing
+    def _to_dev(self, t, dtype=None):
+        if isinstance(t, np.ndarray):
+            t = torch.from_numpy(np.ascontiguousarray(t))
+        t = t.to(self.device, non_blocking=True)
+        if dtype is not None and t.dtype != dtype:
+            t = t.to(dtype)
+        return t.contiguous()
+
+    def unpack(self, batch, num_ways, want_text):
+        """-> (EpisodeBatch on device, feats [R,D], text rows [Rt,T] or None, head_rows [B,N] or None)"""
+        if isinstance(batch, EpisodeBatch):
+            eb = batch.to(self.device)
+            return eb, eb.bank.feats, (eb.bank.text if want_text else None), (eb.head_class if want_text else None)
+        # the reference's torchmeta batch dict (fumi.py:129-144): [[ids, text, im], targets]
+        (tr_ids, tr_text, tr_im), tr_y = batch["train"]
+        (te_ids, te_text, te_im), te_y = batch["test"]
+        B, NK, D = tr_im.shape
+        NQ = te_im.shape[1]
+        tr_y, te_y = self._to_dev(tr_y, torch.int64), self._to_dev(te_y, torch.int64)
+        feats = torch.cat([self._to_dev(tr_im, torch.float32).reshape(B * NK, D),
+                           self._to_dev(te_im, torch.float32).reshape(B * NQ, D)], 0)
+        ar = torch.arange(B * (NK + NQ), device=self.device, dtype=torch.int64)
+        eb = EpisodeBatch(bank=None, sup_rows=ar[:B * NK].view(B, NK).contiguous(),
+                          qry_rows=ar[B * NK:].view(B, NQ).contiguous(), sup_y=tr_y, qry_y=te_y,
+                          sup_ids=tr_ids, qry_ids=te_ids, head_class=None)
+        text_rows = head_rows = None
+        if want_text:
+            first = first_row_of_each_label(tr_y, num_ways)                         # [B,N]
+            tr_text = self._to_dev(tr_text, torch.float32)
+            text_rows = torch.gather(tr_text, 1, first.unsqueeze(-1).expand(B, num_ways, tr_text.shape[-1]))
+            text_rows = text_rows.reshape(B * num_ways, -1).contiguous()
+            head_rows = torch.arange(B * num_ways, device=self.device, dtype=torch.int64).view(B, num_ways)
+        return eb, feats, text_rows, head_rows
+
+    @staticmethod
+    def _grad(p):
+        if p.grad is None:
+            p.grad = torch.zeros_like(p)
+        return p.grad
+
+    def _world(self):
+        if dist.is_available() and dist.is_initialized():
+            return dist.get_world_size()
+        return 1
+
+    def _allreduce_grads(self, params, loss_acc):
+        """Tasks are sharded across ranks: one sum all-reduce of the meta-gradient
+        (flat buffer when the optimizer provides one) + the two scalars."""
+        if self._world() == 1:
+            return
+        flat = getattr(params[0], "_fumi_flat_grad", None)
+        if flat is not None and all(getattr(p, "_fumi_flat_grad", None) is flat for p in params):
+            dist.all_reduce(flat)
+        else:
+            for p in params:
+                dist.all_reduce(p.grad)
+        dist.all_reduce(loss_acc)
+        loss_acc /= self._world()
+
+    # ------------------------------------------------------------------ FuMI
+    def hypernet(self, model, text_rows, keep=False):
+        """hyper_net(text): Linear-ReLU-Linear(-Tanh)  (fumi.py:70-107,109-113)."""
+        l0, l2 = model.hyper_net[0], model.hyper_net[2]
+        u = self.linear_fwd(text_rows, l0.weight, l0.bias, act=1)
+        hp = self.linear_fwd(u, l2.weight, l2.bias, act=2 if model.norm_hypernet else 0, precision=0)
+        return (hp, u) if keep else hp
+
+    def _check_im_net(self, hidden, emb_dim):
+        if list(hidden) != [H0, H1]:
+            raise NotImplementedError(f"this build adapts an image MLP with --im_hid_dim {H0} {H1} (the reference "
+                                      f"default); got {list(hidden)}")
+        if emb_dim % 4:
+            raise NotImplementedError("--im_emb_dim must be a multiple of 4")
+
+    def fumi_batch(self, model, batch, steps, step_size, train, return_state=False):
+        self._check_im_net(model.im_hid_dim, model.im_emb_dim)
+        N = model.n_way
+        eb, feats, text_rows, head_rows = self.unpack(batch, N, want_text=True)
+        if model.text_encoder_type == "rand":
+            text_rows = 2 * torch.rand(text_rows.shape[0], model.text_emb_dim, device=self.device) - 1   # fumi.py:200-202
+        B, NK = eb.sup_rows.shape
+        NQ = eb.qry_rows.shape[1]
+        lin0, lin1 = model.im_net.linear0, model.im_net.linear1
+        p_drop = float(model.dropout_rate) if (train and model.dropout_rate > 0) else 0.0
+        if p_drop > 0:
+            model.dropout_seed += 1
+        world = self._world()
+        rank = dist.get_rank() if world > 1 else 0
+        cfg = self.make_cfg(N, NK, NQ, steps, step_size, dropout_p=p_drop,
+                            dropout_seed=(int(getattr(model, "dropout_base_seed", 0)) << 20) + model.dropout_seed,
+                            task_offset=rank * B, save=train or return_state)
+        hp_table, u = self.hypernet(model, text_rows, keep=True)
+        proj = self.linear_fwd(feats, lin0.weight, None, act=0)
+        gram = self.gram(feats, eb.sup_rows, eb.qry_rows)
+        out = self.episode_fwd(cfg, proj, eb, gram, lin0.bias, lin1.weight, lin1.bias, hp_table, head_rows)
+        la = self.loss_acc(out["task_loss"], out["task_acc"])
+        res = dict(loss_acc=la, preds=out["preds"], logits=out["logits"], qry_y=eb.qry_y, task_loss=out["task_loss"],
+                   task_acc=out["task_acc"], cfg=cfg, stash=out["stash"] if (train or return_state) else None,
+                   hp_table=hp_table, head_rows=head_rows, batch=eb)
+        if not train:
+            return res
+        # ---- outer backward (fumi.py:190-192): gradients of sum_b task_loss / B_global
+        d_proj = torch.zeros_like(proj)
+        d_head, (pb0, pw1, pb1, P) = self.episode_bwd(cfg, proj, eb, gram, out["stash"], 1.0 / (B * world), d_proj)
+        self.reduce_parts(pb0, P, self._grad(lin0.bias))
+        self.reduce_parts(pw1, P, self._grad(lin1.weight))
+        self.reduce_parts(pb1, P, self._grad(lin1.bias))
+        self.linear_wgrad(d_proj, feats, self._grad(lin0.weight))                # dW0 = d_proj^T X
+        d_hp = torch.zeros_like(hp_table)
+        _lib.check(self.L.fumi_scatter_add_rows(_lib.ptr(d_head), _lib.ptr(head_rows.reshape(-1)), B * N, HD,
+                                                _lib.ptr(d_hp), self._stream()), "fumi_scatter_add_rows")
+        self.launches += 1
+        if model.norm_hypernet:
+            _lib.check(self.L.fumi_tanh_bwd(_lib.ptr(hp_table), _lib.ptr(d_hp), d_hp.numel(), self._stream()),
+                       "fumi_tanh_bwd")
+            self.launches += 1
+        l0, l2 = model.hyper_net[0], model.hyper_net[2]
+        self.linear_wgrad(d_hp, u, self._grad(l2.weight), self._grad(l2.bias), precision=0)
+        d_u = self.linear_dgrad(d_hp, l2.weight, gate=u)
+        self.linear_wgrad(d_u, text_rows, self._grad(l0.weight), self._grad(l0.bias))
+        self._allreduce_grads([p for p in model.parameters() if p.requires_grad], la)
+        return res
+
+    # ------------------------------------------------------------------ MAML
+    def maml_batch(self, model, batch, steps, step_size, train, first_order=False, return_state=False):
+        self._check_im_net(model.hidden_dims, model.im_embed_dim)
+        N = model.n_way
+        eb, feats, _, _ = self.unpack(batch, N, want_text=False)
+        B, NK = eb.sup_rows.shape
+        NQ = eb.qry_rows.shape[1]
+        lin0, lin1, fin = model.net.lin_0, model.net.lin_1, model.net.lin_final
+        world = self._world()
+        cfg = self.make_cfg(N, NK, NQ, steps, step_size, first_order=first_order, save=train or return_state)
+        head_table = torch.cat([fin.weight, fin.bias.unsqueeze(1)], 1).contiguous()      # [N, 65]
+        proj = self.linear_fwd(feats, lin0.weight, None, act=0)
+        gram = self.gram(feats, eb.sup_rows, eb.qry_rows)
+        out = self.episode_fwd(cfg, proj, eb, gram, lin0.bias, lin1.weight, lin1.bias, head_table, None)
+        la = self.loss_acc(out["task_loss"], out["task_acc"])
+        res = dict(loss_acc=la, preds=out["preds"], logits=out["logits"], qry_y=eb.qry_y, cfg=cfg,
+                   stash=out["stash"] if (train or return_state) else None, batch=eb)
+        if not train:
+            return res
+        d_proj = torch.zeros_like(proj)
+        d_head, (pb0, pw1, pb1, P) = self.episode_bwd(cfg, proj, eb, gram, out["stash"], 1.0 / (B * world), d_proj)
+        self.reduce_parts(pb0, P, self._grad(lin0.bias))
+        self.reduce_parts(pw1, P, self._grad(lin1.weight))
+        self.reduce_parts(pb1, P, self._grad(lin1.bias))
+        self.linear_wgrad(d_proj, feats, self._grad(lin0.weight))
+        d_fin = self._new(N * HD)
+        self.reduce_parts(d_head.reshape(B, N * HD), B, d_fin)                   # shared head: sum over tasks
+        d_fin = d_fin.view(N, HD)
+        self._grad(fin.weight).copy_(d_fin[:, :H1])
+        self._grad(fin.bias).copy_(d_fin[:, H1])
+        self._allreduce_grads(list(model.parameters()), la)
+        return res
+
+    # ------------------------------------------------------------------ AM3 (meta-test scoring)
+    def am3_batch(self, model, batch, num_ways):
+        """AM3.evaluate in eval mode (am3.py:159-200): prototypes, distances, argmin, CE."""
+        N = num_ways
+        if isinstance(batch, EpisodeBatch):
+            eb = batch.to(self.device)
+            feats, text_rows, class_rows = eb.bank.feats, eb.bank.text, eb.head_class
+            sup_text_row = None
+        else:
+            eb, feats, text_rows, class_rows = self.unpack(batch, N, want_text=True)
+        P = model.prototype_dim
+        emb = self.linear_fwd(feats, model.image_encoder.weight, model.image_encoder.bias)
+        g0, g3, h0, h3 = model.g[0], model.g[3], model.h[0], model.h[3]
+        t = self.linear_fwd(self.linear_fwd(text_rows, g0.weight, g0.bias, act=1), g3.weight, g3.bias)
+        lam = self.linear_fwd(self.linear_fwd(t, h0.weight, h0.bias, act=1), h3.weight, h3.bias, act=3, precision=0)
+        B, NK = eb.sup_rows.shape
+        NQ = eb.qry_rows.shape[1]
+        protos, dist_, preds = self._new(B, N, P), self._new(B, NQ, N), self._new(B, NQ, dtype=torch.int64)
+        task_loss = self._new(B)
+        fixed = -1 if model.lamda_fixed is None else int(model.lamda_fixed)
+        _lib.check(self.L.fumi_am3_score(
+            _lib.ptr(emb), _lib.ptr(t), _lib.ptr(lam.reshape(-1)), _lib.ptr(eb.sup_rows), _lib.ptr(eb.qry_rows),
+            _lib.ptr(eb.sup_y), _lib.ptr(eb.qry_y), _lib.ptr(class_rows), B, N, NK, NQ, P, fixed, _lib.ptr(protos),
+            _lib.ptr(dist_), _lib.ptr(preds), _lib.ptr(task_loss), self._stream()), "fumi_am3_score")
+        self.launches += 1
+        # per-support-row lamda as the reference returns it (am3.py:208): lamda of the row's class
+        label_lam = torch.gather(lam.reshape(-1)[class_rows], 1, eb.sup_y)
+        if fixed == 0:
+            label_lam = torch.zeros_like(label_lam)
+        elif fixed == 1:
+            label_lam = torch.ones_like(label_lam)
+        return dict(task_loss=task_loss, preds=preds, dist=dist_, protos=protos, sup_lamda=label_lam, batch=eb)

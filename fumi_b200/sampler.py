@@ -1,0 +1,99 @@
+"""Host front-end of the native episodic task sampler (fumi_sampler_* in the C ABI).
+
+Replaces the reference loader stack for the path (fumi/dataset/data.py:73-84,125-188 +
+torchmeta 1.7.0): the class tables are built once, and each meta-batch is a set of index
+arrays (image ids into the HBM feature bank + labels) instead of collated feature tensors.
+
+The reference draws from three global generators.  To stay a drop-in,
+the native sampler *borrows* the live state of Python's ``random`` and of the torch CPU
+generator for the duration of a call and writes it back, so a host program that seeds them as
+fumi/main.py:51-53 does gets the reference's task stream.
+"""
+import ctypes as C
+import random
+
+import numpy as np
+import torch
+
+from . import _lib
+
+
+def _torch_state_get():
+    s = torch.get_rng_state().numpy()
+    st = np.empty(626, np.uint32)
+    st[:624] = s[24:24 + 624 * 8].view(np.uint64).astype(np.uint32)
+    st[624] = np.uint32(s[16:24].view(np.uint64)[0])      # next
+    st[625] = np.uint32(s[8:12].view(np.int32)[0])        # left
+    return st, s
+
+
+def _torch_state_set(st, raw):
+    raw = raw.copy()
+    raw[24:24 + 624 * 8].view(np.uint64)[:] = st[:624].astype(np.uint64)
+    raw[16:24].view(np.uint64)[0] = np.uint64(st[624])
+    raw[8:12].view(np.int32)[0] = np.int32(st[625])
+    torch.set_rng_state(torch.from_numpy(raw))
+
+
+def class_tables(cat_of, categories):
+    """(offsets[C+1], ids) -- per split-class ascending image ids (data.py:395-414)."""
+    cat_of = np.asarray(cat_of)
+    order = np.argsort(cat_of, kind="stable")
+    sorted_cat = cat_of[order]
+    starts = np.searchsorted(sorted_cat, categories, side="left")
+    ends = np.searchsorted(sorted_cat, categories, side="right")
+    sizes = ends - starts
+    offsets = np.zeros(len(categories) + 1, np.int64)
+    np.cumsum(sizes, out=offsets[1:])
+    ids = np.concatenate([order[s:e] for s, e in zip(starts, ends)]).astype(np.int64)
+    return offsets, ids
+
+
+class EpisodeSampler:
+    """One split's loader: ``next_batch(B)`` -> dict of int64 index arrays (host, pinned if asked)."""
+
+    def __init__(self, cat_of, categories, num_ways, num_shots, num_query, num_threads=0):
+        self.categories = np.asarray(categories, np.int64)
+        self.N, self.K, self.Q = int(num_ways), int(num_shots), int(num_query)
+        self.offsets, self.ids = class_tables(cat_of, self.categories)
+        self.num_threads = num_threads
+        h = C.c_void_p()
+        _lib.check(_lib.lib().fumi_sampler_create(_lib.ptr(self.offsets), _lib.ptr(self.ids),
+                                                  len(self.categories), self.N, self.K, self.Q, C.byref(h)),
+                   "fumi_sampler_create")
+        self._h = h
+
+    def __del__(self):
+        h, self._h = getattr(self, "_h", None), None
+        if h:
+            _lib.lib().fumi_sampler_destroy(h)
+
+    def new_iterator(self):
+        """Equivalent of iter(loader): the DataLoader draws its base seed from the torch stream."""
+        st, raw = _torch_state_get()
+        _lib.check(_lib.lib().fumi_sampler_new_iterator(self._h, _lib.ptr(st)), "fumi_sampler_new_iterator")
+        _torch_state_set(st, raw)
+
+    def next_batch(self, batch_size, out=None):
+        B, N, K, Q = int(batch_size), self.N, self.K, self.Q
+        if out is None:
+            out = {k: np.empty((B, n), np.int64) for k, n in
+                   (("classes", N), ("label_perm", N), ("sup_ids", N * K), ("qry_ids", N * Q),
+                    ("sup_y", N * K), ("qry_y", N * Q), ("head_class", N),
+                    ("sup_rows", N * K), ("qry_rows", N * Q))}
+        ver, key, gauss = random.getstate()
+        py = np.asarray(key, np.uint32)
+        st, raw = _torch_state_get()
+        try:
+            _lib.check(_lib.lib().fumi_sampler_next(
+                self._h, B, _lib.ptr(py), _lib.ptr(st), *[_lib.ptr(out[k]) for k in
+                ("classes", "label_perm", "sup_ids", "qry_ids", "sup_y", "qry_y", "head_class",
+                 "sup_rows", "qry_rows")],
+                self.num_threads), "fumi_sampler_next")
+        except _lib.FumiError as e:
+            if "smaller than the minimum" in str(e):
+                raise ValueError(str(e).split(": ", 2)[-1]) from None     # torchmeta raises ValueError
+            raise
+        random.setstate((ver, tuple(int(x) for x in py), gauss))
+        _torch_state_set(st, raw)
+        return out

@@ -1,0 +1,228 @@
+/*
+ * fumi_b200.h -- C ABI of libfumi_b200.so: the B200 (sm_100a) implementation of FuMI's
+ * episodic inner-loop adaptation path.
+ *
+ * The reference (s-a-malik/fumi) is pure Python and has no FFI; its boundary for this path is
+ * the Python call surface listed in SURVEY.md section 8(b).  Each entry point below names the
+ * reference code it replaces (paths relative to the reference root).  The host-side mirror of
+ * that call surface lives in fumi_b200/ (Python) and binds these symbols through ctypes
+ * (INTEGRATION.md shows the binding a reference maintainer would add).
+ *
+ * Conventions
+ *   - Plain C types only.  Unless a parameter is marked HOST, every pointer is a DEVICE pointer
+ *     owned by the caller (typically a torch tensor's data_ptr()); nothing is allocated or freed
+ *     behind the caller's back except the opaque host-side sampler handle.
+ *   - `stream` is a cudaStream_t passed as void*; all device work is enqueued on it and the call
+ *     returns without synchronising.
+ *   - Every function returns 0 on success or a negative fumi_status; the message of the last
+ *     failure on the calling thread is available from fumi_last_error().  There is no CPU
+ *     fallback: without a CUDA device the compute entry points fail with FUMI_ERR_CUDA.
+ *   - Matrices are row-major and dense.  Arithmetic is fp32 (reference: torch float32);
+ *     indices, labels and predictions are int64 (reference: torch int64).
+ *   - Shapes: B tasks per call, N ways, NK support rows and NQ query rows per task (grouped by
+ *     class in tuple order, as the torchmeta collate produces them), D image-feature dim,
+ *     H0/H1 hidden dims of the adapted image MLP (only 256/64, the reference default
+ *     --im_hid_dim, is compiled), HD = H1 + 1 (head weights + bias, fumi.py:76-79).
+ */
+#ifndef FUMI_B200_H_
+#define FUMI_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define FUMI_B200_ABI_VERSION 1
+
+typedef enum {
+    FUMI_OK = 0,
+    FUMI_ERR_ARG = -1,         /* bad argument / unsupported shape */
+    FUMI_ERR_CUDA = -2,        /* CUDA runtime error (includes: no device) */
+    FUMI_ERR_UNSUPPORTED = -3, /* configuration the reference accepts but this build does not */
+    FUMI_ERR_DATA = -4         /* data-dependent failure (e.g. class smaller than K+Q) */
+} fumi_status;
+
+/* Per-call description of the episode (reference flags: utils/utils.py:80-90,120-128,160-179). */
+typedef struct {
+    int32_t num_ways;      /* N   --num_ways                                              */
+    int32_t num_support;   /* NK  = N * --num_shots                                       */
+    int32_t num_query;     /* NQ  = N * query shots (--num_shots_test | int(100/N))       */
+    int32_t hid0;          /* H0  --im_hid_dim[0] (256)                                   */
+    int32_t hid1;          /* H1  --im_hid_dim[1] (64)                                    */
+    int32_t steps;         /* --num_train_adapt_steps | --num_test_adapt_steps            */
+    float step_size;       /* --step_size (inner SGD learning rate alpha)                 */
+    float dropout_p;       /* --dropout in train mode, 0 in eval mode / MAML              */
+    uint64_t dropout_seed; /* counter-based masks: f(seed, task, pass, layer, row, col)   */
+    int64_t task_offset;   /* global index of task 0 of this call (dropout counters, multi-GPU shards) */
+    int32_t first_order;   /* maml.py:177 --first_order (FuMI always 0, fumi.py:176)      */
+    int32_t reserved;
+} fumi_episode_cfg;
+
+int fumi_abi_version(void);
+const char* fumi_last_error(void);
+/* Number of SMs of the current device (grid sizing); negative fumi_status on failure. */
+int fumi_device_sm_count(void);
+
+/* ------------------------------------------------------------------------------------------
+ * Dense layers shared by the path.
+ * fumi_linear_fwd: y[M,N] = act(x[M,K] . w[N,K]^T + bias[N])        (bias may be NULL)
+ *   replaces F.linear + ReLU of: the first image layer im_net.linear0 applied to every feature
+ *   row once per outer step (fumi.py:215 via MetaLinear; hoisted out of the per-task loop, see
+ *   DESIGN.md "Gram form"), the hypernetwork layers (fumi.py:70-107,109-113) and AM3's
+ *   image_encoder / g / h (am3.py:105-126).  act: 0 none, 1 ReLU, 2 tanh, 3 sigmoid.
+ *   precision: 0 = fp32 FMA, 1 = tcgen05 3xTF32 split (fp32-accurate tensor-core path).
+ * fumi_linear_wgrad: dw[N,K] (+)= dy[M,N]^T . x[M,K]; db[N] (+)= column sums of dy (db may be NULL)
+ *   replaces the autograd weight gradients of the same layers in outer_loss.backward()
+ *   (fumi.py:192).
+ * fumi_linear_dgrad: dx[M,K] = (dy[M,N] . w[N,K]) * (gate ? gate[M,K] > 0 : 1)
+ *   (ReLU backward through the hypernetwork hidden layer).
+ * ---------------------------------------------------------------------------------------- */
+int fumi_linear_fwd(const float* x, const float* w, const float* bias, float* y,
+                    int64_t M, int64_t N, int64_t K, int32_t act, int32_t precision, void* stream);
+int fumi_linear_wgrad(const float* dy, const float* x, float* dw, float* db,
+                      int64_t M, int64_t N, int64_t K, int32_t accumulate, int32_t precision, void* stream);
+int fumi_linear_dgrad(const float* dy, const float* w, const float* gate, float* dx,
+                      int64_t M, int64_t N, int64_t K, void* stream);
+/* y = y * (1 - out*out) style activation backward for act 2 (tanh): dy *= 1 - y^2, in place. */
+int fumi_tanh_bwd(const float* y, float* dy, int64_t n, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Episode Gram blocks (the HBM-bound gather of the path).
+ * gram[b, i, j] = <feats[row(b,i)], feats[sup_rows[b,j]]>, i over the NK support rows then the NQ
+ * query rows of task b.  Each sampled feature row is read from HBM once per task.
+ * Replaces the per-task re-application of the adapted first layer, F.linear(x, W0 - alpha*dW0...)
+ * (fumi.py:161,178 with torchmeta's updated 'linear0.weight'): see DESIGN.md "Gram form".
+ * Also the GPU-resident replacement of the loader's per-sample feature copies
+ * (dataset/data.py:545,571-577): rows are gathered straight from the HBM feature bank.
+ * ---------------------------------------------------------------------------------------- */
+int fumi_gram(const float* feats, int64_t num_rows, int64_t D,
+              const int64_t* sup_rows, const int64_t* qry_rows,
+              int64_t B, int32_t NK, int32_t NQ, float* gram, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Fused inner loop + query scoring   (fumi.py:148-185, maml.py:158-183)
+ *   proj        [R, H0]   feature rows through the meta-initial first layer, no bias
+ *   sup_rows    [B, NK]   row of proj for each support sample;  qry_rows [B, NQ]
+ *   sup_y,qry_y           labels in [0, N)
+ *   gram        [B, NK+NQ, NK] from fumi_gram
+ *   b0 [H0], w1 [H1,H0], b1 [H1]  meta-initial im_net.linear0.bias / linear1.*
+ *   head_table  [Rh, HD]  head initialisations: hypernetwork outputs (FuMI, fumi.py:156,198-212)
+ *                         or the shared lin_final [weight|bias] (MAML, maml.py:28)
+ *   head_rows   [B, N]    row of head_table initialising label i of task b; NULL = rows 0..N-1
+ *                         for every task (MAML)
+ * outputs
+ *   logits [B,NQ,N], preds [B,NQ] (argmax, lowest index on ties: torch.max, fumi.py:180),
+ *   task_loss [B] (mean CE of the task's queries, fumi.py:182), task_acc [B] (fumi.py:185,329-331)
+ *   stash: NULL for inference; otherwise fumi_episode_stash_floats(cfg)*B floats that
+ *          fumi_episode_bwd consumes (adapted state + per-step activations).  The adapted state
+ *          (hp, W1, b1, b0 and the first-layer coefficient matrix S with W0_task = W0 - alpha S^T X)
+ *          can be read back from it for parity dumps: fumi_stash_layout().
+ * ---------------------------------------------------------------------------------------- */
+int64_t fumi_episode_stash_floats(const fumi_episode_cfg* cfg);
+typedef struct {
+    int64_t per_task;   /* floats per task                                   */
+    int64_t S;          /* [NK,H0]  offset of the first-layer coefficient S  */
+    int64_t w1t;        /* [H0,H1]  adapted linear1.weight, TRANSPOSED       */
+    int64_t b0;         /* [H0]     adapted linear0.bias                     */
+    int64_t b1;         /* [H1]     adapted linear1.bias                     */
+    int64_t head;       /* [N,HD]   adapted head                             */
+    int64_t steps;      /* start of the per-step activation records          */
+    int64_t per_step;
+} fumi_stash_layout_t;
+int fumi_stash_layout(const fumi_episode_cfg* cfg, fumi_stash_layout_t* out /* HOST */);
+
+int fumi_episode_fwd(const fumi_episode_cfg* cfg, int64_t B,
+                     const float* proj, const int64_t* sup_rows, const int64_t* qry_rows,
+                     const int64_t* sup_y, const int64_t* qry_y, const float* gram,
+                     const float* b0, const float* w1, const float* b1,
+                     const float* head_table, const int64_t* head_rows,
+                     float* logits, int64_t* preds, float* task_loss, float* task_acc,
+                     float* stash, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Hand-written backward of the same fused step: exact second-order meta-gradient
+ * (outer_loss.backward() through create_graph=True inner steps, fumi.py:165-176,190-192;
+ * maml.py:173-177,188-190).  Gradients are of  loss_scale * sum_b task_loss[b].
+ *   d_proj     [R, H0]   += dLoss/d proj rows (atomic scatter-add; zero it first)
+ *   d_head     [B, N, HD] = dLoss/d head init of each task
+ *   d_b0_parts [P, H0], d_w1_parts [P, H1*H0] (layout [H1,H0]), d_b1_parts [P, H1]:
+ *       per-CTA partial sums, P = fumi_episode_bwd_parts(); reduce with fumi_reduce_parts.
+ * ---------------------------------------------------------------------------------------- */
+int fumi_episode_bwd_parts(void);
+int fumi_episode_bwd(const fumi_episode_cfg* cfg, int64_t B,
+                     const float* proj, const int64_t* sup_rows, const int64_t* qry_rows,
+                     const int64_t* sup_y, const int64_t* qry_y, const float* gram,
+                     const float* stash, float loss_scale,
+                     float* d_proj, float* d_head,
+                     float* d_b0_parts, float* d_w1_parts, float* d_b1_parts, void* stream);
+/* out[n] (+)= sum_p parts[p, n]  (deterministic order) */
+int fumi_reduce_parts(const float* parts, int64_t P, int64_t n, float* out, int32_t accumulate, void* stream);
+/* table[rows[i], :] += src[i, :]  for i < n   (scatter-add of per-task head gradients into
+ * the per-class hypernetwork-output gradient; deterministic when rows are unique) */
+int fumi_scatter_add_rows(const float* src, const int64_t* rows, int64_t n, int64_t width,
+                          float* table, void* stream);
+/* loss = sum(task_loss)/B, acc = sum(task_acc)/B  (fumi.py:187-188) -> out[0], out[1] */
+int fumi_reduce_loss_acc(const float* task_loss, const float* task_acc, int64_t B, float* out, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Outer-loop optimizer step: torch.optim.Adam(lr, weight_decay) as built by init_optim
+ * (utils/utils.py:280-283): L2 term added to the gradient, bias correction with 1-based `step`.
+ * decoupled != 0 gives AdamW (utils.py:289-290).  One fused launch over the flat parameter buffer.
+ * ---------------------------------------------------------------------------------------- */
+int fumi_adam_step(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, int64_t n,
+                   float lr, float beta1, float beta2, float eps, float weight_decay,
+                   int64_t step, int32_t decoupled, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * AM3 meta-test scoring (am3.py:159-200; utils/utils.py:302-402), eval mode.
+ *   emb        [R, P]   image_encoder(feature rows)       (fumi_linear_fwd)
+ *   text_proto [C, P]   g(text) per class row             (fumi_linear_fwd x2)
+ *   lamda      [C]      sigmoid(h(g(text))) per class row; lamda_fixed < 0 = use it, 0 / 1 override
+ *   class_rows [B, N]   class row of label i
+ * outputs: dist [B,NQ,N] squared distances, preds [B,NQ] (argmin, lowest index on ties),
+ *          task_loss [B] = sum over the task's queries of CE(-dist) (divide by B*NQ for the mean).
+ * ---------------------------------------------------------------------------------------- */
+int fumi_am3_score(const float* emb, const float* text_proto, const float* lamda,
+                   const int64_t* sup_rows, const int64_t* qry_rows,
+                   const int64_t* sup_y, const int64_t* qry_y, const int64_t* class_rows,
+                   int64_t B, int32_t N, int32_t NK, int32_t NQ, int32_t P, int32_t lamda_fixed,
+                   float* protos, float* dist, int64_t* preds, float* task_loss, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Episodic task sampler (HOST side, native): bit-exact restatement of
+ * BatchMetaDataLoader(ClassSplitter(InatAnim(...), shuffle=True, K, Q).seed(0)) --
+ * dataset/data.py:73-84,125-188,377-414 + torchmeta 1.7.0.
+ * The three generator streams of the reference are explicit:
+ *   py_state    HOST uint32[625]  CPython `random` MT19937 state (random.getstate()[1])
+ *   torch_state HOST uint32[626]  torch CPU generator: 624 key words, then next index, then `left`
+ *                                  (unpacked from torch.get_rng_state() by the host wrapper)
+ *   the split's own RandomState(0) stream lives inside the handle.
+ * Both external states are read and written back, so the host program's other consumers
+ * (model init, torch.randperm elsewhere) stay in sequence.
+ * All sampler pointers are HOST pointers.
+ * ---------------------------------------------------------------------------------------- */
+typedef struct fumi_sampler fumi_sampler;
+/* class_offsets[C+1], class_image_ids[class_offsets[C]]: ascending image ids of split-class c. */
+int fumi_sampler_create(const int64_t* class_offsets, const int64_t* class_image_ids, int64_t C,
+                        int32_t N, int32_t K, int32_t Q, fumi_sampler** out);
+void fumi_sampler_destroy(fumi_sampler* s);
+/* iter(loader): burns the DataLoader base seed (2 x u32) from the torch stream. */
+int fumi_sampler_new_iterator(fumi_sampler* s, uint32_t* torch_state);
+/* One meta-batch.  classes[B,N] split-class per tuple position, label_perm[B,N] label of tuple
+ * position p, sup_ids[B,N*K], qry_ids[B,N*Q] image ids, sup_y / qry_y labels,
+ * head_class[B,N] split-class carrying label i, sup_rows / qry_rows = position of each image in
+ * class_image_ids (row of the split's HBM feature matrix, which is stored in that order).
+ * num_threads <= 0: hardware concurrency. */
+int fumi_sampler_next(fumi_sampler* s, int64_t B, uint32_t* py_state, uint32_t* torch_state,
+                      int64_t* classes, int64_t* label_perm, int64_t* sup_ids, int64_t* qry_ids,
+                      int64_t* sup_y, int64_t* qry_y, int64_t* head_class,
+                      int64_t* sup_rows, int64_t* qry_rows, int32_t num_threads);
+/* CPython hash(tuple of small non-negative ints) -- exposed for tests. */
+int64_t fumi_py_tuple_hash(const int64_t* items, int64_t n);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* FUMI_B200_H_ */

@@ -57,15 +57,28 @@ def hypernet_backward(hyper, text, u, hp, dhp, tanh=False):
     return dWh1, dbh1, dWh2, dbh2
 
 
-def _mlp(X, th, m0, m1):
+def _mlp(X, th, m0, m1, force=None, ties=None):
+    """force = (R0 bool [n,H0], R1 bool [n,H1]) overrides the ReLU gates (used to compare against an
+    implementation whose rounding resolved a near-zero pre-activation the other way); every
+    overridden entry's |pre-activation| is appended to `ties`."""
     W0, b0, W1, b1, Wh, bh = th
     Z0 = X @ W0.T + b0
-    M0 = (Z0 > 0).astype(X.dtype)
+    R0 = Z0 > 0
+    if force is not None:
+        if ties is not None:
+            ties.extend(np.abs(Z0[R0 != force[0]]).tolist())
+        R0 = force[0]
+    M0 = R0.astype(X.dtype)
     if m0 is not None:
         M0 = M0 * m0
     H0 = Z0 * M0
     Z1 = H0 @ W1.T + b1
-    M1 = (Z1 > 0).astype(X.dtype)
+    R1 = Z1 > 0
+    if force is not None:
+        if ties is not None:
+            ties.extend(np.abs(Z1[R1 != force[1]]).tolist())
+        R1 = force[1]
+    M1 = R1.astype(X.dtype)
     if m1 is not None:
         M1 = M1 * m1
     H1 = Z1 * M1
@@ -74,7 +87,7 @@ def _mlp(X, th, m0, m1):
 
 
 def episode(X, y, Xq, yq, im, hp0, alpha, steps, masks=None, want_grad=False, first_order=False,
-            loss_scale=1.0):
+            loss_scale=1.0, relu_gates=None):
     """One task.  im = (W0,b0,W1,b1) meta-parameters; hp0 [N,65] head init (hypernet output for
     FuMI, lin_final [W|b] for MAML).  masks: None or dict(m0=[S+1,n?,H0], m1=[S+1,.,H1]) given as
     lists: masks['sup'][s] = (m0 [NK,H0], m1 [NK,H1]) and masks['qry'] = (m0q, m1q).
@@ -88,10 +101,10 @@ def episode(X, y, Xq, yq, im, hp0, alpha, steps, masks=None, want_grad=False, fi
     Y = np.zeros((n, N), dt)
     Y[np.arange(n), y] = 1
     th = [W0, b0, W1, b1, hp[:, :-1].copy(), hp[:, -1].copy()]
-    cache, step_losses = [], []
+    cache, step_losses, ties = [], [], []
     for s in range(steps):
         m0, m1 = (masks["sup"][s] if masks is not None else (None, None))
-        M0, H0, M1, H1, L = _mlp(X, th, m0, m1)
+        M0, H0, M1, H1, L = _mlp(X, th, m0, m1, None if relu_gates is None else relu_gates[s], ties)
         step_losses.append(_ce_mean(L, y))
         P = _softmax(L)
         dL = (P - Y) / n
@@ -111,7 +124,7 @@ def episode(X, y, Xq, yq, im, hp0, alpha, steps, masks=None, want_grad=False, fi
     loss = _ce_mean(Lq, yq)
     preds = Lq.argmax(axis=1)                     # first max on ties, as torch.max (fumi.py:180)
     acc = float(np.mean(preds == yq))
-    out = dict(loss=loss, acc=acc, preds=preds.astype(np.int64), logits=Lq, step_losses=step_losses,
+    out = dict(loss=loss, acc=acc, preds=preds.astype(np.int64), logits=Lq, step_losses=step_losses, relu_ties=ties,
                adapted=(th[0], th[1], th[2], th[3], np.concatenate([th[4], th[5][:, None]], 1)))
     if not want_grad:
         return out
@@ -167,7 +180,8 @@ def episode(X, y, Xq, yq, im, hp0, alpha, steps, masks=None, want_grad=False, fi
     return out
 
 
-def fumi_batch(params, batch, alpha, steps, tanh=False, masks=None, want_grad=False, dtype=np.float32):
+def fumi_batch(params, batch, alpha, steps, tanh=False, masks=None, want_grad=False, dtype=np.float32,
+               relu_gates=None):
     """FuMI meta-batch (fumi.py:115-196).  params: dict keyed by the reference state_dict names.
     batch: dict(sup_x [B,NK,D], sup_y, qry_x [B,NQ,D], qry_y, class_text [B,N,T] = description
     embedding of the class carrying label i, picked as fumi.py:207-210)."""
@@ -181,7 +195,8 @@ def fumi_batch(params, batch, alpha, steps, tanh=False, masks=None, want_grad=Fa
         u, hp0 = hypernet_forward(hyper, text, tanh)
         r = episode(np.asarray(batch["sup_x"][b], dtype), batch["sup_y"][b], np.asarray(batch["qry_x"][b], dtype),
                     batch["qry_y"][b], im, hp0, alpha, steps, masks=None if masks is None else masks[b],
-                    want_grad=want_grad, loss_scale=1.0 / B)
+                    want_grad=want_grad, loss_scale=1.0 / B,
+                    relu_gates=None if relu_gates is None else relu_gates[b])
         r["hp0"] = hp0
         if want_grad:
             dW0, db0, dW1, db1, dhp0 = r["grads"]

@@ -1,0 +1,57 @@
+// TEST INFRASTRUCTURE ONLY (see cuda_emu.h).
+#include "cuda_emu.h"
+
+#include <string>
+
+namespace fumi_emu {
+thread_local uint3_emu t_threadIdx;
+uint3_emu g_blockIdx;
+dim3 g_blockDim, g_gridDim;
+char* dyn_smem = nullptr;
+pthread_barrier_t g_barrier;
+
+void launch_impl(const std::function<void()>& body, dim3 grid, dim3 block, size_t smem) {
+    const unsigned nthreads = block.x * block.y * block.z;
+    g_blockDim = block;
+    g_gridDim = grid;
+    void* mem = nullptr;
+    if (posix_memalign(&mem, 128, smem + 128) != 0) abort();
+    // poison the dynamic shared memory so reads of unwritten locations show up as NaN
+    std::memset(mem, 0xFF, smem + 128);
+    dyn_smem = static_cast<char*>(mem);
+    pthread_barrier_init(&g_barrier, nullptr, nthreads);
+    std::vector<std::thread> pool;
+    pool.reserve(nthreads);
+    for (unsigned t = 0; t < nthreads; ++t) {
+        pool.emplace_back([&, t]() {
+            t_threadIdx.x = t % block.x;
+            t_threadIdx.y = (t / block.x) % block.y;
+            t_threadIdx.z = t / (block.x * block.y);
+            for (unsigned bz = 0; bz < grid.z; ++bz)
+                for (unsigned by = 0; by < grid.y; ++by)
+                    for (unsigned bx = 0; bx < grid.x; ++bx) {
+                        if (t == 0) { g_blockIdx.x = bx; g_blockIdx.y = by; g_blockIdx.z = bz; }
+                        pthread_barrier_wait(&g_barrier);
+                        body();
+                        pthread_barrier_wait(&g_barrier);
+                    }
+        });
+    }
+    for (auto& th : pool) th.join();
+    pthread_barrier_destroy(&g_barrier);
+    free(mem);
+    dyn_smem = nullptr;
+}
+}  // namespace fumi_emu
+
+// ---- stand-ins for fumi_b200/csrc/common.cu (which needs the CUDA runtime)
+#include "../../include/fumi_b200.h"
+static thread_local std::string g_last_error;
+void fumi_set_error(const std::string& msg) { g_last_error = msg; }
+int fumi_cuda_fail(cudaError_t, const char* what) { g_last_error = what; return FUMI_ERR_CUDA; }
+extern "C" int fumi_abi_version(void) { return FUMI_B200_ABI_VERSION; }
+extern "C" const char* fumi_last_error(void) { return g_last_error.c_str(); }
+extern "C" int fumi_device_sm_count(void) {
+    const char* e = getenv("FUMI_EMU_SMS");       // fewer "SMs" than tasks exercises the per-CTA task loop
+    return e ? atoi(e) : 2;
+}

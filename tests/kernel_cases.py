@@ -1,0 +1,316 @@
+"""Parity cases shared by the host-emulation tests (CPU, here) and the GPU tests (B200 box).
+
+Each function takes a torch device and drives the product's public host API (fumi_b200.fumi /
+maml / am3 / engine -> C ABI), then checks against the golden vectors produced by the reference
+and against the CPU oracle.  Tolerances: integers / predictions bit-exact; fp32 within 1e-4
+relative (north_star), tensor-normalised: max|a-b| / max|b|.
+"""
+import types
+
+import numpy as np
+import torch
+
+from fumi_b200 import engine as engine_mod
+from fumi_b200 import fumi as fumi_mod
+from fumi_b200 import maml as maml_mod
+from fumi_b200 import am3 as am3_mod
+from fumi_b200.data.bank import EpisodeBatch, FeatureBank
+from fumi_b200.optim import FusedAdam
+from oracle import episode_np
+
+from helpers import argv_int, flat_batch, load_golden, params_of, relerr
+
+TOL = 1e-4
+
+
+def _args(g, device, **kw):
+    a = types.SimpleNamespace(device=torch.device(device), step_size=float(g["alpha"]),
+                              num_train_adapt_steps=int(g["steps"]), num_test_adapt_steps=int(g["steps"]),
+                              first_order=bool(g["first_order"]) if "first_order" in g else False)
+    a.__dict__.update(kw)
+    return a
+
+
+def _torchmeta_batch(g, bank):
+    """The reference's batch dict rebuilt from golden ids: [[ids, text, im], targets]."""
+    t = torch.from_numpy
+    sup_text = bank.text[bank.cat_of[g["sup_ids"]]]
+    qry_text = bank.text[bank.cat_of[g["qry_ids"]]]
+    return {"train": [[t(g["sup_ids"]), t(sup_text), t(bank.feats[g["sup_ids"]])], t(g["sup_y"])],
+            "test": [[t(g["qry_ids"]), t(qry_text), t(bank.feats[g["qry_ids"]])], t(g["qry_y"])]}
+
+
+def _bank_batch(g, bank, device, N):
+    """Index form: whole synthetic bank resident on the device, rows = image ids."""
+    fb = FeatureBank(feats=torch.from_numpy(bank.feats).to(device), text=torch.from_numpy(bank.text).to(device),
+                     ids=np.arange(bank.feats.shape[0]), categories=np.arange(bank.text.shape[0]))
+    from helpers import class_text_rows
+    cats = class_text_rows(bank, g["sup_ids"], g["sup_y"], N)
+    return EpisodeBatch(bank=fb, sup_rows=torch.from_numpy(g["sup_ids"]), qry_rows=torch.from_numpy(g["qry_ids"]),
+                        sup_y=torch.from_numpy(g["sup_y"]), qry_y=torch.from_numpy(g["qry_y"]),
+                        sup_ids=g["sup_ids"], qry_ids=g["qry_ids"], head_class=torch.from_numpy(cats))
+
+
+def _load(model, params, device):
+    model.load_state_dict({k: torch.from_numpy(v) for k, v in params.items()})
+    return model.to(device)
+
+
+def make_fumi(g, bank, params, device, dropout=0.0):
+    argv = str(g["argv"])
+    m = fumi_mod.FUMI(n_way=argv_int(g, "--num_ways", 5), im_emb_dim=bank.feats.shape[1], im_hid_dim=[256, 64],
+                      text_encoder="BERT", text_emb_dim=bank.text.shape[1], text_hid_dim=256, dropout_rate=dropout,
+                      norm_hypernet="--norm_hypernet" in argv)
+    return _load(m, params, device)
+
+
+def check_adapted(res, g, eng, bank, N):
+    """Adapted head / W1 / biases and the materialised W0 rows against the reference's."""
+    lay = eng.stash_layout(res["cfg"])
+    B = g["sup_ids"].shape[0]
+    st = res["stash"].cpu().numpy().reshape(B, lay.per_task)
+    NK = g["sup_ids"].shape[1]
+    for b in range(B):
+        head = st[b, lay.head:lay.head + N * 65].reshape(N, 65)
+        w1 = st[b, lay.w1t:lay.w1t + 256 * 64].reshape(256, 64).T
+        assert relerr(head, g["hp_adapted"][b]) < TOL
+        assert relerr(w1, g["W1_adapted"][b]) < TOL
+        assert relerr(st[b, lay.b1:lay.b1 + 64], g["b1_adapted"][b]) < TOL
+        assert relerr(st[b, lay.b0:lay.b0 + 256], g["b0_adapted"][b]) < TOL
+    # W0_task = W0 - alpha * S^T X   (Gram form <-> the reference's materialised linear0.weight)
+    S = st[0, lay.S:lay.S + NK * 256].reshape(NK, 256)
+    X = bank.feats[g["sup_ids"][0]]
+    return S, X
+
+
+def fumi_train_case(device, name, via="dict"):
+    g, bank = load_golden(name)
+    N = argv_int(g, "--num_ways", 5)
+    params = params_of(g)
+    model = make_fumi(g, bank, params, device)
+    opt = FusedAdam(model.parameters(), lr=float(g["lr"]), weight_decay=float(g["wd"]))
+    args = _args(g, device)
+    batch = _torchmeta_batch(g, bank) if via == "dict" else _bank_batch(g, bank, device, N)
+    eng = model._get_engine(device)
+    # forward only first: the adapted state (the backward reuses the S slots for its adjoint)
+    fw = eng.fumi_batch(model, batch, steps=int(g["steps"]), step_size=float(g["alpha"]), train=False,
+                        return_state=True)
+    S, X = check_adapted(fw, g, eng, bank, N)
+    W0_task = params["im_net.linear0.weight"][:16] - float(g["alpha"]) * (S.T @ X)[:16]
+    assert relerr(W0_task, g["W0_adapted_t0_rows16"]) < TOL
+    res = eng.fumi_batch(model, batch, steps=int(g["steps"]), step_size=float(g["alpha"]), train=True)
+    assert np.array_equal(res["preds"].cpu().numpy(), g["preds"]), "query predictions must be bit-exact"
+    assert relerr(res["logits"].cpu().numpy(), g["logits"]) < TOL
+    la = res["loss_acc"].cpu().numpy()
+    assert abs(la[0] - float(g["loss"])) < TOL * abs(float(g["loss"]))
+    assert abs(la[1] - float(g["acc"])) < 1e-6
+    gmax = max(np.abs(g["grad:" + k]).max() for k in params)
+    for k, p in model.named_parameters():
+        got, ref = p.grad.cpu().numpy(), g["grad:" + k]
+        if k == "hyper_net.2.bias":       # true gradient is exactly 0: absolute check
+            assert np.abs(got - ref).max() < 1e-4 * gmax
+        else:
+            assert relerr(got, ref) < 2e-4, (k, relerr(got, ref))
+    # Adam normalises noise-level gradient entries (|g| ~ eps) into +-lr steps, so the optimizer kernel is
+    # checked on the reference's own gradient; the gradient itself was checked just above.
+    for k, p in model.named_parameters():
+        p.grad.copy_(torch.from_numpy(g["grad:" + k]).to(device))
+    opt.step()
+    for k, p in model.named_parameters():
+        ref = g["post:" + k]
+        assert np.abs(p.detach().cpu().numpy() - ref).max() <= 1e-7 + 2e-6 * np.abs(ref).max(), k
+    return res
+
+
+def fumi_evaluate_api_case(device, name):
+    """Through FUMI.evaluate exactly as the reference loop calls it (fumi.py:242,316)."""
+    g, bank = load_golden(name)
+    model = make_fumi(g, bank, params_of(g), device)
+    opt = FusedAdam(model.parameters(), lr=float(g["lr"]), weight_decay=float(g["wd"]))
+    loss, acc, preds, targets = model.evaluate(_args(g, device), _torchmeta_batch(g, bank), opt, task="train")
+    assert loss.dtype == np.float32 and loss.shape == () and acc.shape == ()
+    assert preds.dtype == torch.float32 and preds.shape == tuple(g["preds"].shape)       # fumi.py:140,180
+    assert np.array_equal(preds.cpu().numpy().astype(np.int64), g["preds"])
+    assert np.array_equal(targets.cpu().numpy(), g["qry_y"])
+    assert abs(float(loss) - float(g["loss"])) < TOL * abs(float(g["loss"]))
+    for k, p in model.named_parameters():          # one optimizer step was taken (fumi.py:193)
+        ref, pre = g["post:" + k], g["param:" + k]
+        big = np.abs(g["grad:" + k] + float(g["wd"]) * pre) > 1e-5
+        assert np.abs(p.detach().cpu().numpy() - ref)[big].max() <= 1e-6, k
+        assert np.abs(p.detach().cpu().numpy() - pre).max() <= 1.01 * float(g["lr"]) + 1e-7
+
+
+def fumi_test_case(device, name, via="dict"):
+    g, bank = load_golden(name)
+    gp, _ = load_golden("fumi_test_n5k1_full")
+    params = params_of(gp)
+    model = make_fumi(g, bank, params, device, dropout=0.25)          # eval mode: dropout layers inert
+    batch = _torchmeta_batch(g, bank) if via == "dict" else _bank_batch(g, bank, device, 5)
+    eng = model._get_engine(device)
+    model.eval()
+    res = eng.fumi_batch(model, batch, steps=int(g["steps"]), step_size=float(g["alpha"]), train=False,
+                         return_state=True)
+    assert np.array_equal(res["preds"].cpu().numpy(), g["preds"])
+    la = res["loss_acc"].cpu().numpy()
+    assert abs(la[1] - float(g["acc"])) < 1e-6
+    # A 100-step unroll is discontinuous in the ReLU gates: a pre-activation within rounding distance of 0
+    # (|z| ~ 1e-6) can be gated either way by two correct fp32 implementations, after which the two
+    # trajectories differ by a finite amount.  So: (1) the kernel must equal the fp64 oracle run with the
+    # kernel's own gates to 1e-4, and every gate that differs from the oracle's must be such a tie;
+    # (2) where no gate differs, the reference's golden logits must be met to 1e-4 as well.
+    steps, NK = int(g["steps"]), g["sup_ids"].shape[1]
+    lay = eng.stash_layout(res["cfg"])
+    B = g["sup_ids"].shape[0]
+    st = res["stash"].cpu().numpy().reshape(B, lay.per_task)
+    gates = []
+    for b in range(B):
+        recs = [st[b, lay.steps + s * lay.per_step:] for s in range(steps)]
+        gates.append([(r[:NK * 256].reshape(NK, 256) > 0, r[NK * 256:NK * 320].reshape(NK, 64) > 0) for r in recs])
+    fb = flat_batch(g, bank, 5)
+    o64 = episode_np.fumi_batch(params, fb, float(g["alpha"]), steps, dtype=np.float64, relu_gates=gates)
+    logits = res["logits"].cpu().numpy()
+    assert relerr(logits, o64["logits"]) < TOL
+    n_ties = 0
+    for b, t in enumerate(o64["tasks"]):
+        assert all(z < 1e-5 for z in t["relu_ties"]), ("gate differs on a non-tie", b, max(t["relu_ties"]))
+        n_ties += len(t["relu_ties"])
+        lay_head = st[b, lay.head:lay.head + 5 * 65].reshape(5, 65)
+        assert relerr(lay_head, t["adapted"][4]) < TOL
+        assert relerr(st[b, lay.w1t:lay.w1t + 256 * 64].reshape(256, 64).T, t["adapted"][2]) < TOL
+        if not t["relu_ties"]:
+            assert relerr(logits[b], g["logits"][b]) < TOL
+            assert relerr(lay_head, g["hp_adapted"][b]) < TOL
+    if n_ties == 0:
+        assert abs(la[0] - float(g["loss"])) < TOL * abs(float(g["loss"]))
+        check_adapted(res, g, eng, bank, 5)
+    else:
+        assert abs(la[0] - float(g["loss"])) < 1e-2 * abs(float(g["loss"]))
+    return n_ties
+
+
+def maml_case(device, name):
+    g, bank = load_golden(name)
+    params = params_of(g)
+    model = _load(maml_mod.PureImageNetwork(im_embed_dim=bank.feats.shape[1], n_way=5, hidden_dims=[256, 64]), params,
+                  device)
+    train = "train" in name
+    opt = FusedAdam(model.parameters(), lr=float(g["lr"]), weight_decay=float(g["wd"])) if train else None
+    loss, acc = maml_mod.evaluate(_args(g, device), model, _torchmeta_batch(g, bank), opt,
+                                  task="train" if train else "test")
+    res = maml_mod.evaluate.last
+    assert np.array_equal(res["preds"].cpu().numpy(), g["preds"])
+    assert relerr(res["logits"].cpu().numpy(), g["logits"]) < TOL
+    assert abs(float(loss) - float(g["loss"])) < TOL * abs(float(g["loss"]))
+    assert abs(float(acc) - float(g["acc"])) < 1e-6
+    if train:
+        for k, p in model.named_parameters():
+            assert relerr(p.grad.cpu().numpy(), g["grad:" + k]) < 2e-4, k
+            # parameters moved by about lr in the direction of -grad (exact Adam check: fumi_train_case)
+            ref, pre = g["post:" + k], g["param:" + k]
+            assert np.abs(p.detach().cpu().numpy() - pre).max() <= 1.01 * float(g["lr"]) + 1e-7
+            big = np.abs(g["grad:" + k] + float(g["wd"]) * pre) > 1e-5
+            assert np.abs(p.detach().cpu().numpy() - ref)[big].max() <= 1e-6, k
+
+
+def am3_case(device, name="am3_test_n10k5_d512"):
+    g, bank = load_golden(name)
+    m = am3_mod.AM3(im_encoder="precomputed", im_emb_dim=bank.feats.shape[1], text_encoder="BERT",
+                    text_emb_dim=bank.text.shape[1], text_hid_dim=256, prototype_dim=64, dropout=0.25)
+    model = _load(m, params_of(g), device)
+    out = model.evaluate(batch=_torchmeta_batch(g, bank), optimizer=None, scheduler=None, num_ways=10, device=device,
+                         task="test")
+    loss, acc, f1, prec, rec, lam, preds, trues, qidx, sidx, slam = out
+    assert np.array_equal(preds, g["preds"])
+    assert abs(float(loss) - float(g["loss"])) < TOL * abs(float(g["loss"]))
+    for a, k in ((acc, "acc"), (f1, "f1"), (prec, "prec"), (rec, "rec")):
+        assert abs(float(a) - float(g[k])) < 1e-9, k
+    assert abs(float(lam) - float(g["avg_lamda"])) < 1e-6
+    assert relerr(slam, g["sup_lamda"]) < TOL
+    assert np.array_equal(qidx, g["qry_ids"]) and np.array_equal(sidx, g["sup_ids"])
+
+
+def dropout_case(device, name="fumi_train_n5k5_d512", p=0.25, seed=77):
+    """Counter-based dropout masks: the device path must equal the oracle fed the same masks."""
+    from fumi_b200.dropout import mask_array
+    g, bank = load_golden(name)
+    N = 5
+    params = params_of(g)
+    model = make_fumi(g, bank, params, device, dropout=p)
+    model.train()
+    model.dropout_base_seed = 0
+    model.dropout_seed = seed - 1          # fumi_batch advances it by one per training batch
+    eng = model._get_engine(device)
+    steps, alpha = int(g["steps"]), float(g["alpha"])
+    res = eng.fumi_batch(model, _torchmeta_batch(g, bank), steps=steps, step_size=alpha, train=True)
+    fb = flat_batch(g, bank, N)
+    B, NK = g["sup_ids"].shape
+    NQ = g["qry_ids"].shape[1]
+    masks = []
+    for b in range(B):
+        sup = [(mask_array(seed, b, s, 0, NK, 256, p), mask_array(seed, b, s, 1, NK, 64, p)) for s in range(steps)]
+        qry = (mask_array(seed, b, steps, 0, NQ, 256, p), mask_array(seed, b, steps, 1, NQ, 64, p))
+        masks.append(dict(sup=sup, qry=qry))
+    ref = episode_np.fumi_batch(params, fb, alpha, steps, masks=masks, want_grad=True, dtype=np.float32)
+    kept = np.mean([m["qry"][0] > 0 for m in masks])
+    assert abs(kept - (1 - p)) < 0.02, "mask keep-rate is off"
+    assert relerr(res["logits"].cpu().numpy(), ref["logits"]) < TOL
+    assert np.array_equal(res["preds"].cpu().numpy(), ref["preds"])
+    for k, q in model.named_parameters():
+        if k != "hyper_net.2.bias":
+            assert relerr(q.grad.cpu().numpy(), ref["grads"][k]) < 2e-4, k
+
+
+def dense_case(device):
+    eng = engine_mod.EpisodeEngine(device)
+    rs = np.random.RandomState(3)
+    for (M, N, K) in [(37, 65, 24), (300, 256, 512), (5, 1, 256), (130, 129, 20)]:
+        x, w, b = rs.randn(M, K).astype(np.float32), (rs.randn(N, K) / np.sqrt(K)).astype(np.float32), rs.randn(N).astype(np.float32)
+        t = lambda a: torch.from_numpy(a).to(device)
+        for act, f in ((0, lambda v: v), (1, lambda v: np.maximum(v, 0)), (2, np.tanh),
+                       (3, lambda v: 1 / (1 + np.exp(-v)))):
+            y = eng.linear_fwd(t(x), t(w), t(b), act=act, precision=0).cpu().numpy()
+            want = f(x.astype(np.float64) @ w.T.astype(np.float64) + b)
+            assert relerr(y, want) < 1e-5, (M, N, K, act)
+        dy = rs.randn(M, N).astype(np.float32)
+        dw, db = torch.empty(N, K, device=device), torch.empty(N, device=device)
+        eng.linear_wgrad(t(dy), t(x), dw, db, precision=0)
+        assert relerr(dw.cpu().numpy(), dy.astype(np.float64).T @ x) < 1e-5
+        assert relerr(db.cpu().numpy(), dy.astype(np.float64).sum(0)) < 1e-5
+        eng.linear_wgrad(t(dy), t(x), dw, None, accumulate=True, precision=0)
+        assert relerr(dw.cpu().numpy(), 2 * (dy.astype(np.float64).T @ x)) < 1e-5
+        gate = rs.randn(M, K).astype(np.float32)
+        dx = eng.linear_dgrad(t(dy), t(w), t(gate)).cpu().numpy()
+        assert relerr(dx, (dy.astype(np.float64) @ w) * (gate > 0)) < 1e-5
+
+
+def gram_case(device):
+    eng = engine_mod.EpisodeEngine(device)
+    rs = np.random.RandomState(4)
+    for (R, D, B, NK, NQ) in [(300, 64, 3, 25, 40), (500, 132, 2, 100, 70), (64, 2048, 2, 5, 100)]:
+        feats = rs.randn(R, D).astype(np.float32)
+        sup, qry = rs.randint(0, R, size=(B, NK)), rs.randint(0, R, size=(B, NQ))
+        t = lambda a: torch.from_numpy(a).to(device)
+        g = eng.gram(t(feats), t(sup), t(qry)).cpu().numpy()
+        f64 = feats.astype(np.float64)
+        for b in range(B):
+            rows = np.concatenate([sup[b], qry[b]])
+            assert relerr(g[b], f64[rows] @ f64[sup[b]].T) < 1e-5
+
+
+def adam_case(device):
+    rs = np.random.RandomState(5)
+    shapes = [(7, 13), (64,), (33, 5)]
+    ps = [torch.nn.Parameter(torch.from_numpy(rs.randn(*s).astype(np.float32)).to(device)) for s in shapes]
+    ref = [p.detach().cpu().clone().requires_grad_(True) for p in ps]
+    for decoupled in (False, True):
+        mine = FusedAdam(ps, lr=1e-2, weight_decay=0.1, decoupled=decoupled)
+        theirs = (torch.optim.AdamW if decoupled else torch.optim.Adam)(ref, lr=1e-2, weight_decay=0.1)
+        for it in range(3):
+            for p, r in zip(ps, ref):
+                gr = torch.from_numpy(rs.randn(*p.shape).astype(np.float32))
+                p.grad.copy_(gr.to(device))
+                r.grad = gr.clone()
+            mine.step()
+            theirs.step()
+            for p, r in zip(ps, ref):
+                assert np.abs(p.detach().cpu().numpy() - r.detach().numpy()).max() < 2e-6

@@ -1,0 +1,69 @@
+"""Kernel bodies on the host emulation (tests/emu): the same parity cases the GPU tests run.
+
+TEST INFRASTRUCTURE: the emulation library is libfumi_b200's own kernel source compiled for the CPU
+with a CUDA shim; it checks indexing / synchronisation / math where no GPU exists.  The GPU
+results are what counts (tests/test_gpu_parity.py, -m gpu)."""
+import os
+import sys
+
+import pytest
+
+from fumi_b200 import _lib
+
+sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), "emu"))
+import kernel_cases as kc  # noqa: E402
+
+
+@pytest.fixture(scope="module", autouse=True)
+def emu_lib():
+    import build_emu
+    saved = (_lib._LIB, _lib._EMULATION)
+    _lib.load(build_emu.build(), emulation=True)
+    yield
+    _lib._LIB, _lib._EMULATION = saved
+
+
+def test_dense():
+    kc.dense_case("cpu")
+
+
+def test_gram():
+    kc.gram_case("cpu")
+
+
+def test_adam():
+    kc.adam_case("cpu")
+
+
+@pytest.mark.parametrize("via", ["dict", "bank"])
+def test_fumi_train_n5k5(via):
+    kc.fumi_train_case("cpu", "fumi_train_n5k5_d512", via=via)
+
+
+def test_fumi_train_tanh():
+    kc.fumi_train_case("cpu", "fumi_train_n5k5_d512_tanh")
+
+
+def test_fumi_train_n20k5_multitile():
+    kc.fumi_train_case("cpu", "fumi_train_n20k5_d512")
+
+
+def test_fumi_evaluate_api():
+    kc.fumi_evaluate_api_case("cpu", "fumi_train_n5k5_d512")
+
+
+def test_fumi_test_n5k1_100_steps():
+    kc.fumi_test_case("cpu", "fumi_test_n5k1_full")
+
+
+@pytest.mark.parametrize("name", ["maml_train_n5k5_d512", "maml_train_n5k5_d512_fo", "maml_test_n5k5_d512"])
+def test_maml(name):
+    kc.maml_case("cpu", name)
+
+
+def test_am3():
+    kc.am3_case("cpu")
+
+
+def test_dropout_masks():
+    kc.dropout_case("cpu")

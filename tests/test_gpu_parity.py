@@ -1,0 +1,74 @@
+"""Parity of the CUDA path (through the C ABI) against the reference's golden vectors and the CPU
+oracle, on a real B200.  Same cases as tests/test_emu_kernels.py, device = cuda:0."""
+import numpy as np
+import pytest
+import torch
+
+import kernel_cases as kc
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+
+
+@pytest.fixture(scope="module", autouse=True)
+def real_library():
+    from fumi_b200 import _lib
+    assert not _lib.is_emulation(), "GPU tests must run on the CUDA build of libfumi_b200.so"
+    assert _lib.lib().fumi_device_sm_count() > 0
+    yield
+
+
+def test_dense():
+    kc.dense_case(DEV)
+
+
+def test_gram():
+    kc.gram_case(DEV)
+
+
+def test_adam():
+    kc.adam_case(DEV)
+
+
+@pytest.mark.parametrize("via", ["dict", "bank"])
+def test_fumi_train_n5k5(via):
+    kc.fumi_train_case(DEV, "fumi_train_n5k5_d512", via=via)
+
+
+def test_fumi_train_tanh():
+    kc.fumi_train_case(DEV, "fumi_train_n5k5_d512_tanh")
+
+
+def test_fumi_train_n20k5_multitile():
+    kc.fumi_train_case(DEV, "fumi_train_n20k5_d512")
+
+
+def test_fumi_evaluate_api():
+    kc.fumi_evaluate_api_case(DEV, "fumi_train_n5k5_d512")
+
+
+@pytest.mark.parametrize("name", ["fumi_test_n5k1_full", "fumi_test_n5k5_full"])
+@pytest.mark.parametrize("via", ["dict", "bank"])
+def test_fumi_meta_test_100_steps(name, via):
+    kc.fumi_test_case(DEV, name, via=via)
+
+
+@pytest.mark.parametrize("name", ["maml_train_n5k5_d512", "maml_train_n5k5_d512_fo", "maml_test_n5k5_d512"])
+def test_maml(name):
+    kc.maml_case(DEV, name)
+
+
+def test_am3():
+    kc.am3_case(DEV)
+
+
+def test_dropout_masks():
+    kc.dropout_case(DEV)
+
+
+def test_no_cpu_path():
+    """The product refuses non-CUDA devices instead of falling back."""
+    from fumi_b200 import _lib
+    from fumi_b200.engine import EpisodeEngine
+    with pytest.raises(_lib.FumiError):
+        EpisodeEngine("cpu")

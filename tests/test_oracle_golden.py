@@ -117,14 +117,16 @@ def test_flat_sampler_matches_reference_loader(name, N, K, Qtrain):
     # main.py:51-53 seeds after the loaders are built (seed flag default 123)
     torch.manual_seed(123); np.random.seed(123); random.seed(123)
     # model init consumes the torch stream before any iterator exists
-    from fumi_b200.models import build_reference_init
-    build_reference_init("maml", num_ways=N, im_emb_dim=16, text_emb_dim=8)
-    started = set()
+    from fumi_b200.maml import PureImageNetwork
+    PureImageNetwork(im_embed_dim=16, n_way=N, hidden_dims=[256, 64])
+    # iterator creation order of oracle/make_golden.py: iter(val), 1 val batch, iter(train), iter(test), ...
     for i, split in enumerate(g["order"]):
         split = str(split)
-        if split not in started:
-            samplers[split].new_iterator()
-            started.add(split)
+        if i == 0:
+            samplers["val"].new_iterator()
+        if i == 1:
+            samplers["train"].new_iterator()
+            samplers["test"].new_iterator()
         b = samplers[split].next_batch(B)
         assert np.array_equal(b["sup_ids"], g[f"b{i}_sup_ids"]), (i, split)
         assert np.array_equal(b["qry_ids"], g[f"b{i}_qry_ids"]), (i, split)
