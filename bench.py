@@ -1,0 +1,351 @@
+"""Benchmark of the FuMI episodic inner-loop path (BASELINE.json: meta-train tasks/s).
+
+    python bench.py --gpus N --steps K --warmup W           our arm (one process per GPU; torchrun for N>1)
+    python bench.py --impl reference --steps K --warmup W   the reference's CPU path on the host cores
+
+Workload at N=1 = BASELINE.json configs[1]: FuMI 5-way 5-shot meta-train, 5 inner steps,
+4096 tasks per meta-batch per GPU (query 32/class, dropout 0.25, Adam lr 3e-5 wd 5e-4: the
+reference defaults, utils.py:19-229), on the synthetic iNat-Anim-shaped bank.
+A "step" = one meta-batch: hypernetwork, first-layer projection of the split's bank, Gram blocks
+of every task, fused inner loop + query scoring, second-order backward, dW0, (all-reduce), Adam.
+
+Prints ONE JSON line (contract in the task statement): value = whole-job tasks/s with the sampled
+indices already resident in HBM; e2e = the same through the public API (native host sampler ->
+pinned buffers -> H2D -> FUMI.evaluate -> D2H of loss/acc) inside the timed region.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+WORKLOADS = {
+    # name: (model, N, K, Q, steps, train)
+    "fumi_train_5w5s": ("fumi", 5, 5, 32, 5, True),          # BASELINE configs[1] (default)
+    "maml_train_5w5s": ("maml", 5, 5, 32, 5, True),          # configs[2]
+    "fumi_test_5w5s": ("fumi", 5, 5, 20, 100, False),        # headline meta-test metric
+    "fumi_test_5w1s": ("fumi", 5, 1, 20, 100, False),        # configs[0]
+    "fumi_train_20w5s": ("fumi", 20, 5, 32, 10, True),       # configs[4]
+}
+
+
+def algorithmic_bytes(N, K, Q, D, T, train):
+    """B_fwd = 4(NK+NQ)D + 4NT + 8(NK+NQ) + 4 NQ N + 8 NQ ; B_train = B_fwd + 4(NK+NQ)D."""
+    NK, NQ = N * K, N * Q
+    b = 4 * (NK + NQ) * D + 4 * N * T + 8 * (NK + NQ) + 4 * NQ * N + 8 * NQ
+    return b + (4 * (NK + NQ) * D if train else 0)
+
+
+def peaks():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            p = json.load(f)
+        return float(p["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    except Exception:
+        return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md recipe)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.proc, self.lines = index, None, []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "100", "-i", str(self.index)], stdout=subprocess.PIPE, text=True)
+            threading.Thread(target=lambda: self.lines.extend(self.proc.stdout), daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1])); mx.append(float(f[2]))
+            except ValueError:
+                continue
+            for nm, v in zip(names, f[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(nm)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+def make_args(model, N, K, Q, steps, train, device, D, T, tasks, dropout):
+    from fumi_b200 import utils
+    a = utils.parser().parse_args(["--model", model, "--num_ways", str(N), "--num_shots", str(K),
+                                   "--num_shots_test", str(Q), "--batch_size", str(tasks),
+                                   "--num_train_adapt_steps", str(steps), "--num_test_adapt_steps", str(steps),
+                                   "--im_emb_dim", str(D), "--text_emb_dim", str(T), "--dropout", str(dropout),
+                                   "--synthetic", "--wandb_offline"])
+    a.device = device
+    return a
+
+
+# ------------------------------------------------------------------------------------------ CPU leg
+def cpu_reference_leg(wl, D, T, steps_k, warmup, budget_s, tasks_per_batch=4, seed=123):
+    """The reference's CPU path for the same episode shape: oracle/episode_torch.py (autograd port of
+    fumi.py:148-193 / maml.py:158-191, per-task Python loop, batch_size 4) + torch Adam, all host
+    threads.  The reference itself cannot travel to the GPU box: kind='port'."""
+    import torch
+    from oracle import episode_torch
+    from fumi_b200.data.synth import class_split, make_bank
+    from fumi_b200.sampler import EpisodeSampler
+    from fumi_b200 import fumi as fumi_mod, maml as maml_mod
+    import random
+    model_name, N, K, Q, steps, train = WORKLOADS[wl]
+    torch.set_num_threads(os.cpu_count())
+    bank = make_bank(num_images=673 * 62, num_classes=673, im_dim=D, text_dim=T, min_per_class=60)
+    cats = class_split(673)[0 if train else 2]
+    sampler = EpisodeSampler(bank.cat_of, cats, N, K, Q)
+    torch.manual_seed(seed); np.random.seed(seed); random.seed(seed)
+    if model_name == "fumi":
+        m = fumi_mod.FUMI(n_way=N, im_emb_dim=D, im_hid_dim=[256, 64], text_encoder="BERT", text_emb_dim=T,
+                          text_hid_dim=256, dropout_rate=0.0, norm_hypernet=False)
+    else:
+        m = maml_mod.PureImageNetwork(im_embed_dim=D, n_way=N, hidden_dims=[256, 64])
+    params = {k: v for k, v in m.named_parameters()}
+    opt = torch.optim.Adam(list(params.values()), lr=3e-5, weight_decay=5e-4)
+    feats, text = torch.from_numpy(bank.feats), torch.from_numpy(bank.text)
+    sampler.new_iterator()
+
+    def one_batch():
+        b = sampler.next_batch(tasks_per_batch)
+        t = lambda a: torch.from_numpy(a)
+        batch = dict(sup_x=feats[t(b["sup_ids"])], qry_x=feats[t(b["qry_ids"])], sup_y=t(b["sup_y"]), qry_y=t(b["qry_y"]),
+                     class_text=text[t(cats[b["head_class"]])])
+        if model_name == "fumi":
+            episode_torch.fumi_batch(params, batch, 0.01, steps, train=train)
+        else:
+            episode_torch.maml_batch(params, batch, 0.01, steps, train=train)
+        if train:
+            opt.step()
+
+    for _ in range(warmup):
+        one_batch()
+    per_step, t_all0 = [], time.perf_counter()
+    for _ in range(steps_k):
+        t0 = time.perf_counter()
+        one_batch()
+        per_step.append(time.perf_counter() - t0)
+        if time.perf_counter() - t_all0 > budget_s:
+            break
+    tot = sum(per_step)
+    return dict(value=tasks_per_batch * len(per_step) / tot, unit="tasks/s", cores=torch.get_num_threads(), kind="port",
+                sample=f"{len(per_step)} meta-batches x {tasks_per_batch} tasks (reference --batch_size 4), "
+                       f"{wl}, D={D}, autograd port oracle/episode_torch.py, dropout off, torch Adam",
+                ms_per_step=1e3 * tot / len(per_step), steps_done=len(per_step))
+
+
+# ------------------------------------------------------------------------------------------ our arm
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="fumi_train_5w5s", choices=sorted(WORKLOADS))
+    ap.add_argument("--tasks", type=int, default=4096, help="tasks per meta-batch per GPU")
+    ap.add_argument("--bank_images", type=int, default=195605)
+    ap.add_argument("--bank_classes", type=int, default=673)
+    ap.add_argument("--im_dim", type=int, default=2048)
+    ap.add_argument("--text_dim", type=int, default=768)
+    ap.add_argument("--dropout", type=float, default=0.25)
+    ap.add_argument("--precision", type=int, default=int(os.environ.get("FUMI_PRECISION", "0")))
+    ap.add_argument("--cpu_budget_s", type=float, default=15.0)
+    ap.add_argument("--no_cpu_baseline", action="store_true")
+    ap.add_argument("--no_kernel_pass", action="store_true")
+    a = ap.parse_args()
+    rank = int(os.environ.get("RANK", 0))
+    world = int(os.environ.get("WORLD_SIZE", 1))
+    local = int(os.environ.get("LOCAL_RANK", 0))
+    model_name, N, K, Q, steps, train = WORKLOADS[a.workload]
+    metric = ("meta-train tasks/sec" if train else "meta-test episodes/sec") + \
+        f" ({model_name.upper() if model_name != 'fumi' else 'FuMI'} {N}-way {K}-shot, {steps} inner steps)"
+    unit = "tasks/s" if train else "episodes/s"
+    cfg_common = {"workload": a.workload, "num_ways": N, "num_shots": K, "query_per_class": Q, "inner_steps": steps,
+                  "tasks_per_batch_per_gpu": a.tasks, "im_dim": a.im_dim, "text_dim": a.text_dim,
+                  "hidden": [256, 64], "parallelism": f"tasks sharded over {a.gpus} GPU(s), 1 NCCL all-reduce/step"}
+
+    if a.impl == "reference":
+        if rank != 0:
+            return
+        r = cpu_reference_leg(a.workload, a.im_dim, a.text_dim, a.steps, a.warmup, budget_s=240.0)
+        line = {"impl": "reference", "metric": metric, "value": r["value"], "unit": unit, "n_gpus": a.gpus,
+                "steps": r["steps_done"], "warmup": a.warmup, "ms_per_step": r["ms_per_step"], "higher_is_better": True,
+                "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+                "data": "synthetic iNat-Anim-shaped bank (fumi_b200.data.synth, RandomState(2022))",
+                "config": dict(cfg_common, tasks_per_batch_per_gpu=4, dropout=0.0),
+                "cpu_baseline": {"value": r["value"], "unit": unit, "cores": r["cores"], "kind": r["kind"],
+                                 "sample": r["sample"]},
+                "e2e": {"value": r["value"], "unit": unit, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+        print(json.dumps(line))
+        return
+
+    import torch
+    import torch.distributed as dist
+    torch.cuda.set_device(local)
+    device = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=device)
+    from fumi_b200 import fumi as fumi_mod, maml as maml_mod, utils
+    from fumi_b200.data.loader import EpisodeLoader
+    from fumi_b200.data.bank import FeatureBank
+    from fumi_b200.data.synth import class_split, make_bank
+    from fumi_b200.sampler import EpisodeSampler
+    import random
+
+    args = make_args(model_name, N, K, Q, steps, train, device, a.im_dim, a.text_dim, a.tasks, a.dropout)
+    args.first_order = False
+    t0 = time.time()
+    bank = make_bank(num_images=a.bank_images, num_classes=a.bank_classes, im_dim=a.im_dim, text_dim=a.text_dim)
+    cats = class_split(a.bank_classes)[0 if train else 2]
+    sampler = EpisodeSampler(bank.cat_of, cats, N, K, Q)
+    fb = FeatureBank(feats=torch.from_numpy(bank.feats[sampler.ids]).to(device),
+                     text=torch.from_numpy(bank.text[cats]).to(device), ids=sampler.ids, categories=cats)
+    loader = EpisodeLoader(fb, sampler, a.tasks)
+    t_setup = time.time() - t0
+    seed = 123 + rank                                   # ranks draw independent task streams (weak scaling)
+    torch.manual_seed(123); np.random.seed(123); random.seed(123)
+    model = utils.init_model(args, {})                   # same initial weights on every rank
+    opt = utils.init_optim(args, model) if train else None
+    torch.manual_seed(seed); random.seed(seed)
+    eng = model._get_engine(device)
+    eng.precision = a.precision
+    sampler.new_iterator()
+
+    def run_resident(batch):
+        if model_name == "fumi":
+            eng.fumi_batch(model, batch, steps=steps, step_size=args.step_size, train=train)
+        else:
+            eng.maml_batch(model, batch, steps=steps, step_size=args.step_size, train=train, first_order=False)
+        if train:
+            opt.step()
+
+    def run_api(batch):
+        if model_name == "fumi":
+            return model.evaluate(args, batch, opt, task="train" if train else "test")
+        return maml_mod.evaluate(args, model, batch, opt, task="train" if train else "test")
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- leg 1: device-resident inputs (value)
+    batches = [loader.next_batch().to(device) for _ in range(a.warmup + a.steps)]
+    torch.cuda.synchronize()
+    model.train(train)
+    for i in range(a.warmup):
+        run_resident(batches[i])
+    barrier()
+    clocks = ClockSampler(local)
+    clocks.start()
+    l0 = eng.launches
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for i in range(a.steps):
+        run_resident(batches[a.warmup + i])
+    e1.record()
+    barrier()
+    ms = torch.tensor([e0.elapsed_time(e1)], device=device)
+    launches = eng.launches - l0 + (a.steps if train else 0)          # + one fused Adam launch per step
+    clk = clocks.stop()
+    if world > 1:
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    ms_value = float(ms.item())
+
+    # ---- leg 2: end to end through the public API, host buffers (e2e)
+    for i in range(2):
+        run_api(loader.next_batch())
+    barrier()
+    h2d = d2h = 0
+    e0.record()
+    for i in range(a.steps):
+        b = loader.next_batch()
+        if i == 0:
+            h2d = sum(t.numel() * 8 for t in (b.sup_rows, b.qry_rows, b.sup_y, b.qry_y, b.head_class))
+            d2h = 8                                                     # loss + acc (fumi.py:195-196)
+        run_api(b)
+    e1.record()
+    barrier()
+    ms2 = torch.tensor([e0.elapsed_time(e1)], device=device)
+    if world > 1:
+        dist.all_reduce(ms2, op=dist.ReduceOp.MAX)
+    ms_e2e = float(ms2.item())
+
+    # ---- per-kernel pass (CUDA events around every C-ABI call, on the launching stream)
+    kernels, roof = {}, None
+    peak, peak_src = peaks()
+    bytes_task = algorithmic_bytes(N, K, Q, a.im_dim, a.text_dim, train)
+    if not a.no_kernel_pass:
+        eng.profile = {}
+        nprof = min(3, a.steps)
+        for i in range(nprof):
+            run_resident(batches[a.warmup + i])
+        torch.cuda.synchronize()
+        for name, evs in eng.profile.items():
+            ts = [x.elapsed_time(y) for x, y in evs]
+            kernels[name] = {"ms_per_step": sum(ts) / nprof, "calls_per_step": len(ts) / nprof}
+        eng.profile = None
+        top = max(kernels, key=lambda k: kernels[k]["ms_per_step"])
+        dur = kernels[top]["ms_per_step"] / kernels[top]["calls_per_step"] * 1e-3
+        ach = bytes_task * a.tasks / dur / 1e9
+        roof = {"kernel": top, "bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
+                "traffic": None, "peak_source": peak_src, "launch_ms": dur * 1e3,
+                "algorithmic_bytes_per_task": bytes_task,
+                "note": "achieved = SURVEY 8(d) bytes/task x tasks / launch time of the longest kernel; "
+                        "fumi_gram is the kernel that actually streams those bytes (see by_kernel)"}
+        roof["by_kernel"] = {k: {"ms": v["ms_per_step"],
+                                 "hbm_frac_if_alone": bytes_task * a.tasks / (v["ms_per_step"] * 1e-3) / 1e9 / peak}
+                             for k, v in sorted(kernels.items(), key=lambda kv: -kv[1]["ms_per_step"])}
+        step_gbs = bytes_task * a.tasks / (ms_value / a.steps * 1e-3) / 1e9
+        roof["whole_step"] = {"achieved": step_gbs, "frac": step_gbs / peak}
+
+    cpu = None
+    if rank == 0 and world == 1 and not a.no_cpu_baseline:
+        r = cpu_reference_leg(a.workload, a.im_dim, a.text_dim, 10 ** 6, 1, budget_s=a.cpu_budget_s)
+        cpu = {"value": r["value"], "unit": unit, "cores": r["cores"], "kind": r["kind"], "sample": r["sample"]}
+
+    if rank == 0:
+        total_tasks = a.tasks * world * a.steps
+        line = {"metric": metric, "value": total_tasks / (ms_value * 1e-3), "unit": unit, "n_gpus": world,
+                "steps": a.steps, "warmup": a.warmup, "ms_per_step": ms_value / a.steps, "higher_is_better": True,
+                "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+                "data": "synthetic iNat-Anim-shaped bank (fumi_b200.data.synth, RandomState(2022)); random-init weights",
+                "config": dict(cfg_common, dropout=a.dropout if train else 0.0, dense_precision=a.precision,
+                               bank_rows=int(fb.feats.shape[0]), bank_classes=int(len(cats)),
+                               l2_policy="per-step gathered input (tasks x rows x 8 KB) far exceeds the 126 MB L2",
+                               setup_s=round(t_setup, 1)),
+                "clocks": clk,
+                "e2e": {"value": total_tasks / (ms_e2e * 1e-3), "unit": unit, "h2d_bytes_per_step": h2d,
+                        "d2h_bytes_per_step": d2h, "ms_per_step": ms_e2e / a.steps,
+                        "path": "EpisodeLoader.next_batch (native sampler, pinned) -> evaluate() -> loss/acc to host"},
+                "gpu_launches": launches, "roofline": roof, "cpu_baseline": cpu, "kernels": kernels}
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,92 @@
+"""Episodic loaders over a GPU-resident feature bank: drop-in for dataset.data.get_dataset.
+
+Reference: fumi/dataset/data.py:25-86 (get_dataset -> three BatchMetaDataLoader) and 125-188
+(get_inat_anim: train split with Q = --num_shots_test, val/test with Q = int(100 / N), each
+ClassSplitter seeded 0).  A loader here has the same iteration contract -- ``iter(loader)`` starts a
+new DataLoader iterator (which burns the torch base seed), ``next`` yields one meta-batch, forever --
+but the batch is an EpisodeBatch of indices into the split's FeatureBank instead of collated tensors.
+"""
+import json
+import os
+import random
+
+import numpy as np
+import torch
+
+from .bank import EpisodeBatch, FeatureBank
+from .synth import INAT_ANIM_CLASSES, INAT_ANIM_IMAGES, class_split, make_bank
+from ..sampler import EpisodeSampler
+
+_KEYS = ("classes", "label_perm", "sup_ids", "qry_ids", "sup_y", "qry_y", "head_class", "sup_rows", "qry_rows")
+
+
+class EpisodeLoader:
+    def __init__(self, bank, sampler, batch_size, pin_memory=True):
+        self.bank, self.sampler, self.batch_size = bank, sampler, int(batch_size)
+        self.pin = bool(pin_memory) and bank.feats.is_cuda
+        self.dataset = sampler          # len(loader.dataset) parity is not meaningful for episodes
+
+    def _host_buffers(self):
+        N, K, Q, B = self.sampler.N, self.sampler.K, self.sampler.Q, self.batch_size
+        widths = dict(classes=N, label_perm=N, sup_ids=N * K, qry_ids=N * Q, sup_y=N * K, qry_y=N * Q,
+                      head_class=N, sup_rows=N * K, qry_rows=N * Q)
+        ts = {k: torch.empty((B, w), dtype=torch.int64, pin_memory=self.pin) for k, w in widths.items()}
+        return ts, {k: t.numpy() for k, t in ts.items()}
+
+    def next_batch(self):
+        ts, arrs = self._host_buffers()
+        self.sampler.next_batch(self.batch_size, out=arrs)
+        return EpisodeBatch(bank=self.bank, sup_rows=ts["sup_rows"], qry_rows=ts["qry_rows"], sup_y=ts["sup_y"],
+                            qry_y=ts["qry_y"], sup_ids=arrs["sup_ids"], qry_ids=arrs["qry_ids"],
+                            head_class=ts["head_class"], host=arrs)
+
+    def __iter__(self):
+        self.sampler.new_iterator()
+        while True:
+            yield self.next_batch()
+
+
+def build_loaders(feats, text, cat_of, num_ways, num_shots, num_shots_test, batch_size, device, num_threads=0):
+    """(train, val, test) EpisodeLoaders.  feats [M,D] / text [C,T] / cat_of [M] are host arrays."""
+    C = text.shape[0]
+    loaders = []
+    for split, cats in zip(("train", "val", "test"), class_split(C)):
+        # each InatAnim constructor reseeds the three global generators (data.py:320-322)
+        random.seed(0); np.random.seed(0); torch.manual_seed(0)
+        Q = num_shots_test if split == "train" else int(100 / num_ways)
+        sampler = EpisodeSampler(cat_of, cats, num_ways, num_shots, Q, num_threads=num_threads)
+        bank = FeatureBank(feats=torch.from_numpy(np.ascontiguousarray(feats[sampler.ids])).to(device),
+                           text=torch.from_numpy(np.ascontiguousarray(text[cats])).to(device),
+                           ids=sampler.ids, categories=np.asarray(cats))
+        loaders.append(EpisodeLoader(bank, sampler, batch_size))
+    return tuple(loaders)
+
+
+def load_arrays(args):
+    """Host arrays (feats, text, cat_of) from --data_dir, or the synthetic banks with --synthetic.
+
+    On-disk layout accepted: <data_dir>/iNat-Anim/bank.npz with arrays feats [M,D] f32, text [C,T] f32
+    (description embeddings, precomputed), cat_of [M] i64.  The reference's inat_anim.json +
+    image_embeddings_*.hdf5 pair (data.py:373-430) converts to it with tools in DESIGN.md "next"."""
+    if getattr(args, "synthetic", False):
+        b = make_bank(num_images=int(os.environ.get("FUMI_SYNTH_IMAGES", INAT_ANIM_IMAGES)),
+                      num_classes=int(os.environ.get("FUMI_SYNTH_CLASSES", INAT_ANIM_CLASSES)),
+                      im_dim=args.im_emb_dim, text_dim=args.text_emb_dim)
+        return b.feats, b.text, b.cat_of
+    path = os.path.join(args.data_dir, "iNat-Anim", "bank.npz")
+    if not os.path.exists(path):
+        raise FileNotFoundError(f"{path} not found (pass --synthetic for the synthetic iNat-Anim-shaped banks)")
+    z = np.load(path)
+    return z["feats"], z["text"], z["cat_of"]
+
+
+def get_dataset(args):
+    """dataset.data.get_dataset (data.py:25-86): (train_loader, val_loader, test_loader, dictionary)."""
+    if args.dataset != "inat-anim":
+        raise NotImplementedError()          # data.py:71; CUB / supervised-inat-anim are outside the path
+    if args.text_encoder != "BERT":
+        raise NotImplementedError("only precomputed description embeddings (--text_encoder BERT) are built")
+    feats, text, cat_of = load_arrays(args)
+    bs = args.tasks_per_batch if getattr(args, "tasks_per_batch", None) else args.batch_size
+    tl, vl, te = build_loaders(feats, text, cat_of, args.num_ways, args.num_shots, args.num_shots_test, bs, args.device)
+    return tl, vl, te, {}

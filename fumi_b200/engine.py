@@ -47,6 +47,19 @@ class EpisodeEngine:
         self.L = _lib.lib()
         self.precision = precision       # 0: fp32 FMA dense layers, 1: tcgen05 3xTF32
         self.launches = 0                # kernels launched through this engine (bench: gpu_launches)
+        self.profile = None              # dict name -> [cuda event pairs] while bench.py profiles kernels
+
+    def _call(self, name, fn, *args):
+        """Invoke one C-ABI entry point; under bench.py's per-kernel pass bracket it with CUDA events
+        on the launching stream."""
+        if self.profile is None or self.device.type != "cuda":
+            return _lib.check(fn(*args), name)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        rc = _lib.check(fn(*args), name)
+        e1.record()
+        self.profile.setdefault(name, []).append((e0, e1))
+        return rc
 
     # ------------------------------------------------------------------ thin wrappers over the C ABI
     def _stream(self):
@@ -59,26 +72,25 @@ class EpisodeEngine:
         M, K = x.shape
         N = w.shape[0]
         y = self._new(M, N)
-        _lib.check(self.L.fumi_linear_fwd(_lib.ptr(x), _lib.ptr(w), _lib.ptr(bias), _lib.ptr(y), M, N, K, act,
-                                          self.precision if precision is None else precision, self._stream()),
-                   "fumi_linear_fwd")
+        self._call("fumi_linear_fwd", self.L.fumi_linear_fwd, _lib.ptr(x), _lib.ptr(w), _lib.ptr(bias), _lib.ptr(y), M, N, K, act,
+                                          self.precision if precision is None else precision, self._stream())
         self.launches += 1
         return y
 
     def linear_wgrad(self, dy, x, dw, db=None, accumulate=False, precision=None):
         M, N = dy.shape
         K = x.shape[1]
-        _lib.check(self.L.fumi_linear_wgrad(_lib.ptr(dy), _lib.ptr(x), _lib.ptr(dw), _lib.ptr(db), M, N, K,
+        self._call("fumi_linear_wgrad", self.L.fumi_linear_wgrad, _lib.ptr(dy), _lib.ptr(x), _lib.ptr(dw), _lib.ptr(db), M, N, K,
                                             int(accumulate), self.precision if precision is None else precision,
-                                            self._stream()), "fumi_linear_wgrad")
+                                            self._stream())
         self.launches += 2 + (db is not None)
 
     def linear_dgrad(self, dy, w, gate=None):
         M, N = dy.shape
         K = w.shape[1]
         dx = self._new(M, K)
-        _lib.check(self.L.fumi_linear_dgrad(_lib.ptr(dy), _lib.ptr(w), _lib.ptr(gate), _lib.ptr(dx), M, N, K,
-                                            self._stream()), "fumi_linear_dgrad")
+        self._call("fumi_linear_dgrad", self.L.fumi_linear_dgrad, _lib.ptr(dy), _lib.ptr(w), _lib.ptr(gate), _lib.ptr(dx), M, N, K,
+                                            self._stream())
         self.launches += 1
         return dx
 
@@ -86,8 +98,8 @@ class EpisodeEngine:
         B, NK = sup_rows.shape
         NQ = qry_rows.shape[1]
         g = self._new(B, NK + NQ, NK)
-        _lib.check(self.L.fumi_gram(_lib.ptr(feats), feats.shape[0], feats.shape[1], _lib.ptr(sup_rows),
-                                    _lib.ptr(qry_rows), B, NK, NQ, _lib.ptr(g), self._stream()), "fumi_gram")
+        self._call("fumi_gram", self.L.fumi_gram, _lib.ptr(feats), feats.shape[0], feats.shape[1], _lib.ptr(sup_rows),
+                                    _lib.ptr(qry_rows), B, NK, NQ, _lib.ptr(g), self._stream())
         self.launches += 1
         return g
 
@@ -108,11 +120,11 @@ class EpisodeEngine:
         slots = B if cfg.reserved else min(B, max(1, _lib.check(self.L.fumi_device_sm_count(), "sm_count")))
         out = dict(logits=self._new(B, NQ, N), preds=self._new(B, NQ, dtype=torch.int64), task_loss=self._new(B),
                    task_acc=self._new(B), stash=self._new(slots * per), stash_per_task=per)
-        _lib.check(self.L.fumi_episode_fwd(
+        self._call("fumi_episode_fwd", self.L.fumi_episode_fwd, 
             C.byref(cfg), B, _lib.ptr(proj), _lib.ptr(eb.sup_rows), _lib.ptr(eb.qry_rows), _lib.ptr(eb.sup_y),
             _lib.ptr(eb.qry_y), _lib.ptr(gram), _lib.ptr(b0), _lib.ptr(w1), _lib.ptr(b1), _lib.ptr(head_table),
             _lib.ptr(head_rows), _lib.ptr(out["logits"]), _lib.ptr(out["preds"]), _lib.ptr(out["task_loss"]),
-            _lib.ptr(out["task_acc"]), _lib.ptr(out["stash"]), self._stream()), "fumi_episode_fwd")
+            _lib.ptr(out["task_acc"]), _lib.ptr(out["stash"]), self._stream())
         self.launches += 1
         return out
 
@@ -122,22 +134,22 @@ class EpisodeEngine:
         parts = torch.zeros(P * (H0 + H0 * H1 + H1), dtype=torch.float32, device=self.device)
         pb0, pw1, pb1 = parts[:P * H0], parts[P * H0:P * (H0 + H0 * H1)], parts[P * (H0 + H0 * H1):]
         d_head = self._new(B, N, HD)
-        _lib.check(self.L.fumi_episode_bwd(
+        self._call("fumi_episode_bwd", self.L.fumi_episode_bwd, 
             C.byref(cfg), B, _lib.ptr(proj), _lib.ptr(eb.sup_rows), _lib.ptr(eb.qry_rows), _lib.ptr(eb.sup_y),
             _lib.ptr(eb.qry_y), _lib.ptr(gram), _lib.ptr(stash), float(loss_scale), _lib.ptr(d_proj), _lib.ptr(d_head),
-            _lib.ptr(pb0), _lib.ptr(pw1), _lib.ptr(pb1), self._stream()), "fumi_episode_bwd")
+            _lib.ptr(pb0), _lib.ptr(pw1), _lib.ptr(pb1), self._stream())
         self.launches += 2
         return d_head, (pb0, pw1, pb1, P)
 
     def reduce_parts(self, parts, P, out):
         n = out.numel()
-        _lib.check(self.L.fumi_reduce_parts(_lib.ptr(parts), P, n, _lib.ptr(out), 0, self._stream()), "fumi_reduce_parts")
+        self._call("fumi_reduce_parts", self.L.fumi_reduce_parts, _lib.ptr(parts), P, n, _lib.ptr(out), 0, self._stream())
         self.launches += 1
 
     def loss_acc(self, task_loss, task_acc):
         out = self._new(2)
-        _lib.check(self.L.fumi_reduce_loss_acc(_lib.ptr(task_loss), _lib.ptr(task_acc), task_loss.numel(),
-                                               _lib.ptr(out), self._stream()), "fumi_reduce_loss_acc")
+        self._call("fumi_reduce_loss_acc", self.L.fumi_reduce_loss_acc, _lib.ptr(task_loss), _lib.ptr(task_acc), task_loss.numel(),
+                                               _lib.ptr(out), self._stream())
         self.launches += 1
         return out
 
@@ -251,12 +263,11 @@ class EpisodeEngine:
         self.reduce_parts(pb1, P, self._grad(lin1.bias))
         self.linear_wgrad(d_proj, feats, self._grad(lin0.weight))                # dW0 = d_proj^T X
         d_hp = torch.zeros_like(hp_table)
-        _lib.check(self.L.fumi_scatter_add_rows(_lib.ptr(d_head), _lib.ptr(head_rows.reshape(-1)), B * N, HD,
-                                                _lib.ptr(d_hp), self._stream()), "fumi_scatter_add_rows")
+        self._call("fumi_scatter_add_rows", self.L.fumi_scatter_add_rows, _lib.ptr(d_head), _lib.ptr(head_rows.reshape(-1)), B * N, HD,
+                                                _lib.ptr(d_hp), self._stream())
         self.launches += 1
         if model.norm_hypernet:
-            _lib.check(self.L.fumi_tanh_bwd(_lib.ptr(hp_table), _lib.ptr(d_hp), d_hp.numel(), self._stream()),
-                       "fumi_tanh_bwd")
+            self._call("fumi_tanh_bwd", self.L.fumi_tanh_bwd, _lib.ptr(hp_table), _lib.ptr(d_hp), d_hp.numel(), self._stream())
             self.launches += 1
         l0, l2 = model.hyper_net[0], model.hyper_net[2]
         self.linear_wgrad(d_hp, u, self._grad(l2.weight), self._grad(l2.bias), precision=0)
@@ -318,10 +329,10 @@ class EpisodeEngine:
         protos, dist_, preds = self._new(B, N, P), self._new(B, NQ, N), self._new(B, NQ, dtype=torch.int64)
         task_loss = self._new(B)
         fixed = -1 if model.lamda_fixed is None else int(model.lamda_fixed)
-        _lib.check(self.L.fumi_am3_score(
+        self._call("fumi_am3_score", self.L.fumi_am3_score, 
             _lib.ptr(emb), _lib.ptr(t), _lib.ptr(lam.reshape(-1)), _lib.ptr(eb.sup_rows), _lib.ptr(eb.qry_rows),
             _lib.ptr(eb.sup_y), _lib.ptr(eb.qry_y), _lib.ptr(class_rows), B, N, NK, NQ, P, fixed, _lib.ptr(protos),
-            _lib.ptr(dist_), _lib.ptr(preds), _lib.ptr(task_loss), self._stream()), "fumi_am3_score")
+            _lib.ptr(dist_), _lib.ptr(preds), _lib.ptr(task_loss), self._stream())
         self.launches += 1
         # per-support-row lamda as the reference returns it (am3.py:208): lamda of the row's class
         label_lam = torch.gather(lam.reshape(-1)[class_rows], 1, eb.sup_y)
