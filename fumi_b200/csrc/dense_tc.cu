@@ -1,16 +1,406 @@
-// tcgen05 (5th-gen tensor core) 3xTF32 path of the dense layers -- filled in after the fp32 path is
-// parity-green.  Until then precision=1 is refused loudly rather than silently
-// falling back.
+// tcgen05 (5th-gen tensor core) dense contraction with fp32-level accuracy: "3xTF32".
+//
+//   C[M,N] (=|+=) act( A[M,K] . B[N,K]^T + bias[N] ),      A = A_hi + A_lo,  B = B_hi + B_lo
+//   A.B^T ~= A_hi.B_hi^T + A_lo.B_hi^T + A_hi.B_lo^T       (dropped term ~2^-22 relative)
+//
+// where x_hi = tf32-rounded x (low 13 mantissa bits zero) and x_lo = x - x_hi are produced once by
+// fumi_split_tf32 (static feature bank: at load time; weights: once per outer step).  This is the
+// path of the real dense contractions of FuMI: the hypernetwork layers (fumi.py:70-107), the first
+// image layer applied to the whole split bank once per outer step (fumi.py:215, hoisted; see
+// DESIGN.md) and its weight gradient dW0 = d_proj^T X (fumi.py:192), which runs as the same
+// "both operands K-major" kernel on a pre-transposed copy of the bank with split-K.
+//
+// Structure (one 128x256 output tile per CTA, 320 threads):
+//   warp 0   : TMA producer  -- cp.async.bulk.tensor 2D, SWIZZLE_128B boxes [32 fp32 x rows] of the four
+//              operand planes into a 2-stage shared-memory ring, mbarrier complete_tx
+//   warp 1   : MMA issuer    -- one elected thread issues tcgen05.mma.kind::tf32 (M128 N256 K8): per 32-wide
+//              k stage the 8 small cross products (lo.hi, hi.lo) first, then the 4 hi.hi products, into a
+//              FRESH 256-column TMEM accumulator (two ping-pong buffers = all 512 TMEM columns);
+//              tcgen05.commit releases the smem stage and publishes the TMEM buffer
+//   warps 2-9: accumulate + epilogue -- every stage: tcgen05.ld 32x32b.x32 TMEM -> registers and add into
+//              128 fp32 register accumulators per thread with round-to-nearest; at the end bias +
+//              activation and float4 stores (or fp32 atomics for split-K partial tiles).
+// Why two levels: the tensor core adds into its accumulator with truncation, a bias that grows linearly
+// with the number of accumulated MMAs (measured 5.6e-6 relative at K=768 in a single accumulator, 10x
+// plain fp32); restarting the accumulator every stage keeps <= 4 significant truncations per partial sum.
+// Out-of-range rows / k are zero-filled by TMA, so M, N, K need no padding (leading dims: multiple of 4).
+#include <cuda.h>
+#include <cuda_runtime.h>
+
 #include <cstdint>
+#include <cstring>
 
 #include "../../include/fumi_b200.h"
 #include "common.cuh"
 
+namespace {
+
+constexpr int BM = 128, BN = 256, BK = 32;          // BK fp32 = 128 bytes = one swizzle row
+constexpr int kStages = 2;
+constexpr int kThreadsTc = 320;
+constexpr uint32_t kABytes = BM * BK * 4;           // 16 KB per plane
+constexpr uint32_t kBBytes = BN * BK * 4;           // 32 KB per plane
+constexpr uint32_t kStageBytes = 2 * kABytes + 2 * kBBytes;   // 96 KB
+constexpr uint32_t kSmemBytes = kStages * kStageBytes + 1024 /*align*/ + 256 /*barriers*/;
+
+struct TcParams {
+    CUtensorMap a_hi, a_lo, b_hi, b_lo;
+    float* C;
+    const float* bias;
+    int64_t M, N, ldc;
+    int k_tiles;            // total BK tiles along K
+    int k_tiles_per_split;
+    int act;
+    int atomic;             // 1: atomicAdd partial tiles (split-K / accumulate); bias & act must be off
+};
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return static_cast<uint32_t>(__cvta_generic_to_shared(p)); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "WAIT_LOOP:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra WAIT_DONE;\n"
+        "bra WAIT_LOOP;\n"
+        "WAIT_DONE:\n"
+        "}\n" ::"r"(bar), "r"(parity)
+        : "memory");
+}
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+        ::"r"(dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(bar), "r"(c0), "r"(c1)
+        : "memory");
+}
+// K-major, SWIZZLE_128B shared-memory matrix descriptor (cute::UMMA::SmemDescriptor bit layout):
+// start>>4 [0,14) | LBO>>4 [16,30) | SBO>>4 [32,46) | version=1 [46,48) | layout SWIZZLE_128B=2 [61,64)
+__device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t saddr) {
+    return uint64_t((saddr & 0x3FFFF) >> 4) | (uint64_t(1) << 16) | (uint64_t(1024 >> 4) << 32) | (uint64_t(1) << 46) |
+           (uint64_t(2) << 61);
+}
+__device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t da, uint64_t db, uint32_t idesc, uint32_t accum) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "setp.ne.b32 p, %4, 0;\n"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n"
+        "}\n" ::"r"(tmem_d), "l"(da), "l"(db), "r"(idesc), "r"(accum)
+        : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ float act_f(float v, int act) {
+    if (act == 1) return fmaxf(v, 0.f);
+    if (act == 2) return tanhf(v);
+    if (act == 3) return 1.f / (1.f + expf(-v));
+    return v;
+}
+
+__global__ void __launch_bounds__(kThreadsTc, 1) gemm_tf32x3_kernel(const __grid_constant__ TcParams p) {
+    extern __shared__ uint8_t smem_dyn[];
+    const uint32_t base = (smem_u32(smem_dyn) + 1023u) & ~1023u;          // SWIZZLE_128B atoms: 1024 B aligned
+    const uint32_t bars = base + kStages * kStageBytes;     // full[2], empty[2], tmem_full[2], tmem_empty[2], tmem_ptr
+    const uint32_t full_bar = bars, empty_bar = bars + 8 * kStages, tmem_full_bar = bars + 16 * kStages;
+    const uint32_t tmem_empty_bar = tmem_full_bar + 16;
+    const uint32_t tmem_slot = tmem_empty_bar + 16;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int m0 = blockIdx.x * BM, n0 = blockIdx.y * BN;
+    const int kt0 = blockIdx.z * p.k_tiles_per_split;
+    const int kt1 = min(p.k_tiles, kt0 + p.k_tiles_per_split);
+    const int nk = kt1 - kt0;
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < kStages; ++s) { mbar_init(full_bar + 8 * s, 1); mbar_init(empty_bar + 8 * s, 1); }
+        for (int b = 0; b < 2; ++b) { mbar_init(tmem_full_bar + 8 * b, 1); mbar_init(tmem_empty_bar + 8 * b, 8); }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 1) {       // TMEM: two 256-column x 128-lane fp32 accumulators (all 512 columns)
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "n"(2 * BN) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    uint32_t tmem_base;
+    asm volatile("ld.shared.b32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
+
+    if (warp == 0) {
+        // ===== TMA producer =====
+        if (lane == 0 && nk > 0) {
+            for (int it = 0; it < nk; ++it) {
+                const int s = it % kStages;
+                const uint32_t ph = (it / kStages) & 1;
+                mbar_wait(empty_bar + 8 * s, ph ^ 1);
+                const uint32_t st = base + s * kStageBytes;
+                mbar_expect_tx(full_bar + 8 * s, kStageBytes);
+                const int kc = (kt0 + it) * BK;
+                tma_load_2d(st, &p.a_hi, full_bar + 8 * s, kc, m0);
+                tma_load_2d(st + kABytes, &p.a_lo, full_bar + 8 * s, kc, m0);
+                tma_load_2d(st + 2 * kABytes, &p.b_hi, full_bar + 8 * s, kc, n0);
+                tma_load_2d(st + 2 * kABytes + kBBytes, &p.b_lo, full_bar + 8 * s, kc, n0);
+            }
+        }
+    } else if (warp == 1) {
+        // ===== MMA issuer =====
+        if (lane == 0 && nk > 0) {
+            // instruction descriptor (cute::UMMA::InstrDescriptor): D=f32, A=B=tf32, K-major both, N>>3, M>>4
+            const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | (uint32_t(BN >> 3) << 17) | (uint32_t(BM >> 4) << 24);
+            for (int it = 0; it < nk; ++it) {
+                const int s = it % kStages;
+                const uint32_t ph = (it / kStages) & 1;
+                const int tb = it & 1;                                   // TMEM ping-pong buffer of this stage
+                mbar_wait(tmem_empty_bar + 8 * tb, ((it >> 1) & 1) ^ 1);  // accumulate warps drained it
+                mbar_wait(full_bar + 8 * s, ph);
+                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                const uint32_t st = base + s * kStageBytes;
+                const uint32_t td = tmem_base + uint32_t(tb * BN);
+#pragma unroll
+                for (int k = 0; k < BK / 8; ++k) {                       // small cross products first
+                    const uint64_t ahi = umma_desc_sw128(st + k * 32), alo = umma_desc_sw128(st + kABytes + k * 32);
+                    const uint64_t bhi = umma_desc_sw128(st + 2 * kABytes + k * 32);
+                    const uint64_t blo = umma_desc_sw128(st + 2 * kABytes + kBBytes + k * 32);
+                    umma_tf32(td, alo, bhi, idesc, k != 0);
+                    umma_tf32(td, ahi, blo, idesc, 1);
+                }
+#pragma unroll
+                for (int k = 0; k < BK / 8; ++k) {
+                    const uint64_t ahi = umma_desc_sw128(st + k * 32);
+                    const uint64_t bhi = umma_desc_sw128(st + 2 * kABytes + k * 32);
+                    umma_tf32(td, ahi, bhi, idesc, 1);
+                }
+                umma_commit(empty_bar + 8 * s);        // frees the smem stage once these MMAs retire
+                umma_commit(tmem_full_bar + 8 * tb);   // this stage's partial sums are complete
+            }
+        }
+    } else {
+        // ===== accumulate + epilogue: warps 2..9; lane quarter = warp % 4, column half = (warp - 2) / 4 =====
+        const int q = warp & 3, half = (warp - 2) >> 2;
+        const int row = m0 + q * 32 + lane;
+        float acc[128];
+#pragma unroll
+        for (int j = 0; j < 128; ++j) acc[j] = 0.f;
+        for (int it = 0; it < nk; ++it) {
+            const int tb = it & 1;
+            mbar_wait(tmem_full_bar + 8 * tb, (it >> 1) & 1);
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+#pragma unroll
+            for (int c = 0; c < 4; ++c) {
+                uint32_t v[32];
+                const uint32_t taddr = tmem_base + (uint32_t(q * 32) << 16) + uint32_t(tb * BN + half * 128 + c * 32);
+                asm volatile(
+                    "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+                    "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,"
+                    "%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
+                    : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
+                      "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]),
+                      "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]),
+                      "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+                    : "r"(taddr));
+                asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+                for (int j = 0; j < 32; ++j) acc[c * 32 + j] += __uint_as_float(v[j]);
+            }
+            asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+            __syncwarp();
+            if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(tmem_empty_bar + 8 * tb) : "memory");
+        }
+        if (nk > 0 && row < p.M) {
+#pragma unroll
+            for (int c = 0; c < 4; ++c) {
+                const int col0 = n0 + half * 128 + c * 32;
+                if (col0 >= p.N) break;
+                float* crow = p.C + int64_t(row) * p.ldc + col0;
+                const int ncols = min(32, int(p.N) - col0);
+                if (p.atomic) {
+#pragma unroll
+                    for (int j = 0; j < 32; ++j)
+                        if (j < ncols) atomicAdd(crow + j, acc[c * 32 + j]);
+                } else if (ncols == 32 && (p.ldc & 3) == 0) {
+#pragma unroll
+                    for (int j = 0; j < 32; j += 4) {
+                        float4 o;
+                        o.x = act_f(acc[c * 32 + j] + (p.bias ? p.bias[col0 + j] : 0.f), p.act);
+                        o.y = act_f(acc[c * 32 + j + 1] + (p.bias ? p.bias[col0 + j + 1] : 0.f), p.act);
+                        o.z = act_f(acc[c * 32 + j + 2] + (p.bias ? p.bias[col0 + j + 2] : 0.f), p.act);
+                        o.w = act_f(acc[c * 32 + j + 3] + (p.bias ? p.bias[col0 + j + 3] : 0.f), p.act);
+                        *reinterpret_cast<float4*>(crow + j) = o;
+                    }
+                } else {
+#pragma unroll
+                    for (int j = 0; j < 32; ++j)
+                        if (j < ncols) crow[j] = act_f(acc[c * 32 + j] + (p.bias ? p.bias[col0 + j] : 0.f), p.act);
+                }
+            }
+        }
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    if (warp == 1) {
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(2 * BN) : "memory");
+    }
+}
+
+// x -> hi (tf32 round-to-nearest, stored as fp32 with 13 zero low mantissa bits) and lo = x - hi
+__global__ void split_tf32_kernel(const float* __restrict__ x, float* __restrict__ hi, float* __restrict__ lo, int64_t n) {
+    for (int64_t i = int64_t(blockIdx.x) * blockDim.x + threadIdx.x; i < n; i += int64_t(gridDim.x) * blockDim.x) {
+        const float v = x[i];
+        uint32_t h;
+        asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(h) : "f"(v));
+        const float hf = __uint_as_float(h);
+        hi[i] = hf;
+        lo[i] = v - hf;
+    }
+}
+
+// x[R,Ccols] -> hiT / loT [Ccols, ldt] (transposed, split), 32x32 tiles through shared memory
+__global__ void transpose_split_tf32_kernel(const float* __restrict__ x, float* __restrict__ hiT, float* __restrict__ loT,
+                                            int64_t R, int64_t Ccols, int64_t ldt) {
+    __shared__ float tile[32][33];
+    const int64_t r0 = int64_t(blockIdx.x) * 32, c0 = int64_t(blockIdx.y) * 32;
+    for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+        const int64_t r = r0 + i, c = c0 + threadIdx.x;
+        tile[i][threadIdx.x] = (r < R && c < Ccols) ? x[r * Ccols + c] : 0.f;
+    }
+    __syncthreads();
+    for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+        const int64_t c = c0 + i, r = r0 + threadIdx.x;
+        if (c < Ccols && r < ldt) {
+            const float v = r < R ? tile[threadIdx.x][i] : 0.f;
+            uint32_t h;
+            asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(h) : "f"(v));
+            const float hf = __uint_as_float(h);
+            hiT[c * ldt + r] = hf;
+            loT[c * ldt + r] = v - hf;
+        }
+    }
+}
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn get_encode() {
+    static EncodeTiledFn fn = nullptr;
+    if (!fn) {
+        void* ptr = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &q) == cudaSuccess &&
+            q == cudaDriverEntryPointSuccess)
+            fn = reinterpret_cast<EncodeTiledFn>(ptr);
+    }
+    return fn;
+}
+
+// 2D fp32 row-major [rows, cols] with leading dimension ld (floats); box = [BK cols x box_rows]
+int make_map(CUtensorMap* m, const float* ptr, int64_t rows, int64_t cols, int64_t ld, int box_rows) {
+    EncodeTiledFn enc = get_encode();
+    if (!enc) { fumi_set_error("cuTensorMapEncodeTiled is not available from the driver"); return FUMI_ERR_CUDA; }
+    cuuint64_t dims[2] = {cuuint64_t(cols), cuuint64_t(rows)};
+    cuuint64_t strides[1] = {cuuint64_t(ld) * 4};
+    cuuint32_t box[2] = {cuuint32_t(BK), cuuint32_t(box_rows)};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(ptr), dims, strides, box, estr,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+        fumi_set_error("cuTensorMapEncodeTiled failed with CUresult " + std::to_string(int(r)));
+        return FUMI_ERR_CUDA;
+    }
+    return FUMI_OK;
+}
+
+}  // namespace
+
+extern "C" int fumi_split_tf32(const float* x, float* hi, float* lo, int64_t n, void* stream) {
+    FUMI_CHECK_ARG(n >= 0, "n < 0");
+    if (n == 0) return FUMI_OK;
+    FUMI_CHECK_ARG(x && hi && lo, "null pointer");
+    int64_t blocks = (n + 255) / 256;
+    if (blocks > 148 * 16) blocks = 148 * 16;
+    split_tf32_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(x, hi, lo, n);
+    FUMI_CHECK_LAUNCH("split_tf32_kernel");
+    return FUMI_OK;
+}
+
+extern "C" int fumi_transpose_split_tf32(const float* x, float* hiT, float* loT, int64_t R, int64_t C, int64_t ldt,
+                                         void* stream) {
+    FUMI_CHECK_ARG(R >= 1 && C >= 1 && ldt >= R && (ldt & 3) == 0, "need ldt >= R and ldt % 4 == 0");
+    FUMI_CHECK_ARG(x && hiT && loT, "null pointer");
+    dim3 grid((unsigned)((ldt + 31) / 32), (unsigned)((C + 31) / 32));
+    FUMI_CHECK_ARG(grid.y <= 65535, "too many columns");
+    transpose_split_tf32_kernel<<<grid, dim3(32, 8), 0, (cudaStream_t)stream>>>(x, hiT, loT, R, C, ldt);
+    FUMI_CHECK_LAUNCH("transpose_split_tf32_kernel");
+    return FUMI_OK;
+}
+
+extern "C" int fumi_gemm_tf32x3(const float* a_hi, const float* a_lo, const float* b_hi, const float* b_lo,
+                                const float* bias, float* c, int64_t M, int64_t N, int64_t K, int64_t lda, int64_t ldb,
+                                int64_t ldc, int32_t act, int32_t accumulate, int32_t split_k, void* stream) {
+    FUMI_CHECK_ARG(M >= 1 && N >= 1 && K >= 1, "bad shape");
+    FUMI_CHECK_ARG(a_hi && a_lo && b_hi && b_lo && c, "null pointer");
+    FUMI_CHECK_ARG(lda >= K && ldb >= K && ldc >= N && (lda & 3) == 0 && (ldb & 3) == 0,
+                   "leading dimensions must cover K / N and be multiples of 4 floats (TMA 16-byte strides)");
+    FUMI_CHECK_ARG(act >= 0 && act <= 3, "act must be 0..3");
+    FUMI_CHECK_ARG((uintptr_t(a_hi) | uintptr_t(a_lo) | uintptr_t(b_hi) | uintptr_t(b_lo)) % 16 == 0,
+                   "operand planes must be 16-byte aligned");
+    TcParams p;
+    std::memset(&p, 0, sizeof(p));
+    int rc;
+    if ((rc = make_map(&p.a_hi, a_hi, M, K, lda, BM)) != FUMI_OK) return rc;
+    if ((rc = make_map(&p.a_lo, a_lo, M, K, lda, BM)) != FUMI_OK) return rc;
+    if ((rc = make_map(&p.b_hi, b_hi, N, K, ldb, BN)) != FUMI_OK) return rc;
+    if ((rc = make_map(&p.b_lo, b_lo, N, K, ldb, BN)) != FUMI_OK) return rc;
+    p.C = c; p.bias = bias; p.M = M; p.N = N; p.ldc = ldc; p.act = act;
+    p.k_tiles = int((K + BK - 1) / BK);
+    const int64_t tiles = ((M + BM - 1) / BM) * ((N + BN - 1) / BN);
+    int splits = split_k;
+    if (splits <= 0 && (bias != nullptr || act != 0)) splits = 1;     // fused epilogue needs whole-K tiles
+    if (splits <= 0) {                                   // auto: fill the SMs when there are few output tiles
+        int sms = fumi_device_sm_count();
+        if (sms <= 0) return sms;
+        splits = tiles >= sms ? 1 : int((sms + tiles - 1) / tiles);
+        if (splits > p.k_tiles / 4) splits = p.k_tiles / 4 > 0 ? p.k_tiles / 4 : 1;
+    }
+    if (splits > p.k_tiles) splits = p.k_tiles;
+    p.k_tiles_per_split = (p.k_tiles + splits - 1) / splits;
+    splits = (p.k_tiles + p.k_tiles_per_split - 1) / p.k_tiles_per_split;
+    p.atomic = (splits > 1 || accumulate) ? 1 : 0;
+    if (p.atomic) {
+        FUMI_CHECK_ARG(bias == nullptr && act == 0, "bias / activation cannot be fused into a split-K or accumulating GEMM");
+        if (!accumulate) {
+            cudaError_t e = cudaMemset2DAsync(c, ldc * 4, 0, N * 4, M, (cudaStream_t)stream);
+            if (e != cudaSuccess) return fumi_cuda_fail(e, "cudaMemset2DAsync");
+        }
+    }
+    static bool attr_done = false;
+    if (!attr_done) {
+        cudaError_t e = cudaFuncSetAttribute(gemm_tf32x3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(kSmemBytes));
+        if (e != cudaSuccess) return fumi_cuda_fail(e, "cudaFuncSetAttribute(gemm_tf32x3)");
+        attr_done = true;
+    }
+    dim3 grid((unsigned)((M + BM - 1) / BM), (unsigned)((N + BN - 1) / BN), (unsigned)splits);
+    FUMI_CHECK_ARG(grid.y <= 65535 && grid.z <= 65535, "grid too large");
+    gemm_tf32x3_kernel<<<grid, kThreadsTc, kSmemBytes, (cudaStream_t)stream>>>(p);
+    FUMI_CHECK_LAUNCH("gemm_tf32x3_kernel");
+    return FUMI_OK;
+}
+
+// precision=1 entry points of fumi_linear_fwd / fumi_linear_wgrad take *unsplit* operands; the engine uses the
+// prepared-plane API above instead, so these only exist to fail loudly if somebody asks for them.
 int fumi_linear_fwd_tc(const float*, const float*, const float*, float*, int64_t, int64_t, int64_t, int32_t, void*) {
-    fumi_set_error("fumi_linear_fwd: precision=1 (tcgen05 3xTF32) is not built yet");
+    fumi_set_error("precision=1 runs on pre-split operand planes: use fumi_split_tf32 + fumi_gemm_tf32x3");
     return FUMI_ERR_UNSUPPORTED;
 }
 int fumi_linear_wgrad_tc(const float*, const float*, float*, int64_t, int64_t, int64_t, int32_t, void*) {
-    fumi_set_error("fumi_linear_wgrad: precision=1 (tcgen05 3xTF32) is not built yet");
+    fumi_set_error("precision=1 runs on pre-split operand planes: use fumi_transpose_split_tf32 + fumi_gemm_tf32x3");
     return FUMI_ERR_UNSUPPORTED;
 }

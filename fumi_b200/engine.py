@@ -94,6 +94,67 @@ class EpisodeEngine:
         self.launches += 1
         return dx
 
+    # ---- tcgen05 3xTF32 path (precision 1): operands are (hi, lo) plane pairs ---------------------
+    def split_tf32(self, x):
+        x = x.contiguous()
+        hi, lo = torch.empty_like(x), torch.empty_like(x)
+        self._call("fumi_split_tf32", self.L.fumi_split_tf32, _lib.ptr(x), _lib.ptr(hi), _lib.ptr(lo), x.numel(),
+                   self._stream())
+        self.launches += 1
+        return hi, lo
+
+    def transpose_split_tf32(self, x):
+        """x [R,C] -> (hiT, loT) [C, ldt] with ldt = R rounded up to 32 (K-major planes over the rows)."""
+        R, Cc = x.shape
+        ldt = (R + 31) // 32 * 32
+        hiT, loT = self._new(Cc, ldt), self._new(Cc, ldt)
+        self._call("fumi_transpose_split_tf32", self.L.fumi_transpose_split_tf32, _lib.ptr(x), _lib.ptr(hiT),
+                   _lib.ptr(loT), R, Cc, ldt, self._stream())
+        self.launches += 1
+        return hiT, loT
+
+    def gemm_tc(self, a, b, bias=None, act=0, out=None, accumulate=False, split_k=0, K=None):
+        """out[M,N] (=|+=) act(A . B^T + bias) on tcgen05; a, b = (hi, lo) planes [rows, ld] with K <= ld."""
+        M, lda = a[0].shape
+        N, ldb = b[0].shape
+        K = min(lda, ldb) if K is None else K
+        if out is None:
+            out = self._new(M, N)
+        self._call("fumi_gemm_tf32x3", self.L.fumi_gemm_tf32x3, _lib.ptr(a[0]), _lib.ptr(a[1]), _lib.ptr(b[0]),
+                   _lib.ptr(b[1]), _lib.ptr(bias), _lib.ptr(out), M, N, K, lda, ldb, out.stride(0), act,
+                   int(accumulate), split_k, self._stream())
+        self.launches += 1
+        return out
+
+    def _feat_planes(self, feats, bank):
+        """(hi, lo) of the feature matrix; cached on the FeatureBank (static data, split once)."""
+        if bank is not None:
+            if getattr(bank, "_tf32", None) is None:
+                bank._tf32 = self.split_tf32(feats)
+            return bank._tf32
+        return self.split_tf32(feats)
+
+    def _feat_planes_T(self, feats, bank):
+        if bank is not None:
+            if getattr(bank, "_tf32T", None) is None:
+                bank._tf32T = self.transpose_split_tf32(feats)
+            return bank._tf32T
+        return self.transpose_split_tf32(feats)
+
+    def project_rows(self, feats, bank, w0):
+        """proj = X W0^T (first image layer over every feature row, no bias)."""
+        if self.precision == 1:
+            return self.gemm_tc(self._feat_planes(feats, bank), self.split_tf32(w0))
+        return self.linear_fwd(feats, w0, None, act=0, precision=0)
+
+    def wgrad_rows(self, d_proj, feats, bank, dw0):
+        """dW0 = d_proj^T X."""
+        if self.precision == 1:
+            R = d_proj.shape[0]
+            self.gemm_tc(self.transpose_split_tf32(d_proj), self._feat_planes_T(feats, bank), out=dw0, K=R)
+        else:
+            self.linear_wgrad(d_proj, feats, dw0, precision=0)
+
     def gram(self, feats, sup_rows, qry_rows):
         B, NK = sup_rows.shape
         NQ = qry_rows.shape[1]
@@ -217,7 +278,10 @@ class EpisodeEngine:
     def hypernet(self, model, text_rows, keep=False):
         """hyper_net(text): Linear-ReLU-Linear(-Tanh)  (fumi.py:70-107,109-113)."""
         l0, l2 = model.hyper_net[0], model.hyper_net[2]
-        u = self.linear_fwd(text_rows, l0.weight, l0.bias, act=1)
+        if self.precision == 1 and text_rows.shape[1] % 4 == 0:
+            u = self.gemm_tc(self.split_tf32(text_rows), self.split_tf32(l0.weight), bias=l0.bias, act=1)
+        else:
+            u = self.linear_fwd(text_rows, l0.weight, l0.bias, act=1, precision=0)
         hp = self.linear_fwd(u, l2.weight, l2.bias, act=2 if model.norm_hypernet else 0, precision=0)
         return (hp, u) if keep else hp
 
@@ -246,7 +310,7 @@ class EpisodeEngine:
                             dropout_seed=(int(getattr(model, "dropout_base_seed", 0)) << 20) + model.dropout_seed,
                             task_offset=rank * B, save=train or return_state)
         hp_table, u = self.hypernet(model, text_rows, keep=True)
-        proj = self.linear_fwd(feats, lin0.weight, None, act=0)
+        proj = self.project_rows(feats, eb.bank, lin0.weight)
         gram = self.gram(feats, eb.sup_rows, eb.qry_rows)
         out = self.episode_fwd(cfg, proj, eb, gram, lin0.bias, lin1.weight, lin1.bias, hp_table, head_rows)
         la = self.loss_acc(out["task_loss"], out["task_acc"])
@@ -261,7 +325,7 @@ class EpisodeEngine:
         self.reduce_parts(pb0, P, self._grad(lin0.bias))
         self.reduce_parts(pw1, P, self._grad(lin1.weight))
         self.reduce_parts(pb1, P, self._grad(lin1.bias))
-        self.linear_wgrad(d_proj, feats, self._grad(lin0.weight))                # dW0 = d_proj^T X
+        self.wgrad_rows(d_proj, feats, eb.bank, self._grad(lin0.weight))         # dW0 = d_proj^T X
         d_hp = torch.zeros_like(hp_table)
         self._call("fumi_scatter_add_rows", self.L.fumi_scatter_add_rows, _lib.ptr(d_head), _lib.ptr(head_rows.reshape(-1)), B * N, HD,
                                                 _lib.ptr(d_hp), self._stream())
@@ -272,7 +336,7 @@ class EpisodeEngine:
         l0, l2 = model.hyper_net[0], model.hyper_net[2]
         self.linear_wgrad(d_hp, u, self._grad(l2.weight), self._grad(l2.bias), precision=0)
         d_u = self.linear_dgrad(d_hp, l2.weight, gate=u)
-        self.linear_wgrad(d_u, text_rows, self._grad(l0.weight), self._grad(l0.bias))
+        self.linear_wgrad(d_u, text_rows, self._grad(l0.weight), self._grad(l0.bias), precision=0)
         self._allreduce_grads([p for p in model.parameters() if p.requires_grad], la)
         return res
 
@@ -287,7 +351,7 @@ class EpisodeEngine:
         world = self._world()
         cfg = self.make_cfg(N, NK, NQ, steps, step_size, first_order=first_order, save=train or return_state)
         head_table = torch.cat([fin.weight, fin.bias.unsqueeze(1)], 1).contiguous()      # [N, 65]
-        proj = self.linear_fwd(feats, lin0.weight, None, act=0)
+        proj = self.project_rows(feats, eb.bank, lin0.weight)
         gram = self.gram(feats, eb.sup_rows, eb.qry_rows)
         out = self.episode_fwd(cfg, proj, eb, gram, lin0.bias, lin1.weight, lin1.bias, head_table, None)
         la = self.loss_acc(out["task_loss"], out["task_acc"])
@@ -300,7 +364,7 @@ class EpisodeEngine:
         self.reduce_parts(pb0, P, self._grad(lin0.bias))
         self.reduce_parts(pw1, P, self._grad(lin1.weight))
         self.reduce_parts(pb1, P, self._grad(lin1.bias))
-        self.linear_wgrad(d_proj, feats, self._grad(lin0.weight))
+        self.wgrad_rows(d_proj, feats, eb.bank, self._grad(lin0.weight))
         d_fin = self._new(N * HD)
         self.reduce_parts(d_head.reshape(B, N * HD), B, d_fin)                   # shared head: sum over tasks
         d_fin = d_fin.view(N, HD)
@@ -320,10 +384,16 @@ class EpisodeEngine:
         else:
             eb, feats, text_rows, class_rows = self.unpack(batch, N, want_text=True)
         P = model.prototype_dim
-        emb = self.linear_fwd(feats, model.image_encoder.weight, model.image_encoder.bias)
+        if self.precision == 1:
+            emb = self.gemm_tc(self._feat_planes(feats, eb.bank), self.split_tf32(model.image_encoder.weight),
+                               bias=model.image_encoder.bias)
+        else:
+            emb = self.linear_fwd(feats, model.image_encoder.weight, model.image_encoder.bias, precision=0)
         g0, g3, h0, h3 = model.g[0], model.g[3], model.h[0], model.h[3]
-        t = self.linear_fwd(self.linear_fwd(text_rows, g0.weight, g0.bias, act=1), g3.weight, g3.bias)
-        lam = self.linear_fwd(self.linear_fwd(t, h0.weight, h0.bias, act=1), h3.weight, h3.bias, act=3, precision=0)
+        t = self.linear_fwd(self.linear_fwd(text_rows, g0.weight, g0.bias, act=1, precision=0), g3.weight, g3.bias,
+                            precision=0)
+        lam = self.linear_fwd(self.linear_fwd(t, h0.weight, h0.bias, act=1, precision=0), h3.weight, h3.bias, act=3,
+                              precision=0)
         B, NK = eb.sup_rows.shape
         NQ = eb.qry_rows.shape[1]
         protos, dist_, preds = self._new(B, N, P), self._new(B, NQ, N), self._new(B, NQ, dtype=torch.int64)

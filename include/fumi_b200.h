@@ -89,6 +89,28 @@ int fumi_linear_dgrad(const float* dy, const float* w, const float* gate, float*
 int fumi_tanh_bwd(const float* y, float* dy, int64_t n, void* stream);
 
 /* ------------------------------------------------------------------------------------------
+ * tcgen05 tensor-core path of the same dense layers, fp32-accurate "3xTF32":
+ *   x = hi + lo with hi = tf32(x);   A.B^T ~= A_hi.B_hi^T + A_lo.B_hi^T + A_hi.B_lo^T
+ * fumi_split_tf32: hi[i] = tf32-rounded x[i] (fp32 container), lo[i] = x[i] - hi[i].  Static data
+ *   (the HBM feature bank) is split once; weights once per outer step.
+ * fumi_transpose_split_tf32: x[R,C] -> hiT/loT [C, ldt] (ldt >= R, multiple of 4; pad zero-filled):
+ *   K-major operand planes for the weight-gradient contraction over rows (dW0 = d_proj^T X).
+ * fumi_gemm_tf32x3: C[M,N] (=|+=) act(A[M,K] . B[N,K]^T + bias[N]); both operands K-contiguous with
+ *   leading dimensions lda/ldb (floats, multiples of 4, planes 16-byte aligned).  TMA-fed tcgen05.mma
+ *   (kind::tf32, M128 N256 K8) with the accumulator in TMEM.  split_k: 0 = auto, n = split K into n
+ *   slices (partial tiles are combined with fp32 atomics; bias/act must then be off, as with accumulate).
+ * Replaces: F.linear of the hypernetwork (fumi.py:70-107,109-113) and of im_net.linear0 over the bank
+ * (fumi.py:215), and the linear0.weight gradient of outer_loss.backward() (fumi.py:192).
+ * ---------------------------------------------------------------------------------------- */
+int fumi_split_tf32(const float* x, float* hi, float* lo, int64_t n, void* stream);
+int fumi_transpose_split_tf32(const float* x, float* hiT, float* loT, int64_t R, int64_t C, int64_t ldt,
+                              void* stream);
+int fumi_gemm_tf32x3(const float* a_hi, const float* a_lo, const float* b_hi, const float* b_lo,
+                     const float* bias, float* c, int64_t M, int64_t N, int64_t K,
+                     int64_t lda, int64_t ldb, int64_t ldc, int32_t act, int32_t accumulate, int32_t split_k,
+                     void* stream);
+
+/* ------------------------------------------------------------------------------------------
  * Episode Gram blocks (the HBM-bound gather of the path).
  * gram[b, i, j] = <feats[row(b,i)], feats[sup_rows[b,j]]>, i over the NK support rows then the NQ
  * query rows of task b.  Each sampled feature row is read from HBM once per task.

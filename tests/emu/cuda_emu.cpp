@@ -55,3 +55,16 @@ extern "C" int fumi_device_sm_count(void) {
     const char* e = getenv("FUMI_EMU_SMS");       // fewer "SMs" than tasks exercises the per-CTA task loop
     return e ? atoi(e) : 2;
 }
+
+// tcgen05 entry points cannot be emulated: they fail loudly here (GPU tests cover them).
+int fumi_linear_fwd_tc(const float*, const float*, const float*, float*, int64_t, int64_t, int64_t, int32_t, void*) {
+    g_last_error = "tcgen05 path is not emulated"; return FUMI_ERR_UNSUPPORTED; }
+int fumi_linear_wgrad_tc(const float*, const float*, float*, int64_t, int64_t, int64_t, int32_t, void*) {
+    g_last_error = "tcgen05 path is not emulated"; return FUMI_ERR_UNSUPPORTED; }
+extern "C" int fumi_split_tf32(const float*, float*, float*, int64_t, void*) {
+    g_last_error = "tcgen05 path is not emulated"; return FUMI_ERR_UNSUPPORTED; }
+extern "C" int fumi_transpose_split_tf32(const float*, float*, float*, int64_t, int64_t, int64_t, void*) {
+    g_last_error = "tcgen05 path is not emulated"; return FUMI_ERR_UNSUPPORTED; }
+extern "C" int fumi_gemm_tf32x3(const float*, const float*, const float*, const float*, const float*, float*, int64_t,
+                                int64_t, int64_t, int64_t, int64_t, int64_t, int32_t, int32_t, int32_t, void*) {
+    g_last_error = "tcgen05 path is not emulated"; return FUMI_ERR_UNSUPPORTED; }

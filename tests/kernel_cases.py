@@ -83,11 +83,41 @@ def check_adapted(res, g, eng, bank, N):
     return S, X
 
 
-def fumi_train_case(device, name, via="dict"):
+def gemm_tc_case(device):
+    """tcgen05 3xTF32 GEMM: fp32-level accuracy against fp64, ragged M / N / K, split-K, fused epilogue."""
+    eng = engine_mod.EpisodeEngine(device, precision=1)
+    rs = np.random.RandomState(8)
+    t = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(device)
+    for (M, N, K, split) in [(128, 256, 32, 1), (128, 256, 64, 1), (403, 256, 768, 1), (1000, 64, 512, 1),
+                             (300, 65, 100, 1), (256, 2048, 5000, 0), (256, 512, 4100, 7), (37, 300, 36, 1)]:
+        a = (rs.randn(M, K) * rs.uniform(0.1, 3, size=(M, 1))).astype(np.float32)
+        b = (rs.randn(N, K) / np.sqrt(K)).astype(np.float32)
+        bias = rs.randn(N).astype(np.float32)
+        want = a.astype(np.float64) @ b.astype(np.float64).T
+        ap, bp = eng.split_tf32(t(a)), eng.split_tf32(t(b))
+        assert np.array_equal((ap[0] + ap[1]).cpu().numpy(), a), "hi + lo must reconstruct x exactly"
+        got = eng.gemm_tc(ap, bp, split_k=split).cpu().numpy()
+        err = relerr(got, want)
+        f32 = relerr(a @ b.T, want)
+        assert err < max(4 * f32, 2e-6), (M, N, K, split, err, f32)
+        if split == 1:
+            got = eng.gemm_tc(ap, bp, bias=t(bias), act=1).cpu().numpy()
+            assert relerr(got, np.maximum(want + bias, 0)) < max(4 * f32, 2e-6), (M, N, K, "bias+relu")
+        acc = eng.gemm_tc(ap, bp, split_k=split, out=torch.ones(M, N, device=device), accumulate=True).cpu().numpy()
+        assert relerr(acc, want + 1) < max(4 * f32, 2e-6), (M, N, K, "accumulate")
+    # weight-gradient form: C = X1^T X2 through transposed planes
+    R, C1, C2 = 1234, 256, 512
+    x1, x2 = rs.randn(R, C1).astype(np.float32), rs.randn(R, C2).astype(np.float32)
+    got = eng.gemm_tc(eng.transpose_split_tf32(t(x1)), eng.transpose_split_tf32(t(x2)), K=R).cpu().numpy()
+    assert relerr(got, x1.astype(np.float64).T @ x2.astype(np.float64)) < 2e-6
+
+
+def fumi_train_case(device, name, via="dict", precision=0):
     g, bank = load_golden(name)
     N = argv_int(g, "--num_ways", 5)
     params = params_of(g)
     model = make_fumi(g, bank, params, device)
+    model._get_engine(device).precision = precision
     opt = FusedAdam(model.parameters(), lr=float(g["lr"]), weight_decay=float(g["wd"]))
     args = _args(g, device)
     batch = _torchmeta_batch(g, bank) if via == "dict" else _bank_batch(g, bank, device, N)

@@ -22,6 +22,15 @@ def test_dense():
     kc.dense_case(DEV)
 
 
+def test_gemm_tcgen05_3xtf32():
+    kc.gemm_tc_case(DEV)
+
+
+@pytest.mark.parametrize("via", ["dict", "bank"])
+def test_fumi_train_tensor_core_dense(via):
+    kc.fumi_train_case(DEV, "fumi_train_n5k5_d512", via=via, precision=1)
+
+
 def test_gram():
     kc.gram_case(DEV)
 
