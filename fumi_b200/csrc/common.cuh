@@ -33,14 +33,15 @@ constexpr int kHD = kH1 + 1;      // head row: 64 weights + 1 bias (fumi.py:76-7
 constexpr int kMaxWays = 32;
 constexpr int kMaxSupport = 128;  // NK rows per task
 
-// Counter-based dropout mask shared by forward and backward (and mirrored in
-// fumi_b200/dropout.py for parity tests): keep iff hash32 >= p * 2^32.
-__host__ __device__ inline uint32_t fumi_mask_hash(uint64_t seed, uint64_t task, uint32_t pass, uint32_t layer,
-                                                   uint32_t row, uint32_t col) {
+// Counter-based dropout mask shared by forward and backward (and mirrored in fumi_b200/dropout.py for
+// parity tests).  One 64-bit hash covers the four columns 4g..4g+3 of a row: column c uses the 16-bit field
+// (c & 3) and is kept iff field >= floor(p * 65536).
+__host__ __device__ inline uint64_t fumi_mask_hash64(uint64_t seed, uint64_t task, uint32_t pass, uint32_t layer,
+                                                     uint32_t row, uint32_t col_group) {
     uint64_t x = seed ^ (task * 0x9E3779B97F4A7C15ULL);
-    x += (uint64_t(pass) << 40) ^ (uint64_t(layer) << 32) ^ (uint64_t(row) << 12) ^ uint64_t(col);
+    x += (uint64_t(pass) << 40) ^ (uint64_t(layer) << 32) ^ (uint64_t(row) << 12) ^ uint64_t(col_group);
     x ^= x >> 30; x *= 0xBF58476D1CE4E5B9ULL;       // splitmix64 finaliser
     x ^= x >> 27; x *= 0x94D049BB133111EBULL;
     x ^= x >> 31;
-    return uint32_t(x >> 32);
+    return x;
 }

@@ -24,6 +24,7 @@
 #include "../../include/fumi_b200.h"
 #include "common.cuh"
 #include "launch.cuh"
+#include "warp_mma.cuh"
 
 namespace {
 
@@ -86,9 +87,10 @@ __host__ __device__ inline Layout make_layout(const fumi_episode_cfg& c) {
     return L;
 }
 
-// Shared-memory carve-up (floats).  TR = rows per tile.
-template <int TR>
+// Shared-memory carve-up (floats).  Buffers hold TR = max(support tile, query tile) rows.
 struct Smem {
+    float* sS;     // [TRS][H0]   (forward, single support tile) first-layer coefficient S, updated in place
+    float* sA;     // [TRS][H0]   (forward, single support tile) projected support rows A = X W0^T
     float* w1t;    // [H0][kW1S]  adapted W1^T
     float* aw1t;   // [H0][kW1S]  (backward) adjoint of W1^T
     float* h0t;    // [TR][H0]
@@ -112,18 +114,19 @@ struct Smem {
     int* ys;       // [TR]        labels of the tile
 };
 
-template <int TR, bool BWD>
+template <int TR, bool BWD, int TRC = 0>
 __host__ __device__ inline size_t smem_floats() {
     size_t f = size_t(kH0) * kW1S + size_t(TR) * kH0 + 2 * size_t(TR) * kH1 + size_t(TR) * kLS + size_t(TR) * kGS +
                2 * size_t(kMaxWays) * kHD + kH1 + 2 * TR + 2 * TR /*rows (8B)*/ + TR;
     if (BWD) f += size_t(kH0) * kW1S + size_t(TR) * kH0 + 2 * size_t(TR) * kH1 + size_t(TR) * kLS +
                   size_t(kMaxWays) * kHD + 2 * kH1;
+    f += 2 * size_t(TRC) * kH0;
     return f + 16;
 }
 
-template <int TR, bool BWD>
-__device__ inline Smem<TR> carve(float* base) {
-    Smem<TR> s;
+template <int TR, bool BWD, int TRC = 0>
+__device__ inline Smem carve(float* base) {
+    Smem s;
     float* p = base;
     s.rows = reinterpret_cast<long long*>(p); p += 2 * TR;     // 8-byte aligned: first
     s.w1t = p; p += kH0 * kW1S;
@@ -151,23 +154,28 @@ __device__ inline Smem<TR> carve(float* base) {
     } else {
         s.tt = s.rz1t = s.rh1t = s.rlt = s.aw1t = s.rhp = s.ab1 = s.rb1 = nullptr;
     }
+    s.sS = p; p += TRC * kH0;
+    s.sA = p; p += TRC * kH0;
     return s;
 }
 
 __device__ inline float dropout_scale(const fumi_episode_cfg& c) {
     return c.dropout_p > 0.f ? 1.f / (1.f - c.dropout_p) : 1.f;
 }
-__device__ inline bool dropout_keep(const fumi_episode_cfg& c, int64_t task, int pass, int layer, int row, int col) {
-    if (!(c.dropout_p > 0.f)) return true;
-    const uint32_t thr = uint32_t(fminf(c.dropout_p * 4294967296.f, 4294967040.f));
-    return fumi_mask_hash(c.dropout_seed, uint64_t(task), uint32_t(pass), uint32_t(layer), uint32_t(row),
-                          uint32_t(col)) >= thr;
+// 64 mask bits cover columns 4g..4g+3 of one row: 16-bit field (col & 3), keep iff field >= p * 65536
+__device__ inline uint64_t dropout_bits(const fumi_episode_cfg& c, int64_t task, int pass, int layer, int row, int col) {
+    return fumi_mask_hash64(c.dropout_seed, uint64_t(task), uint32_t(pass), uint32_t(layer), uint32_t(row),
+                            uint32_t(col >> 2));
+}
+__device__ inline uint32_t dropout_thr(const fumi_episode_cfg& c) { return uint32_t(c.dropout_p * 65536.f); }
+__device__ inline bool dropout_keep_bits(uint64_t bits, int col, uint32_t thr) {
+    return uint32_t((bits >> (16 * (col & 3))) & 0xFFFFu) >= thr;
 }
 
 // ---- tile loaders -----------------------------------------------------------------------------
 // rows / labels / Gram rows of tile [r0, r0+tr) of the support (qry=false) or query set of task b.
 template <int TR>
-__device__ inline void load_tile_meta(const EpiParams& P, const Smem<TR>& s, int64_t b, bool qry, int r0, int tr) {
+__device__ inline void load_tile_meta(const EpiParams& P, const Smem& s, int64_t b, bool qry, int r0, int tr) {
     const int n = P.cfg.num_support, m = P.cfg.num_query;
     const int tid = threadIdx.x;
     if (tid < TR) {
@@ -189,8 +197,9 @@ __device__ inline void load_tile_meta(const EpiParams& P, const Smem<TR>& s, int
 }
 
 // (a) Z0 = A - alpha * G S + b0 -> H0 = relu(Z0) * dropout.   thread == column h.
-template <int TR>
-__device__ inline void tile_h0(const EpiParams& P, const Smem<TR>& s, int64_t task, const float* Scur, float b0h,
+// CACHED: S and the projected rows A come from shared memory (single support tile); else from global.
+template <int TR, bool CACHED>
+__device__ inline void tile_h0(const EpiParams& P, const Smem& s, int64_t task, const float* Scur, float b0h,
                                int r0, int tr, int pass) {
     const int h = threadIdx.x;
     const int n = P.cfg.num_support;
@@ -202,7 +211,7 @@ __device__ inline void tile_h0(const EpiParams& P, const Smem<TR>& s, int64_t ta
         for (int j = 0; j < n4; j += 4) {
             float sv[4];
 #pragma unroll
-            for (int q = 0; q < 4; ++q) sv[q] = (j + q < n) ? Scur[int64_t(j + q) * kH0 + h] : 0.f;
+            for (int q = 0; q < 4; ++q) sv[q] = (j + q < n) ? Scur[(j + q) * kH0 + h] : 0.f;
 #pragma unroll
             for (int i = 0; i < TR; ++i) {
                 const float4 g = *reinterpret_cast<const float4*>(&s.gt[i * kGS + j]);
@@ -215,12 +224,15 @@ __device__ inline void tile_h0(const EpiParams& P, const Smem<TR>& s, int64_t ta
     }
     const float alpha = P.cfg.step_size;
     const float sc = dropout_scale(P.cfg);
+    const bool drop = P.cfg.dropout_p > 0.f;
+    const uint32_t thr = dropout_thr(P.cfg);
 #pragma unroll
     for (int i = 0; i < TR; ++i) {
         float v = 0.f;
         if (i < tr) {
-            const float z = P.proj[s.rows[i] * kH0 + h] + b0h - alpha * acc[i];
-            if (z > 0.f && dropout_keep(P.cfg, task, pass, 0, r0 + i, h)) v = z * sc;
+            const float a = CACHED ? s.sA[i * kH0 + h] : P.proj[s.rows[i] * kH0 + h];
+            const float z = a + b0h - alpha * acc[i];
+            if (z > 0.f && (!drop || dropout_keep_bits(dropout_bits(P.cfg, task, pass, 0, r0 + i, h), h, thr))) v = z * sc;
         }
         s.h0t[i * kH0 + h] = v;
     }
@@ -228,7 +240,7 @@ __device__ inline void tile_h0(const EpiParams& P, const Smem<TR>& s, int64_t ta
 
 // (b) Z1 = H0 W1^T + b1 -> H1.   thread == (o, row group).
 template <int TR>
-__device__ inline void tile_h1(const EpiParams& P, const Smem<TR>& s, int64_t task, int r0, int tr, int pass) {
+__device__ inline void tile_h1(const EpiParams& P, const Smem& s, int64_t task, int r0, int tr, int pass) {
     constexpr int RPT = TR / 4;
     const int o = threadIdx.x & 63, ig = threadIdx.x >> 6;
     float acc[RPT];
@@ -247,6 +259,8 @@ __device__ inline void tile_h1(const EpiParams& P, const Smem<TR>& s, int64_t ta
         }
     }
     const float sc = dropout_scale(P.cfg);
+    const bool drop = P.cfg.dropout_p > 0.f;
+    const uint32_t thr = dropout_thr(P.cfg);
     const float b = s.b1s[o];
 #pragma unroll
     for (int ii = 0; ii < RPT; ++ii) {
@@ -254,7 +268,8 @@ __device__ inline void tile_h1(const EpiParams& P, const Smem<TR>& s, int64_t ta
         float v = 0.f;
         if (i < tr) {
             const float z = acc[ii] + b;
-            if (z > 0.f && dropout_keep(P.cfg, task, pass, 1, r0 + i, o)) v = z * sc;
+            if (z > 0.f && (!drop || dropout_keep_bits(dropout_bits(P.cfg, task, pass, 1, r0 + i, o), o, thr)))
+                v = z * sc;
         }
         s.h1t[i * kH1 + o] = v;
     }
@@ -262,7 +277,7 @@ __device__ inline void tile_h1(const EpiParams& P, const Smem<TR>& s, int64_t ta
 
 // (c) logits = H1 . head[:, :64]^T + head[:, 64]
 template <int TR>
-__device__ inline void tile_logits(const EpiParams& P, const Smem<TR>& s, int tr) {
+__device__ inline void tile_logits(const EpiParams& P, const Smem& s, int tr) {
     const int N = P.cfg.num_ways;
     for (int idx = threadIdx.x; idx < TR * N; idx += kThreads) {
         const int i = idx / N, c = idx - i * N;
@@ -327,10 +342,15 @@ __device__ inline void cols_from_h1(const float* Y /*[TR][H1]*/, const float* Wt
 }
 
 // ------------------------------------------------------------------------------------ forward
-template <int TR, bool MULTI>
+// TRS / TRQ: rows per support / query tile.  MULTI: more than one support tile (NK > TRS): S ping-pongs in
+// the L2-resident workspace and the W1 update is accumulated in registers until all tiles of the step are
+// done.  Otherwise (the common case, NK <= 32) S and the projected support rows stay in shared memory for
+// the whole task: the support set is staged once and reused by all inner steps.
+template <int TRS, int TRQ, bool MULTI>
 __global__ void __launch_bounds__(kThreads, 1) episode_fwd_kernel(EpiParams P) {
+    constexpr int TRM = TRS > TRQ ? TRS : TRQ;
     FUMI_DYN_SMEM(float, smem_raw);
-    const Smem<TR> s = carve<TR, false>(smem_raw);
+    const Smem s = carve<TRM, false, MULTI ? 0 : TRS>(smem_raw);
     const fumi_episode_cfg& c = P.cfg;
     const int tid = threadIdx.x;
     const int n = c.num_support, m = c.num_query, N = c.num_ways, steps = c.steps;
@@ -343,7 +363,7 @@ __global__ void __launch_bounds__(kThreads, 1) episode_fwd_kernel(EpiParams P) {
         const int64_t task = c.task_offset + b;
         float* slot = P.stash + (P.save ? b : int64_t(blockIdx.x)) * P.slot_floats;
         float* Sbuf[2] = {slot + L.S0, slot + L.S1};
-        // ---- task prologue: W1^T, biases, head init
+        // ---- task prologue: W1^T, biases, head init (and the projected support rows)
         for (int idx = tid; idx < kH0 * kH1; idx += kThreads) {
             const int o = idx / kH0, k = idx - o * kH0;        // w1 is [H1][H0] row-major
             s.w1t[k * kW1S + o] = P.w1[idx];
@@ -355,12 +375,15 @@ __global__ void __launch_bounds__(kThreads, 1) episode_fwd_kernel(EpiParams P) {
             const int64_t r = P.head_rows ? P.head_rows[b * N + cc] : cc;
             s.hp[idx] = P.head_table[r * kHD + o];
         }
+        if (!MULTI) {
+            for (int i = 0; i < n; ++i) s.sA[i * kH0 + tid] = P.proj[P.sup_rows[b * n + i] * kH0 + tid];
+        }
         if (tid == 0) { task_sum[0] = 0.f; task_sum[1] = 0.f; }
         __syncthreads();
 
         int cur = 0;
         for (int st = 0; st < steps; ++st) {
-            const float* Scur = st > 0 ? Sbuf[cur] : nullptr;       // S_0 == 0
+            const float* Scur = st > 0 ? (MULTI ? Sbuf[cur] : s.sS) : nullptr;       // S_0 == 0
             float* Snext = Sbuf[cur ^ 1];
             float* rec = P.save ? slot + L.steps + int64_t(st) * L.per_step : nullptr;
             float db0 = 0.f, db1 = 0.f;
@@ -370,17 +393,17 @@ __global__ void __launch_bounds__(kThreads, 1) episode_fwd_kernel(EpiParams P) {
                 for (int q = 0; q < (MULTI ? 64 : 1); ++q) dw1[q] = 0.f;
             }
             for (int idx = tid; idx < N * kHD; idx += kThreads) s.dhp[idx] = 0.f;
-            for (int r0 = 0; r0 < n; r0 += TR) {
-                const int tr = min(TR, n - r0);
-                load_tile_meta<TR>(P, s, b, false, r0, tr);
+            for (int r0 = 0; r0 < n; r0 += TRS) {
+                const int tr = min(TRS, n - r0);
+                load_tile_meta<TRS>(P, s, b, false, r0, tr);
                 __syncthreads();
-                tile_h0<TR>(P, s, task, Scur, b0h, r0, tr, st);
+                tile_h0<TRS, !MULTI>(P, s, task, Scur, b0h, r0, tr, st);
                 __syncthreads();
-                tile_h1<TR>(P, s, task, r0, tr, st);
+                tile_h1<TRS>(P, s, task, r0, tr, st);
                 __syncthreads();
-                tile_logits<TR>(P, s, tr);
+                tile_logits<TRS>(P, s, tr);
                 __syncthreads();
-                if (tid < TR) {                                    // dL = (softmax - onehot) / n
+                if (tid < TRS) {                                   // dL = (softmax - onehot) / n
                     float* l = &s.lt[tid * kLS];
                     if (tid < tr) {
                         float mx, sum;
@@ -406,7 +429,7 @@ __global__ void __launch_bounds__(kThreads, 1) episode_fwd_kernel(EpiParams P) {
                 {
                     const float sc = dropout_scale(c);
 #pragma unroll
-                    for (int ii = 0; ii < TR / 4; ++ii) {
+                    for (int ii = 0; ii < TRS / 4; ++ii) {
                         const int i = kg_ + 4 * ii;
                         float dz = 0.f;
                         if (i < tr && s.h1t[i * kH1 + o_] > 0.f) {
@@ -423,19 +446,23 @@ __global__ void __launch_bounds__(kThreads, 1) episode_fwd_kernel(EpiParams P) {
                     for (int i = 0; i < tr; ++i) a += s.dz1t[i * kH1 + tid];
                     db1 += a;
                 }
-                // (f) dZ0 = (dZ1 W1) * mask ; S_next = S_cur + dZ0
+                // (f) dZ0 = (dZ1 W1) * mask ; S += dZ0
                 {
-                    float acc[TR];
+                    float acc[TRS];
 #pragma unroll
-                    for (int i = 0; i < TR; ++i) acc[i] = 0.f;
-                    cols_from_h1<TR>(s.dz1t, s.w1t, 1.f, acc);
+                    for (int i = 0; i < TRS; ++i) acc[i] = 0.f;
+                    cols_from_h1<TRS>(s.dz1t, s.w1t, 1.f, acc);
                     const float sc = dropout_scale(c);
 #pragma unroll
-                    for (int i = 0; i < TR; ++i) {
+                    for (int i = 0; i < TRS; ++i) {
                         if (i < tr) {
                             const float dz0 = s.h0t[i * kH0 + tid] > 0.f ? acc[i] * sc : 0.f;
-                            const int64_t off = int64_t(r0 + i) * kH0 + tid;
-                            Snext[off] = (Scur ? Scur[off] : 0.f) + dz0;
+                            if (MULTI) {
+                                const int64_t off = int64_t(r0 + i) * kH0 + tid;
+                                Snext[off] = (Scur ? Scur[off] : 0.f) + dz0;
+                            } else {            // single tile: every Z0 of this step is done, update in place
+                                s.sS[i * kH0 + tid] = (st > 0 ? s.sS[i * kH0 + tid] : 0.f) + dz0;
+                            }
                             db0 += dz0;
                         }
                     }
@@ -454,11 +481,11 @@ __global__ void __launch_bounds__(kThreads, 1) episode_fwd_kernel(EpiParams P) {
                 __syncthreads();                                    // (f) done reading W1^T
                 // (g) W1 -= alpha * dZ1^T H0
                 if (MULTI) {
-                    outer_rows<TR>(s.h0t, s.dz1t, [&](int kk, int, int, float a0, float a1, float a2, float a3) {
+                    outer_rows<TRS>(s.h0t, s.dz1t, [&](int kk, int, int, float a0, float a1, float a2, float a3) {
                         dw1[kk] += a0; dw1[kk + 1] += a1; dw1[kk + 2] += a2; dw1[kk + 3] += a3;
                     });
                 } else {
-                    outer_rows<TR>(s.h0t, s.dz1t, [&](int, int k, int o, float a0, float a1, float a2, float a3) {
+                    outer_rows<TRS>(s.h0t, s.dz1t, [&](int, int k, int o, float a0, float a1, float a2, float a3) {
                         s.w1t[(k + 0) * kW1S + o] -= alpha * a0;
                         s.w1t[(k + 1) * kW1S + o] -= alpha * a1;
                         s.w1t[(k + 2) * kW1S + o] -= alpha * a2;
@@ -481,16 +508,16 @@ __global__ void __launch_bounds__(kThreads, 1) episode_fwd_kernel(EpiParams P) {
         }
 
         // ---- query scoring
-        const float* Sfin = steps > 0 ? Sbuf[cur] : nullptr;
-        for (int r0 = 0; r0 < m; r0 += TR) {
-            const int tr = min(TR, m - r0);
-            load_tile_meta<TR>(P, s, b, true, r0, tr);
+        const float* Sfin = steps > 0 ? (MULTI ? Sbuf[cur] : s.sS) : nullptr;
+        for (int r0 = 0; r0 < m; r0 += TRQ) {
+            const int tr = min(TRQ, m - r0);
+            load_tile_meta<TRQ>(P, s, b, true, r0, tr);
             __syncthreads();
-            tile_h0<TR>(P, s, task, Sfin, b0h, r0, tr, steps);
+            tile_h0<TRQ, false>(P, s, task, Sfin, b0h, r0, tr, steps);
             __syncthreads();
-            tile_h1<TR>(P, s, task, r0, tr, steps);
+            tile_h1<TRQ>(P, s, task, r0, tr, steps);
             __syncthreads();
-            tile_logits<TR>(P, s, tr);
+            tile_logits<TRQ>(P, s, tr);
             __syncthreads();
             if (tid < tr) {
                 const float* l = &s.lt[tid * kLS];
@@ -525,6 +552,369 @@ __global__ void __launch_bounds__(kThreads, 1) episode_fwd_kernel(EpiParams P) {
             slot[L.b0 + tid] = b0h;
             if (tid < kH1) slot[L.b1 + tid] = s.b1s[tid];
             for (int idx = tid; idx < N * kHD; idx += kThreads) slot[L.head + idx] = s.hp[idx];
+            if (!MULTI) {                                           // final S where the backward expects it
+                float* Sout = Sbuf[steps & 1];
+                for (int i = 0; i < n; ++i) Sout[int64_t(i) * kH0 + tid] = steps > 0 ? s.sS[i * kH0 + tid] : 0.f;
+            }
+        }
+        __syncthreads();
+    }
+}
+
+// ------------------------------------------------------------------------------------ forward (tensor core)
+// Single-support-tile forward (NK <= 32, the common case): all GEMM-shaped ops run as warp-level 3xTF32
+// mma.sync tiles (warp_mma.cuh) on the fp32 tiles in shared memory.  MT = 1 for NK <= 16, else 2
+// (rows padded with zeros to 16*MT).  Warp w of 8 owns hidden units [32w, 32w+32) of the 256-wide ops and
+// output units [8w, 8w+8) of the 64-wide op.  Query rows go through in tiles of 32.
+constexpr int kS0 = kH0 + 4;     // row stride of [rows][H0] tiles (A operand: conflict-free fragment loads)
+constexpr int kS1 = kH1 + 4;     // row stride of [rows][H1] tiles and of W1^T [H0][H1]
+constexpr int kSS = kH0 + 8;     // row stride of S (B operand, k = row)
+constexpr int kSG = 36;          // row stride of a Gram tile with up to 32 columns
+constexpr int kMaxQueryRows = 640;
+
+struct SmemM {
+    float *w1t, *h0t, *h1t, *dz1t, *lt, *gS, *gQ, *sS, *sA, *hp, *dhp, *b0s, *db0s, *b1s, *rowv, *rowc;
+    long long* rowsQ;
+    int *ysQ, *ysS;
+};
+__host__ __device__ inline size_t smem_m_floats() {
+    return size_t(kH0) * kS1 + 32 * kS0 + 2 * 32 * kS1 + 32 * kLS + 2 * 32 * kSG + 32 * kSS + 32 * kH0 +
+           2 * kMaxWays * kHD + 2 * kH0 + kH1 + 64 + 2 * kMaxQueryRows + kMaxQueryRows + 32 + 16;
+}
+__device__ inline SmemM carve_m(float* p) {
+    SmemM s;
+    s.rowsQ = reinterpret_cast<long long*>(p); p += 2 * kMaxQueryRows;
+    s.w1t = p; p += kH0 * kS1;
+    s.h0t = p; p += 32 * kS0;
+    s.h1t = p; p += 32 * kS1;
+    s.dz1t = p; p += 32 * kS1;
+    s.lt = p; p += 32 * kLS;
+    s.gS = p; p += 32 * kSG;
+    s.gQ = p; p += 32 * kSG;
+    s.sS = p; p += 32 * kSS;
+    s.sA = p; p += 32 * kH0;
+    s.hp = p; p += kMaxWays * kHD;
+    s.dhp = p; p += kMaxWays * kHD;
+    s.b0s = p; p += kH0;
+    s.db0s = p; p += kH0;
+    s.b1s = p; p += kH1;
+    s.rowv = p; p += 32;
+    s.rowc = p; p += 32;
+    s.ysQ = reinterpret_cast<int*>(p); p += kMaxQueryRows;
+    s.ysS = reinterpret_cast<int*>(p); p += 32;
+    return s;
+}
+
+// H0 tile: Z0 = A + b0 - alpha * (G S) -> relu, dropout.  `Apre`: the projected rows (row stride lda_pre).
+template <int MT>
+__device__ __forceinline__ void mma_tile_h0(const EpiParams& P, const SmemM& s, int64_t task, const float* G,
+                                            bool use_s, int K8, const float* Apre, int lda_pre, int r0, int tr,
+                                            int pass) {
+    const int w = threadIdx.x >> 5;
+    float acc[MT][4][4];
+#pragma unroll
+    for (int i = 0; i < MT; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+#pragma unroll
+            for (int q = 0; q < 4; ++q) acc[i][j][q] = 0.f;
+    if (use_s) warp_gemm_3xtf32<MT, 4, false, false>(G, kSG, s.sS + 32 * w, kSS, K8, 1.f, acc);
+    const float alpha = P.cfg.step_size, sc = dropout_scale(P.cfg);
+    const bool drop = P.cfg.dropout_p > 0.f;
+    const uint32_t thr = dropout_thr(P.cfg);
+    uint64_t bits = 0;
+    warp_tile_foreach<MT, 4>(acc, [&](int i, int hh, float& c) {
+        const int h = 32 * w + hh;
+        float v = 0.f;
+        if (i < tr) {
+            const float z = Apre[i * lda_pre + h] + s.b0s[h] - alpha * c;
+            if (drop && (hh & 1) == 0) bits = dropout_bits(P.cfg, task, pass, 0, r0 + i, h);
+            if (z > 0.f && (!drop || dropout_keep_bits(bits, h, thr))) v = z * sc;
+        }
+        s.h0t[i * kS0 + h] = v;
+    });
+}
+
+// H1 tile: Z1 = H0 W1^T + b1 -> relu, dropout
+template <int MT>
+__device__ __forceinline__ void mma_tile_h1(const EpiParams& P, const SmemM& s, int64_t task, int r0, int tr, int pass) {
+    const int w = threadIdx.x >> 5;
+    float acc[MT][1][4];
+#pragma unroll
+    for (int i = 0; i < MT; ++i)
+#pragma unroll
+        for (int q = 0; q < 4; ++q) acc[i][0][q] = 0.f;
+    warp_gemm_3xtf32<MT, 1, false, false>(s.h0t, kS0, s.w1t + 8 * w, kS1, kH0, 1.f, acc);
+    const float sc = dropout_scale(P.cfg);
+    const bool drop = P.cfg.dropout_p > 0.f;
+    const uint32_t thr = dropout_thr(P.cfg);
+    uint64_t bits = 0;
+    warp_tile_foreach<MT, 1>(acc, [&](int i, int oo, float& c) {
+        const int o = 8 * w + oo;
+        float v = 0.f;
+        if (i < tr) {
+            const float z = c + s.b1s[o];
+            if (drop && (oo & 1) == 0) bits = dropout_bits(P.cfg, task, pass, 1, r0 + i, o);
+            if (z > 0.f && (!drop || dropout_keep_bits(bits, o, thr))) v = z * sc;
+        }
+        s.h1t[i * kS1 + o] = v;
+    });
+}
+
+__device__ __forceinline__ void m_tile_logits(const EpiParams& P, const SmemM& s, int rows, int tr) {
+    const int N = P.cfg.num_ways;
+    for (int idx = threadIdx.x; idx < rows * N; idx += kThreads) {
+        const int i = idx / N, c = idx - i * N;
+        float l = 0.f;
+        if (i < tr) {
+            l = s.hp[c * kHD + kH1];
+            for (int o = 0; o < kH1; ++o) l = fmaf(s.h1t[i * kS1 + o], s.hp[c * kHD + o], l);
+        }
+        s.lt[i * kLS + c] = l;
+    }
+}
+
+template <int MT>
+__global__ void __launch_bounds__(kThreads, 1) episode_fwd_mma_kernel(EpiParams P) {
+    constexpr int RS = 16 * MT;                       // padded support rows
+    FUMI_DYN_SMEM(float, smem_raw);
+    const SmemM s = carve_m(smem_raw);
+    const fumi_episode_cfg& c = P.cfg;
+    const int tid = threadIdx.x, w = tid >> 5;
+    const int n = c.num_support, m = c.num_query, N = c.num_ways, steps = c.steps;
+    const int n8 = (n + 7) & ~7;
+    const float alpha = c.step_size;
+    const Layout L = make_layout(c);
+    const int o_ = tid & 63, kg_ = tid >> 6;
+    __shared__ float task_sum[2];
+
+    for (int i = 0; i < 32; ++i) s.sS[i * kSS + tid] = 0.f;         // pad rows of S stay zero for the whole kernel
+    for (int idx = tid; idx < 32 * kSG; idx += kThreads) { s.gS[idx] = 0.f; s.gQ[idx] = 0.f; }
+    __syncthreads();
+
+    for (int64_t b = blockIdx.x; b < P.B; b += gridDim.x) {
+        const int64_t task = c.task_offset + b;
+        float* slot = P.stash + (P.save ? b : int64_t(blockIdx.x)) * P.slot_floats;
+        // ---- task prologue: everything the inner loop needs is staged in shared memory once
+        // (global -> shared copies go through register batches: a store to shared memory may alias a later
+        //  global load as far as the compiler knows, which would serialise load latencies)
+        {
+            float v[16];
+#pragma unroll 1
+            for (int o0 = 0; o0 < kH1; o0 += 16) {               // w1 is [H1][H0] row-major; thread == k
+#pragma unroll
+                for (int q = 0; q < 16; ++q) v[q] = __ldg(&P.w1[(o0 + q) * kH0 + tid]);
+#pragma unroll
+                for (int q = 0; q < 16; ++q) s.w1t[tid * kS1 + o0 + q] = v[q];
+            }
+#pragma unroll 1
+            for (int i0 = 0; i0 < RS; i0 += 16) {
+#pragma unroll
+                for (int q = 0; q < 16; ++q)
+                    v[q] = (i0 + q < n) ? __ldg(&P.proj[__ldg(&P.sup_rows[b * n + i0 + q]) * kH0 + tid]) : 0.f;
+#pragma unroll
+                for (int q = 0; q < 16; ++q) s.sA[(i0 + q) * kH0 + tid] = v[q];
+            }
+        }
+        s.b0s[tid] = __ldg(&P.b0[tid]);
+        if (tid < kH1) s.b1s[tid] = __ldg(&P.b1[tid]);
+        for (int idx = tid; idx < N * kHD; idx += kThreads) {
+            const int cc = idx / kHD, o = idx - cc * kHD;
+            const int64_t r = P.head_rows ? __ldg(&P.head_rows[b * N + cc]) : cc;
+            s.hp[idx] = __ldg(&P.head_table[r * kHD + o]);
+        }
+        for (int idx = tid; idx < n * n; idx += kThreads) {
+            const int i = idx / n, j = idx - i * n;
+            s.gS[i * kSG + j] = __ldg(&P.gram[(b * int64_t(n + m) + i) * n + j]);
+        }
+        if (tid < 32) s.ysS[tid] = tid < n ? int(P.sup_y[b * n + tid]) : 0;
+        for (int idx = tid; idx < m; idx += kThreads) {
+            s.rowsQ[idx] = P.qry_rows[b * m + idx];
+            s.ysQ[idx] = int(P.qry_y[b * m + idx]);
+        }
+        if (tid == 0) { task_sum[0] = 0.f; task_sum[1] = 0.f; }
+        __syncthreads();
+
+        for (int st = 0; st < steps; ++st) {
+            float* rec = P.save ? slot + L.steps + int64_t(st) * L.per_step : nullptr;
+            for (int idx = tid; idx < N * kHD; idx += kThreads) s.dhp[idx] = 0.f;
+            mma_tile_h0<MT>(P, s, task, s.gS, st > 0, n8, s.sA, kH0, 0, n, st);
+            __syncthreads();
+            mma_tile_h1<MT>(P, s, task, 0, n, st);
+            __syncthreads();
+            m_tile_logits(P, s, RS, n);
+            __syncthreads();
+            if (tid < RS) {                                    // dL = (softmax - onehot) / n
+                float* l = &s.lt[tid * kLS];
+                if (tid < n) {
+                    float mx, sum;
+                    row_softmax(l, N, mx, sum);
+                    const float inv = 1.f / sum, invn = 1.f / float(n);
+                    const int y = s.ysS[tid];
+                    for (int cc = 0; cc < N; ++cc) {
+                        const float p = expf(l[cc] - mx) * inv;
+                        l[cc] = (p - (cc == y ? 1.f : 0.f)) * invn;
+                    }
+                } else {
+                    for (int cc = 0; cc < N; ++cc) l[cc] = 0.f;
+                }
+            }
+            __syncthreads();
+            // head gradient; dZ1 (uses the pre-update head)
+            for (int idx = tid; idx < N * kHD; idx += kThreads) {
+                const int cc = idx / kHD, o = idx - cc * kHD;
+                float a = 0.f;
+                for (int i = 0; i < n; ++i) a = fmaf(s.lt[i * kLS + cc], o < kH1 ? s.h1t[i * kS1 + o] : 1.f, a);
+                s.dhp[idx] = a;
+            }
+            {
+                const float sc = dropout_scale(c);
+#pragma unroll
+                for (int ii = 0; ii < RS / 4; ++ii) {
+                    const int i = kg_ + 4 * ii;
+                    float dz = 0.f;
+                    if (i < n && s.h1t[i * kS1 + o_] > 0.f) {
+                        float dh = 0.f;
+                        for (int cc = 0; cc < N; ++cc) dh = fmaf(s.lt[i * kLS + cc], s.hp[cc * kHD + o_], dh);
+                        dz = dh * sc;
+                    }
+                    s.dz1t[i * kS1 + o_] = dz;
+                }
+            }
+            __syncthreads();
+            float db1 = 0.f;
+            if (tid < kH1) for (int i = 0; i < n; ++i) db1 += s.dz1t[i * kS1 + tid];
+            // dZ0 = (dZ1 W1) * gate ;  S += dZ0 ;  db0 = column sums of dZ0
+            {
+                float acc[MT][4][4];
+#pragma unroll
+                for (int i = 0; i < MT; ++i)
+#pragma unroll
+                    for (int j = 0; j < 4; ++j)
+#pragma unroll
+                        for (int q = 0; q < 4; ++q) acc[i][j][q] = 0.f;
+                warp_gemm_3xtf32<MT, 4, false, true>(s.dz1t, kS1, s.w1t + 32 * w * kS1, kS1, kH1, 1.f, acc);
+                const float sc = dropout_scale(c);
+                float colsum[4][2];
+#pragma unroll
+                for (int j = 0; j < 4; ++j) colsum[j][0] = colsum[j][1] = 0.f;
+                warp_tile_foreach<MT, 4>(acc, [&](int i, int hh, float& cv) {
+                    const int h = 32 * w + hh;
+                    const float dz0 = (i < n && s.h0t[i * kS0 + h] > 0.f) ? cv * sc : 0.f;
+                    if (i < n) s.sS[i * kSS + h] = (st > 0 ? s.sS[i * kSS + h] : 0.f) + dz0;
+                    colsum[hh >> 3][hh & 1] += dz0;
+                });
+                const int lane = tid & 31;
+#pragma unroll
+                for (int j = 0; j < 4; ++j)
+#pragma unroll
+                    for (int q = 0; q < 2; ++q) {
+                        float v = colsum[j][q];
+                        v += __shfl_xor_sync(0xffffffffu, v, 4);
+                        v += __shfl_xor_sync(0xffffffffu, v, 8);
+                        v += __shfl_xor_sync(0xffffffffu, v, 16);
+                        if ((lane >> 2) == 0) s.db0s[32 * w + 8 * j + 2 * (lane & 3) + q] = v;
+                    }
+            }
+            if (rec) {                                          // records for the backward
+                for (int i = 0; i < n; ++i) rec[L.oH0 + int64_t(i) * kH0 + tid] = s.h0t[i * kS0 + tid];
+                for (int idx = tid; idx < n * kH1; idx += kThreads) {
+                    const int i = idx / kH1, o = idx - i * kH1;
+                    rec[L.oH1 + idx] = s.h1t[i * kS1 + o];
+                    rec[L.oDZ1 + idx] = s.dz1t[i * kS1 + o];
+                }
+                for (int idx = tid; idx < n * N; idx += kThreads) {
+                    const int i = idx / N, cc = idx - i * N;
+                    rec[L.oDL + idx] = s.lt[i * kLS + cc];
+                }
+                for (int idx = tid; idx < N * kHD; idx += kThreads) rec[L.oHP + idx] = s.hp[idx];
+            }
+            __syncthreads();                                    // everyone is done reading W1^T and the old head
+            // W1 -= alpha * dZ1^T H0   (rows of W1^T owned by this warp: h in [32w, 32w+32))
+            {
+                float acc[2][8][4];
+#pragma unroll
+                for (int i = 0; i < 2; ++i)
+#pragma unroll
+                    for (int j = 0; j < 8; ++j)
+#pragma unroll
+                        for (int q = 0; q < 4; ++q) acc[i][j][q] = 0.f;
+                warp_gemm_3xtf32<2, 8, true, false>(s.h0t + 32 * w, kS0, s.dz1t, kS1, RS, 1.f, acc);
+                warp_tile_foreach<2, 8>(acc, [&](int hh, int o, float& cv) {
+                    s.w1t[(32 * w + hh) * kS1 + o] -= alpha * cv;
+                });
+            }
+            for (int idx = tid; idx < N * kHD; idx += kThreads) s.hp[idx] -= alpha * s.dhp[idx];
+            if (tid < kH1) s.b1s[tid] -= alpha * db1;
+            s.b0s[tid] -= alpha * s.db0s[tid];
+            __syncthreads();
+        }
+
+        // ---- query scoring, 32 rows per tile
+        for (int r0 = 0; r0 < m; r0 += 32) {
+            const int tr = min(32, m - r0);
+            {
+                float v[32];
+#pragma unroll
+                for (int i = 0; i < 32; ++i) v[i] = i < tr ? __ldg(&P.proj[s.rowsQ[r0 + i] * kH0 + tid]) : 0.f;
+                float gv[4];
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {                      // 32 x n Gram tile: <= 4 elements per thread
+                    const int idx = tid + q * kThreads;
+                    const int i = idx / n, j = idx - i * n;
+                    gv[q] = (idx < 32 * n && i < tr) ? __ldg(&P.gram[(b * int64_t(n + m) + n + r0 + i) * n + j]) : 0.f;
+                }
+#pragma unroll
+                for (int i = 0; i < 32; ++i) s.h0t[i * kS0 + tid] = v[i];
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    const int idx = tid + q * kThreads;
+                    const int i = idx / n, j = idx - i * n;
+                    if (idx < 32 * n) s.gQ[i * kSG + j] = gv[q];
+                }
+            }
+            __syncthreads();
+            mma_tile_h0<2>(P, s, task, s.gQ, steps > 0, n8, s.h0t, kS0, r0, tr, steps);
+            __syncthreads();
+            mma_tile_h1<2>(P, s, task, r0, tr, steps);
+            __syncthreads();
+            m_tile_logits(P, s, 32, tr);
+            __syncthreads();
+            if (tid < tr) {
+                const float* l = &s.lt[tid * kLS];
+                float mx, sum;
+                row_softmax(l, N, mx, sum);
+                int best = 0;
+                for (int cc = 1; cc < N; ++cc) if (l[cc] > l[best]) best = cc;   // first max (torch.max)
+                const int y = s.ysQ[r0 + tid];
+                s.rowv[tid] = (logf(sum) + mx) - l[y];
+                s.rowc[tid] = best == y ? 1.f : 0.f;
+                const int64_t q = b * m + r0 + tid;
+                P.preds[q] = best;
+                for (int cc = 0; cc < N; ++cc) P.logits[q * N + cc] = l[cc];
+            }
+            __syncthreads();
+            if (tid == 0) {
+                float a = task_sum[0], k = task_sum[1];
+                for (int i = 0; i < tr; ++i) { a += s.rowv[i]; k += s.rowc[i]; }
+                task_sum[0] = a; task_sum[1] = k;
+            }
+        }
+        __syncthreads();
+        if (tid == 0) {
+            P.task_loss[b] = task_sum[0] / float(m);
+            P.task_acc[b] = task_sum[1] / float(m);
+        }
+        if (P.save) {                                               // adapted state
+            for (int idx = tid; idx < kH0 * kH1; idx += kThreads) {
+                const int k = idx / kH1, o = idx - k * kH1;
+                slot[L.w1t + idx] = s.w1t[k * kS1 + o];
+            }
+            slot[L.b0 + tid] = s.b0s[tid];
+            if (tid < kH1) slot[L.b1 + tid] = s.b1s[tid];
+            for (int idx = tid; idx < N * kHD; idx += kThreads) slot[L.head + idx] = s.hp[idx];
+            float* Sout = slot + ((steps & 1) ? L.S1 : L.S0);      // final S where the backward expects it
+            for (int i = 0; i < n; ++i) Sout[int64_t(i) * kH0 + tid] = steps > 0 ? s.sS[i * kSS + tid] : 0.f;
         }
         __syncthreads();
     }
@@ -536,7 +926,7 @@ __global__ void __launch_bounds__(kThreads, 1) episode_fwd_kernel(EpiParams P) {
 template <int TR>
 __global__ void __launch_bounds__(kThreads, 1) episode_bwd_kernel(EpiParams P) {
     FUMI_DYN_SMEM(float, smem_raw);
-    const Smem<TR> s = carve<TR, true>(smem_raw);
+    const Smem s = carve<TR, true, 0>(smem_raw);
     const fumi_episode_cfg& c = P.cfg;
     const int tid = threadIdx.x;
     const int n = c.num_support, m = c.num_query, N = c.num_ways, steps = c.steps;
@@ -571,7 +961,7 @@ __global__ void __launch_bounds__(kThreads, 1) episode_bwd_kernel(EpiParams P) {
             const int tr = min(TR, m - r0);
             load_tile_meta<TR>(P, s, b, true, r0, tr);
             __syncthreads();
-            tile_h0<TR>(P, s, task, Sfin, b0h, r0, tr, steps);
+            tile_h0<TR, false>(P, s, task, Sfin, b0h, r0, tr, steps);
             __syncthreads();
             tile_h1<TR>(P, s, task, r0, tr, steps);
             __syncthreads();
@@ -878,7 +1268,17 @@ int grid_for(int64_t B) {
     return int(B < sms ? B : sms);
 }
 
-constexpr int kTRF = 32;   // forward rows per tile
+#ifdef FUMI_EMU
+#define FUMI_SET_SMEM_ATTR(kern, bytes) ((void)0)
+#else
+#define FUMI_SET_SMEM_ATTR(kern, bytes)                                                                        \
+    do {                                                                                                       \
+        cudaError_t e__ = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, int(bytes)); \
+        if (e__ != cudaSuccess) return fumi_cuda_fail(e__, "cudaFuncSetAttribute(episode kernel)");            \
+    } while (0)
+#endif
+
+constexpr int kTRF = 32;   // forward query rows per tile
 constexpr int kTRB = 16;   // backward rows per tile (two W1-sized buffers live in shared memory)
 
 }  // namespace
@@ -927,21 +1327,31 @@ extern "C" int fumi_episode_fwd(const fumi_episode_cfg* cfg, int64_t B, const fl
     P.slot_floats = make_layout(*cfg).per_task;
     const int grid = grid_for(B);
     if (grid <= 0) return grid;
-    const size_t smem = smem_floats<kTRF, false>() * sizeof(float);
-#ifndef FUMI_EMU
-    static bool attr_done = false;
-    if (!attr_done) {
-        cudaError_t e = cudaFuncSetAttribute(episode_fwd_kernel<kTRF, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem));
-        if (e == cudaSuccess) e = cudaFuncSetAttribute(episode_fwd_kernel<kTRF, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem));
-        if (e != cudaSuccess) return fumi_cuda_fail(e, "cudaFuncSetAttribute(episode_fwd)");
-        attr_done = true;
-    }
-#endif
-    if (cfg->num_support > kTRF) {
-        FUMI_LAUNCH((episode_fwd_kernel<kTRF, true>), grid, kThreads, smem, stream, P);
-    } else {
-        FUMI_LAUNCH((episode_fwd_kernel<kTRF, false>), grid, kThreads, smem, stream, P);
-    }
+    const int nk = cfg->num_support;
+#define FUMI_FWD_CASE(TRS, MULTI)                                                                              \
+    do {                                                                                                       \
+        constexpr int TRM_ = (TRS) > kTRF ? (TRS) : kTRF;                                                      \
+        const size_t smem = smem_floats<TRM_, false, (MULTI) ? 0 : (TRS)>() * sizeof(float);                   \
+        auto kern = episode_fwd_kernel<(TRS), kTRF, (MULTI)>;                                                   \
+        FUMI_SET_SMEM_ATTR(kern, smem);                                                                        \
+        FUMI_LAUNCH(kern, grid, kThreads, smem, stream, P);                                                    \
+    } while (0)
+    const bool use_mma = nk <= 32 && cfg->num_query <= kMaxQueryRows;
+    if (use_mma) {
+        const size_t smem = smem_m_floats() * sizeof(float);
+        if (nk <= 16) {
+            FUMI_SET_SMEM_ATTR(episode_fwd_mma_kernel<1>, smem);
+            FUMI_LAUNCH(episode_fwd_mma_kernel<1>, grid, kThreads, smem, stream, P);
+        } else {
+            FUMI_SET_SMEM_ATTR(episode_fwd_mma_kernel<2>, smem);
+            FUMI_LAUNCH(episode_fwd_mma_kernel<2>, grid, kThreads, smem, stream, P);
+        }
+    } else if (nk > 32) FUMI_FWD_CASE(32, true);
+    else if (nk > 28) FUMI_FWD_CASE(32, false);
+    else if (nk > 16) FUMI_FWD_CASE(28, false);
+    else if (nk > 8) FUMI_FWD_CASE(16, false);
+    else FUMI_FWD_CASE(8, false);
+#undef FUMI_FWD_CASE
     FUMI_CHECK_LAUNCH("episode_fwd_kernel");
     return FUMI_OK;
 }

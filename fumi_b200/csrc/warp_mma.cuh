@@ -1,0 +1,125 @@
+// Warp-level tensor-core building block for the per-task contractions of the episode kernels.
+//
+// The per-task matrices are small (NK = 25 rows at 5-way 5-shot): a tcgen05 tile (M >= 64 per CTA, operands
+// staged as 4-byte TF32 planes) would idle most of the array and does not fit next to the task state in
+// shared memory, so these contractions use warp-synchronous mma.sync.m16n8k8 TF32 on fragments read straight
+// from the fp32 tiles in shared memory, with the same fp32-accurate 3-pass split as dense_tc.cu:
+//      x = hi + lo,  hi = tf32(x);      a*b ~= a_lo*b_hi + a_hi*b_lo + a_hi*b_hi
+// Measured on B200 (tools/mma_bench.cu): mma.sync TF32 478 MAC/clk/SM vs FFMA 124, so 3 passes are ~1.3x the
+// FFMA *peak* while needing ~10x fewer issue slots and half the shared-memory wavefronts of the FFMA loops
+// (which ran LDS-bound at 16-19 % of the FMA pipe).
+// The tensor core adds into its accumulator with truncation; to keep fp32-grade results every 32-wide slice
+// of K starts from a zero accumulator (cross terms first, then hi*hi) and is added to the running sum with
+// an ordinary round-to-nearest FADD.
+#pragma once
+
+#include <cstdint>
+
+#ifdef FUMI_EMU
+#include "cuda_emu.h"
+#else
+__device__ __forceinline__ void fumi_mma_tf32(float (&c)[4], const uint32_t (&a)[4], const uint32_t (&b)[2]) {
+    asm volatile("mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+                 : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+                 : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b[0]), "r"(b[1]));
+}
+__device__ __forceinline__ uint32_t fumi_tf32_hi(float x) {
+    uint32_t h;
+    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(h) : "f"(x));
+    return h;
+}
+#endif
+
+// hi = x with the 13 low mantissa bits cleared (one LOP3; cvt.rna.tf32 expands to ~8 instructions on sm_100),
+// lo = x - hi exactly (<= 13 significant bits, of which the tensor core keeps 11: error 2^-21 relative to x).
+__device__ __forceinline__ void fumi_split(float x, uint32_t& hi, uint32_t& lo) {
+    hi = __float_as_uint(x) & 0xFFFFE000u;
+    lo = __float_as_uint(x - __uint_as_float(hi));
+}
+
+// acc[mt][nt][0..3] (+)= A[16*MT x K] . B[K x 8*NT] for one warp.
+//   element A(m,k) = A[m*lda + k]  (ATRANS: A[k*lda + m]);   element B(k,n) = B[k*ldb + n]  (BTRANS: B[n*ldb + k])
+//   bscale multiplies B on load (folds -alpha into an operand).  K is a multiple of 8; rows/cols beyond the
+//   logical extent must hold zeros in shared memory.
+// Fragment ownership (PTX m16n8k8.tf32): g = lane/4, t = lane%4
+//   a0 (g, t)  a1 (g+8, t)  a2 (g, t+4)  a3 (g+8, t+4);  b0 (k=t, n=g)  b1 (k=t+4, n=g)
+//   c0 (g, 2t) c1 (g, 2t+1) c2 (g+8, 2t) c3 (g+8, 2t+1)
+template <int MT, int NT, bool ATRANS, bool BTRANS>
+__device__ __forceinline__ void warp_gemm_3xtf32(const float* __restrict__ A, int lda, const float* __restrict__ B, int ldb,
+                                                 int K, float bscale, float (&acc)[MT][NT][4]) {
+    const int lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
+    for (int k0 = 0; k0 < K; k0 += 32) {
+        float part[MT][NT][4];
+#pragma unroll
+        for (int i = 0; i < MT; ++i)
+#pragma unroll
+            for (int j = 0; j < NT; ++j)
+#pragma unroll
+                for (int q = 0; q < 4; ++q) part[i][j][q] = 0.f;
+        const int kend = (K - k0) < 32 ? (K - k0) : 32;
+        // pass 0: cross terms (small), pass 1: hi*hi
+#pragma unroll
+        for (int pass = 0; pass < 2; ++pass) {
+            for (int kk = 0; kk < kend; kk += 8) {
+                const int k = k0 + kk;
+                uint32_t ahi[MT][4], alo[MT][4];
+#pragma unroll
+                for (int i = 0; i < MT; ++i) {
+                    const int m = i * 16 + g;
+                    float v0, v1, v2, v3;
+                    if (ATRANS) {
+                        v0 = A[(k + t) * lda + m]; v1 = A[(k + t) * lda + m + 8];
+                        v2 = A[(k + t + 4) * lda + m]; v3 = A[(k + t + 4) * lda + m + 8];
+                    } else {
+                        v0 = A[m * lda + k + t]; v1 = A[(m + 8) * lda + k + t];
+                        v2 = A[m * lda + k + t + 4]; v3 = A[(m + 8) * lda + k + t + 4];
+                    }
+                    fumi_split(v0, ahi[i][0], alo[i][0]);
+                    fumi_split(v1, ahi[i][1], alo[i][1]);
+                    fumi_split(v2, ahi[i][2], alo[i][2]);
+                    fumi_split(v3, ahi[i][3], alo[i][3]);
+                }
+#pragma unroll
+                for (int j = 0; j < NT; ++j) {
+                    const int n = j * 8 + g;
+                    float w0, w1;
+                    if (BTRANS) { w0 = B[n * ldb + k + t]; w1 = B[n * ldb + k + t + 4]; }
+                    else        { w0 = B[(k + t) * ldb + n]; w1 = B[(k + t + 4) * ldb + n]; }
+                    uint32_t bhi[2], blo[2];
+                    fumi_split(w0 * bscale, bhi[0], blo[0]);
+                    fumi_split(w1 * bscale, bhi[1], blo[1]);
+#pragma unroll
+                    for (int i = 0; i < MT; ++i) {
+                        if (pass == 0) {
+                            fumi_mma_tf32(part[i][j], alo[i], bhi);
+                            fumi_mma_tf32(part[i][j], ahi[i], blo);
+                        } else {
+                            fumi_mma_tf32(part[i][j], ahi[i], bhi);
+                        }
+                    }
+                }
+            }
+        }
+#pragma unroll
+        for (int i = 0; i < MT; ++i)
+#pragma unroll
+            for (int j = 0; j < NT; ++j)
+#pragma unroll
+                for (int q = 0; q < 4; ++q) acc[i][j][q] += part[i][j][q];
+    }
+}
+
+// Visit the accumulator elements this lane owns: f(m, n, value&)
+template <int MT, int NT, typename F>
+__device__ __forceinline__ void warp_tile_foreach(float (&acc)[MT][NT][4], F f) {
+    const int lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
+#pragma unroll
+    for (int i = 0; i < MT; ++i)
+#pragma unroll
+        for (int j = 0; j < NT; ++j) {
+            f(i * 16 + g, j * 8 + 2 * t, acc[i][j][0]);
+            f(i * 16 + g, j * 8 + 2 * t + 1, acc[i][j][1]);
+            f(i * 16 + g + 8, j * 8 + 2 * t, acc[i][j][2]);
+            f(i * 16 + g + 8, j * 8 + 2 * t + 1, acc[i][j][3]);
+        }
+}

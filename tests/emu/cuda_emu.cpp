@@ -9,6 +9,8 @@ uint3_emu g_blockIdx;
 dim3 g_blockDim, g_gridDim;
 char* dyn_smem = nullptr;
 pthread_barrier_t g_barrier;
+pthread_barrier_t g_warp_barrier[64];
+WarpXchg g_xchg[64];
 
 void launch_impl(const std::function<void()>& body, dim3 grid, dim3 block, size_t smem) {
     const unsigned nthreads = block.x * block.y * block.z;
@@ -20,6 +22,11 @@ void launch_impl(const std::function<void()>& body, dim3 grid, dim3 block, size_
     std::memset(mem, 0xFF, smem + 128);
     dyn_smem = static_cast<char*>(mem);
     pthread_barrier_init(&g_barrier, nullptr, nthreads);
+    const unsigned nwarps = (nthreads + 31) / 32;
+    for (unsigned w = 0; w < nwarps; ++w) {
+        const unsigned cnt = (w + 1) * 32 <= nthreads ? 32 : nthreads - w * 32;
+        pthread_barrier_init(&g_warp_barrier[w], nullptr, cnt);
+    }
     std::vector<std::thread> pool;
     pool.reserve(nthreads);
     for (unsigned t = 0; t < nthreads; ++t) {
@@ -39,6 +46,7 @@ void launch_impl(const std::function<void()>& body, dim3 grid, dim3 block, size_
     }
     for (auto& th : pool) th.join();
     pthread_barrier_destroy(&g_barrier);
+    for (unsigned w = 0; w < nwarps; ++w) pthread_barrier_destroy(&g_warp_barrier[w]);
     free(mem);
     dyn_smem = nullptr;
 }

@@ -72,6 +72,54 @@ static inline float atomicAdd(float* addr, float v) {
     return f;
 }
 
+static inline float __uint_as_float(uint32_t u) { float f; std::memcpy(&f, &u, 4); return f; }
+static inline uint32_t __float_as_uint(float f) { uint32_t u; std::memcpy(&u, &f, 4); return u; }
+#define __forceinline__ inline
+template <typename T> static inline T __ldg(const T* p) { return *p; }
+
+// ---- warp-collective emulation: tf32 rounding and mma.sync.m16n8k8 (TF32 inputs, fp32 accumulate)
+namespace fumi_emu {
+extern pthread_barrier_t g_warp_barrier[64];
+struct WarpXchg { uint32_t a[32][4]; uint32_t b[32][2]; };
+extern WarpXchg g_xchg[64];
+}
+static inline void __syncwarp() { pthread_barrier_wait(&fumi_emu::g_warp_barrier[fumi_emu::t_threadIdx.x >> 5]); }
+static inline uint32_t fumi_tf32_hi(float x) {               // cvt.rna.tf32.f32: round to nearest, ties away
+    uint32_t u = __float_as_uint(x);
+    u += 0x1000u;
+    return u & 0xFFFFE000u;
+}
+static inline float fumi_emu_tf32_trunc(uint32_t u) { return __uint_as_float(u & 0xFFFFE000u); }
+static inline void fumi_mma_tf32(float (&c)[4], const uint32_t (&a)[4], const uint32_t (&b)[2]) {
+    const int w = fumi_emu::t_threadIdx.x >> 5, lane = fumi_emu::t_threadIdx.x & 31, g = lane >> 2, t = lane & 3;
+    fumi_emu::WarpXchg& x = fumi_emu::g_xchg[w];
+    for (int i = 0; i < 4; ++i) x.a[lane][i] = a[i];
+    for (int i = 0; i < 2; ++i) x.b[lane][i] = b[i];
+    __syncwarp();
+    // A(m,k): lane (m%8)*4 + k%4, reg (m>=8) + 2*(k>=4);  B(k,n): lane n*4 + k%4, reg (k>=4)
+    auto A = [&](int m, int k) { return fumi_emu_tf32_trunc(x.a[(m & 7) * 4 + (k & 3)][(m >> 3) + 2 * (k >> 2)]); };
+    auto B = [&](int k, int n) { return fumi_emu_tf32_trunc(x.b[n * 4 + (k & 3)][k >> 2]); };
+    const int rows[4] = {g, g, g + 8, g + 8}, cols[4] = {2 * t, 2 * t + 1, 2 * t, 2 * t + 1};
+    float out[4];
+    for (int q = 0; q < 4; ++q) {
+        float s = c[q];
+        for (int k = 0; k < 8; ++k) s += A(rows[q], k) * B(k, cols[q]);
+        out[q] = s;
+    }
+    __syncwarp();
+    for (int q = 0; q < 4; ++q) c[q] = out[q];
+}
+
+static inline float __shfl_xor_sync(unsigned, float v, int lane_mask) {
+    const int w = fumi_emu::t_threadIdx.x >> 5, lane = fumi_emu::t_threadIdx.x & 31;
+    fumi_emu::WarpXchg& x = fumi_emu::g_xchg[w];
+    x.a[lane][0] = __float_as_uint(v);
+    __syncwarp();
+    const float r = __uint_as_float(x.a[lane ^ lane_mask][0]);
+    __syncwarp();
+    return r;
+}
+
 using std::max;
 using std::min;
 static inline long min(long a, long long b) { return a < b ? a : long(b); }
