@@ -64,7 +64,7 @@ struct EpiParams {
 };
 
 struct Layout {
-    int64_t per_task, S0, S1, w1t, b0, b1, head, steps, per_step, oH0, oH1, oDZ1, oDL, oHP;
+    int64_t per_task, S0, S1, w1t, b0, b1, head, steps, per_step, oH0, oH1, oDZ1, oDL, oHP, qH0, qH1, qLG;
 };
 
 __host__ __device__ inline Layout make_layout(const fumi_episode_cfg& c) {
@@ -83,7 +83,12 @@ __host__ __device__ inline Layout make_layout(const fumi_episode_cfg& c) {
     L.oDL = L.oDZ1 + n * kH1;
     L.oHP = L.oDL + ((n * N + 3) / 4) * 4;
     L.per_step = L.oHP + ((N * kHD + 3) / 4) * 4;
-    L.per_task = L.steps + int64_t(c.steps) * L.per_step;
+    // query activations of the final forward (tensor-core path: the backward does not recompute them)
+    const int64_t mq = c.num_query;
+    L.qH0 = L.steps + int64_t(c.steps) * L.per_step;
+    L.qH1 = L.qH0 + mq * kH0;
+    L.qLG = L.qH1 + mq * kH1;
+    L.per_task = L.qLG + ((mq * N + 3) / 4) * 4;
     return L;
 }
 
@@ -880,6 +885,17 @@ __global__ void __launch_bounds__(kThreads, 1) episode_fwd_mma_kernel(EpiParams 
             __syncthreads();
             m_tile_logits(P, s, 32, tr);
             __syncthreads();
+            if (P.save) {                                       // query activations for the backward
+                for (int i = 0; i < tr; ++i) slot[L.qH0 + int64_t(r0 + i) * kH0 + tid] = s.h0t[i * kS0 + tid];
+                for (int idx = tid; idx < tr * kH1; idx += kThreads) {
+                    const int i = idx / kH1, o = idx - i * kH1;
+                    slot[L.qH1 + int64_t(r0) * kH1 + idx] = s.h1t[i * kS1 + o];
+                }
+                for (int idx = tid; idx < tr * N; idx += kThreads) {
+                    const int i = idx / N, cc = idx - i * N;
+                    slot[L.qLG + int64_t(r0) * N + idx] = s.lt[i * kLS + cc];
+                }
+            }
             if (tid < tr) {
                 const float* l = &s.lt[tid * kLS];
                 float mx, sum;
@@ -916,6 +932,480 @@ __global__ void __launch_bounds__(kThreads, 1) episode_fwd_mma_kernel(EpiParams 
             float* Sout = slot + ((steps & 1) ? L.S1 : L.S0);      // final S where the backward expects it
             for (int i = 0; i < n; ++i) Sout[int64_t(i) * kH0 + tid] = steps > 0 ? s.sS[i * kSS + tid] : 0.f;
         }
+        __syncthreads();
+    }
+}
+
+// ------------------------------------------------------------------------------------ backward (tensor core)
+// Reverse sweep for NK <= 32 on warp-level 3xTF32 tiles.  Same recursion as episode_bwd_kernel /
+// oracle/episode_np.py; differences: rows go through in tiles of 16 (MT = 1) because W1^T and its adjoint
+// (2 x 68 KB) share the SM's shared memory with the tiles; the query activations come from the forward's
+// stash instead of being recomputed; the adjoint of S lives in the task's (L2-resident) workspace slot.
+struct SmemB {
+    float *w1t, *aw1t, *h0t, *tt, *h1t, *dz1t, *rzh, *lt, *rlt, *gS, *gQ, *hp, *ahp, *rhp, *b1s, *ab1, *rb1, *ab0s, *rb0s,
+        *gb0s;
+    long long* rows;
+    int* ys;
+};
+__host__ __device__ inline size_t smem_b_floats() {
+    return 2 * size_t(kH0) * kS1 + 2 * 16 * kS0 + 3 * 16 * kS1 + 2 * 16 * kLS + 32 * kSG + 16 * kSG + 3 * kMaxWays * kHD +
+           3 * kH1 + 3 * kH0 + 32 + 16 + 16;
+}
+__device__ inline SmemB carve_b(float* p) {
+    SmemB s;
+    s.rows = reinterpret_cast<long long*>(p); p += 32;
+    s.w1t = p; p += kH0 * kS1;
+    s.aw1t = p; p += kH0 * kS1;
+    s.h0t = p; p += 16 * kS0;          // h0t and tt are adjacent: together a [32][kS0] buffer
+    s.tt = p; p += 16 * kS0;
+    s.dz1t = p; p += 16 * kS1;         // dz1t and rzh are adjacent: together a [32][kS1] buffer
+    s.rzh = p; p += 16 * kS1;
+    s.h1t = p; p += 16 * kS1;
+    s.lt = p; p += 16 * kLS;
+    s.rlt = p; p += 16 * kLS;
+    s.gS = p; p += 32 * kSG;
+    s.gQ = p; p += 16 * kSG;
+    s.hp = p; p += kMaxWays * kHD;
+    s.ahp = p; p += kMaxWays * kHD;
+    s.rhp = p; p += kMaxWays * kHD;
+    s.b1s = p; p += kH1;
+    s.ab1 = p; p += kH1;
+    s.rb1 = p; p += kH1;
+    s.ab0s = p; p += kH0;
+    s.rb0s = p; p += kH0;
+    s.gb0s = p; p += kH0;
+    s.ys = reinterpret_cast<int*>(p); p += 16;
+    return s;
+}
+
+__device__ __forceinline__ void atomic_add2(float* addr, float a, float b) {
+#ifdef FUMI_EMU
+    atomicAdd(addr, a);
+    atomicAdd(addr + 1, b);
+#else
+    asm volatile("red.global.add.v2.f32 [%0], {%1, %2};" ::"l"(addr), "f"(a), "f"(b) : "memory");
+#endif
+}
+
+// column sums of a warp's [16*MT x 32] slab held in MMA layout -> dst[32w + col] (+)=, one owner lane per column
+template <int MT>
+__device__ __forceinline__ void slab_colsum(float (&acc)[MT][4][4], float* dst, bool accumulate) {
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+#pragma unroll
+    for (int j = 0; j < 4; ++j)
+#pragma unroll
+        for (int q = 0; q < 2; ++q) {
+            float v = 0.f;
+#pragma unroll
+            for (int i = 0; i < MT; ++i) v += acc[i][j][q] + acc[i][j][q + 2];
+            v += __shfl_xor_sync(0xffffffffu, v, 4);
+            v += __shfl_xor_sync(0xffffffffu, v, 8);
+            v += __shfl_xor_sync(0xffffffffu, v, 16);
+            if ((lane >> 2) == 0) {
+                float* d = dst + 32 * w + 8 * j + 2 * (lane & 3) + q;
+                *d = accumulate ? *d + v : v;
+            }
+        }
+}
+
+__global__ void __launch_bounds__(kThreads, 1) episode_bwd_mma_kernel(EpiParams P) {
+    FUMI_DYN_SMEM(float, smem_raw);
+    const SmemB s = carve_b(smem_raw);
+    const fumi_episode_cfg& c = P.cfg;
+    const int tid = threadIdx.x, w = tid >> 5, lane = tid & 31;
+    const int n = c.num_support, m = c.num_query, N = c.num_ways, steps = c.steps;
+    const float alpha = c.step_size;
+    const Layout L = make_layout(c);
+    const int o_ = tid & 63, kg_ = tid >> 6;
+    const float sc = dropout_scale(c);
+
+    for (int idx = tid; idx < 32 * kSG; idx += kThreads) s.gS[idx] = 0.f;
+    for (int idx = tid; idx < 16 * kSG; idx += kThreads) s.gQ[idx] = 0.f;
+    __syncthreads();
+
+    for (int64_t b = blockIdx.x; b < P.B; b += gridDim.x) {
+        float* slot = P.stash + b * P.slot_floats;
+        float* aS = slot + L.S0;           // adjoint of S  [n][H0]
+        float* bZ = slot + L.S1;           // bar_Z0 rows of the current step [n][H0]
+        // ---- adapted state, zeroed adjoints
+        {
+            float v[16];
+#pragma unroll 1
+            for (int o0 = 0; o0 < kH1; o0 += 16) {
+#pragma unroll
+                for (int q = 0; q < 16; ++q) v[q] = __ldg(&slot[L.w1t + tid * kH1 + o0 + q]);
+#pragma unroll
+                for (int q = 0; q < 16; ++q) { s.w1t[tid * kS1 + o0 + q] = v[q]; s.aw1t[tid * kS1 + o0 + q] = 0.f; }
+            }
+        }
+        s.ab0s[tid] = 0.f;
+        if (tid < kH1) { s.b1s[tid] = slot[L.b1 + tid]; s.ab1[tid] = 0.f; }
+        for (int idx = tid; idx < N * kHD; idx += kThreads) { s.hp[idx] = slot[L.head + idx]; s.ahp[idx] = 0.f; }
+        for (int idx = tid; idx < n * n; idx += kThreads) {
+            const int i = idx / n, j = idx - i * n;
+            s.gS[i * kSG + j] = __ldg(&P.gram[(b * int64_t(n + m) + i) * n + j]);
+        }
+        for (int j = 0; j < n; ++j) aS[int64_t(j) * kH0 + tid] = 0.f;
+        __syncthreads();
+
+        // ---- query pass (activations from the forward's stash)
+        const float qscale = P.loss_scale / float(m);
+        for (int r0 = 0; r0 < m; r0 += 16) {
+            const int tr = min(16, m - r0);
+            {
+                float v[16];
+#pragma unroll
+                for (int i = 0; i < 16; ++i) v[i] = i < tr ? __ldg(&slot[L.qH0 + int64_t(r0 + i) * kH0 + tid]) : 0.f;
+                float u[4], g2[2];
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    const int idx = tid + q * kThreads;
+                    u[q] = idx < tr * kH1 ? __ldg(&slot[L.qH1 + int64_t(r0) * kH1 + idx]) : 0.f;
+                }
+#pragma unroll
+                for (int q = 0; q < 2; ++q) {
+                    const int idx = tid + q * kThreads;
+                    const int i = idx / n, j = idx - i * n;
+                    g2[q] = (idx < 16 * n && i < tr) ? __ldg(&P.gram[(b * int64_t(n + m) + n + r0 + i) * n + j]) : 0.f;
+                }
+#pragma unroll
+                for (int i = 0; i < 16; ++i) s.h0t[i * kS0 + tid] = v[i];
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    const int idx = tid + q * kThreads;
+                    s.h1t[(idx / kH1) * kS1 + (idx % kH1)] = u[q];
+                }
+#pragma unroll
+                for (int q = 0; q < 2; ++q) {
+                    const int idx = tid + q * kThreads;
+                    if (idx < 16 * n) s.gQ[(idx / n) * kSG + (idx % n)] = g2[q];
+                }
+            }
+            if (tid < 16) {
+                s.rows[tid] = tid < tr ? P.qry_rows[b * m + r0 + tid] : 0;
+                float* l = &s.lt[tid * kLS];
+                if (tid < tr) {
+                    for (int cc = 0; cc < N; ++cc) l[cc] = slot[L.qLG + int64_t(r0 + tid) * N + cc];
+                    float mx, sum;
+                    row_softmax(l, N, mx, sum);
+                    const float inv = 1.f / sum;
+                    const int y = int(P.qry_y[b * m + r0 + tid]);
+                    for (int cc = 0; cc < N; ++cc) l[cc] = (expf(l[cc] - mx) * inv - (cc == y ? 1.f : 0.f)) * qscale;
+                } else {
+                    for (int cc = 0; cc < N; ++cc) l[cc] = 0.f;
+                }
+            }
+            __syncthreads();
+            for (int idx = tid; idx < N * kHD; idx += kThreads) {              // a_head += dLq^T [H1q | 1]
+                const int cc = idx / kHD, o = idx - cc * kHD;
+                float a = 0.f;
+                for (int i = 0; i < tr; ++i) a = fmaf(s.lt[i * kLS + cc], o < kH1 ? s.h1t[i * kS1 + o] : 1.f, a);
+                s.ahp[idx] += a;
+            }
+#pragma unroll
+            for (int ii = 0; ii < 4; ++ii) {                                   // dZ1q
+                const int i = kg_ + 4 * ii;
+                float dz = 0.f;
+                if (i < tr && s.h1t[i * kS1 + o_] > 0.f) {
+                    float dh = 0.f;
+                    for (int cc = 0; cc < N; ++cc) dh = fmaf(s.lt[i * kLS + cc], s.hp[cc * kHD + o_], dh);
+                    dz = dh * sc;
+                }
+                s.dz1t[i * kS1 + o_] = dz;
+            }
+            __syncthreads();
+            if (tid < kH1) {
+                float a = 0.f;
+                for (int i = 0; i < tr; ++i) a += s.dz1t[i * kS1 + tid];
+                s.ab1[tid] += a;
+            }
+            {   // a_W1 += dZ1q^T H0q   (rows h of W1^T owned by this warp)
+                float acc[2][8][4];
+#pragma unroll
+                for (int i = 0; i < 2; ++i)
+#pragma unroll
+                    for (int j = 0; j < 8; ++j)
+#pragma unroll
+                        for (int q = 0; q < 4; ++q) acc[i][j][q] = 0.f;
+                warp_gemm_3xtf32<2, 8, true, false>(s.h0t + 32 * w, kS0, s.dz1t, kS1, 16, 1.f, acc);
+                warp_tile_foreach<2, 8>(acc, [&](int hh, int o, float& cv) { s.aw1t[(32 * w + hh) * kS1 + o] += cv; });
+            }
+            {   // dZ0q = (dZ1q W1) * gate  -> tt, d_proj, a_b0
+                float acc[1][4][4];
+#pragma unroll
+                for (int j = 0; j < 4; ++j)
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) acc[0][j][q] = 0.f;
+                warp_gemm_3xtf32<1, 4, false, true>(s.dz1t, kS1, s.w1t + 32 * w * kS1, kS1, kH1, 1.f, acc);
+                warp_tile_foreach<1, 4>(acc, [&](int i, int hh, float& cv) {
+                    const int h = 32 * w + hh;
+                    cv = (i < tr && s.h0t[i * kS0 + h] > 0.f) ? cv * sc : 0.f;
+                    s.tt[i * kS0 + h] = cv;
+                });
+                const int g = lane >> 2, t = lane & 3;
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    const int h = 32 * w + 8 * j + 2 * t;
+                    if (g < tr) atomic_add2(&P.d_proj[s.rows[g] * kH0 + h], acc[0][j][0], acc[0][j][1]);
+                    if (g + 8 < tr) atomic_add2(&P.d_proj[s.rows[g + 8] * kH0 + h], acc[0][j][2], acc[0][j][3]);
+                }
+                slab_colsum<1>(acc, s.ab0s, true);
+            }
+            __syncthreads();
+            if (steps > 0) {   // a_S -= alpha * Gq^T dZ0q
+                float acc[2][4][4];
+#pragma unroll
+                for (int i = 0; i < 2; ++i)
+#pragma unroll
+                    for (int j = 0; j < 4; ++j)
+#pragma unroll
+                        for (int q = 0; q < 4; ++q) acc[i][j][q] = 0.f;
+                warp_gemm_3xtf32<2, 4, true, false>(s.gQ, kSG, s.tt + 32 * w, kS0, 16, 1.f, acc);
+                warp_tile_foreach<2, 4>(acc, [&](int j, int hh, float& cv) {
+                    if (j < n) aS[int64_t(j) * kH0 + 32 * w + hh] -= alpha * cv;
+                });
+            }
+            __syncthreads();
+        }
+
+        // ---- inner steps in reverse
+        if (!c.first_order) {
+            for (int st = steps - 1; st >= 0; --st) {
+                const float* rec = slot + L.steps + int64_t(st) * L.per_step;
+                // head of this step (pre-update); undo W1_{s+1} = W1_s - alpha dZ1^T H0 with all rows at once:
+                // (h0t|tt) is a [32][kS0] buffer and (dz1t|rzh) a [32][kS1] buffer
+                for (int idx = tid; idx < N * kHD; idx += kThreads) { s.hp[idx] = rec[L.oHP + idx]; s.rhp[idx] = 0.f; }
+                if (tid < kH1) s.rb1[tid] = 0.f;
+                s.rb0s[tid] = 0.f;
+                s.gb0s[tid] = -alpha * s.ab0s[tid];
+                {
+                    float v[32];
+#pragma unroll
+                    for (int i = 0; i < 32; ++i) v[i] = i < n ? __ldg(&rec[L.oH0 + int64_t(i) * kH0 + tid]) : 0.f;
+                    float u[8];
+#pragma unroll
+                    for (int q = 0; q < 8; ++q) {
+                        const int idx = tid + q * kThreads;
+                        u[q] = idx < n * kH1 ? __ldg(&rec[L.oDZ1 + idx]) : 0.f;
+                    }
+#pragma unroll
+                    for (int i = 0; i < 32; ++i) s.h0t[i * kS0 + tid] = v[i];
+#pragma unroll
+                    for (int q = 0; q < 8; ++q) {
+                        const int idx = tid + q * kThreads;
+                        s.dz1t[(idx / kH1) * kS1 + (idx % kH1)] = u[q];
+                    }
+                }
+                __syncthreads();
+                {
+                    float acc[2][8][4];
+#pragma unroll
+                    for (int i = 0; i < 2; ++i)
+#pragma unroll
+                        for (int j = 0; j < 8; ++j)
+#pragma unroll
+                            for (int q = 0; q < 4; ++q) acc[i][j][q] = 0.f;
+                    warp_gemm_3xtf32<2, 8, true, false>(s.h0t + 32 * w, kS0, s.dz1t, kS1, 32, 1.f, acc);
+                    warp_tile_foreach<2, 8>(acc, [&](int hh, int o, float& cv) { s.w1t[(32 * w + hh) * kS1 + o] += alpha * cv; });
+                }
+                float rw[2][8][4];                       // this step's contribution to a_W1 (own rows), over both tiles
+#pragma unroll
+                for (int i = 0; i < 2; ++i)
+#pragma unroll
+                    for (int j = 0; j < 8; ++j)
+#pragma unroll
+                        for (int q = 0; q < 4; ++q) rw[i][j][q] = 0.f;
+                __syncthreads();
+
+                for (int r0 = 0; r0 < n; r0 += 16) {
+                    const int tr = min(16, n - r0);
+                    {
+                        float v[16], a2[16];
+#pragma unroll
+                        for (int i = 0; i < 16; ++i) {
+                            v[i] = i < tr ? __ldg(&rec[L.oH0 + int64_t(r0 + i) * kH0 + tid]) : 0.f;
+                            a2[i] = i < tr ? aS[int64_t(r0 + i) * kH0 + tid] : 0.f;
+                        }
+                        float u[4], d[4];
+#pragma unroll
+                        for (int q = 0; q < 4; ++q) {
+                            const int idx = tid + q * kThreads;
+                            u[q] = idx < tr * kH1 ? __ldg(&rec[L.oH1 + int64_t(r0) * kH1 + idx]) : 0.f;
+                            d[q] = idx < tr * kH1 ? __ldg(&rec[L.oDZ1 + int64_t(r0) * kH1 + idx]) : 0.f;
+                        }
+                        const float gb0 = s.gb0s[tid];
+#pragma unroll
+                        for (int i = 0; i < 16; ++i) {
+                            s.h0t[i * kS0 + tid] = v[i];
+                            s.tt[i * kS0 + tid] = (i < tr && v[i] > 0.f) ? (a2[i] + gb0) * sc : 0.f;      // (12r) r_dH0
+                        }
+#pragma unroll
+                        for (int q = 0; q < 4; ++q) {
+                            const int idx = tid + q * kThreads;
+                            s.h1t[(idx / kH1) * kS1 + (idx % kH1)] = u[q];
+                            s.dz1t[(idx / kH1) * kS1 + (idx % kH1)] = d[q];
+                        }
+                    }
+                    for (int idx = tid; idx < 16 * kLS; idx += kThreads) {
+                        const int i = idx / kLS, cc = idx - i * kLS;
+                        s.lt[idx] = (i < tr && cc < N) ? rec[L.oDL + int64_t(r0 + i) * N + cc] : 0.f;
+                    }
+                    if (tid < 16) {
+                        s.rows[tid] = tid < tr ? P.sup_rows[b * n + r0 + tid] : 0;
+                        s.ys[tid] = tid < tr ? int(P.sup_y[b * n + r0 + tid]) : 0;
+                    }
+                    __syncthreads();
+                    // (11r)+(10r)+(9r): r_dH1 = gate1 * (r_dH0 W1^T + H0 (g_W1)^T + g_b1),  g_W1 = -alpha a_W1
+                    {
+                        float acc[1][1][4] = {{{0.f, 0.f, 0.f, 0.f}}};
+                        warp_gemm_3xtf32<1, 1, false, false>(s.tt, kS0, s.w1t + 8 * w, kS1, kH0, 1.f, acc);
+                        warp_gemm_3xtf32<1, 1, false, false>(s.h0t, kS0, s.aw1t + 8 * w, kS1, kH0, -alpha, acc);
+                        warp_tile_foreach<1, 1>(acc, [&](int i, int oo, float& cv) {
+                            const int o = 8 * w + oo;
+                            s.rzh[i * kS1 + o] = (i < tr && s.h1t[i * kS1 + o] > 0.f) ? (cv - alpha * s.ab1[o]) * sc : 0.f;
+                        });
+                    }
+                    // r_W1 += dZ1^T r_dH0 ;  r_H0 = dZ1 g_W1 (kept in registers)
+                    warp_gemm_3xtf32<2, 8, true, false>(s.tt + 32 * w, kS0, s.dz1t, kS1, 16, 1.f, rw);
+                    float rh0[1][4][4];
+#pragma unroll
+                    for (int j = 0; j < 4; ++j)
+#pragma unroll
+                        for (int q = 0; q < 4; ++q) rh0[0][j][q] = 0.f;
+                    warp_gemm_3xtf32<1, 4, false, true>(s.dz1t, kS1, s.aw1t + 32 * w * kS1, kS1, kH1, -alpha, rh0);
+                    __syncthreads();
+                    // (8r)+(7r): r_dL = r_dH1 Wh^T + H1 (g_Wh)^T + g_bh ; r_head += dL^T r_dH1
+                    for (int idx = tid; idx < 16 * N; idx += kThreads) {
+                        const int i = idx / N, cc = idx - i * N;
+                        float a = 0.f;
+                        if (i < tr) {
+                            a = -alpha * s.ahp[cc * kHD + kH1];
+                            for (int o = 0; o < kH1; ++o) {
+                                a = fmaf(s.rzh[i * kS1 + o], s.hp[cc * kHD + o], a);
+                                a = fmaf(s.h1t[i * kS1 + o], -alpha * s.ahp[cc * kHD + o], a);
+                            }
+                        }
+                        s.rlt[i * kLS + cc] = a;
+                    }
+                    for (int idx = tid; idx < N * kH1; idx += kThreads) {
+                        const int cc = idx / kH1, o = idx - cc * kH1;
+                        float a = 0.f;
+                        for (int i = 0; i < tr; ++i) a = fmaf(s.lt[i * kLS + cc], s.rzh[i * kS1 + o], a);
+                        s.rhp[cc * kHD + o] += a;
+                    }
+                    __syncthreads();
+                    // (6r) r_L = P * (r_dL - <P, r_dL>) / n ; (7r) r_H1 = dL g_Wh  (overwrites rzh)
+                    if (tid < tr) {
+                        const int y = s.ys[tid];
+                        float dot = 0.f;
+                        for (int cc = 0; cc < N; ++cc) {
+                            const float p = s.lt[tid * kLS + cc] * float(n) + (cc == y ? 1.f : 0.f);
+                            dot = fmaf(p, s.rlt[tid * kLS + cc], dot);
+                        }
+                        for (int cc = 0; cc < N; ++cc) {
+                            const float p = s.lt[tid * kLS + cc] * float(n) + (cc == y ? 1.f : 0.f);
+                            s.rlt[tid * kLS + cc] = p * (s.rlt[tid * kLS + cc] - dot) / float(n);
+                        }
+                    }
+#pragma unroll
+                    for (int ii = 0; ii < 4; ++ii) {
+                        const int i = kg_ + 4 * ii;
+                        float a = 0.f;
+                        if (i < tr)
+                            for (int cc = 0; cc < N; ++cc) a = fmaf(s.lt[i * kLS + cc], -alpha * s.ahp[cc * kHD + o_], a);
+                        s.rzh[i * kS1 + o_] = a;
+                    }
+                    __syncthreads();
+                    // (5r) r_H1 += r_L Wh ; r_head += r_L^T [H1 | 1] ; (4r) r_Z1 = r_H1 * gate1
+#pragma unroll
+                    for (int ii = 0; ii < 4; ++ii) {
+                        const int i = kg_ + 4 * ii;
+                        float a = s.rzh[i * kS1 + o_];
+                        if (i < tr)
+                            for (int cc = 0; cc < N; ++cc) a = fmaf(s.rlt[i * kLS + cc], s.hp[cc * kHD + o_], a);
+                        s.rzh[i * kS1 + o_] = (i < tr && s.h1t[i * kS1 + o_] > 0.f) ? a * sc : 0.f;
+                    }
+                    for (int idx = tid; idx < N * kHD; idx += kThreads) {
+                        const int cc = idx / kHD, o = idx - cc * kHD;
+                        float a = 0.f;
+                        for (int i = 0; i < tr; ++i) a = fmaf(s.rlt[i * kLS + cc], o < kH1 ? s.h1t[i * kS1 + o] : 1.f, a);
+                        s.rhp[idx] += a;
+                    }
+                    __syncthreads();
+                    // (3r) r_H0 += r_Z1 W1 ; r_W1 += r_Z1^T H0 ; r_b1 += sum r_Z1
+                    if (tid < kH1) {
+                        float a = 0.f;
+                        for (int i = 0; i < tr; ++i) a += s.rzh[i * kS1 + tid];
+                        s.rb1[tid] += a;
+                    }
+                    warp_gemm_3xtf32<1, 4, false, true>(s.rzh, kS1, s.w1t + 32 * w * kS1, kS1, kH1, 1.f, rh0);
+                    warp_gemm_3xtf32<2, 8, true, false>(s.h0t + 32 * w, kS0, s.rzh, kS1, 16, 1.f, rw);
+                    // (2r) bar_Z0 = r_H0 * gate0 ; (1r) a_A (d_proj), a_b0 ; bar_Z0 rows parked in the workspace
+                    {
+                        const int g = lane >> 2, t = lane & 3;
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) {
+                            const int h = 32 * w + 8 * j + 2 * t;
+#pragma unroll
+                            for (int q = 0; q < 4; ++q) {
+                                const int i = g + (q >> 1) * 8;
+                                float& cv = rh0[0][j][q];
+                                cv = (i < tr && s.h0t[i * kS0 + h + (q & 1)] > 0.f) ? cv * sc : 0.f;
+                            }
+                            if (g < tr) {
+                                atomic_add2(&P.d_proj[s.rows[g] * kH0 + h], rh0[0][j][0], rh0[0][j][1]);
+                                bZ[int64_t(r0 + g) * kH0 + h] = rh0[0][j][0];
+                                bZ[int64_t(r0 + g) * kH0 + h + 1] = rh0[0][j][1];
+                            }
+                            if (g + 8 < tr) {
+                                atomic_add2(&P.d_proj[s.rows[g + 8] * kH0 + h], rh0[0][j][2], rh0[0][j][3]);
+                                bZ[int64_t(r0 + g + 8) * kH0 + h] = rh0[0][j][2];
+                                bZ[int64_t(r0 + g + 8) * kH0 + h + 1] = rh0[0][j][3];
+                            }
+                        }
+                        slab_colsum<1>(rh0, s.rb0s, true);
+                    }
+                    __syncthreads();
+                }
+                // ---- end of reversed step: fold the contributions into the adjoints; a_S -= alpha G bar_Z0
+                warp_tile_foreach<2, 8>(rw, [&](int hh, int o, float& cv) { s.aw1t[(32 * w + hh) * kS1 + o] += cv; });
+                for (int idx = tid; idx < N * kHD; idx += kThreads) s.ahp[idx] += s.rhp[idx];
+                if (tid < kH1) s.ab1[tid] += s.rb1[tid];
+                s.ab0s[tid] += s.rb0s[tid];
+                {
+                    float v[32];
+#pragma unroll
+                    for (int i = 0; i < 32; ++i) v[i] = i < n ? bZ[int64_t(i) * kH0 + tid] : 0.f;
+#pragma unroll
+                    for (int i = 0; i < 32; ++i) s.h0t[i * kS0 + tid] = v[i];
+                }
+                __syncthreads();
+                {
+                    float acc[2][4][4];
+#pragma unroll
+                    for (int i = 0; i < 2; ++i)
+#pragma unroll
+                        for (int j = 0; j < 4; ++j)
+#pragma unroll
+                            for (int q = 0; q < 4; ++q) acc[i][j][q] = 0.f;
+                    warp_gemm_3xtf32<2, 4, false, false>(s.gS, kSG, s.h0t + 32 * w, kS0, 32, 1.f, acc);
+                    warp_tile_foreach<2, 4>(acc, [&](int j, int hh, float& cv) {
+                        if (j < n) aS[int64_t(j) * kH0 + 32 * w + hh] -= alpha * cv;
+                    });
+                }
+                __syncthreads();
+            }
+        }
+
+        // ---- task epilogue: head gradient per task, shared-parameter gradients into this CTA's partials
+        for (int idx = tid; idx < N * kHD; idx += kThreads) P.d_head[b * N * kHD + idx] = s.ahp[idx];
+        float* pw = P.d_w1_parts + int64_t(blockIdx.x) * kH0 * kH1;
+        for (int idx = tid; idx < kH0 * kH1; idx += kThreads) {
+            const int o = idx / kH0, k = idx - o * kH0;                         // [H1][H0] like linear1.weight
+            pw[idx] += s.aw1t[k * kS1 + o];
+        }
+        P.d_b0_parts[int64_t(blockIdx.x) * kH0 + tid] += s.ab0s[tid];
+        if (tid < kH1) P.d_b1_parts[int64_t(blockIdx.x) * kH1 + tid] += s.ab1[tid];
         __syncthreads();
     }
 }
@@ -1379,6 +1869,13 @@ extern "C" int fumi_episode_bwd(const fumi_episode_cfg* cfg, int64_t B, const fl
     P.d_b0_parts = d_b0_parts; P.d_w1_parts = d_w1_parts; P.d_b1_parts = d_b1_parts;
     const int grid = grid_for(B);
     if (grid <= 0) return grid;
+    if (cfg->num_support <= 32 && cfg->num_query <= kMaxQueryRows) {      // tensor-core path (pairs with fwd_mma)
+        const size_t smem_b = smem_b_floats() * sizeof(float);
+        FUMI_SET_SMEM_ATTR(episode_bwd_mma_kernel, smem_b);
+        FUMI_LAUNCH(episode_bwd_mma_kernel, grid, kThreads, smem_b, stream, P);
+        FUMI_CHECK_LAUNCH("episode_bwd_mma_kernel");
+        return FUMI_OK;
+    }
     const size_t smem = smem_floats<kTRB, true>() * sizeof(float);
 #ifndef FUMI_EMU
     static bool attr_done = false;
