@@ -7,14 +7,17 @@
 // materialised per-task weights (fumi.py:161,178) -- see episode.cu for how G is consumed --
 // and the loader's per-sample feature copies (dataset/data.py:545,571-577).
 //
-// fp32 FMA version: one CTA = (task, 64-row i tile, 32-row j tile); both tiles are staged through
-// shared memory in DC-wide slices of the feature dimension; 4x4 register tile per thread with
-// float4 reads along d (row strides chosen so both reads are bank-conflict free).
+// One CTA = (task, 64-row i tile, 32-row j tile); both tiles are staged through shared memory in DC-wide
+// slices of the feature dimension (coalesced float4 row reads); each of the 4 warps owns 16 rows x 32
+// columns of the output and accumulates it with warp-level 3xTF32 tensor-core tiles (warp_mma.cuh:
+// fp32-accurate split, accumulator restarted every 32 features).  Row stride 68 makes both fragment reads
+// bank-conflict free.
 #include <cstdint>
 
 #include "../../include/fumi_b200.h"
 #include "common.cuh"
 #include "launch.cuh"
+#include "warp_mma.cuh"
 
 namespace {
 
@@ -37,64 +40,46 @@ __global__ void __launch_bounds__(GT) gram_kernel(const float* __restrict__ feat
     }
     if (tid < TJ) srow[tid] = tid < nj ? sup_rows[b * NK + j0 + tid] : -1;
     __syncthreads();
-    // thread tile: rows i = ii*16 + ti (ti = tid/8), cols j = jj*8 + tj (tj = tid%8)
-    const int ti = tid >> 3, tj = tid & 7;
-    float acc[4][4];
+    // warp w: rows [16w, 16w+16) of the i tile, all 32 columns of the j tile
+    const int w = tid >> 5;
+    float acc[1][4][4];
 #pragma unroll
-    for (int a = 0; a < 4; ++a)
+    for (int j = 0; j < 4; ++j)
 #pragma unroll
-        for (int c = 0; c < 4; ++c) acc[a][c] = 0.f;
+        for (int q = 0; q < 4; ++q) acc[0][j][q] = 0.f;
     for (int64_t d0 = 0; d0 < D; d0 += DC) {
         // stage the slice: (TI + TJ) rows x DC floats, float4 per thread, coalesced along d
-        for (int idx = tid; idx < (TI + TJ) * (DC / 4); idx += GT) {
-            const int r = idx / (DC / 4), q = (idx - r * (DC / 4)) * 4;
-            const long long row = r < TI ? xrow[r] : srow[r - TI];
-            float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (row >= 0) {
-                const int64_t d = d0 + q;
-                const float* src = feats + row * D + d;
-                if (d + 3 < D) v = *reinterpret_cast<const float4*>(src);
-                else {
-                    if (d < D) v.x = src[0];
-                    if (d + 1 < D) v.y = src[1];
-                    if (d + 2 < D) v.z = src[2];
+        {
+            float4 v[12];
+#pragma unroll
+            for (int q = 0; q < 12; ++q) {                     // (64 + 32) rows x 16 float4 = 1536 = 12 per thread x 128
+                const int idx = tid + q * GT;
+                v[q] = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (idx < (TI + TJ) * (DC / 4)) {
+                    const int r = idx / (DC / 4), c4 = (idx - r * (DC / 4)) * 4;
+                    const long long row = r < TI ? xrow[r] : srow[r - TI];
+                    const int64_t d = d0 + c4;
+                    if (row >= 0 && d + 3 < D) v[q] = __ldg(reinterpret_cast<const float4*>(feats + row * D + d));
                 }
             }
-            float* dst = r < TI ? &Xs[r * ST + q] : &Ss[(r - TI) * ST + q];
-            *reinterpret_cast<float4*>(dst) = v;
-        }
-        __syncthreads();
-#pragma unroll 4
-        for (int q = 0; q < DC; q += 4) {
-            float4 x[4], s[4];
 #pragma unroll
-            for (int a = 0; a < 4; ++a) x[a] = *reinterpret_cast<const float4*>(&Xs[(a * 16 + ti) * ST + q]);
-#pragma unroll
-            for (int c = 0; c < 4; ++c) s[c] = *reinterpret_cast<const float4*>(&Ss[(c * 8 + tj) * ST + q]);
-#pragma unroll
-            for (int a = 0; a < 4; ++a)
-#pragma unroll
-                for (int c = 0; c < 4; ++c) {
-                    float v = acc[a][c];
-                    v = fmaf(x[a].x, s[c].x, v);
-                    v = fmaf(x[a].y, s[c].y, v);
-                    v = fmaf(x[a].z, s[c].z, v);
-                    v = fmaf(x[a].w, s[c].w, v);
-                    acc[a][c] = v;
+            for (int q = 0; q < 12; ++q) {
+                const int idx = tid + q * GT;
+                if (idx < (TI + TJ) * (DC / 4)) {
+                    const int r = idx / (DC / 4), c4 = (idx - r * (DC / 4)) * 4;
+                    float* dst = r < TI ? &Xs[r * ST + c4] : &Ss[(r - TI) * ST + c4];
+                    *reinterpret_cast<float4*>(dst) = v[q];
                 }
+            }
         }
         __syncthreads();
+        warp_gemm_3xtf32<1, 4, false, true>(Xs + 16 * w * ST, ST, Ss, ST, DC, 1.f, acc);
+        __syncthreads();
     }
-#pragma unroll
-    for (int a = 0; a < 4; ++a) {
-        const int i = a * 16 + ti;
-        if (i >= ni) continue;
-#pragma unroll
-        for (int c = 0; c < 4; ++c) {
-            const int j = c * 8 + tj;
-            if (j < nj) gram[(b * int64_t(NK + NQ) + i0 + i) * NK + j0 + j] = acc[a][c];
-        }
-    }
+    warp_tile_foreach<1, 4>(acc, [&](int ii, int j, float& v) {
+        const int i = 16 * w + ii;
+        if (i < ni && j < nj) gram[(b * int64_t(NK + NQ) + i0 + i) * NK + j0 + j] = v;
+    });
 }
 
 }  // namespace
@@ -105,6 +90,7 @@ extern "C" int fumi_gram(const float* feats, int64_t num_rows, int64_t D, const 
                          const int64_t* qry_rows, int64_t B, int32_t NK, int32_t NQ, float* gram, void* stream) {
     FUMI_CHECK_ARG(B >= 0 && NK >= 1 && NK <= kMaxSupport && NQ >= 0 && D >= 1 && num_rows >= 1, "bad shape");
     FUMI_CHECK_ARG((D & 3) == 0, "feature dim must be a multiple of 4 (float4 rows)");
+    FUMI_CHECK_ARG((uintptr_t(feats) & 15) == 0, "feature matrix must be 16-byte aligned");
     if (B == 0) return FUMI_OK;
     FUMI_CHECK_ARG(feats && sup_rows && (qry_rows || NQ == 0) && gram, "null pointer");
     FUMI_CHECK_ARG(B <= 65535, "at most 65535 tasks per call");
