@@ -33,15 +33,26 @@ constexpr int kHD = kH1 + 1;      // head row: 64 weights + 1 bias (fumi.py:76-7
 constexpr int kMaxWays = 32;
 constexpr int kMaxSupport = 128;  // NK rows per task
 
-// Counter-based dropout mask shared by forward and backward (and mirrored in fumi_b200/dropout.py for
-// parity tests).  One 64-bit hash covers the four columns 4g..4g+3 of a row: column c uses the 16-bit field
-// (c & 3) and is kept iff field >= floor(p * 65536).
-__host__ __device__ inline uint64_t fumi_mask_hash64(uint64_t seed, uint64_t task, uint32_t pass, uint32_t layer,
-                                                     uint32_t row, uint32_t col_group) {
-    uint64_t x = seed ^ (task * 0x9E3779B97F4A7C15ULL);
-    x += (uint64_t(pass) << 40) ^ (uint64_t(layer) << 32) ^ (uint64_t(row) << 12) ^ uint64_t(col_group);
-    x ^= x >> 30; x *= 0xBF58476D1CE4E5B9ULL;       // splitmix64 finaliser
-    x ^= x >> 27; x *= 0x94D049BB133111EBULL;
-    x ^= x >> 31;
+// Counter-based dropout mask shared by forward and backward (and mirrored in fumi_b200/dropout.py for parity
+// tests).  32-bit integer hashing only (the 64-bit multiplies of a splitmix were ~25 instructions per mask):
+//   base  = mix(seed, task, pass, layer)                       once per tile
+//   h32   = lowbias32(base + row * 0xC2B2AE35 + (col >> 1) * 0x27D4EB2F)
+//   field = (col & 1) ? h32 >> 16 : h32 & 0xFFFF ;  keep iff field >= floor(p * 65536)
+// One hash serves the two adjacent columns a lane owns in the MMA accumulator layout.
+__host__ __device__ inline uint32_t fumi_lowbias32(uint32_t x) {
+    x ^= x >> 16; x *= 0x7FEB352Du;
+    x ^= x >> 15; x *= 0x846CA68Bu;
+    x ^= x >> 16;
     return x;
+}
+__host__ __device__ inline uint32_t fumi_mask_base(uint64_t seed, uint64_t task, uint32_t pass, uint32_t layer) {
+    uint32_t x = fumi_lowbias32(uint32_t(seed) ^ 0x9E3779B9u);
+    x = fumi_lowbias32(x ^ uint32_t(seed >> 32));
+    x = fumi_lowbias32(x + uint32_t(task) * 0x85EBCA6Bu);
+    x = fumi_lowbias32(x ^ uint32_t(task >> 32));
+    x = fumi_lowbias32(x + pass * 0x9E3779B1u + layer * 0x61C88647u);
+    return x;
+}
+__host__ __device__ inline uint32_t fumi_mask_pair(uint32_t base, uint32_t row, uint32_t col) {
+    return fumi_lowbias32(base + row * 0xC2B2AE35u + (col >> 1) * 0x27D4EB2Fu);
 }

@@ -167,14 +167,16 @@ __device__ inline Smem carve(float* base) {
 __device__ inline float dropout_scale(const fumi_episode_cfg& c) {
     return c.dropout_p > 0.f ? 1.f / (1.f - c.dropout_p) : 1.f;
 }
-// 64 mask bits cover columns 4g..4g+3 of one row: 16-bit field (col & 3), keep iff field >= p * 65536
-__device__ inline uint64_t dropout_bits(const fumi_episode_cfg& c, int64_t task, int pass, int layer, int row, int col) {
-    return fumi_mask_hash64(c.dropout_seed, uint64_t(task), uint32_t(pass), uint32_t(layer), uint32_t(row),
-                            uint32_t(col >> 2));
+// one 32-bit hash per (row, column pair): even column -> low 16 bits, odd column -> high 16 bits
+__device__ inline uint32_t dropout_base(const fumi_episode_cfg& c, int64_t task, int pass, int layer) {
+    return fumi_mask_base(c.dropout_seed, uint64_t(task), uint32_t(pass), uint32_t(layer));
+}
+__device__ inline uint32_t dropout_bits(uint32_t base, int row, int col) {
+    return fumi_mask_pair(base, uint32_t(row), uint32_t(col));
 }
 __device__ inline uint32_t dropout_thr(const fumi_episode_cfg& c) { return uint32_t(c.dropout_p * 65536.f); }
-__device__ inline bool dropout_keep_bits(uint64_t bits, int col, uint32_t thr) {
-    return uint32_t((bits >> (16 * (col & 3))) & 0xFFFFu) >= thr;
+__device__ inline bool dropout_keep_bits(uint32_t bits, int col, uint32_t thr) {
+    return ((col & 1) ? (bits >> 16) : (bits & 0xFFFFu)) >= thr;
 }
 
 // ---- tile loaders -----------------------------------------------------------------------------
@@ -231,13 +233,14 @@ __device__ inline void tile_h0(const EpiParams& P, const Smem& s, int64_t task, 
     const float sc = dropout_scale(P.cfg);
     const bool drop = P.cfg.dropout_p > 0.f;
     const uint32_t thr = dropout_thr(P.cfg);
+    const uint32_t dbase = drop ? dropout_base(P.cfg, task, pass, 0) : 0u;
 #pragma unroll
     for (int i = 0; i < TR; ++i) {
         float v = 0.f;
         if (i < tr) {
             const float a = CACHED ? s.sA[i * kH0 + h] : P.proj[s.rows[i] * kH0 + h];
             const float z = a + b0h - alpha * acc[i];
-            if (z > 0.f && (!drop || dropout_keep_bits(dropout_bits(P.cfg, task, pass, 0, r0 + i, h), h, thr))) v = z * sc;
+            if (z > 0.f && (!drop || dropout_keep_bits(dropout_bits(dbase, r0 + i, h), h, thr))) v = z * sc;
         }
         s.h0t[i * kH0 + h] = v;
     }
@@ -266,6 +269,7 @@ __device__ inline void tile_h1(const EpiParams& P, const Smem& s, int64_t task, 
     const float sc = dropout_scale(P.cfg);
     const bool drop = P.cfg.dropout_p > 0.f;
     const uint32_t thr = dropout_thr(P.cfg);
+    const uint32_t dbase = drop ? dropout_base(P.cfg, task, pass, 1) : 0u;
     const float b = s.b1s[o];
 #pragma unroll
     for (int ii = 0; ii < RPT; ++ii) {
@@ -273,7 +277,7 @@ __device__ inline void tile_h1(const EpiParams& P, const Smem& s, int64_t task, 
         float v = 0.f;
         if (i < tr) {
             const float z = acc[ii] + b;
-            if (z > 0.f && (!drop || dropout_keep_bits(dropout_bits(P.cfg, task, pass, 1, r0 + i, o), o, thr)))
+            if (z > 0.f && (!drop || dropout_keep_bits(dropout_bits(dbase, r0 + i, o), o, thr)))
                 v = z * sc;
         }
         s.h1t[i * kH1 + o] = v;
@@ -571,6 +575,32 @@ __global__ void __launch_bounds__(kThreads, 1) episode_fwd_kernel(EpiParams P) {
 // mma.sync tiles (warp_mma.cuh) on the fp32 tiles in shared memory.  MT = 1 for NK <= 16, else 2
 // (rows padded with zeros to 16*MT).  Warp w of 8 owns hidden units [32w, 32w+32) of the 256-wide ops and
 // output units [8w, 8w+8) of the 64-wide op.  Query rows go through in tiles of 32.
+// Phase profiler (diagnostics only; enabled by fumi_debug_phase_profile(1)): thread 0 of each CTA adds the SM
+// cycles between consecutive marks to g_phase[id]; read back with fumi_debug_read_phases.
+__device__ unsigned long long g_phase[64];
+__device__ int g_phase_on = 0;
+struct PhaseClock {
+    long long last;
+    bool on;
+    __device__ __forceinline__ void start() {
+#ifndef FUMI_EMU
+        on = g_phase_on != 0 && threadIdx.x == 0;
+        if (on) last = clock64();
+#else
+        on = false; last = 0;
+#endif
+    }
+    __device__ __forceinline__ void mark(int id) {
+#ifndef FUMI_EMU
+        if (on) {
+            const long long t = clock64();
+            atomicAdd(&g_phase[id], (unsigned long long)(t - last));
+            last = t;
+        }
+#endif
+    }
+};
+
 constexpr int kS0 = kH0 + 4;     // row stride of [rows][H0] tiles (A operand: conflict-free fragment loads)
 constexpr int kS1 = kH1 + 4;     // row stride of [rows][H1] tiles and of W1^T [H0][H1]
 constexpr int kSS = kH0 + 8;     // row stride of S (B operand, k = row)
@@ -627,13 +657,14 @@ __device__ __forceinline__ void mma_tile_h0(const EpiParams& P, const SmemM& s, 
     const float alpha = P.cfg.step_size, sc = dropout_scale(P.cfg);
     const bool drop = P.cfg.dropout_p > 0.f;
     const uint32_t thr = dropout_thr(P.cfg);
-    uint64_t bits = 0;
+    const uint32_t dbase = drop ? dropout_base(P.cfg, task, pass, 0) : 0u;
+    uint32_t bits = 0;
     warp_tile_foreach<MT, 4>(acc, [&](int i, int hh, float& c) {
         const int h = 32 * w + hh;
         float v = 0.f;
         if (i < tr) {
             const float z = Apre[i * lda_pre + h] + s.b0s[h] - alpha * c;
-            if (drop && (hh & 1) == 0) bits = dropout_bits(P.cfg, task, pass, 0, r0 + i, h);
+            if (drop && (hh & 1) == 0) bits = dropout_bits(dbase, r0 + i, h);
             if (z > 0.f && (!drop || dropout_keep_bits(bits, h, thr))) v = z * sc;
         }
         s.h0t[i * kS0 + h] = v;
@@ -653,13 +684,14 @@ __device__ __forceinline__ void mma_tile_h1(const EpiParams& P, const SmemM& s, 
     const float sc = dropout_scale(P.cfg);
     const bool drop = P.cfg.dropout_p > 0.f;
     const uint32_t thr = dropout_thr(P.cfg);
-    uint64_t bits = 0;
+    const uint32_t dbase = drop ? dropout_base(P.cfg, task, pass, 1) : 0u;
+    uint32_t bits = 0;
     warp_tile_foreach<MT, 1>(acc, [&](int i, int oo, float& c) {
         const int o = 8 * w + oo;
         float v = 0.f;
         if (i < tr) {
             const float z = c + s.b1s[o];
-            if (drop && (oo & 1) == 0) bits = dropout_bits(P.cfg, task, pass, 1, r0 + i, o);
+            if (drop && (oo & 1) == 0) bits = dropout_bits(dbase, r0 + i, o);
             if (z > 0.f && (!drop || dropout_keep_bits(bits, o, thr))) v = z * sc;
         }
         s.h1t[i * kS1 + o] = v;
@@ -672,8 +704,15 @@ __device__ __forceinline__ void m_tile_logits(const EpiParams& P, const SmemM& s
         const int i = idx / N, c = idx - i * N;
         float l = 0.f;
         if (i < tr) {
-            l = s.hp[c * kHD + kH1];
-            for (int o = 0; o < kH1; ++o) l = fmaf(s.h1t[i * kS1 + o], s.hp[c * kHD + o], l);
+            float l0 = s.hp[c * kHD + kH1], l1 = 0.f, l2 = 0.f, l3 = 0.f;      // 4 chains instead of one 64-long one
+#pragma unroll 4
+            for (int o = 0; o < kH1; o += 4) {
+                l0 = fmaf(s.h1t[i * kS1 + o], s.hp[c * kHD + o], l0);
+                l1 = fmaf(s.h1t[i * kS1 + o + 1], s.hp[c * kHD + o + 1], l1);
+                l2 = fmaf(s.h1t[i * kS1 + o + 2], s.hp[c * kHD + o + 2], l2);
+                l3 = fmaf(s.h1t[i * kS1 + o + 3], s.hp[c * kHD + o + 3], l3);
+            }
+            l = (l0 + l1) + (l2 + l3);
         }
         s.lt[i * kLS + c] = l;
     }
@@ -692,6 +731,8 @@ __global__ void __launch_bounds__(kThreads, 1) episode_fwd_mma_kernel(EpiParams 
     const Layout L = make_layout(c);
     const int o_ = tid & 63, kg_ = tid >> 6;
     __shared__ float task_sum[2];
+    PhaseClock pc;
+    pc.start();
 
     for (int i = 0; i < 32; ++i) s.sS[i * kSS + tid] = 0.f;         // pad rows of S stay zero for the whole kernel
     for (int idx = tid; idx < 32 * kSG; idx += kThreads) { s.gS[idx] = 0.f; s.gQ[idx] = 0.f; }
@@ -739,16 +780,20 @@ __global__ void __launch_bounds__(kThreads, 1) episode_fwd_mma_kernel(EpiParams 
         }
         if (tid == 0) { task_sum[0] = 0.f; task_sum[1] = 0.f; }
         __syncthreads();
+        pc.mark(20);    // prologue
 
         for (int st = 0; st < steps; ++st) {
             float* rec = P.save ? slot + L.steps + int64_t(st) * L.per_step : nullptr;
             for (int idx = tid; idx < N * kHD; idx += kThreads) s.dhp[idx] = 0.f;
             mma_tile_h0<MT>(P, s, task, s.gS, st > 0, n8, s.sA, kH0, 0, n, st);
             __syncthreads();
+            pc.mark(21);    // s: H0
             mma_tile_h1<MT>(P, s, task, 0, n, st);
             __syncthreads();
+            pc.mark(22);    // s: H1 (K=256)
             m_tile_logits(P, s, RS, n);
             __syncthreads();
+            pc.mark(23);    // s: logits
             if (tid < RS) {                                    // dL = (softmax - onehot) / n
                 float* l = &s.lt[tid * kLS];
                 if (tid < n) {
@@ -765,6 +810,7 @@ __global__ void __launch_bounds__(kThreads, 1) episode_fwd_mma_kernel(EpiParams 
                 }
             }
             __syncthreads();
+            pc.mark(24);    // s: softmax
             // head gradient; dZ1 (uses the pre-update head)
             for (int idx = tid; idx < N * kHD; idx += kThreads) {
                 const int cc = idx / kHD, o = idx - cc * kHD;
@@ -787,6 +833,7 @@ __global__ void __launch_bounds__(kThreads, 1) episode_fwd_mma_kernel(EpiParams 
                 }
             }
             __syncthreads();
+            pc.mark(25);    // s: dhp, dZ1
             float db1 = 0.f;
             if (tid < kH1) for (int i = 0; i < n; ++i) db1 += s.dz1t[i * kS1 + tid];
             // dZ0 = (dZ1 W1) * gate ;  S += dZ0 ;  db0 = column sums of dZ0
@@ -835,6 +882,7 @@ __global__ void __launch_bounds__(kThreads, 1) episode_fwd_mma_kernel(EpiParams 
                 for (int idx = tid; idx < N * kHD; idx += kThreads) rec[L.oHP + idx] = s.hp[idx];
             }
             __syncthreads();                                    // everyone is done reading W1^T and the old head
+            pc.mark(26);    // s: dZ0 gemm, S update, stash
             // W1 -= alpha * dZ1^T H0   (rows of W1^T owned by this warp: h in [32w, 32w+32))
             {
                 float acc[2][8][4];
@@ -853,6 +901,7 @@ __global__ void __launch_bounds__(kThreads, 1) episode_fwd_mma_kernel(EpiParams 
             if (tid < kH1) s.b1s[tid] -= alpha * db1;
             s.b0s[tid] -= alpha * s.db0s[tid];
             __syncthreads();
+            pc.mark(27);    // s: W1 update gemm
         }
 
         // ---- query scoring, 32 rows per tile
@@ -879,12 +928,16 @@ __global__ void __launch_bounds__(kThreads, 1) episode_fwd_mma_kernel(EpiParams 
                 }
             }
             __syncthreads();
+            pc.mark(28);    // q: loads
             mma_tile_h0<2>(P, s, task, s.gQ, steps > 0, n8, s.h0t, kS0, r0, tr, steps);
             __syncthreads();
+            pc.mark(29);    // q: H0
             mma_tile_h1<2>(P, s, task, r0, tr, steps);
             __syncthreads();
+            pc.mark(30);    // q: H1
             m_tile_logits(P, s, 32, tr);
             __syncthreads();
+            pc.mark(31);    // q: logits
             if (P.save) {                                       // query activations for the backward
                 for (int i = 0; i < tr; ++i) slot[L.qH0 + int64_t(r0 + i) * kH0 + tid] = s.h0t[i * kS0 + tid];
                 for (int idx = tid; idx < tr * kH1; idx += kThreads) {
@@ -915,6 +968,7 @@ __global__ void __launch_bounds__(kThreads, 1) episode_fwd_mma_kernel(EpiParams 
                 for (int i = 0; i < tr; ++i) { a += s.rowv[i]; k += s.rowc[i]; }
                 task_sum[0] = a; task_sum[1] = k;
             }
+            pc.mark(32);    // q: stash, softmax, loss
         }
         __syncthreads();
         if (tid == 0) {
@@ -933,6 +987,7 @@ __global__ void __launch_bounds__(kThreads, 1) episode_fwd_mma_kernel(EpiParams 
             for (int i = 0; i < n; ++i) Sout[int64_t(i) * kH0 + tid] = steps > 0 ? s.sS[i * kSS + tid] : 0.f;
         }
         __syncthreads();
+        pc.mark(33);    // epilogue (adapted state out)
     }
 }
 
@@ -1018,6 +1073,8 @@ __global__ void __launch_bounds__(kThreads, 1) episode_bwd_mma_kernel(EpiParams 
     const Layout L = make_layout(c);
     const int o_ = tid & 63, kg_ = tid >> 6;
     const float sc = dropout_scale(c);
+    PhaseClock pc;
+    pc.start();
 
     for (int idx = tid; idx < 32 * kSG; idx += kThreads) s.gS[idx] = 0.f;
     for (int idx = tid; idx < 16 * kSG; idx += kThreads) s.gQ[idx] = 0.f;
@@ -1047,9 +1104,17 @@ __global__ void __launch_bounds__(kThreads, 1) episode_bwd_mma_kernel(EpiParams 
         }
         for (int j = 0; j < n; ++j) aS[int64_t(j) * kH0 + tid] = 0.f;
         __syncthreads();
+        pc.mark(0);     // prologue
 
         // ---- query pass (activations from the forward's stash)
         const float qscale = P.loss_scale / float(m);
+        float aSq[2][4][4];                  // Gq^T dZ0q summed over the query tiles (this warp's 32 columns)
+#pragma unroll
+        for (int i = 0; i < 2; ++i)
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
+#pragma unroll
+                for (int q = 0; q < 4; ++q) aSq[i][j][q] = 0.f;
         for (int r0 = 0; r0 < m; r0 += 16) {
             const int tr = min(16, m - r0);
             {
@@ -1081,11 +1146,16 @@ __global__ void __launch_bounds__(kThreads, 1) episode_bwd_mma_kernel(EpiParams 
                     if (idx < 16 * n) s.gQ[(idx / n) * kSG + (idx % n)] = g2[q];
                 }
             }
+            for (int idx = tid; idx < 16 * N; idx += kThreads) {
+                const int i = idx / N, cc = idx - i * N;
+                s.rlt[i * kLS + cc] = i < tr ? __ldg(&slot[L.qLG + int64_t(r0) * N + idx]) : 0.f;
+            }
+            if (tid < 16) s.rows[tid] = tid < tr ? P.qry_rows[b * m + r0 + tid] : 0;
+            __syncthreads();
             if (tid < 16) {
-                s.rows[tid] = tid < tr ? P.qry_rows[b * m + r0 + tid] : 0;
                 float* l = &s.lt[tid * kLS];
                 if (tid < tr) {
-                    for (int cc = 0; cc < N; ++cc) l[cc] = slot[L.qLG + int64_t(r0 + tid) * N + cc];
+                    for (int cc = 0; cc < N; ++cc) l[cc] = s.rlt[tid * kLS + cc];
                     float mx, sum;
                     row_softmax(l, N, mx, sum);
                     const float inv = 1.f / sum;
@@ -1096,6 +1166,7 @@ __global__ void __launch_bounds__(kThreads, 1) episode_bwd_mma_kernel(EpiParams 
                 }
             }
             __syncthreads();
+            pc.mark(1);     // q: loads + softmax
             for (int idx = tid; idx < N * kHD; idx += kThreads) {              // a_head += dLq^T [H1q | 1]
                 const int cc = idx / kHD, o = idx - cc * kHD;
                 float a = 0.f;
@@ -1114,6 +1185,7 @@ __global__ void __launch_bounds__(kThreads, 1) episode_bwd_mma_kernel(EpiParams 
                 s.dz1t[i * kS1 + o_] = dz;
             }
             __syncthreads();
+            pc.mark(2);     // q: a_head, dZ1q
             if (tid < kH1) {
                 float a = 0.f;
                 for (int i = 0; i < tr; ++i) a += s.dz1t[i * kS1 + tid];
@@ -1152,21 +1224,18 @@ __global__ void __launch_bounds__(kThreads, 1) episode_bwd_mma_kernel(EpiParams 
                 slab_colsum<1>(acc, s.ab0s, true);
             }
             __syncthreads();
-            if (steps > 0) {   // a_S -= alpha * Gq^T dZ0q
-                float acc[2][4][4];
-#pragma unroll
-                for (int i = 0; i < 2; ++i)
-#pragma unroll
-                    for (int j = 0; j < 4; ++j)
-#pragma unroll
-                        for (int q = 0; q < 4; ++q) acc[i][j][q] = 0.f;
-                warp_gemm_3xtf32<2, 4, true, false>(s.gQ, kSG, s.tt + 32 * w, kS0, 16, 1.f, acc);
-                warp_tile_foreach<2, 4>(acc, [&](int j, int hh, float& cv) {
-                    if (j < n) aS[int64_t(j) * kH0 + 32 * w + hh] -= alpha * cv;
-                });
-            }
+            pc.mark(3);     // q: a_W1 gemm, dZ0q gemm, atomics
+            if (steps > 0)     // a_S -= alpha * Gq^T dZ0q  (kept in registers until the last query tile)
+                warp_gemm_3xtf32<2, 4, true, false>(s.gQ, kSG, s.tt + 32 * w, kS0, 16, 1.f, aSq);
             __syncthreads();
+            pc.mark(4);     // q: a_S gemm
         }
+        if (steps > 0) {
+            warp_tile_foreach<2, 4>(aSq, [&](int j, int hh, float& cv) {
+                if (j < n) aS[int64_t(j) * kH0 + 32 * w + hh] = -alpha * cv;          // a_S starts from zero
+            });
+        }
+        __syncthreads();
 
         // ---- inner steps in reverse
         if (!c.first_order) {
@@ -1216,6 +1285,7 @@ __global__ void __launch_bounds__(kThreads, 1) episode_bwd_mma_kernel(EpiParams 
 #pragma unroll
                         for (int q = 0; q < 4; ++q) rw[i][j][q] = 0.f;
                 __syncthreads();
+                pc.mark(5);     // s: loads + undo W1
 
                 for (int r0 = 0; r0 < n; r0 += 16) {
                     const int tr = min(16, n - r0);
@@ -1255,6 +1325,7 @@ __global__ void __launch_bounds__(kThreads, 1) episode_bwd_mma_kernel(EpiParams 
                         s.ys[tid] = tid < tr ? int(P.sup_y[b * n + r0 + tid]) : 0;
                     }
                     __syncthreads();
+                    pc.mark(6);     // s: tile loads
                     // (11r)+(10r)+(9r): r_dH1 = gate1 * (r_dH0 W1^T + H0 (g_W1)^T + g_b1),  g_W1 = -alpha a_W1
                     {
                         float acc[1][1][4] = {{{0.f, 0.f, 0.f, 0.f}}};
@@ -1274,16 +1345,21 @@ __global__ void __launch_bounds__(kThreads, 1) episode_bwd_mma_kernel(EpiParams 
                         for (int q = 0; q < 4; ++q) rh0[0][j][q] = 0.f;
                     warp_gemm_3xtf32<1, 4, false, true>(s.dz1t, kS1, s.aw1t + 32 * w * kS1, kS1, kH1, -alpha, rh0);
                     __syncthreads();
+                    pc.mark(7);     // s: r_dH1 gemms (K=256 x2), r_W1 gemm, r_H0 gemm
                     // (8r)+(7r): r_dL = r_dH1 Wh^T + H1 (g_Wh)^T + g_bh ; r_head += dL^T r_dH1
                     for (int idx = tid; idx < 16 * N; idx += kThreads) {
                         const int i = idx / N, cc = idx - i * N;
                         float a = 0.f;
                         if (i < tr) {
-                            a = -alpha * s.ahp[cc * kHD + kH1];
-                            for (int o = 0; o < kH1; ++o) {
-                                a = fmaf(s.rzh[i * kS1 + o], s.hp[cc * kHD + o], a);
-                                a = fmaf(s.h1t[i * kS1 + o], -alpha * s.ahp[cc * kHD + o], a);
+                            float a0 = -alpha * s.ahp[cc * kHD + kH1], a1 = 0.f, a2 = 0.f, a3 = 0.f;
+#pragma unroll 4
+                            for (int o = 0; o < kH1; o += 2) {
+                                a0 = fmaf(s.rzh[i * kS1 + o], s.hp[cc * kHD + o], a0);
+                                a1 = fmaf(s.h1t[i * kS1 + o], -alpha * s.ahp[cc * kHD + o], a1);
+                                a2 = fmaf(s.rzh[i * kS1 + o + 1], s.hp[cc * kHD + o + 1], a2);
+                                a3 = fmaf(s.h1t[i * kS1 + o + 1], -alpha * s.ahp[cc * kHD + o + 1], a3);
                             }
+                            a = (a0 + a1) + (a2 + a3);
                         }
                         s.rlt[i * kLS + cc] = a;
                     }
@@ -1294,6 +1370,7 @@ __global__ void __launch_bounds__(kThreads, 1) episode_bwd_mma_kernel(EpiParams 
                         s.rhp[cc * kHD + o] += a;
                     }
                     __syncthreads();
+                    pc.mark(8);     // s: r_dL, r_head (FMA)
                     // (6r) r_L = P * (r_dL - <P, r_dL>) / n ; (7r) r_H1 = dL g_Wh  (overwrites rzh)
                     if (tid < tr) {
                         const int y = s.ys[tid];
@@ -1316,6 +1393,7 @@ __global__ void __launch_bounds__(kThreads, 1) episode_bwd_mma_kernel(EpiParams 
                         s.rzh[i * kS1 + o_] = a;
                     }
                     __syncthreads();
+                    pc.mark(9);     // s: softmax jacobian, r_H1
                     // (5r) r_H1 += r_L Wh ; r_head += r_L^T [H1 | 1] ; (4r) r_Z1 = r_H1 * gate1
 #pragma unroll
                     for (int ii = 0; ii < 4; ++ii) {
@@ -1332,6 +1410,7 @@ __global__ void __launch_bounds__(kThreads, 1) episode_bwd_mma_kernel(EpiParams 
                         s.rhp[idx] += a;
                     }
                     __syncthreads();
+                    pc.mark(10);    // s: r_Z1, r_head
                     // (3r) r_H0 += r_Z1 W1 ; r_W1 += r_Z1^T H0 ; r_b1 += sum r_Z1
                     if (tid < kH1) {
                         float a = 0.f;
@@ -1366,6 +1445,7 @@ __global__ void __launch_bounds__(kThreads, 1) episode_bwd_mma_kernel(EpiParams 
                         slab_colsum<1>(rh0, s.rb0s, true);
                     }
                     __syncthreads();
+                    pc.mark(11);    // s: r_H0 gemm, r_W1 gemm, bar_Z0, atomics
                 }
                 // ---- end of reversed step: fold the contributions into the adjoints; a_S -= alpha G bar_Z0
                 warp_tile_foreach<2, 8>(rw, [&](int hh, int o, float& cv) { s.aw1t[(32 * w + hh) * kS1 + o] += cv; });
@@ -1380,6 +1460,7 @@ __global__ void __launch_bounds__(kThreads, 1) episode_bwd_mma_kernel(EpiParams 
                     for (int i = 0; i < 32; ++i) s.h0t[i * kS0 + tid] = v[i];
                 }
                 __syncthreads();
+                pc.mark(12);    // s: fold adjoints, reload bar_Z0
                 {
                     float acc[2][4][4];
 #pragma unroll
@@ -1389,11 +1470,37 @@ __global__ void __launch_bounds__(kThreads, 1) episode_bwd_mma_kernel(EpiParams 
 #pragma unroll
                             for (int q = 0; q < 4; ++q) acc[i][j][q] = 0.f;
                     warp_gemm_3xtf32<2, 4, false, false>(s.gS, kSG, s.h0t + 32 * w, kS0, 32, 1.f, acc);
-                    warp_tile_foreach<2, 4>(acc, [&](int j, int hh, float& cv) {
-                        if (j < n) aS[int64_t(j) * kH0 + 32 * w + hh] -= alpha * cv;
-                    });
+                    float old[2][4][4];                              // batched read-modify-write of a_S
+                    {
+                        const int g = lane >> 2, t = lane & 3;
+#pragma unroll
+                        for (int i = 0; i < 2; ++i)
+#pragma unroll
+                            for (int j = 0; j < 4; ++j)
+#pragma unroll
+                                for (int q = 0; q < 4; q += 2) {
+                                    const int row = i * 16 + g + (q >> 1) * 8;
+                                    const float2 v = row < n ? *reinterpret_cast<const float2*>(
+                                                                   &aS[int64_t(row) * kH0 + 32 * w + j * 8 + 2 * t])
+                                                             : make_float2(0.f, 0.f);
+                                    old[i][j][q] = v.x; old[i][j][q + 1] = v.y;
+                                }
+#pragma unroll
+                        for (int i = 0; i < 2; ++i)
+#pragma unroll
+                            for (int j = 0; j < 4; ++j)
+#pragma unroll
+                                for (int q = 0; q < 4; q += 2) {
+                                    const int row = i * 16 + g + (q >> 1) * 8;
+                                    if (row < n)
+                                        *reinterpret_cast<float2*>(&aS[int64_t(row) * kH0 + 32 * w + j * 8 + 2 * t]) =
+                                            make_float2(old[i][j][q] - alpha * acc[i][j][q],
+                                                        old[i][j][q + 1] - alpha * acc[i][j][q + 1]);
+                                }
+                    }
                 }
                 __syncthreads();
+                pc.mark(13);    // s: a_S gemm
             }
         }
 
@@ -1407,6 +1514,7 @@ __global__ void __launch_bounds__(kThreads, 1) episode_bwd_mma_kernel(EpiParams 
         P.d_b0_parts[int64_t(blockIdx.x) * kH0 + tid] += s.ab0s[tid];
         if (tid < kH1) P.d_b1_parts[int64_t(blockIdx.x) * kH1 + tid] += s.ab1[tid];
         __syncthreads();
+        pc.mark(14);    // epilogue
     }
 }
 
@@ -1887,5 +1995,25 @@ extern "C" int fumi_episode_bwd(const fumi_episode_cfg* cfg, int64_t B, const fl
 #endif
     FUMI_LAUNCH((episode_bwd_kernel<kTRB>), grid, kThreads, smem, stream, P);
     FUMI_CHECK_LAUNCH("episode_bwd_kernel");
+    return FUMI_OK;
+}
+
+// ---- diagnostics (not part of the reference-facing surface): per-phase SM-cycle counters of the episode kernels
+extern "C" int fumi_debug_phase_profile(int enable) {
+#ifndef FUMI_EMU
+    unsigned long long zeros[64] = {0};
+    cudaError_t e = cudaMemcpyToSymbol(g_phase, zeros, sizeof(zeros));
+    if (e == cudaSuccess) e = cudaMemcpyToSymbol(g_phase_on, &enable, sizeof(int));
+    if (e != cudaSuccess) return fumi_cuda_fail(e, "fumi_debug_phase_profile");
+#endif
+    return FUMI_OK;
+}
+extern "C" int fumi_debug_read_phases(unsigned long long* out64 /* HOST, 64 entries */) {
+#ifndef FUMI_EMU
+    cudaError_t e = cudaMemcpyFromSymbol(out64, g_phase, sizeof(unsigned long long) * 64);
+    if (e != cudaSuccess) return fumi_cuda_fail(e, "fumi_debug_read_phases");
+#else
+    for (int i = 0; i < 64; ++i) out64[i] = 0;
+#endif
     return FUMI_OK;
 }

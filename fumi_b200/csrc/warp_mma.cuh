@@ -48,18 +48,25 @@ template <int MT, int NT, bool ATRANS, bool BTRANS>
 __device__ __forceinline__ void warp_gemm_3xtf32(const float* __restrict__ A, int lda, const float* __restrict__ B, int ldb,
                                                  int K, float bscale, float (&acc)[MT][NT][4]) {
     const int lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
+    // Small tile counts: one pass over the fragments with two accumulators per tile (cross terms / hi*hi):
+    // half the shared-memory reads and splits, and two independent MMA chains per tile.  Large tile counts
+    // (register budget): two passes over the 32-wide slice into one accumulator.
+    constexpr bool kOnePass = MT * NT <= 8;
     for (int k0 = 0; k0 < K; k0 += 32) {
         float part[MT][NT][4];
+        float cross[kOnePass ? MT : 1][kOnePass ? NT : 1][4];
 #pragma unroll
         for (int i = 0; i < MT; ++i)
 #pragma unroll
             for (int j = 0; j < NT; ++j)
 #pragma unroll
-                for (int q = 0; q < 4; ++q) part[i][j][q] = 0.f;
+                for (int q = 0; q < 4; ++q) {
+                    part[i][j][q] = 0.f;
+                    if (kOnePass) cross[i][j][q] = 0.f;
+                }
         const int kend = (K - k0) < 32 ? (K - k0) : 32;
-        // pass 0: cross terms (small), pass 1: hi*hi
 #pragma unroll
-        for (int pass = 0; pass < 2; ++pass) {
+        for (int pass = 0; pass < (kOnePass ? 1 : 2); ++pass) {
             for (int kk = 0; kk < kend; kk += 8) {
                 const int k = k0 + kk;
                 uint32_t ahi[MT][4], alo[MT][4];
@@ -90,7 +97,11 @@ __device__ __forceinline__ void warp_gemm_3xtf32(const float* __restrict__ A, in
                     fumi_split(w1 * bscale, bhi[1], blo[1]);
 #pragma unroll
                     for (int i = 0; i < MT; ++i) {
-                        if (pass == 0) {
+                        if (kOnePass) {
+                            fumi_mma_tf32(cross[i][j], alo[i], bhi);
+                            fumi_mma_tf32(part[i][j], ahi[i], bhi);
+                            fumi_mma_tf32(cross[i][j], ahi[i], blo);
+                        } else if (pass == 0) {                    // cross terms first, then hi*hi
                             fumi_mma_tf32(part[i][j], alo[i], bhi);
                             fumi_mma_tf32(part[i][j], ahi[i], blo);
                         } else {
@@ -105,7 +116,8 @@ __device__ __forceinline__ void warp_gemm_3xtf32(const float* __restrict__ A, in
 #pragma unroll
             for (int j = 0; j < NT; ++j)
 #pragma unroll
-                for (int q = 0; q < 4; ++q) acc[i][j][q] += part[i][j][q];
+                for (int q = 0; q < 4; ++q)
+                    acc[i][j][q] += kOnePass ? (part[i][j][q] + cross[i][j][q]) : part[i][j][q];
     }
 }
 

@@ -8,26 +8,38 @@ import numpy as np
 _M = np.uint64(0xFFFFFFFFFFFFFFFF)
 
 
-def mask_hash64(seed, task, pas, layer, row, col_group):
-    """fumi_mask_hash64 of csrc/common.cuh: one 64-bit hash per (row, 4-column group)."""
+_U32 = np.uint32
+
+
+def _lowbias32(x):
+    x = np.asarray(x, np.uint32)
     with np.errstate(over="ignore"):
-        x = np.uint64(seed) ^ (np.uint64(task) * np.uint64(0x9E3779B97F4A7C15))
-        x = x + ((np.uint64(pas) << np.uint64(40)) ^ (np.uint64(layer) << np.uint64(32))
-                 ^ (np.asarray(row, np.uint64) << np.uint64(12)) ^ np.asarray(col_group, np.uint64))
-        x ^= x >> np.uint64(30)
-        x = x * np.uint64(0xBF58476D1CE4E5B9)
-        x ^= x >> np.uint64(27)
-        x = x * np.uint64(0x94D049BB133111EB)
-        x ^= x >> np.uint64(31)
+        x = x ^ (x >> _U32(16)); x = x * _U32(0x7FEB352D)
+        x = x ^ (x >> _U32(15)); x = x * _U32(0x846CA68B)
+        x = x ^ (x >> _U32(16))
+    return x
+
+
+def mask_base(seed, task, pas, layer):
+    """fumi_mask_base of csrc/common.cuh."""
+    seed, task = int(seed), int(task)
+    with np.errstate(over="ignore"):
+        x = _lowbias32(_U32(seed & 0xFFFFFFFF) ^ _U32(0x9E3779B9))
+        x = _lowbias32(x ^ _U32((seed >> 32) & 0xFFFFFFFF))
+        x = _lowbias32(x + _U32(task & 0xFFFFFFFF) * _U32(0x85EBCA6B))
+        x = _lowbias32(x ^ _U32((task >> 32) & 0xFFFFFFFF))
+        x = _lowbias32(x + _U32(pas) * _U32(0x9E3779B1) + _U32(layer) * _U32(0x61C88647))
     return x
 
 
 def mask_array(seed, task, pas, layer, rows, cols, p):
-    """[rows, cols] float32 mask with entries 0 or 1/(1-p): column c uses the 16-bit field (c & 3) of the hash
-    of its (row, 4-column group); kept iff field >= floor(p * 65536)."""
-    r, c = np.meshgrid(np.arange(rows, dtype=np.uint64), np.arange(cols, dtype=np.uint64), indexing="ij")
-    bits = mask_hash64(seed, task, pas, layer, r, c >> np.uint64(2))
-    field = (bits >> (np.uint64(16) * (c & np.uint64(3)))) & np.uint64(0xFFFF)
-    thr = np.uint64(int(np.float32(p) * np.float32(65536.0)))
+    """[rows, cols] float32 mask with entries 0 or 1/(1-p): one 32-bit hash per (row, column pair); the even
+    column uses its low 16 bits, the odd one the high 16 bits; kept iff field >= floor(p * 65536)."""
+    r, c = np.meshgrid(np.arange(rows, dtype=np.uint32), np.arange(cols, dtype=np.uint32), indexing="ij")
+    base = mask_base(seed, task, pas, layer)
+    with np.errstate(over="ignore"):
+        h = _lowbias32(base + r * _U32(0xC2B2AE35) + (c >> _U32(1)) * _U32(0x27D4EB2F))
+    field = np.where((c & _U32(1)) == 1, h >> _U32(16), h & _U32(0xFFFF))
+    thr = _U32(int(np.float32(p) * np.float32(65536.0)))
     keep = field >= thr
     return keep.astype(np.float32) * np.float32(1.0 / (1.0 - np.float32(p)))

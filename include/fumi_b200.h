@@ -244,6 +244,14 @@ int fumi_sampler_next(fumi_sampler* s, int64_t B, uint32_t* py_state, uint32_t* 
 /* CPython hash(tuple of small non-negative ints) -- exposed for tests. */
 int64_t fumi_py_tuple_hash(const int64_t* items, int64_t n);
 
+/* ------------------------------------------------------------------------------------------
+ * Diagnostics (no reference counterpart): per-phase SM-cycle counters of the episode kernels, summed over
+ * CTAs by thread 0 of each.  fumi_debug_phase_profile(1) zeroes and enables them, (0) disables;
+ * fumi_debug_read_phases copies the 64 counters to a HOST array (phase ids: csrc/episode.cu pc.mark).
+ * ---------------------------------------------------------------------------------------- */
+int fumi_debug_phase_profile(int enable);
+int fumi_debug_read_phases(unsigned long long* out64);
+
 #ifdef __cplusplus
 }
 #endif
