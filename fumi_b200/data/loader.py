@@ -8,7 +8,9 @@ but the batch is an EpisodeBatch of indices into the split's FeatureBank instead
 """
 import json
 import os
+import queue
 import random
+import threading
 
 import numpy as np
 import torch
@@ -21,10 +23,17 @@ _KEYS = ("classes", "label_perm", "sup_ids", "qry_ids", "sup_y", "qry_y", "head_
 
 
 class EpisodeLoader:
-    def __init__(self, bank, sampler, batch_size, pin_memory=True):
+    """prefetch = n > 0: a background thread samples up to n meta-batches ahead on private copies of the two
+    generator states (snapshotted when the iterator is created); when a batch is handed out, the global
+    `random` / torch generator states are set to what they were right after that batch was drawn, so the
+    host program observes the same generator sequence as with the synchronous loader."""
+
+    def __init__(self, bank, sampler, batch_size, pin_memory=True, prefetch=0):
         self.bank, self.sampler, self.batch_size = bank, sampler, int(batch_size)
         self.pin = bool(pin_memory) and bank.feats.is_cuda
+        self.prefetch = int(prefetch)
         self.dataset = sampler          # len(loader.dataset) parity is not meaningful for episodes
+        self._stop = None
 
     def _host_buffers(self):
         N, K, Q, B = self.sampler.N, self.sampler.K, self.sampler.Q, self.batch_size
@@ -40,10 +49,56 @@ class EpisodeLoader:
                             qry_y=ts["qry_y"], sup_ids=arrs["sup_ids"], qry_ids=arrs["qry_ids"],
                             head_class=ts["head_class"], host=arrs)
 
+    def _make(self, ts, arrs):
+        return EpisodeBatch(bank=self.bank, sup_rows=ts["sup_rows"], qry_rows=ts["qry_rows"], sup_y=ts["sup_y"],
+                            qry_y=ts["qry_y"], sup_ids=arrs["sup_ids"], qry_ids=arrs["qry_ids"],
+                            head_class=ts["head_class"], host=arrs)
+
+    def close(self):
+        if self._stop is not None:
+            self._stop.set()
+            self._stop = None
+
     def __iter__(self):
         self.sampler.new_iterator()
-        while True:
-            yield self.next_batch()
+        if self.prefetch <= 0:
+            while True:
+                yield self.next_batch()
+        from ..sampler import _torch_state_get, _torch_state_set
+        self.close()
+        ver, key, gauss = random.getstate()
+        py = np.asarray(key, np.uint32)
+        st, raw = _torch_state_get()
+        q = queue.Queue(maxsize=self.prefetch)
+        stop = self._stop = threading.Event()
+
+        def worker():
+            try:
+                while not stop.is_set():
+                    ts, arrs = self._host_buffers()
+                    self.sampler.next_batch_states(self.batch_size, py, st, arrs)
+                    item = (ts, arrs, py.copy(), st.copy())
+                    while not stop.is_set():
+                        try:
+                            q.put(item, timeout=0.1)
+                            break
+                        except queue.Full:
+                            pass
+            except Exception as e:          # surfaced on the consumer side
+                q.put(e)
+
+        threading.Thread(target=worker, daemon=True).start()
+        try:
+            while True:
+                item = q.get()
+                if isinstance(item, Exception):
+                    raise item
+                ts, arrs, py_after, st_after = item
+                random.setstate((ver, tuple(int(x) for x in py_after), gauss))
+                _torch_state_set(st_after, raw)
+                yield self._make(ts, arrs)
+        finally:
+            stop.set()
 
 
 def build_loaders(feats, text, cat_of, num_ways, num_shots, num_shots_test, batch_size, device, num_threads=0):

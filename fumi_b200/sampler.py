@@ -65,8 +65,11 @@ class EpisodeSampler:
 
     def __del__(self):
         h, self._h = getattr(self, "_h", None), None
-        if h:
-            _lib.lib().fumi_sampler_destroy(h)
+        try:
+            if h:
+                _lib.lib().fumi_sampler_destroy(h)
+        except Exception:      # interpreter shutdown
+            pass
 
     def new_iterator(self):
         """Equivalent of iter(loader): the DataLoader draws its base seed from the torch stream."""
@@ -74,19 +77,19 @@ class EpisodeSampler:
         _lib.check(_lib.lib().fumi_sampler_new_iterator(self._h, _lib.ptr(st)), "fumi_sampler_new_iterator")
         _torch_state_set(st, raw)
 
-    def next_batch(self, batch_size, out=None):
+    def empty_out(self, batch_size):
         B, N, K, Q = int(batch_size), self.N, self.K, self.Q
-        if out is None:
-            out = {k: np.empty((B, n), np.int64) for k, n in
-                   (("classes", N), ("label_perm", N), ("sup_ids", N * K), ("qry_ids", N * Q),
-                    ("sup_y", N * K), ("qry_y", N * Q), ("head_class", N),
-                    ("sup_rows", N * K), ("qry_rows", N * Q))}
-        ver, key, gauss = random.getstate()
-        py = np.asarray(key, np.uint32)
-        st, raw = _torch_state_get()
+        return {k: np.empty((B, n), np.int64) for k, n in
+                (("classes", N), ("label_perm", N), ("sup_ids", N * K), ("qry_ids", N * Q),
+                 ("sup_y", N * K), ("qry_y", N * Q), ("head_class", N),
+                 ("sup_rows", N * K), ("qry_rows", N * Q))}
+
+    def next_batch_states(self, batch_size, py_state, torch_state, out):
+        """One meta-batch on explicit generator states (uint32[625] / uint32[626], advanced in place).
+        Touches no global state: safe to call from a prefetch thread (the C call releases the GIL)."""
         try:
             _lib.check(_lib.lib().fumi_sampler_next(
-                self._h, B, _lib.ptr(py), _lib.ptr(st), *[_lib.ptr(out[k]) for k in
+                self._h, int(batch_size), _lib.ptr(py_state), _lib.ptr(torch_state), *[_lib.ptr(out[k]) for k in
                 ("classes", "label_perm", "sup_ids", "qry_ids", "sup_y", "qry_y", "head_class",
                  "sup_rows", "qry_rows")],
                 self.num_threads), "fumi_sampler_next")
@@ -94,6 +97,15 @@ class EpisodeSampler:
             if "smaller than the minimum" in str(e):
                 raise ValueError(str(e).split(": ", 2)[-1]) from None     # torchmeta raises ValueError
             raise
+        return out
+
+    def next_batch(self, batch_size, out=None):
+        if out is None:
+            out = self.empty_out(batch_size)
+        ver, key, gauss = random.getstate()
+        py = np.asarray(key, np.uint32)
+        st, raw = _torch_state_get()
+        self.next_batch_states(batch_size, py, st, out)
         random.setstate((ver, tuple(int(x) for x in py), gauss))
         _torch_state_set(st, raw)
         return out

@@ -95,3 +95,35 @@ def test_native_sampler_matches_reference_loader_golden(name, N, K, Qtrain):
         assert np.array_equal(b["qry_ids"], g[f"b{i}_qry_ids"]), (i, split)
         assert np.array_equal(b["sup_y"], g[f"b{i}_sup_y"]), (i, split)
         assert np.array_equal(b["qry_y"], g[f"b{i}_qry_y"]), (i, split)
+
+
+def test_prefetching_loader_hands_out_the_same_stream_and_states():
+    """EpisodeLoader(prefetch=2) == synchronous loader: same batches, and after each hand-out the global
+    generator states equal the synchronous ones."""
+    from fumi_b200.data.bank import FeatureBank
+    from fumi_b200.data.loader import EpisodeLoader
+    rs = np.random.RandomState(3)
+    C, N, K, Q, B = 40, 5, 2, 6, 9
+    sizes = rs.randint(K + Q, K + Q + 30, size=C)
+    cat_of = np.repeat(np.arange(C), sizes)
+    rs.shuffle(cat_of)
+    feats = torch.zeros(len(cat_of), 4)
+    ref_states, ref_batches = [], []
+    for prefetch in (0, 2):
+        sampler = EpisodeSampler(cat_of, np.arange(C), N, K, Q, num_threads=2)
+        bank = FeatureBank(feats=feats, text=torch.zeros(C, 4), ids=sampler.ids, categories=np.arange(C))
+        loader = EpisodeLoader(bank, sampler, B, pin_memory=False, prefetch=prefetch)
+        random.seed(11); torch.manual_seed(12)
+        it = iter(loader)
+        for i in range(4):
+            b = next(it)
+            snap = (random.getstate(), torch.get_rng_state().clone())
+            if prefetch == 0:
+                ref_batches.append({k: v.copy() for k, v in b.host.items()})
+                ref_states.append(snap)
+            else:
+                for k, v in b.host.items():
+                    assert np.array_equal(v, ref_batches[i][k]), (i, k)
+                assert snap[0] == ref_states[i][0]
+                assert torch.equal(snap[1], ref_states[i][1])
+        loader.close()
