@@ -40,12 +40,14 @@ def first_row_of_each_label(targets, num_ways):
 
 
 class EpisodeEngine:
-    def __init__(self, device, precision=0):
+    def __init__(self, device, precision=None):
         self.device = torch.device(device)
         if self.device.type != "cuda" and not _lib.is_emulation():
             raise _lib.FumiError(f"fumi_b200 runs on CUDA devices only (got {self.device}); there is no CPU path")
         self.L = _lib.lib()
-        self.precision = precision       # 0: fp32 FMA dense layers, 1: tcgen05 3xTF32
+        if precision is None:            # default: tensor cores (the host emulation used by CPU tests has none)
+            precision = 0 if _lib.is_emulation() else 1
+        self.precision = precision       # dense layers: 0 fp32 FMA, 1 tcgen05 3xTF32
         self.launches = 0                # kernels launched through this engine (bench: gpu_launches)
         self.profile = None              # dict name -> [cuda event pairs] while bench.py profiles kernels
 

@@ -291,7 +291,7 @@ def dropout_case(device, name="fumi_train_n5k5_d512", p=0.25, seed=77):
 
 
 def dense_case(device):
-    eng = engine_mod.EpisodeEngine(device)
+    eng = engine_mod.EpisodeEngine(device, precision=0)
     rs = np.random.RandomState(3)
     for (M, N, K) in [(37, 65, 24), (300, 256, 512), (5, 1, 256), (130, 129, 20)]:
         x, w, b = rs.randn(M, K).astype(np.float32), (rs.randn(N, K) / np.sqrt(K)).astype(np.float32), rs.randn(N).astype(np.float32)
