@@ -221,7 +221,8 @@ def main():
     t0 = time.time()
     bank = make_bank(num_images=a.bank_images, num_classes=a.bank_classes, im_dim=a.im_dim, text_dim=a.text_dim)
     cats = class_split(a.bank_classes)[0 if train else 2]
-    sampler = EpisodeSampler(bank.cat_of, cats, N, K, Q)
+    # host sampler threads: share the box's cores between the ranks
+    sampler = EpisodeSampler(bank.cat_of, cats, N, K, Q, num_threads=max(2, (os.cpu_count() or 8) // max(1, world)))
     fb = FeatureBank(feats=torch.from_numpy(bank.feats[sampler.ids]).to(device),
                      text=torch.from_numpy(bank.text[cats]).to(device), ids=sampler.ids, categories=cats)
     loader = EpisodeLoader(fb, sampler, a.tasks)

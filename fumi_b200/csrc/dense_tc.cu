@@ -28,6 +28,7 @@
 #include <cuda_runtime.h>
 
 #include <cstdint>
+#include <cstdlib>
 #include <cstring>
 
 #include "../../include/fumi_b200.h"
@@ -52,6 +53,7 @@ struct TcParams {
     int k_tiles_per_split;
     int act;
     int atomic;             // 1: atomicAdd partial tiles (split-K / accumulate); bias & act must be off
+    int drain;              // k stages accumulated in one TMEM buffer before it is drained into registers
 };
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return static_cast<uint32_t>(__cvta_generic_to_shared(p)); }
@@ -157,8 +159,9 @@ __global__ void __launch_bounds__(kThreadsTc, 1) gemm_tf32x3_kernel(const __grid
             for (int it = 0; it < nk; ++it) {
                 const int s = it % kStages;
                 const uint32_t ph = (it / kStages) & 1;
-                const int tb = it & 1;                                   // TMEM ping-pong buffer of this stage
-                mbar_wait(tmem_empty_bar + 8 * tb, ((it >> 1) & 1) ^ 1);  // accumulate warps drained it
+                const int grp = it / p.drain, sub = it - grp * p.drain;
+                const int tb = grp & 1;                                  // TMEM ping-pong buffer of this group of stages
+                if (sub == 0) mbar_wait(tmem_empty_bar + 8 * tb, ((grp >> 1) & 1) ^ 1);   // accumulate warps drained it
                 mbar_wait(full_bar + 8 * s, ph);
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                 const uint32_t st = base + s * kStageBytes;
@@ -168,7 +171,7 @@ __global__ void __launch_bounds__(kThreadsTc, 1) gemm_tf32x3_kernel(const __grid
                     const uint64_t ahi = umma_desc_sw128(st + k * 32), alo = umma_desc_sw128(st + kABytes + k * 32);
                     const uint64_t bhi = umma_desc_sw128(st + 2 * kABytes + k * 32);
                     const uint64_t blo = umma_desc_sw128(st + 2 * kABytes + kBBytes + k * 32);
-                    umma_tf32(td, alo, bhi, idesc, k != 0);
+                    umma_tf32(td, alo, bhi, idesc, (k | sub) != 0);
                     umma_tf32(td, ahi, blo, idesc, 1);
                 }
 #pragma unroll
@@ -178,7 +181,7 @@ __global__ void __launch_bounds__(kThreadsTc, 1) gemm_tf32x3_kernel(const __grid
                     umma_tf32(td, ahi, bhi, idesc, 1);
                 }
                 umma_commit(empty_bar + 8 * s);        // frees the smem stage once these MMAs retire
-                umma_commit(tmem_full_bar + 8 * tb);   // this stage's partial sums are complete
+                if (sub == p.drain - 1 || it == nk - 1) umma_commit(tmem_full_bar + 8 * tb);   // partial sums complete
             }
         }
     } else {
@@ -188,7 +191,8 @@ __global__ void __launch_bounds__(kThreadsTc, 1) gemm_tf32x3_kernel(const __grid
         float acc[128];
 #pragma unroll
         for (int j = 0; j < 128; ++j) acc[j] = 0.f;
-        for (int it = 0; it < nk; ++it) {
+        const int ngroups = (nk + p.drain - 1) / p.drain;
+        for (int it = 0; it < ngroups; ++it) {
             const int tb = it & 1;
             mbar_wait(tmem_full_bar + 8 * tb, (it >> 1) & 1);
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
@@ -360,6 +364,16 @@ extern "C" int fumi_gemm_tf32x3(const float* a_hi, const float* a_lo, const floa
     if ((rc = make_map(&p.b_hi, b_hi, N, K, ldb, BN)) != FUMI_OK) return rc;
     if ((rc = make_map(&p.b_lo, b_lo, N, K, ldb, BN)) != FUMI_OK) return rc;
     p.C = c; p.bias = bias; p.M = M; p.N = N; p.ldc = ldc; p.act = act;
+    {   // stages per TMEM drain: 1 = best accuracy (<= 4 truncating adds per partial sum), more = fewer drains
+        static int drain = -1;
+        if (drain < 0) {
+            const char* e = getenv("FUMI_GEMM_DRAIN");
+            drain = e ? atoi(e) : 2;
+            if (drain < 1) drain = 1;
+            if (drain > 8) drain = 8;
+        }
+        p.drain = drain;
+    }
     p.k_tiles = int((K + BK - 1) / BK);
     const int64_t tiles = ((M + BM - 1) / BM) * ((N + BN - 1) / BN);
     int splits = split_k;
