@@ -19,6 +19,7 @@
 // All reductions run in a fixed order (no atomics except the scatter into d_proj) so results are
 // reproducible run to run.
 #include <cstdint>
+#include <cstdlib>
 #include <cstring>
 
 #include "../../include/fumi_b200.h"
@@ -991,6 +992,357 @@ __global__ void __launch_bounds__(kThreads, 1) episode_fwd_mma_kernel(EpiParams 
     }
 }
 
+// ------------------------------------------------------------------------------------ forward, 16 warps
+// Same algorithm as episode_fwd_mma_kernel on 512 threads: the phases are latency-bound with 2 warps per
+// scheduler (ncu: issue active 22-28 %, tensor pipe 20 %), so the work of every phase is split over 16 warps:
+// warp w owns hidden units [16w, 16w+16) of the 256-wide ops and the (m tile w/8, n tile w%8) block of the
+// 64-wide op.  Launch bound 512 threads -> 128 registers per thread.
+constexpr int kThreads16 = 512;
+
+template <int MT>
+__device__ __forceinline__ void mma16_tile_h0(const EpiParams& P, const SmemM& s, int64_t task, const float* G, bool use_s,
+                                              int K8, const float* Apre, int lda_pre, int r0, int tr, int pass) {
+    const int w = threadIdx.x >> 5;
+    float acc[MT][2][4];
+#pragma unroll
+    for (int i = 0; i < MT; ++i)
+#pragma unroll
+        for (int j = 0; j < 2; ++j)
+#pragma unroll
+            for (int q = 0; q < 4; ++q) acc[i][j][q] = 0.f;
+    if (use_s) warp_gemm_3xtf32<MT, 2, false, false>(G, kSG, s.sS + 16 * w, kSS, K8, 1.f, acc);
+    const float alpha = P.cfg.step_size, sc = dropout_scale(P.cfg);
+    const bool drop = P.cfg.dropout_p > 0.f;
+    const uint32_t thr = dropout_thr(P.cfg);
+    const uint32_t dbase = drop ? dropout_base(P.cfg, task, pass, 0) : 0u;
+    uint32_t bits = 0;
+    warp_tile_foreach<MT, 2>(acc, [&](int i, int hh, float& c) {
+        const int h = 16 * w + hh;
+        float v = 0.f;
+        if (i < tr) {
+            const float z = Apre[i * lda_pre + h] + s.b0s[h] - alpha * c;
+            if (drop && (hh & 1) == 0) bits = dropout_bits(dbase, r0 + i, h);
+            if (z > 0.f && (!drop || dropout_keep_bits(bits, h, thr))) v = z * sc;
+        }
+        s.h0t[i * kS0 + h] = v;
+    });
+}
+
+template <int MT>
+__device__ __forceinline__ void mma16_tile_h1(const EpiParams& P, const SmemM& s, int64_t task, int r0, int tr, int pass) {
+    const int w = threadIdx.x >> 5, nt = w & 7, mt = w >> 3;
+    if (mt >= MT) return;                                   // NK <= 16: one m tile, warps 8..15 have no block
+    float acc[1][1][4] = {{{0.f, 0.f, 0.f, 0.f}}};
+    warp_gemm_3xtf32<1, 1, false, false>(s.h0t + 16 * mt * kS0, kS0, s.w1t + 8 * nt, kS1, kH0, 1.f, acc);
+    const float sc = dropout_scale(P.cfg);
+    const bool drop = P.cfg.dropout_p > 0.f;
+    const uint32_t thr = dropout_thr(P.cfg);
+    const uint32_t dbase = drop ? dropout_base(P.cfg, task, pass, 1) : 0u;
+    uint32_t bits = 0;
+    warp_tile_foreach<1, 1>(acc, [&](int ii, int oo, float& c) {
+        const int i = 16 * mt + ii, o = 8 * nt + oo;
+        float v = 0.f;
+        if (i < tr) {
+            const float z = c + s.b1s[o];
+            if (drop && (oo & 1) == 0) bits = dropout_bits(dbase, r0 + i, o);
+            if (z > 0.f && (!drop || dropout_keep_bits(bits, o, thr))) v = z * sc;
+        }
+        s.h1t[i * kS1 + o] = v;
+    });
+}
+
+__device__ __forceinline__ void m16_tile_logits(const EpiParams& P, const SmemM& s, int rows, int tr) {
+    const int N = P.cfg.num_ways;
+    for (int idx = threadIdx.x; idx < rows * N; idx += kThreads16) {
+        const int i = idx / N, c = idx - i * N;
+        float l = 0.f;
+        if (i < tr) {
+            float l0 = s.hp[c * kHD + kH1], l1 = 0.f, l2 = 0.f, l3 = 0.f;
+#pragma unroll 4
+            for (int o = 0; o < kH1; o += 4) {
+                l0 = fmaf(s.h1t[i * kS1 + o], s.hp[c * kHD + o], l0);
+                l1 = fmaf(s.h1t[i * kS1 + o + 1], s.hp[c * kHD + o + 1], l1);
+                l2 = fmaf(s.h1t[i * kS1 + o + 2], s.hp[c * kHD + o + 2], l2);
+                l3 = fmaf(s.h1t[i * kS1 + o + 3], s.hp[c * kHD + o + 3], l3);
+            }
+            l = (l0 + l1) + (l2 + l3);
+        }
+        s.lt[i * kLS + c] = l;
+    }
+}
+
+template <int MT>
+__global__ void __launch_bounds__(kThreads16, 1) episode_fwd_mma16_kernel(EpiParams P) {
+    constexpr int RS = 16 * MT;                       // padded support rows
+    constexpr int NT_ = kThreads16;
+    FUMI_DYN_SMEM(float, smem_raw);
+    const SmemM s = carve_m(smem_raw);
+    const fumi_episode_cfg& c = P.cfg;
+    const int tid = threadIdx.x, w = tid >> 5, lane = tid & 31;
+    const int col = tid & 255, half = tid >> 8;       // column-wise copies: two threads per column, rows split
+    const int n = c.num_support, m = c.num_query, N = c.num_ways, steps = c.steps;
+    const int n8 = (n + 7) & ~7;
+    const float alpha = c.step_size;
+    const Layout L = make_layout(c);
+    const int o_ = tid & 63, kg_ = tid >> 6;          // 8 row groups x 64 outputs
+    __shared__ float task_sum[2];
+    PhaseClock pc;
+    pc.start();
+
+    for (int idx = tid; idx < 32 * kSS; idx += NT_) s.sS[idx] = 0.f;     // pad rows of S stay zero for the whole kernel
+    for (int idx = tid; idx < 32 * kSG; idx += NT_) { s.gS[idx] = 0.f; s.gQ[idx] = 0.f; }
+    __syncthreads();
+
+    for (int64_t b = blockIdx.x; b < P.B; b += gridDim.x) {
+        const int64_t task = c.task_offset + b;
+        float* slot = P.stash + (P.save ? b : int64_t(blockIdx.x)) * P.slot_floats;
+        // ---- task prologue: everything the inner loop needs is staged in shared memory once
+        {
+            float v[16];
+#pragma unroll 1
+            for (int o0 = half * 32; o0 < half * 32 + 32; o0 += 16) {     // w1 is [H1][H0] row-major; thread == (k, half)
+#pragma unroll
+                for (int q = 0; q < 16; ++q) v[q] = __ldg(&P.w1[(o0 + q) * kH0 + col]);
+#pragma unroll
+                for (int q = 0; q < 16; ++q) s.w1t[col * kS1 + o0 + q] = v[q];
+            }
+            constexpr int RH = RS / 2;                                    // rows per half
+#pragma unroll
+            for (int q = 0; q < RH; ++q) {
+                const int i = half * RH + q;
+                v[q] = i < n ? __ldg(&P.proj[__ldg(&P.sup_rows[b * n + i]) * kH0 + col]) : 0.f;
+            }
+#pragma unroll
+            for (int q = 0; q < RH; ++q) s.sA[(half * RH + q) * kH0 + col] = v[q];
+        }
+        if (tid < kH0) s.b0s[tid] = __ldg(&P.b0[tid]);
+        if (tid < kH1) s.b1s[tid] = __ldg(&P.b1[tid]);
+        for (int idx = tid; idx < N * kHD; idx += NT_) {
+            const int cc = idx / kHD, o = idx - cc * kHD;
+            const int64_t r = P.head_rows ? __ldg(&P.head_rows[b * N + cc]) : cc;
+            s.hp[idx] = __ldg(&P.head_table[r * kHD + o]);
+        }
+        for (int idx = tid; idx < n * n; idx += NT_) {
+            const int i = idx / n, j = idx - i * n;
+            s.gS[i * kSG + j] = __ldg(&P.gram[(b * int64_t(n + m) + i) * n + j]);
+        }
+        if (tid < 32) s.ysS[tid] = tid < n ? int(P.sup_y[b * n + tid]) : 0;
+        for (int idx = tid; idx < m; idx += NT_) {
+            s.rowsQ[idx] = P.qry_rows[b * m + idx];
+            s.ysQ[idx] = int(P.qry_y[b * m + idx]);
+        }
+        if (tid == 0) { task_sum[0] = 0.f; task_sum[1] = 0.f; }
+        __syncthreads();
+        pc.mark(20);    // prologue
+
+        for (int st = 0; st < steps; ++st) {
+            float* rec = P.save ? slot + L.steps + int64_t(st) * L.per_step : nullptr;
+            mma16_tile_h0<MT>(P, s, task, s.gS, st > 0, n8, s.sA, kH0, 0, n, st);
+            __syncthreads();
+            pc.mark(21);    // s: H0
+            mma16_tile_h1<MT>(P, s, task, 0, n, st);
+            __syncthreads();
+            pc.mark(22);    // s: H1 (K=256)
+            m16_tile_logits(P, s, RS, n);
+            __syncthreads();
+            pc.mark(23);    // s: logits
+            if (tid < RS) {                                    // dL = (softmax - onehot) / n
+                float* l = &s.lt[tid * kLS];
+                if (tid < n) {
+                    float mx, sum;
+                    row_softmax(l, N, mx, sum);
+                    const float inv = 1.f / sum, invn = 1.f / float(n);
+                    const int y = s.ysS[tid];
+                    for (int cc = 0; cc < N; ++cc) {
+                        const float p = expf(l[cc] - mx) * inv;
+                        l[cc] = (p - (cc == y ? 1.f : 0.f)) * invn;
+                    }
+                } else {
+                    for (int cc = 0; cc < N; ++cc) l[cc] = 0.f;
+                }
+            }
+            __syncthreads();
+            pc.mark(24);    // s: softmax
+            // head gradient; dZ1 (uses the pre-update head)
+            for (int idx = tid; idx < N * kHD; idx += NT_) {
+                const int cc = idx / kHD, o = idx - cc * kHD;
+                float a = 0.f;
+                for (int i = 0; i < n; ++i) a = fmaf(s.lt[i * kLS + cc], o < kH1 ? s.h1t[i * kS1 + o] : 1.f, a);
+                s.dhp[idx] = a;
+            }
+            {
+                const float sc = dropout_scale(c);
+#pragma unroll
+                for (int ii = 0; ii < RS / 8; ++ii) {
+                    const int i = kg_ + 8 * ii;
+                    float dz = 0.f;
+                    if (i < n && s.h1t[i * kS1 + o_] > 0.f) {
+                        float dh = 0.f;
+                        for (int cc = 0; cc < N; ++cc) dh = fmaf(s.lt[i * kLS + cc], s.hp[cc * kHD + o_], dh);
+                        dz = dh * sc;
+                    }
+                    s.dz1t[i * kS1 + o_] = dz;
+                }
+            }
+            __syncthreads();
+            pc.mark(25);    // s: dhp, dZ1
+            float db1 = 0.f;
+            if (tid < kH1) for (int i = 0; i < n; ++i) db1 += s.dz1t[i * kS1 + tid];
+            // dZ0 = (dZ1 W1) * gate ;  S += dZ0 ;  db0 = column sums of dZ0
+            {
+                float acc[MT][2][4];
+#pragma unroll
+                for (int i = 0; i < MT; ++i)
+#pragma unroll
+                    for (int j = 0; j < 2; ++j)
+#pragma unroll
+                        for (int q = 0; q < 4; ++q) acc[i][j][q] = 0.f;
+                warp_gemm_3xtf32<MT, 2, false, true>(s.dz1t, kS1, s.w1t + 16 * w * kS1, kS1, kH1, 1.f, acc);
+                const float sc = dropout_scale(c);
+                float colsum[2][2];
+#pragma unroll
+                for (int j = 0; j < 2; ++j) colsum[j][0] = colsum[j][1] = 0.f;
+                warp_tile_foreach<MT, 2>(acc, [&](int i, int hh, float& cv) {
+                    const int h = 16 * w + hh;
+                    const float dz0 = (i < n && s.h0t[i * kS0 + h] > 0.f) ? cv * sc : 0.f;
+                    if (i < n) s.sS[i * kSS + h] = (st > 0 ? s.sS[i * kSS + h] : 0.f) + dz0;
+                    colsum[hh >> 3][hh & 1] += dz0;
+                });
+#pragma unroll
+                for (int j = 0; j < 2; ++j)
+#pragma unroll
+                    for (int q = 0; q < 2; ++q) {
+                        float v = colsum[j][q];
+                        v += __shfl_xor_sync(0xffffffffu, v, 4);
+                        v += __shfl_xor_sync(0xffffffffu, v, 8);
+                        v += __shfl_xor_sync(0xffffffffu, v, 16);
+                        if ((lane >> 2) == 0) s.db0s[16 * w + 8 * j + 2 * (lane & 3) + q] = v;
+                    }
+            }
+            if (rec) {                                          // records for the backward
+                for (int i = half; i < n; i += 2) rec[L.oH0 + int64_t(i) * kH0 + col] = s.h0t[i * kS0 + col];
+                for (int idx = tid; idx < n * kH1; idx += NT_) {
+                    const int i = idx / kH1, o = idx - i * kH1;
+                    rec[L.oH1 + idx] = s.h1t[i * kS1 + o];
+                    rec[L.oDZ1 + idx] = s.dz1t[i * kS1 + o];
+                }
+                for (int idx = tid; idx < n * N; idx += NT_) {
+                    const int i = idx / N, cc = idx - i * N;
+                    rec[L.oDL + idx] = s.lt[i * kLS + cc];
+                }
+                for (int idx = tid; idx < N * kHD; idx += NT_) rec[L.oHP + idx] = s.hp[idx];
+            }
+            __syncthreads();                                    // everyone is done reading W1^T and the old head
+            pc.mark(26);    // s: dZ0 gemm, S update, stash
+            // W1 -= alpha * dZ1^T H0   (rows of W1^T owned by this warp: h in [16w, 16w+16))
+            {
+                float acc[1][8][4];
+#pragma unroll
+                for (int j = 0; j < 8; ++j)
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) acc[0][j][q] = 0.f;
+                warp_gemm_3xtf32<1, 8, true, false>(s.h0t + 16 * w, kS0, s.dz1t, kS1, RS, 1.f, acc);
+                warp_tile_foreach<1, 8>(acc, [&](int hh, int o, float& cv) {
+                    s.w1t[(16 * w + hh) * kS1 + o] -= alpha * cv;
+                });
+            }
+            for (int idx = tid; idx < N * kHD; idx += NT_) s.hp[idx] -= alpha * s.dhp[idx];
+            if (tid < kH1) s.b1s[tid] -= alpha * db1;
+            if (tid < kH0) s.b0s[tid] -= alpha * s.db0s[tid];
+            __syncthreads();
+            pc.mark(27);    // s: W1 update gemm
+        }
+
+        // ---- query scoring, 32 rows per tile
+        for (int r0 = 0; r0 < m; r0 += 32) {
+            const int tr = min(32, m - r0);
+            {
+                float v[16];
+#pragma unroll
+                for (int q = 0; q < 16; ++q) {
+                    const int i = half * 16 + q;
+                    v[q] = i < tr ? __ldg(&P.proj[s.rowsQ[r0 + i] * kH0 + col]) : 0.f;
+                }
+                float gv[2];
+#pragma unroll
+                for (int q = 0; q < 2; ++q) {                      // 32 x n Gram tile: <= 2 elements per thread
+                    const int idx = tid + q * NT_;
+                    const int i = idx / n, j = idx - i * n;
+                    gv[q] = (idx < 32 * n && i < tr) ? __ldg(&P.gram[(b * int64_t(n + m) + n + r0 + i) * n + j]) : 0.f;
+                }
+#pragma unroll
+                for (int q = 0; q < 16; ++q) s.h0t[(half * 16 + q) * kS0 + col] = v[q];
+#pragma unroll
+                for (int q = 0; q < 2; ++q) {
+                    const int idx = tid + q * NT_;
+                    const int i = idx / n, j = idx - i * n;
+                    if (idx < 32 * n) s.gQ[i * kSG + j] = gv[q];
+                }
+            }
+            __syncthreads();
+            pc.mark(28);    // q: loads
+            mma16_tile_h0<2>(P, s, task, s.gQ, steps > 0, n8, s.h0t, kS0, r0, tr, steps);
+            __syncthreads();
+            pc.mark(29);    // q: H0
+            mma16_tile_h1<2>(P, s, task, r0, tr, steps);
+            __syncthreads();
+            pc.mark(30);    // q: H1
+            m16_tile_logits(P, s, 32, tr);
+            __syncthreads();
+            pc.mark(31);    // q: logits
+            if (P.save) {                                       // query activations for the backward
+                for (int i = half; i < tr; i += 2) slot[L.qH0 + int64_t(r0 + i) * kH0 + col] = s.h0t[i * kS0 + col];
+                for (int idx = tid; idx < tr * kH1; idx += NT_) {
+                    const int i = idx / kH1, o = idx - i * kH1;
+                    slot[L.qH1 + int64_t(r0) * kH1 + idx] = s.h1t[i * kS1 + o];
+                }
+                for (int idx = tid; idx < tr * N; idx += NT_) {
+                    const int i = idx / N, cc = idx - i * N;
+                    slot[L.qLG + int64_t(r0) * N + idx] = s.lt[i * kLS + cc];
+                }
+            }
+            if (tid < tr) {
+                const float* l = &s.lt[tid * kLS];
+                float mx, sum;
+                row_softmax(l, N, mx, sum);
+                int best = 0;
+                for (int cc = 1; cc < N; ++cc) if (l[cc] > l[best]) best = cc;   // first max (torch.max)
+                const int y = s.ysQ[r0 + tid];
+                s.rowv[tid] = (logf(sum) + mx) - l[y];
+                s.rowc[tid] = best == y ? 1.f : 0.f;
+                const int64_t q = b * m + r0 + tid;
+                P.preds[q] = best;
+                for (int cc = 0; cc < N; ++cc) P.logits[q * N + cc] = l[cc];
+            }
+            __syncthreads();
+            if (tid == 0) {
+                float a = task_sum[0], k = task_sum[1];
+                for (int i = 0; i < tr; ++i) { a += s.rowv[i]; k += s.rowc[i]; }
+                task_sum[0] = a; task_sum[1] = k;
+            }
+            pc.mark(32);    // q: stash, softmax, loss
+        }
+        __syncthreads();
+        if (tid == 0) {
+            P.task_loss[b] = task_sum[0] / float(m);
+            P.task_acc[b] = task_sum[1] / float(m);
+        }
+        if (P.save) {                                               // adapted state
+            for (int idx = tid; idx < kH0 * kH1; idx += NT_) {
+                const int k = idx / kH1, o = idx - k * kH1;
+                slot[L.w1t + idx] = s.w1t[k * kS1 + o];
+            }
+            if (tid < kH0) slot[L.b0 + tid] = s.b0s[tid];
+            if (tid < kH1) slot[L.b1 + tid] = s.b1s[tid];
+            for (int idx = tid; idx < N * kHD; idx += NT_) slot[L.head + idx] = s.hp[idx];
+            float* Sout = slot + ((steps & 1) ? L.S1 : L.S0);      // final S where the backward expects it
+            for (int i = half; i < n; i += 2) Sout[int64_t(i) * kH0 + col] = steps > 0 ? s.sS[i * kSS + col] : 0.f;
+        }
+        __syncthreads();
+        pc.mark(33);    // epilogue (adapted state out)
+    }
+}
+
 // ------------------------------------------------------------------------------------ backward (tensor core)
 // Reverse sweep for NK <= 32 on warp-level 3xTF32 tiles.  Same recursion as episode_bwd_kernel /
 // oracle/episode_np.py; differences: rows go through in tiles of 16 (MT = 1) because W1^T and its adjoint
@@ -1937,7 +2289,17 @@ extern "C" int fumi_episode_fwd(const fumi_episode_cfg* cfg, int64_t B, const fl
     const bool use_mma = nk <= 32 && cfg->num_query <= kMaxQueryRows;
     if (use_mma) {
         const size_t smem = smem_m_floats() * sizeof(float);
-        if (nk <= 16) {
+        static int warps = -1;
+        if (warps < 0) { const char* e = getenv("FUMI_FWD_WARPS"); warps = (e && atoi(e) == 8) ? 8 : 16; }
+        if (warps == 16) {
+            if (nk <= 16) {
+                FUMI_SET_SMEM_ATTR(episode_fwd_mma16_kernel<1>, smem);
+                FUMI_LAUNCH(episode_fwd_mma16_kernel<1>, grid, kThreads16, smem, stream, P);
+            } else {
+                FUMI_SET_SMEM_ATTR(episode_fwd_mma16_kernel<2>, smem);
+                FUMI_LAUNCH(episode_fwd_mma16_kernel<2>, grid, kThreads16, smem, stream, P);
+            }
+        } else if (nk <= 16) {
             FUMI_SET_SMEM_ATTR(episode_fwd_mma_kernel<1>, smem);
             FUMI_LAUNCH(episode_fwd_mma_kernel<1>, grid, kThreads, smem, stream, P);
         } else {

@@ -67,7 +67,9 @@ __device__ __forceinline__ void warp_gemm_3xtf32(const float* __restrict__ A, in
         const int kend = (K - k0) < 32 ? (K - k0) : 32;
 #pragma unroll
         for (int pass = 0; pass < (kOnePass ? 1 : 2); ++pass) {
-            for (int kk = 0; kk < kend; kk += 8) {
+#pragma unroll
+            for (int kk = 0; kk < 32; kk += 8) {               // fixed trip count: the loads of the next k step overlap the MMAs
+                if (kk >= kend) break;
                 const int k = k0 + kk;
                 uint32_t ahi[MT][4], alo[MT][4];
 #pragma unroll
