@@ -1870,6 +1870,488 @@ __global__ void __launch_bounds__(kThreads, 1) episode_bwd_mma_kernel(EpiParams 
     }
 }
 
+// ------------------------------------------------------------------------------------ backward, 16 warps
+// episode_bwd_mma_kernel on 512 threads (same shared-memory layout).  Warp w owns rows [16w, 16w+16) of the
+// W1^T-shaped adjoints, hidden units [16w, 16w+16) of the 256-wide ops, and in the 64-wide reductions over
+// the 256 hidden units the (n tile w%8, K half w/8) block; the two K halves meet in shared memory.
+template <int MT>
+__device__ __forceinline__ void slab16_colsum(float (&acc)[MT][2][4], float* dst, bool accumulate) {
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+#pragma unroll
+    for (int j = 0; j < 2; ++j)
+#pragma unroll
+        for (int q = 0; q < 2; ++q) {
+            float v = 0.f;
+#pragma unroll
+            for (int i = 0; i < MT; ++i) v += acc[i][j][q] + acc[i][j][q + 2];
+            v += __shfl_xor_sync(0xffffffffu, v, 4);
+            v += __shfl_xor_sync(0xffffffffu, v, 8);
+            v += __shfl_xor_sync(0xffffffffu, v, 16);
+            if ((lane >> 2) == 0) {
+                float* d = dst + 16 * w + 8 * j + 2 * (lane & 3) + q;
+                *d = accumulate ? *d + v : v;
+            }
+        }
+}
+
+__global__ void __launch_bounds__(kThreads16, 1) episode_bwd_mma16_kernel(EpiParams P) {
+    constexpr int NT_ = kThreads16;
+    FUMI_DYN_SMEM(float, smem_raw);
+    const SmemB s = carve_b(smem_raw);
+    const fumi_episode_cfg& c = P.cfg;
+    const int tid = threadIdx.x, w = tid >> 5, lane = tid & 31;
+    const int col = tid & 255, half = tid >> 8;
+    const int n = c.num_support, m = c.num_query, N = c.num_ways, steps = c.steps;
+    const float alpha = c.step_size;
+    const Layout L = make_layout(c);
+    const int o_ = tid & 63, kg_ = tid >> 6;          // 8 row groups x 64 outputs
+    const float sc = dropout_scale(c);
+    PhaseClock pc;
+    pc.start();
+
+    for (int idx = tid; idx < 32 * kSG; idx += NT_) s.gS[idx] = 0.f;
+    for (int idx = tid; idx < 16 * kSG; idx += NT_) s.gQ[idx] = 0.f;
+    __syncthreads();
+
+    for (int64_t b = blockIdx.x; b < P.B; b += gridDim.x) {
+        float* slot = P.stash + b * P.slot_floats;
+        float* aS = slot + L.S0;           // adjoint of S  [n][H0]
+        float* bZ = slot + L.S1;           // bar_Z0 rows of the current step [n][H0]
+        // ---- adapted state, zeroed adjoints
+        {
+            float v[16];
+#pragma unroll 1
+            for (int o0 = half * 32; o0 < half * 32 + 32; o0 += 16) {
+#pragma unroll
+                for (int q = 0; q < 16; ++q) v[q] = __ldg(&slot[L.w1t + col * kH1 + o0 + q]);
+#pragma unroll
+                for (int q = 0; q < 16; ++q) { s.w1t[col * kS1 + o0 + q] = v[q]; s.aw1t[col * kS1 + o0 + q] = 0.f; }
+            }
+        }
+        if (tid < kH0) s.ab0s[tid] = 0.f;
+        if (tid < kH1) { s.b1s[tid] = slot[L.b1 + tid]; s.ab1[tid] = 0.f; }
+        for (int idx = tid; idx < N * kHD; idx += NT_) { s.hp[idx] = slot[L.head + idx]; s.ahp[idx] = 0.f; }
+        for (int idx = tid; idx < n * n; idx += NT_) {
+            const int i = idx / n, j = idx - i * n;
+            s.gS[i * kSG + j] = __ldg(&P.gram[(b * int64_t(n + m) + i) * n + j]);
+        }
+        __syncthreads();
+        pc.mark(0);     // prologue
+
+        // ---- query pass (activations from the forward's stash)
+        const float qscale = P.loss_scale / float(m);
+        float aSq[2][2][4];                  // Gq^T dZ0q summed over the query tiles (this warp's 16 columns)
+#pragma unroll
+        for (int i = 0; i < 2; ++i)
+#pragma unroll
+            for (int j = 0; j < 2; ++j)
+#pragma unroll
+                for (int q = 0; q < 4; ++q) aSq[i][j][q] = 0.f;
+        for (int r0 = 0; r0 < m; r0 += 16) {
+            const int tr = min(16, m - r0);
+            {
+                float v[8];
+#pragma unroll
+                for (int q = 0; q < 8; ++q) {
+                    const int i = half * 8 + q;
+                    v[q] = i < tr ? __ldg(&slot[L.qH0 + int64_t(r0 + i) * kH0 + col]) : 0.f;
+                }
+                float u[2], g1;
+#pragma unroll
+                for (int q = 0; q < 2; ++q) {
+                    const int idx = tid + q * NT_;
+                    u[q] = idx < tr * kH1 ? __ldg(&slot[L.qH1 + int64_t(r0) * kH1 + idx]) : 0.f;
+                }
+                {
+                    const int i = tid / n, j = tid - i * n;
+                    g1 = (tid < 16 * n && i < tr) ? __ldg(&P.gram[(b * int64_t(n + m) + n + r0 + i) * n + j]) : 0.f;
+                }
+#pragma unroll
+                for (int q = 0; q < 8; ++q) s.h0t[(half * 8 + q) * kS0 + col] = v[q];
+#pragma unroll
+                for (int q = 0; q < 2; ++q) {
+                    const int idx = tid + q * NT_;
+                    s.h1t[(idx / kH1) * kS1 + (idx % kH1)] = u[q];
+                }
+                if (tid < 16 * n) s.gQ[(tid / n) * kSG + (tid % n)] = g1;
+            }
+            for (int idx = tid; idx < 16 * N; idx += NT_) {
+                const int i = idx / N, cc = idx - i * N;
+                s.rlt[i * kLS + cc] = i < tr ? __ldg(&slot[L.qLG + int64_t(r0) * N + idx]) : 0.f;
+            }
+            if (tid < 16) s.rows[tid] = tid < tr ? P.qry_rows[b * m + r0 + tid] : 0;
+            __syncthreads();
+            if (tid < 16) {
+                float* l = &s.lt[tid * kLS];
+                if (tid < tr) {
+                    for (int cc = 0; cc < N; ++cc) l[cc] = s.rlt[tid * kLS + cc];
+                    float mx, sum;
+                    row_softmax(l, N, mx, sum);
+                    const float inv = 1.f / sum;
+                    const int y = int(P.qry_y[b * m + r0 + tid]);
+                    for (int cc = 0; cc < N; ++cc) l[cc] = (expf(l[cc] - mx) * inv - (cc == y ? 1.f : 0.f)) * qscale;
+                } else {
+                    for (int cc = 0; cc < N; ++cc) l[cc] = 0.f;
+                }
+            }
+            __syncthreads();
+            pc.mark(1);     // q: loads + softmax
+            for (int idx = tid; idx < N * kHD; idx += NT_) {              // a_head += dLq^T [H1q | 1]
+                const int cc = idx / kHD, o = idx - cc * kHD;
+                float a = 0.f;
+                for (int i = 0; i < tr; ++i) a = fmaf(s.lt[i * kLS + cc], o < kH1 ? s.h1t[i * kS1 + o] : 1.f, a);
+                s.ahp[idx] += a;
+            }
+#pragma unroll
+            for (int ii = 0; ii < 2; ++ii) {                                   // dZ1q
+                const int i = kg_ + 8 * ii;
+                float dz = 0.f;
+                if (i < tr && s.h1t[i * kS1 + o_] > 0.f) {
+                    float dh = 0.f;
+                    for (int cc = 0; cc < N; ++cc) dh = fmaf(s.lt[i * kLS + cc], s.hp[cc * kHD + o_], dh);
+                    dz = dh * sc;
+                }
+                s.dz1t[i * kS1 + o_] = dz;
+            }
+            __syncthreads();
+            pc.mark(2);     // q: a_head, dZ1q
+            if (tid < kH1) {
+                float a = 0.f;
+                for (int i = 0; i < tr; ++i) a += s.dz1t[i * kS1 + tid];
+                s.ab1[tid] += a;
+            }
+            {   // a_W1 += dZ1q^T H0q   (rows h of W1^T owned by this warp)
+                float acc[1][8][4];
+#pragma unroll
+                for (int j = 0; j < 8; ++j)
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) acc[0][j][q] = 0.f;
+                warp_gemm_3xtf32<1, 8, true, false, 0>(s.h0t + 16 * w, kS0, s.dz1t, kS1, 16, 1.f, acc);
+                warp_tile_foreach<1, 8>(acc, [&](int hh, int o, float& cv) { s.aw1t[(16 * w + hh) * kS1 + o] += cv; });
+            }
+            {   // dZ0q = (dZ1q W1) * gate  -> tt, d_proj, a_b0
+                float acc[1][2][4];
+#pragma unroll
+                for (int j = 0; j < 2; ++j)
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) acc[0][j][q] = 0.f;
+                warp_gemm_3xtf32<1, 2, false, true>(s.dz1t, kS1, s.w1t + 16 * w * kS1, kS1, kH1, 1.f, acc);
+                warp_tile_foreach<1, 2>(acc, [&](int i, int hh, float& cv) {
+                    const int h = 16 * w + hh;
+                    cv = (i < tr && s.h0t[i * kS0 + h] > 0.f) ? cv * sc : 0.f;
+                    s.tt[i * kS0 + h] = cv;
+                });
+                const int g = lane >> 2, t = lane & 3;
+#pragma unroll
+                for (int j = 0; j < 2; ++j) {
+                    const int h = 16 * w + 8 * j + 2 * t;
+                    if (g < tr) atomic_add2(&P.d_proj[s.rows[g] * kH0 + h], acc[0][j][0], acc[0][j][1]);
+                    if (g + 8 < tr) atomic_add2(&P.d_proj[s.rows[g + 8] * kH0 + h], acc[0][j][2], acc[0][j][3]);
+                }
+                slab16_colsum<1>(acc, s.ab0s, true);
+            }
+            __syncthreads();
+            pc.mark(3);     // q: a_W1 gemm, dZ0q gemm, atomics
+            if (steps > 0)     // a_S -= alpha * Gq^T dZ0q  (kept in registers until the last query tile)
+                warp_gemm_3xtf32<2, 2, true, false>(s.gQ, kSG, s.tt + 16 * w, kS0, 16, 1.f, aSq);
+            __syncthreads();
+            pc.mark(4);     // q: a_S gemm
+        }
+        if (steps > 0) {
+            warp_tile_foreach<2, 2>(aSq, [&](int j, int hh, float& cv) {
+                if (j < n) aS[int64_t(j) * kH0 + 16 * w + hh] = -alpha * cv;          // a_S starts from zero
+            });
+        }
+        __syncthreads();
+
+        // ---- inner steps in reverse
+        if (!c.first_order) {
+            for (int st = steps - 1; st >= 0; --st) {
+                const float* rec = slot + L.steps + int64_t(st) * L.per_step;
+                for (int idx = tid; idx < N * kHD; idx += NT_) { s.hp[idx] = rec[L.oHP + idx]; s.rhp[idx] = 0.f; }
+                if (tid < kH1) s.rb1[tid] = 0.f;
+                if (tid < kH0) { s.rb0s[tid] = 0.f; s.gb0s[tid] = -alpha * s.ab0s[tid]; }
+                {   // all rows at once: (h0t|tt) is a [32][kS0] buffer and (dz1t|rzh) a [32][kS1] buffer
+                    float v[16];
+#pragma unroll
+                    for (int q = 0; q < 16; ++q) {
+                        const int i = half * 16 + q;
+                        v[q] = i < n ? __ldg(&rec[L.oH0 + int64_t(i) * kH0 + col]) : 0.f;
+                    }
+                    float u[4];
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) {
+                        const int idx = tid + q * NT_;
+                        u[q] = idx < n * kH1 ? __ldg(&rec[L.oDZ1 + idx]) : 0.f;
+                    }
+#pragma unroll
+                    for (int q = 0; q < 16; ++q) s.h0t[(half * 16 + q) * kS0 + col] = v[q];
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) {
+                        const int idx = tid + q * NT_;
+                        s.dz1t[(idx / kH1) * kS1 + (idx % kH1)] = u[q];
+                    }
+                }
+                __syncthreads();
+                {   // undo W1_{s+1} = W1_s - alpha dZ1^T H0
+                    float acc[1][8][4];
+#pragma unroll
+                    for (int j = 0; j < 8; ++j)
+#pragma unroll
+                        for (int q = 0; q < 4; ++q) acc[0][j][q] = 0.f;
+                    warp_gemm_3xtf32<1, 8, true, false, 0>(s.h0t + 16 * w, kS0, s.dz1t, kS1, 32, 1.f, acc);
+                    warp_tile_foreach<1, 8>(acc, [&](int hh, int o, float& cv) { s.w1t[(16 * w + hh) * kS1 + o] += alpha * cv; });
+                }
+                float rw[1][8][4];                       // this step's contribution to a_W1 (own rows), over both tiles
+#pragma unroll
+                for (int j = 0; j < 8; ++j)
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) rw[0][j][q] = 0.f;
+                __syncthreads();
+                pc.mark(5);     // s: loads + undo W1
+
+                for (int r0 = 0; r0 < n; r0 += 16) {
+                    const int tr = min(16, n - r0);
+                    {
+                        float v[8], a2[8];
+#pragma unroll
+                        for (int q = 0; q < 8; ++q) {
+                            const int i = half * 8 + q;
+                            v[q] = i < tr ? __ldg(&rec[L.oH0 + int64_t(r0 + i) * kH0 + col]) : 0.f;
+                            a2[q] = i < tr ? aS[int64_t(r0 + i) * kH0 + col] : 0.f;
+                        }
+                        float u[2], d[2];
+#pragma unroll
+                        for (int q = 0; q < 2; ++q) {
+                            const int idx = tid + q * NT_;
+                            u[q] = idx < tr * kH1 ? __ldg(&rec[L.oH1 + int64_t(r0) * kH1 + idx]) : 0.f;
+                            d[q] = idx < tr * kH1 ? __ldg(&rec[L.oDZ1 + int64_t(r0) * kH1 + idx]) : 0.f;
+                        }
+                        const float gb0 = s.gb0s[col];
+#pragma unroll
+                        for (int q = 0; q < 8; ++q) {
+                            const int i = half * 8 + q;
+                            s.h0t[i * kS0 + col] = v[q];
+                            s.tt[i * kS0 + col] = (i < tr && v[q] > 0.f) ? (a2[q] + gb0) * sc : 0.f;      // (12r) r_dH0
+                        }
+#pragma unroll
+                        for (int q = 0; q < 2; ++q) {
+                            const int idx = tid + q * NT_;
+                            s.h1t[(idx / kH1) * kS1 + (idx % kH1)] = u[q];
+                            s.dz1t[(idx / kH1) * kS1 + (idx % kH1)] = d[q];
+                        }
+                    }
+                    for (int idx = tid; idx < 16 * kLS; idx += NT_) {
+                        const int i = idx / kLS, cc = idx - i * kLS;
+                        s.lt[idx] = (i < tr && cc < N) ? rec[L.oDL + int64_t(r0 + i) * N + cc] : 0.f;
+                    }
+                    if (tid < 16) {
+                        s.rows[tid] = tid < tr ? P.sup_rows[b * n + r0 + tid] : 0;
+                        s.ys[tid] = tid < tr ? int(P.sup_y[b * n + r0 + tid]) : 0;
+                    }
+                    __syncthreads();
+                    pc.mark(6);     // s: tile loads
+                    // (11r)+(10r): r_dZ1 = r_dH0 W1^T + H0 (g_W1)^T over this warp's half of the 256 hidden units
+                    float rz[1][1][4] = {{{0.f, 0.f, 0.f, 0.f}}};
+                    {
+                        const int nt = w & 7, kh = w >> 3;
+                        warp_gemm_3xtf32<1, 1, false, false>(s.tt + 128 * kh, kS0, s.w1t + 128 * kh * kS1 + 8 * nt, kS1, 128,
+                                                             1.f, rz);
+                        warp_gemm_3xtf32<1, 1, false, false>(s.h0t + 128 * kh, kS0, s.aw1t + 128 * kh * kS1 + 8 * nt, kS1, 128,
+                                                             -alpha, rz);
+                        if (kh == 1)
+                            warp_tile_foreach<1, 1>(rz, [&](int i, int oo, float& cv) { s.rzh[i * kS1 + 8 * nt + oo] = cv; });
+                    }
+                    // r_W1 += dZ1^T r_dH0 ;  r_H0 = dZ1 g_W1 (kept in registers)
+                    warp_gemm_3xtf32<1, 8, true, false, 0>(s.tt + 16 * w, kS0, s.dz1t, kS1, 16, 1.f, rw);
+                    float rh0[1][2][4];
+#pragma unroll
+                    for (int j = 0; j < 2; ++j)
+#pragma unroll
+                        for (int q = 0; q < 4; ++q) rh0[0][j][q] = 0.f;
+                    warp_gemm_3xtf32<1, 2, false, true>(s.dz1t, kS1, s.aw1t + 16 * w * kS1, kS1, kH1, -alpha, rh0);
+                    __syncthreads();
+                    if ((w >> 3) == 0) {                   // (9r) r_dH1 = gate1 * (both K halves + g_b1)
+                        const int nt = w & 7;
+                        warp_tile_foreach<1, 1>(rz, [&](int i, int oo, float& cv) {
+                            const int o = 8 * nt + oo;
+                            s.rzh[i * kS1 + o] = (i < tr && s.h1t[i * kS1 + o] > 0.f)
+                                                     ? (cv + s.rzh[i * kS1 + o] - alpha * s.ab1[o]) * sc : 0.f;
+                        });
+                    }
+                    __syncthreads();
+                    pc.mark(7);     // s: r_dH1 gemms (K=256 x2), r_W1 gemm, r_H0 gemm
+                    // (8r)+(7r): r_dL = r_dH1 Wh^T + H1 (g_Wh)^T + g_bh ; r_head += dL^T r_dH1
+                    for (int idx = tid; idx < 16 * N; idx += NT_) {
+                        const int i = idx / N, cc = idx - i * N;
+                        float a = 0.f;
+                        if (i < tr) {
+                            float a0 = -alpha * s.ahp[cc * kHD + kH1], a1 = 0.f, a2 = 0.f, a3 = 0.f;
+#pragma unroll 4
+                            for (int o = 0; o < kH1; o += 2) {
+                                a0 = fmaf(s.rzh[i * kS1 + o], s.hp[cc * kHD + o], a0);
+                                a1 = fmaf(s.h1t[i * kS1 + o], -alpha * s.ahp[cc * kHD + o], a1);
+                                a2 = fmaf(s.rzh[i * kS1 + o + 1], s.hp[cc * kHD + o + 1], a2);
+                                a3 = fmaf(s.h1t[i * kS1 + o + 1], -alpha * s.ahp[cc * kHD + o + 1], a3);
+                            }
+                            a = (a0 + a1) + (a2 + a3);
+                        }
+                        s.rlt[i * kLS + cc] = a;
+                    }
+                    for (int idx = tid; idx < N * kH1; idx += NT_) {
+                        const int cc = idx / kH1, o = idx - cc * kH1;
+                        float a = 0.f;
+                        for (int i = 0; i < tr; ++i) a = fmaf(s.lt[i * kLS + cc], s.rzh[i * kS1 + o], a);
+                        s.rhp[cc * kHD + o] += a;
+                    }
+                    __syncthreads();
+                    pc.mark(8);     // s: r_dL, r_head (FMA)
+                    // (6r) r_L = P * (r_dL - <P, r_dL>) / n ; (7r) r_H1 = dL g_Wh  (overwrites rzh)
+                    if (tid < tr) {
+                        const int y = s.ys[tid];
+                        float dot = 0.f;
+                        for (int cc = 0; cc < N; ++cc) {
+                            const float p = s.lt[tid * kLS + cc] * float(n) + (cc == y ? 1.f : 0.f);
+                            dot = fmaf(p, s.rlt[tid * kLS + cc], dot);
+                        }
+                        for (int cc = 0; cc < N; ++cc) {
+                            const float p = s.lt[tid * kLS + cc] * float(n) + (cc == y ? 1.f : 0.f);
+                            s.rlt[tid * kLS + cc] = p * (s.rlt[tid * kLS + cc] - dot) / float(n);
+                        }
+                    }
+#pragma unroll
+                    for (int ii = 0; ii < 2; ++ii) {
+                        const int i = kg_ + 8 * ii;
+                        float a = 0.f;
+                        if (i < tr)
+                            for (int cc = 0; cc < N; ++cc) a = fmaf(s.lt[i * kLS + cc], -alpha * s.ahp[cc * kHD + o_], a);
+                        s.rzh[i * kS1 + o_] = a;
+                    }
+                    __syncthreads();
+                    pc.mark(9);     // s: softmax jacobian, r_H1
+                    // (5r) r_H1 += r_L Wh ; r_head += r_L^T [H1 | 1] ; (4r) r_Z1 = r_H1 * gate1
+#pragma unroll
+                    for (int ii = 0; ii < 2; ++ii) {
+                        const int i = kg_ + 8 * ii;
+                        float a = s.rzh[i * kS1 + o_];
+                        if (i < tr)
+                            for (int cc = 0; cc < N; ++cc) a = fmaf(s.rlt[i * kLS + cc], s.hp[cc * kHD + o_], a);
+                        s.rzh[i * kS1 + o_] = (i < tr && s.h1t[i * kS1 + o_] > 0.f) ? a * sc : 0.f;
+                    }
+                    for (int idx = tid; idx < N * kHD; idx += NT_) {
+                        const int cc = idx / kHD, o = idx - cc * kHD;
+                        float a = 0.f;
+                        for (int i = 0; i < tr; ++i) a = fmaf(s.rlt[i * kLS + cc], o < kH1 ? s.h1t[i * kS1 + o] : 1.f, a);
+                        s.rhp[idx] += a;
+                    }
+                    __syncthreads();
+                    pc.mark(10);    // s: r_Z1, r_head
+                    // (3r) r_H0 += r_Z1 W1 ; r_W1 += r_Z1^T H0 ; r_b1 += sum r_Z1
+                    if (tid < kH1) {
+                        float a = 0.f;
+                        for (int i = 0; i < tr; ++i) a += s.rzh[i * kS1 + tid];
+                        s.rb1[tid] += a;
+                    }
+                    warp_gemm_3xtf32<1, 2, false, true>(s.rzh, kS1, s.w1t + 16 * w * kS1, kS1, kH1, 1.f, rh0);
+                    warp_gemm_3xtf32<1, 8, true, false, 0>(s.h0t + 16 * w, kS0, s.rzh, kS1, 16, 1.f, rw);
+                    // (2r) bar_Z0 = r_H0 * gate0 ; (1r) a_A (d_proj), a_b0 ; bar_Z0 rows parked in the workspace
+                    {
+                        const int g = lane >> 2, t = lane & 3;
+#pragma unroll
+                        for (int j = 0; j < 2; ++j) {
+                            const int h = 16 * w + 8 * j + 2 * t;
+#pragma unroll
+                            for (int q = 0; q < 4; ++q) {
+                                const int i = g + (q >> 1) * 8;
+                                float& cv = rh0[0][j][q];
+                                cv = (i < tr && s.h0t[i * kS0 + h + (q & 1)] > 0.f) ? cv * sc : 0.f;
+                            }
+                            if (g < tr) {
+                                atomic_add2(&P.d_proj[s.rows[g] * kH0 + h], rh0[0][j][0], rh0[0][j][1]);
+                                *reinterpret_cast<float2*>(&bZ[int64_t(r0 + g) * kH0 + h]) = make_float2(rh0[0][j][0], rh0[0][j][1]);
+                            }
+                            if (g + 8 < tr) {
+                                atomic_add2(&P.d_proj[s.rows[g + 8] * kH0 + h], rh0[0][j][2], rh0[0][j][3]);
+                                *reinterpret_cast<float2*>(&bZ[int64_t(r0 + g + 8) * kH0 + h]) =
+                                    make_float2(rh0[0][j][2], rh0[0][j][3]);
+                            }
+                        }
+                        slab16_colsum<1>(rh0, s.rb0s, true);
+                    }
+                    __syncthreads();
+                    pc.mark(11);    // s: r_H0 gemm, r_W1 gemm, bar_Z0, atomics
+                }
+                // ---- end of reversed step: fold the contributions into the adjoints; a_S -= alpha G bar_Z0
+                warp_tile_foreach<1, 8>(rw, [&](int hh, int o, float& cv) { s.aw1t[(16 * w + hh) * kS1 + o] += cv; });
+                for (int idx = tid; idx < N * kHD; idx += NT_) s.ahp[idx] += s.rhp[idx];
+                if (tid < kH1) s.ab1[tid] += s.rb1[tid];
+                if (tid < kH0) s.ab0s[tid] += s.rb0s[tid];
+                {
+                    float v[16];
+#pragma unroll
+                    for (int q = 0; q < 16; ++q) {
+                        const int i = half * 16 + q;
+                        v[q] = i < n ? bZ[int64_t(i) * kH0 + col] : 0.f;
+                    }
+#pragma unroll
+                    for (int q = 0; q < 16; ++q) s.h0t[(half * 16 + q) * kS0 + col] = v[q];
+                }
+                __syncthreads();
+                pc.mark(12);    // s: fold adjoints, reload bar_Z0
+                {
+                    float acc[2][2][4];
+#pragma unroll
+                    for (int i = 0; i < 2; ++i)
+#pragma unroll
+                        for (int j = 0; j < 2; ++j)
+#pragma unroll
+                            for (int q = 0; q < 4; ++q) acc[i][j][q] = 0.f;
+                    warp_gemm_3xtf32<2, 2, false, false>(s.gS, kSG, s.h0t + 16 * w, kS0, 32, 1.f, acc);
+                    const int g = lane >> 2, t = lane & 3;
+                    float2 old[2][2][2];                             // batched read-modify-write of a_S
+#pragma unroll
+                    for (int i = 0; i < 2; ++i)
+#pragma unroll
+                        for (int j = 0; j < 2; ++j)
+#pragma unroll
+                            for (int q = 0; q < 2; ++q) {
+                                const int row = i * 16 + g + q * 8;
+                                old[i][j][q] = row < n ? *reinterpret_cast<const float2*>(
+                                                             &aS[int64_t(row) * kH0 + 16 * w + j * 8 + 2 * t])
+                                                       : make_float2(0.f, 0.f);
+                            }
+#pragma unroll
+                    for (int i = 0; i < 2; ++i)
+#pragma unroll
+                        for (int j = 0; j < 2; ++j)
+#pragma unroll
+                            for (int q = 0; q < 2; ++q) {
+                                const int row = i * 16 + g + q * 8;
+                                if (row < n)
+                                    *reinterpret_cast<float2*>(&aS[int64_t(row) * kH0 + 16 * w + j * 8 + 2 * t]) =
+                                        make_float2(old[i][j][q].x - alpha * acc[i][j][2 * q],
+                                                    old[i][j][q].y - alpha * acc[i][j][2 * q + 1]);
+                            }
+                }
+                __syncthreads();
+                pc.mark(13);    // s: a_S gemm
+            }
+        }
+
+        // ---- task epilogue: head gradient per task, shared-parameter gradients into this CTA's partials
+        for (int idx = tid; idx < N * kHD; idx += NT_) P.d_head[b * N * kHD + idx] = s.ahp[idx];
+        float* pw = P.d_w1_parts + int64_t(blockIdx.x) * kH0 * kH1;
+        for (int idx = tid; idx < kH0 * kH1; idx += NT_) {
+            const int o = idx / kH0, k = idx - o * kH0;                         // [H1][H0] like linear1.weight
+            pw[idx] += s.aw1t[k * kS1 + o];
+        }
+        if (tid < kH0) P.d_b0_parts[int64_t(blockIdx.x) * kH0 + tid] += s.ab0s[tid];
+        if (tid < kH1) P.d_b1_parts[int64_t(blockIdx.x) * kH1 + tid] += s.ab1[tid];
+        __syncthreads();
+        pc.mark(14);    // epilogue
+    }
+}
+
 // ------------------------------------------------------------------------------------ backward
 // Reverse sweep through the unrolled inner loop with hand-derived Hessian-vector products
 // (oracle/episode_np.py is the line-by-line CPU statement of the same recursion).
@@ -2341,8 +2823,15 @@ extern "C" int fumi_episode_bwd(const fumi_episode_cfg* cfg, int64_t B, const fl
     if (grid <= 0) return grid;
     if (cfg->num_support <= 32 && cfg->num_query <= kMaxQueryRows) {      // tensor-core path (pairs with fwd_mma)
         const size_t smem_b = smem_b_floats() * sizeof(float);
-        FUMI_SET_SMEM_ATTR(episode_bwd_mma_kernel, smem_b);
-        FUMI_LAUNCH(episode_bwd_mma_kernel, grid, kThreads, smem_b, stream, P);
+        static int warps = -1;
+        if (warps < 0) { const char* e = getenv("FUMI_BWD_WARPS"); warps = (e && atoi(e) == 8) ? 8 : 16; }
+        if (warps == 16) {
+            FUMI_SET_SMEM_ATTR(episode_bwd_mma16_kernel, smem_b);
+            FUMI_LAUNCH(episode_bwd_mma16_kernel, grid, kThreads16, smem_b, stream, P);
+        } else {
+            FUMI_SET_SMEM_ATTR(episode_bwd_mma_kernel, smem_b);
+            FUMI_LAUNCH(episode_bwd_mma_kernel, grid, kThreads, smem_b, stream, P);
+        }
         FUMI_CHECK_LAUNCH("episode_bwd_mma_kernel");
         return FUMI_OK;
     }

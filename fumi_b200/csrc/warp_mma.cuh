@@ -44,14 +44,14 @@ __device__ __forceinline__ void fumi_split(float x, uint32_t& hi, uint32_t& lo) 
 // Fragment ownership (PTX m16n8k8.tf32): g = lane/4, t = lane%4
 //   a0 (g, t)  a1 (g+8, t)  a2 (g, t+4)  a3 (g+8, t+4);  b0 (k=t, n=g)  b1 (k=t+4, n=g)
 //   c0 (g, 2t) c1 (g, 2t+1) c2 (g+8, 2t) c3 (g+8, 2t+1)
-template <int MT, int NT, bool ATRANS, bool BTRANS>
+template <int MT, int NT, bool ATRANS, bool BTRANS, int ONEPASS = -1>
 __device__ __forceinline__ void warp_gemm_3xtf32(const float* __restrict__ A, int lda, const float* __restrict__ B, int ldb,
                                                  int K, float bscale, float (&acc)[MT][NT][4]) {
     const int lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
     // Small tile counts: one pass over the fragments with two accumulators per tile (cross terms / hi*hi):
     // half the shared-memory reads and splits, and two independent MMA chains per tile.  Large tile counts
-    // (register budget): two passes over the 32-wide slice into one accumulator.
-    constexpr bool kOnePass = MT * NT <= 8;
+    // (register budget): two passes over the 32-wide slice into one accumulator.  ONEPASS = 0/1 forces a mode.
+    constexpr bool kOnePass = ONEPASS < 0 ? (MT * NT <= 8) : (ONEPASS != 0);
     for (int k0 = 0; k0 < K; k0 += 32) {
         float part[MT][NT][4];
         float cross[kOnePass ? MT : 1][kOnePass ? NT : 1][4];
