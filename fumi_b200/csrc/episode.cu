@@ -1947,40 +1947,47 @@ __global__ void __launch_bounds__(kThreads16, 1) episode_bwd_mma16_kernel(EpiPar
             for (int j = 0; j < 2; ++j)
 #pragma unroll
                 for (int q = 0; q < 4; ++q) aSq[i][j][q] = 0.f;
+        // software prefetch: the next tile's stash rows travel in registers while the current tile is processed
+        float pv[8], pu[2], pg = 0.f, pl = 0.f;
+        long long prow = 0;
+        int py = 0;
+        auto q_load = [&](int r0) {
+            const int tr = min(16, m - r0);
+#pragma unroll
+            for (int q = 0; q < 8; ++q) {
+                const int i = half * 8 + q;
+                pv[q] = i < tr ? __ldg(&slot[L.qH0 + int64_t(r0 + i) * kH0 + col]) : 0.f;
+            }
+#pragma unroll
+            for (int q = 0; q < 2; ++q) {
+                const int idx = tid + q * NT_;
+                pu[q] = idx < tr * kH1 ? __ldg(&slot[L.qH1 + int64_t(r0) * kH1 + idx]) : 0.f;
+            }
+            {
+                const int i = tid / n, j = tid - i * n;
+                pg = (tid < 16 * n && i < tr) ? __ldg(&P.gram[(b * int64_t(n + m) + n + r0 + i) * n + j]) : 0.f;
+            }
+            pl = tid < tr * N ? __ldg(&slot[L.qLG + int64_t(r0) * N + tid]) : 0.f;
+            if (tid < 16) {
+                prow = tid < tr ? P.qry_rows[b * m + r0 + tid] : 0;
+                py = tid < tr ? int(P.qry_y[b * m + r0 + tid]) : 0;
+            }
+        };
+        q_load(0);
         for (int r0 = 0; r0 < m; r0 += 16) {
             const int tr = min(16, m - r0);
-            {
-                float v[8];
 #pragma unroll
-                for (int q = 0; q < 8; ++q) {
-                    const int i = half * 8 + q;
-                    v[q] = i < tr ? __ldg(&slot[L.qH0 + int64_t(r0 + i) * kH0 + col]) : 0.f;
-                }
-                float u[2], g1;
+            for (int q = 0; q < 8; ++q) s.h0t[(half * 8 + q) * kS0 + col] = pv[q];
 #pragma unroll
-                for (int q = 0; q < 2; ++q) {
-                    const int idx = tid + q * NT_;
-                    u[q] = idx < tr * kH1 ? __ldg(&slot[L.qH1 + int64_t(r0) * kH1 + idx]) : 0.f;
-                }
-                {
-                    const int i = tid / n, j = tid - i * n;
-                    g1 = (tid < 16 * n && i < tr) ? __ldg(&P.gram[(b * int64_t(n + m) + n + r0 + i) * n + j]) : 0.f;
-                }
-#pragma unroll
-                for (int q = 0; q < 8; ++q) s.h0t[(half * 8 + q) * kS0 + col] = v[q];
-#pragma unroll
-                for (int q = 0; q < 2; ++q) {
-                    const int idx = tid + q * NT_;
-                    s.h1t[(idx / kH1) * kS1 + (idx % kH1)] = u[q];
-                }
-                if (tid < 16 * n) s.gQ[(tid / n) * kSG + (tid % n)] = g1;
+            for (int q = 0; q < 2; ++q) {
+                const int idx = tid + q * NT_;
+                s.h1t[(idx / kH1) * kS1 + (idx % kH1)] = pu[q];
             }
-            for (int idx = tid; idx < 16 * N; idx += NT_) {
-                const int i = idx / N, cc = idx - i * N;
-                s.rlt[i * kLS + cc] = i < tr ? __ldg(&slot[L.qLG + int64_t(r0) * N + idx]) : 0.f;
-            }
-            if (tid < 16) s.rows[tid] = tid < tr ? P.qry_rows[b * m + r0 + tid] : 0;
+            if (tid < 16 * n) s.gQ[(tid / n) * kSG + (tid % n)] = pg;
+            if (tid < 16 * N) s.rlt[(tid / N) * kLS + (tid % N)] = pl;
+            if (tid < 16) { s.rows[tid] = prow; s.ys[tid] = py; }
             __syncthreads();
+            if (r0 + 16 < m) q_load(r0 + 16);
             if (tid < 16) {
                 float* l = &s.lt[tid * kLS];
                 if (tid < tr) {
@@ -1988,7 +1995,7 @@ __global__ void __launch_bounds__(kThreads16, 1) episode_bwd_mma16_kernel(EpiPar
                     float mx, sum;
                     row_softmax(l, N, mx, sum);
                     const float inv = 1.f / sum;
-                    const int y = int(P.qry_y[b * m + r0 + tid]);
+                    const int y = s.ys[tid];
                     for (int cc = 0; cc < N; ++cc) l[cc] = (expf(l[cc] - mx) * inv - (cc == y ? 1.f : 0.f)) * qscale;
                 } else {
                     for (int cc = 0; cc < N; ++cc) l[cc] = 0.f;
@@ -2092,7 +2099,35 @@ __global__ void __launch_bounds__(kThreads16, 1) episode_bwd_mma16_kernel(EpiPar
                         s.dz1t[(idx / kH1) * kS1 + (idx % kH1)] = u[q];
                     }
                 }
+                // software prefetch of the row tiles of this step (registers), first tile issued before the undo GEMM
+                float tv[8], ta[8], tu[2], td[2], tl = 0.f;
+                long long trow = 0;
+                int ty = 0;
+                auto t_load = [&](int r0) {
+                    const int tr = min(16, n - r0);
+#pragma unroll
+                    for (int q = 0; q < 8; ++q) {
+                        const int i = half * 8 + q;
+                        tv[q] = i < tr ? __ldg(&rec[L.oH0 + int64_t(r0 + i) * kH0 + col]) : 0.f;
+                        ta[q] = i < tr ? aS[int64_t(r0 + i) * kH0 + col] : 0.f;
+                    }
+#pragma unroll
+                    for (int q = 0; q < 2; ++q) {
+                        const int idx = tid + q * NT_;
+                        tu[q] = idx < tr * kH1 ? __ldg(&rec[L.oH1 + int64_t(r0) * kH1 + idx]) : 0.f;
+                        td[q] = idx < tr * kH1 ? __ldg(&rec[L.oDZ1 + int64_t(r0) * kH1 + idx]) : 0.f;
+                    }
+                    {
+                        const int i = tid / kLS, cc = tid - i * kLS;
+                        tl = (i < tr && cc < N) ? __ldg(&rec[L.oDL + int64_t(r0 + i) * N + cc]) : 0.f;
+                    }
+                    if (tid < 16) {
+                        trow = tid < tr ? P.sup_rows[b * n + r0 + tid] : 0;
+                        ty = tid < tr ? int(P.sup_y[b * n + r0 + tid]) : 0;
+                    }
+                };
                 __syncthreads();
+                t_load(0);
                 {   // undo W1_{s+1} = W1_s - alpha dZ1^T H0
                     float acc[1][8][4];
 #pragma unroll
@@ -2113,43 +2148,24 @@ __global__ void __launch_bounds__(kThreads16, 1) episode_bwd_mma16_kernel(EpiPar
                 for (int r0 = 0; r0 < n; r0 += 16) {
                     const int tr = min(16, n - r0);
                     {
-                        float v[8], a2[8];
-#pragma unroll
-                        for (int q = 0; q < 8; ++q) {
-                            const int i = half * 8 + q;
-                            v[q] = i < tr ? __ldg(&rec[L.oH0 + int64_t(r0 + i) * kH0 + col]) : 0.f;
-                            a2[q] = i < tr ? aS[int64_t(r0 + i) * kH0 + col] : 0.f;
-                        }
-                        float u[2], d[2];
-#pragma unroll
-                        for (int q = 0; q < 2; ++q) {
-                            const int idx = tid + q * NT_;
-                            u[q] = idx < tr * kH1 ? __ldg(&rec[L.oH1 + int64_t(r0) * kH1 + idx]) : 0.f;
-                            d[q] = idx < tr * kH1 ? __ldg(&rec[L.oDZ1 + int64_t(r0) * kH1 + idx]) : 0.f;
-                        }
                         const float gb0 = s.gb0s[col];
 #pragma unroll
                         for (int q = 0; q < 8; ++q) {
                             const int i = half * 8 + q;
-                            s.h0t[i * kS0 + col] = v[q];
-                            s.tt[i * kS0 + col] = (i < tr && v[q] > 0.f) ? (a2[q] + gb0) * sc : 0.f;      // (12r) r_dH0
+                            s.h0t[i * kS0 + col] = tv[q];
+                            s.tt[i * kS0 + col] = (i < tr && tv[q] > 0.f) ? (ta[q] + gb0) * sc : 0.f;      // (12r) r_dH0
                         }
 #pragma unroll
                         for (int q = 0; q < 2; ++q) {
                             const int idx = tid + q * NT_;
-                            s.h1t[(idx / kH1) * kS1 + (idx % kH1)] = u[q];
-                            s.dz1t[(idx / kH1) * kS1 + (idx % kH1)] = d[q];
+                            s.h1t[(idx / kH1) * kS1 + (idx % kH1)] = tu[q];
+                            s.dz1t[(idx / kH1) * kS1 + (idx % kH1)] = td[q];
                         }
-                    }
-                    for (int idx = tid; idx < 16 * kLS; idx += NT_) {
-                        const int i = idx / kLS, cc = idx - i * kLS;
-                        s.lt[idx] = (i < tr && cc < N) ? rec[L.oDL + int64_t(r0 + i) * N + cc] : 0.f;
-                    }
-                    if (tid < 16) {
-                        s.rows[tid] = tid < tr ? P.sup_rows[b * n + r0 + tid] : 0;
-                        s.ys[tid] = tid < tr ? int(P.sup_y[b * n + r0 + tid]) : 0;
+                        s.lt[tid] = tl;                                  // 16 x kLS == 512 == one element per thread
+                        if (tid < 16) { s.rows[tid] = trow; s.ys[tid] = ty; }
                     }
                     __syncthreads();
+                    if (r0 + 16 < n) t_load(r0 + 16);
                     pc.mark(6);     // s: tile loads
                     // (11r)+(10r): r_dZ1 = r_dH0 W1^T + H0 (g_W1)^T over this warp's half of the 256 hidden units
                     float rz[1][1][4] = {{{0.f, 0.f, 0.f, 0.f}}};
