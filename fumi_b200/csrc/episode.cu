@@ -1254,32 +1254,35 @@ __global__ void __launch_bounds__(kThreads16, 1) episode_fwd_mma16_kernel(EpiPar
         }
 
         // ---- query scoring, 32 rows per tile
+        // software prefetch: the next query tile's projected rows / Gram rows travel in registers
+        float qv[16], qg[2];
+        auto q_load = [&](int r0) {
+            const int tr = min(32, m - r0);
+#pragma unroll
+            for (int q = 0; q < 16; ++q) {
+                const int i = half * 16 + q;
+                qv[q] = i < tr ? __ldg(&P.proj[s.rowsQ[r0 + i] * kH0 + col]) : 0.f;
+            }
+#pragma unroll
+            for (int q = 0; q < 2; ++q) {                      // 32 x n Gram tile: <= 2 elements per thread
+                const int idx = tid + q * NT_;
+                const int i = idx / n, j = idx - i * n;
+                qg[q] = (idx < 32 * n && i < tr) ? __ldg(&P.gram[(b * int64_t(n + m) + n + r0 + i) * n + j]) : 0.f;
+            }
+        };
+        q_load(0);
         for (int r0 = 0; r0 < m; r0 += 32) {
             const int tr = min(32, m - r0);
-            {
-                float v[16];
 #pragma unroll
-                for (int q = 0; q < 16; ++q) {
-                    const int i = half * 16 + q;
-                    v[q] = i < tr ? __ldg(&P.proj[s.rowsQ[r0 + i] * kH0 + col]) : 0.f;
-                }
-                float gv[2];
+            for (int q = 0; q < 16; ++q) s.h0t[(half * 16 + q) * kS0 + col] = qv[q];
 #pragma unroll
-                for (int q = 0; q < 2; ++q) {                      // 32 x n Gram tile: <= 2 elements per thread
-                    const int idx = tid + q * NT_;
-                    const int i = idx / n, j = idx - i * n;
-                    gv[q] = (idx < 32 * n && i < tr) ? __ldg(&P.gram[(b * int64_t(n + m) + n + r0 + i) * n + j]) : 0.f;
-                }
-#pragma unroll
-                for (int q = 0; q < 16; ++q) s.h0t[(half * 16 + q) * kS0 + col] = v[q];
-#pragma unroll
-                for (int q = 0; q < 2; ++q) {
-                    const int idx = tid + q * NT_;
-                    const int i = idx / n, j = idx - i * n;
-                    if (idx < 32 * n) s.gQ[i * kSG + j] = gv[q];
-                }
+            for (int q = 0; q < 2; ++q) {
+                const int idx = tid + q * NT_;
+                const int i = idx / n, j = idx - i * n;
+                if (idx < 32 * n) s.gQ[i * kSG + j] = qg[q];
             }
             __syncthreads();
+            if (r0 + 32 < m) q_load(r0 + 32);
             pc.mark(28);    // q: loads
             mma16_tile_h0<2>(P, s, task, s.gQ, steps > 0, n8, s.h0t, kS0, r0, tr, steps);
             __syncthreads();
