@@ -176,6 +176,8 @@ def main():
     ap.add_argument("--cpu_budget_s", type=float, default=15.0)
     ap.add_argument("--no_cpu_baseline", action="store_true")
     ap.add_argument("--no_kernel_pass", action="store_true")
+    ap.add_argument("--host_sampler", action="store_true",
+                    help="e2e leg with the all-host native sampler instead of plan (host) + expand (device)")
     a = ap.parse_args()
     rank = int(os.environ.get("RANK", 0))
     world = int(os.environ.get("WORLD_SIZE", 1))
@@ -225,7 +227,8 @@ def main():
     sampler = EpisodeSampler(bank.cat_of, cats, N, K, Q, num_threads=max(2, (os.cpu_count() or 8) // max(1, world)))
     fb = FeatureBank(feats=torch.from_numpy(bank.feats[sampler.ids]).to(device),
                      text=torch.from_numpy(bank.text[cats]).to(device), ids=sampler.ids, categories=cats)
-    loader = EpisodeLoader(fb, sampler, a.tasks)
+    dev_sampler = not a.host_sampler
+    loader = EpisodeLoader(fb, sampler, a.tasks, device_sampler=dev_sampler)
     t_setup = time.time() - t0
     seed = 123 + rank                                   # ranks draw independent task streams (weak scaling)
     torch.manual_seed(123); np.random.seed(123); random.seed(123)
@@ -277,12 +280,25 @@ def main():
         dist.all_reduce(ms, op=dist.ReduceOp.MAX)
     ms_value = float(ms.item())
 
-    # ---- leg 2: end to end through the public API, host buffers (e2e): the native sampler runs on the host
-    # (prefetch thread, 2 batches ahead), indices travel pinned-host -> device, loss/acc come back each step
+    # ---- leg 2: end to end through the public API, host buffers (e2e).  Every step: the sampler's sequential
+    # generator streams advance on the host (prefetch thread, 2 batches ahead) into a pinned plan, the plan
+    # travels host -> device, fumi_sampler_expand builds the index arrays in HBM, evaluate() runs the step and
+    # loss/acc come back.  (--host_sampler: the all-host sampler + pinned index arrays instead.)
     t_s = time.perf_counter()
-    loader.next_batch()
-    sampler_ms = (time.perf_counter() - t_s) * 1e3
-    e2e_loader = EpisodeLoader(fb, sampler, a.tasks, prefetch=2)
+    if dev_sampler:
+        plan = sampler.plan(a.tasks, pin_memory=True)
+        sampler_ms = (time.perf_counter() - t_s) * 1e3
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        sampler.expand(plan, device)
+        ev0.record()
+        sampler.expand(plan, device)
+        ev1.record()
+        torch.cuda.synchronize()
+        expand_ms = ev0.elapsed_time(ev1)
+    else:
+        loader.next_batch()
+        sampler_ms, expand_ms = (time.perf_counter() - t_s) * 1e3, None
+    e2e_loader = EpisodeLoader(fb, sampler, a.tasks, prefetch=2, device_sampler=dev_sampler)
     e2e_it = iter(e2e_loader)
     for i in range(2):
         run_api(next(e2e_it))
@@ -292,7 +308,10 @@ def main():
     for i in range(a.steps):
         b = next(e2e_it)
         if i == 0:
-            h2d = sum(t.numel() * 8 for t in (b.sup_rows, b.qry_rows, b.sup_y, b.qry_y, b.head_class))
+            if dev_sampler:      # the plan: classes, label_perm, head_class (i64), perm_seed (u32), picks (i32)
+                h2d = a.tasks * N * (3 * 8 + 4 + 4 * (K + Q))
+            else:
+                h2d = sum(t.numel() * 8 for t in (b.sup_rows, b.qry_rows, b.sup_y, b.qry_y, b.head_class))
             d2h = 8                                                     # loss + acc (fumi.py:195-196)
         run_api(b)
     e1.record()
@@ -350,8 +369,12 @@ def main():
                 "e2e": {"value": total_tasks / (ms_e2e * 1e-3), "unit": unit, "h2d_bytes_per_step": h2d,
                         "d2h_bytes_per_step": d2h, "ms_per_step": ms_e2e / a.steps,
                         "host_sampler_ms_per_batch": round(sampler_ms, 2), "host_cores": os.cpu_count(),
-                        "path": "EpisodeLoader(prefetch=2): native sampler thread -> pinned index buffers -> H2D -> "
-                                "evaluate() -> loss/acc D2H, every step"},
+                        "device_sampler_ms_per_batch": expand_ms,
+                        "path": ("EpisodeLoader(prefetch=2): fumi_sampler_plan thread -> pinned plan -> H2D -> "
+                                 "fumi_sampler_expand (index arrays built in HBM) -> evaluate() -> loss/acc D2H, "
+                                 "every step") if dev_sampler else
+                                ("EpisodeLoader(prefetch=2): native sampler thread -> pinned index buffers -> H2D -> "
+                                 "evaluate() -> loss/acc D2H, every step")},
                 "gpu_launches": launches, "roofline": roof, "cpu_baseline": cpu, "kernels": kernels}
         print(json.dumps(line))
     if world > 1:

@@ -276,3 +276,56 @@ extern "C" int fumi_sampler_next(fumi_sampler* s, int64_t B, uint32_t* py_state,
     }
     return FUMI_OK;
 }
+
+// Sequential streams only; the per (task, class) permutations run on the device (sampler_expand.cu).
+extern "C" int fumi_sampler_plan(fumi_sampler* s, int64_t B, uint32_t* py_state, uint32_t* torch_state,
+                                 int64_t* classes, int64_t* label_perm, int64_t* head_class,
+                                 uint32_t* perm_seed, int32_t* picks) {
+    if (!s || B <= 0 || !py_state || !torch_state || !classes || !label_perm || !head_class || !perm_seed || !picks) {
+        fumi_set_error("fumi_sampler_plan: null/empty argument");
+        return FUMI_ERR_ARG;
+    }
+    const int N = s->N, K = s->K, Q = s->Q;
+    MT19937 py;                                        // stream 1: all B class tuples first
+    std::memcpy(py.key, py_state, sizeof(py.key));
+    py.pos = int(py_state[624]);
+    for (int64_t b = 0; b < B; ++b) py_sample_range(py, s->C, N, classes + b * N);
+    std::memcpy(py_state, py.key, sizeof(py.key));
+    py_state[624] = uint32_t(py.pos);
+    for (int64_t i = 0; i < B * N; ++i) {
+        const int64_t c = classes[i];
+        const int64_t n_c = s->offsets[c + 1] - s->offsets[c];
+        if (n_c < K + Q) {
+            fumi_set_error("The number of samples for one class (" + std::to_string(n_c) +
+                           ") is smaller than the minimum number of samples per class required (" +
+                           std::to_string(K + Q) + ").");
+            return FUMI_ERR_DATA;
+        }
+    }
+    std::vector<int64_t> slot(size_t(std::max(K, Q)));
+    for (int64_t b = 0; b < B; ++b) {
+        const int64_t h = fumi_py_tuple_hash(classes + b * N, N);
+        for (int p = 0; p < N; ++p) {
+            perm_seed[b * N + p] = uint32_t(uint64_t(h) + uint64_t(classes[b * N + p]));
+            int32_t* pk = picks + (b * N + p) * (K + Q);
+            // stream 2b: the shared RandomState(0) shuffles move positions, whatever they hold
+            for (int k = 0; k < K; ++k) slot[k] = k;
+            np_shuffle(s->shared, slot.data(), K);
+            for (int k = 0; k < K; ++k) pk[k] = int32_t(slot[k]);
+            for (int q = 0; q < Q; ++q) slot[q] = K + q;
+            np_shuffle(s->shared, slot.data(), Q);
+            for (int q = 0; q < Q; ++q) pk[K + q] = int32_t(slot[q]);
+        }
+    }
+    TorchMT tg{torch_state};                           // stream 3: torch.randperm(N) per task
+    for (int64_t b = 0; b < B; ++b) {
+        int64_t* lp = label_perm + b * N;
+        for (int i = 0; i < N; ++i) lp[i] = i;
+        for (int i = 0; i < N - 1; ++i) {
+            uint32_t z = tg.next() % uint32_t(N - i);
+            std::swap(lp[i], lp[i + z]);
+        }
+        for (int p = 0; p < N; ++p) head_class[b * N + lp[p]] = classes[b * N + p];
+    }
+    return FUMI_OK;
+}

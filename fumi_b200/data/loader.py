@@ -28,10 +28,14 @@ class EpisodeLoader:
     `random` / torch generator states are set to what they were right after that batch was drawn, so the
     host program observes the same generator sequence as with the synchronous loader."""
 
-    def __init__(self, bank, sampler, batch_size, pin_memory=True, prefetch=0):
+    def __init__(self, bank, sampler, batch_size, pin_memory=True, prefetch=0, device_sampler=None):
         self.bank, self.sampler, self.batch_size = bank, sampler, int(batch_size)
         self.pin = bool(pin_memory) and bank.feats.is_cuda
         self.prefetch = int(prefetch)
+        # device_sampler: the host only advances the sequential generator streams (fumi_sampler_plan); the
+        # per (task, class) permutations and the index arrays are produced in HBM (fumi_sampler_expand).
+        # Default on a CUDA bank; off = the all-host sampler (fumi_sampler_next) + pinned index buffers.
+        self.device_sampler = bank.feats.is_cuda if device_sampler is None else bool(device_sampler)
         self.dataset = sampler          # len(loader.dataset) parity is not meaningful for episodes
         self._stop = None
 
@@ -42,7 +46,16 @@ class EpisodeLoader:
         ts = {k: torch.empty((B, w), dtype=torch.int64, pin_memory=self.pin) for k, w in widths.items()}
         return ts, {k: t.numpy() for k, t in ts.items()}
 
+    def _expand(self, plan):
+        d = self.sampler.expand(plan, self.bank.feats.device)
+        host = {k: plan[k].numpy() for k in ("classes", "label_perm", "head_class")}
+        return EpisodeBatch(bank=self.bank, sup_rows=d["sup_rows"], qry_rows=d["qry_rows"], sup_y=d["sup_y"],
+                            qry_y=d["qry_y"], sup_ids=d["sup_ids"], qry_ids=d["qry_ids"],
+                            head_class=d["head_class"], host=host)
+
     def next_batch(self):
+        if self.device_sampler:
+            return self._expand(self.sampler.plan(self.batch_size, pin_memory=self.pin))
         ts, arrs = self._host_buffers()
         self.sampler.next_batch(self.batch_size, out=arrs)
         return EpisodeBatch(bank=self.bank, sup_rows=ts["sup_rows"], qry_rows=ts["qry_rows"], sup_y=ts["sup_y"],
@@ -75,9 +88,14 @@ class EpisodeLoader:
         def worker():
             try:
                 while not stop.is_set():
-                    ts, arrs = self._host_buffers()
-                    self.sampler.next_batch_states(self.batch_size, py, st, arrs)
-                    item = (ts, arrs, py.copy(), st.copy())
+                    if self.device_sampler:
+                        plan = self.sampler.empty_plan(self.batch_size, pin_memory=self.pin)
+                        self.sampler.plan_states(self.batch_size, py, st, plan)
+                        item = (plan, None, py.copy(), st.copy())
+                    else:
+                        ts, arrs = self._host_buffers()
+                        self.sampler.next_batch_states(self.batch_size, py, st, arrs)
+                        item = (ts, arrs, py.copy(), st.copy())
                     while not stop.is_set():
                         try:
                             q.put(item, timeout=0.1)
@@ -96,7 +114,7 @@ class EpisodeLoader:
                 ts, arrs, py_after, st_after = item
                 random.setstate((ver, tuple(int(x) for x in py_after), gauss))
                 _torch_state_set(st_after, raw)
-                yield self._make(ts, arrs)
+                yield self._expand(ts) if arrs is None else self._make(ts, arrs)
         finally:
             stop.set()
 

@@ -99,6 +99,70 @@ class EpisodeSampler:
             raise
         return out
 
+    # ---- device-resident form: sequential streams on the host, permutations on the GPU ----
+    def empty_plan(self, batch_size, pin_memory=False):
+        """Host staging tensors of one plan (fumi_sampler_plan outputs)."""
+        B, N, KQ = int(batch_size), self.N, self.K + self.Q
+        mk = lambda shape, dt: torch.empty(shape, dtype=dt, pin_memory=pin_memory)
+        return {"classes": mk((B, N), torch.int64), "label_perm": mk((B, N), torch.int64),
+                "head_class": mk((B, N), torch.int64), "perm_seed": mk((B, N), torch.int32),   # uint32 bits
+                "picks": mk((B, N, KQ), torch.int32)}
+
+    def plan_states(self, batch_size, py_state, torch_state, plan):
+        """Sequential generator streams of one meta-batch on explicit states (thread-safe like
+        next_batch_states); the hash-seeded permutations are left to expand()."""
+        try:
+            _lib.check(_lib.lib().fumi_sampler_plan(
+                self._h, int(batch_size), _lib.ptr(py_state), _lib.ptr(torch_state),
+                *[_lib.ptr(plan[k]) for k in ("classes", "label_perm", "head_class", "perm_seed", "picks")]),
+                "fumi_sampler_plan")
+        except _lib.FumiError as e:
+            if "smaller than the minimum" in str(e):
+                raise ValueError(str(e).split(": ", 2)[-1]) from None
+            raise
+        return plan
+
+    def plan(self, batch_size, plan=None, pin_memory=False):
+        if plan is None:
+            plan = self.empty_plan(batch_size, pin_memory)
+        ver, key, gauss = random.getstate()
+        py = np.asarray(key, np.uint32)
+        st, raw = _torch_state_get()
+        self.plan_states(batch_size, py, st, plan)
+        random.setstate((ver, tuple(int(x) for x in py), gauss))
+        _torch_state_set(st, raw)
+        return plan
+
+    def device_tables(self, device):
+        device = torch.device(device)
+        tabs = getattr(self, "_dev_tables", None)
+        if tabs is None or tabs[0].device != device:
+            tabs = (torch.from_numpy(self.offsets).to(device), torch.from_numpy(self.ids).to(device))
+            self._dev_tables = tabs
+        return tabs
+
+    def expand(self, plan, device):
+        """Upload a plan and run the per (task, class) permutations on `device` (current stream).
+        Returns dict(sup_ids, qry_ids, sup_y, qry_y, sup_rows, qry_rows, head_class, classes, label_perm)
+        of device tensors -- bit-identical to next_batch()."""
+        device = torch.device(device)
+        if device.type != "cuda" and not _lib.is_emulation():
+            raise RuntimeError("EpisodeSampler.expand needs a CUDA device (no CPU fallback; use next_batch for "
+                               "host-resident indices)")
+        offsets, ids = self.device_tables(device)
+        d = {k: v.to(device, non_blocking=True) for k, v in plan.items()}
+        B, N, K, Q = d["classes"].shape[0], self.N, self.K, self.Q
+        out = {k: torch.empty((B, N * w), dtype=torch.int64, device=device)
+               for k, w in (("sup_ids", K), ("qry_ids", Q), ("sup_y", K), ("qry_y", Q), ("sup_rows", K), ("qry_rows", Q))}
+        stream = _lib.stream_ptr(device) if device.type == "cuda" else None
+        _lib.check(_lib.lib().fumi_sampler_expand(
+            _lib.ptr(offsets), _lib.ptr(ids), int(np.diff(self.offsets).max()), _lib.ptr(d["classes"]),
+            _lib.ptr(d["label_perm"]), _lib.ptr(d["perm_seed"]), _lib.ptr(d["picks"]), B, N, K, Q,
+            *[_lib.ptr(out[k]) for k in ("sup_ids", "qry_ids", "sup_y", "qry_y", "sup_rows", "qry_rows")], stream),
+            "fumi_sampler_expand")
+        out.update(head_class=d["head_class"], classes=d["classes"], label_perm=d["label_perm"])
+        return out
+
     def next_batch(self, batch_size, out=None):
         if out is None:
             out = self.empty_out(batch_size)

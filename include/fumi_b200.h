@@ -223,7 +223,7 @@ int fumi_am3_score(const float* emb, const float* text_proto, const float* lamda
  *   the split's own RandomState(0) stream lives inside the handle.
  * Both external states are read and written back, so the host program's other consumers
  * (model init, torch.randperm elsewhere) stay in sequence.
- * All sampler pointers are HOST pointers.
+ * All pointers of fumi_sampler_create / _new_iterator / _next / _plan are HOST pointers.
  * ---------------------------------------------------------------------------------------- */
 typedef struct fumi_sampler fumi_sampler;
 /* class_offsets[C+1], class_image_ids[class_offsets[C]]: ascending image ids of split-class c. */
@@ -241,6 +241,29 @@ int fumi_sampler_next(fumi_sampler* s, int64_t B, uint32_t* py_state, uint32_t* 
                       int64_t* classes, int64_t* label_perm, int64_t* sup_ids, int64_t* qry_ids,
                       int64_t* sup_y, int64_t* qry_y, int64_t* head_class,
                       int64_t* sup_rows, int64_t* qry_rows, int32_t num_threads);
+/* Device-resident form of the same meta-batch, in two calls.
+ * fumi_sampler_plan (HOST, sequential, cheap): advances the three sequential streams exactly as
+ * fumi_sampler_next does -- class tuples from `random`, the split's RandomState(0) support / query
+ * shuffles, torch.randperm(N) labels -- and leaves the independent hash-seeded per (task, class)
+ * permutations (the bulk of the work: one MT19937 seeding + full Fisher-Yates over the class's
+ * images each; torchmeta ClassSplitter_.__getitem__, RandomState((hash(tuple) + c + 0) % 2**32))
+ * to the device.  Outputs (HOST): classes / label_perm / head_class as above, perm_seed[B,N] the
+ * RandomState seed of tuple position p, picks[B,N,K+Q] the position in that permutation's first
+ * K+Q entries taken by support slot k (picks[..,k]) and query slot q (picks[..,K+q]).
+ * fumi_sampler_expand (DEVICE pointers, one kernel, one warp per (task, class)): seeds the
+ * generator, runs numpy's backward Fisher-Yates over the class in shared memory and writes
+ * sup_ids / qry_ids / sup_y / qry_y / sup_rows / qry_rows straight into HBM, so the index arrays the
+ * episode kernels gather by never exist on the host.  class_offsets[C+1] / class_image_ids are the
+ * device copies of the fumi_sampler_create tables; max_class_size = max_c n_c (sizes the shared
+ * memory).  Bit-identical to fumi_sampler_next. */
+int fumi_sampler_plan(fumi_sampler* s, int64_t B, uint32_t* py_state, uint32_t* torch_state,
+                      int64_t* classes, int64_t* label_perm, int64_t* head_class,
+                      uint32_t* perm_seed, int32_t* picks);
+int fumi_sampler_expand(const int64_t* class_offsets, const int64_t* class_image_ids, int64_t max_class_size,
+                        const int64_t* classes, const int64_t* label_perm, const uint32_t* perm_seed,
+                        const int32_t* picks, int64_t B, int32_t N, int32_t K, int32_t Q,
+                        int64_t* sup_ids, int64_t* qry_ids, int64_t* sup_y, int64_t* qry_y,
+                        int64_t* sup_rows, int64_t* qry_rows, void* stream);
 /* CPython hash(tuple of small non-negative ints) -- exposed for tests. */
 int64_t fumi_py_tuple_hash(const int64_t* items, int64_t n);
 

@@ -7,7 +7,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(os.path.dirname(HERE))
 CSRC = os.path.join(ROOT, "fumi_b200", "csrc")
 OUT = os.path.join(HERE, "libfumi_emu.so")
-SRCS = ["episode.cu", "gram.cu", "dense.cu", "optim.cu", "am3.cu", "sampler.cpp"]
+SRCS = ["episode.cu", "gram.cu", "dense.cu", "optim.cu", "am3.cu", "sampler.cpp", "sampler_expand.cu"]
 
 
 def build(force=False):

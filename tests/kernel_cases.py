@@ -344,3 +344,95 @@ def adam_case(device):
             theirs.step()
             for p, r in zip(ps, ref):
                 assert np.abs(p.detach().cpu().numpy() - r.detach().numpy()).max() < 2e-6
+
+
+# ------------------------------------------------------------------------------------------------
+# device sampler (fumi_sampler_plan + fumi_sampler_expand)
+# ------------------------------------------------------------------------------------------------
+def device_sampler_golden_case(device, name, N, K, Qtrain):
+    """Image ids / labels produced in device memory == the reference loader's goldens, iterators interleaved."""
+    import random
+    from fumi_b200.data.synth import class_split
+    from fumi_b200.sampler import EpisodeSampler
+    g, bank = load_golden(name)
+    C = bank.text.shape[0]
+    B = g["b0_sup_ids"].shape[0]
+    samplers = {}
+    for split, cats in zip(("train", "val", "test"), class_split(C)):
+        samplers[split] = EpisodeSampler(bank.cat_of, cats, N, K, Qtrain if split == "train" else int(100 / N))
+    torch.manual_seed(123); np.random.seed(123); random.seed(123)          # main.py:51-53
+    maml_mod.PureImageNetwork(im_embed_dim=16, n_way=N, hidden_dims=[256, 64])
+    for i, split in enumerate(g["order"]):
+        split = str(split)
+        if i == 0:
+            samplers["val"].new_iterator()
+        if i == 1:
+            samplers["train"].new_iterator()
+            samplers["test"].new_iterator()
+        d = samplers[split].expand(samplers[split].plan(B), device)
+        for k in ("sup_ids", "qry_ids", "sup_y", "qry_y"):
+            assert d[k].device.type == torch.device(device).type
+            assert np.array_equal(d[k].cpu().numpy(), g[f"b{i}_{k}"]), (i, split, k)
+
+
+def device_sampler_vs_host_case(device, sizes_hi=900, B=64):
+    """Device expansion == the all-host native sampler (itself pinned to the oracle and the goldens) on ragged
+    class sizes incl. one class needing a second 624-word generator block, and the generator states agree."""
+    import random
+    from fumi_b200.sampler import EpisodeSampler
+    rs = np.random.RandomState(3)
+    C = 40
+    n_c = rs.randint(40, sizes_hi, size=C)
+    n_c[3] = 1500
+    n_c[7] = 40
+    cat_of = np.repeat(np.arange(C), n_c)
+    rs.shuffle(cat_of)
+    for (N, K, Q) in ((5, 5, 32), (5, 1, 20), (10, 5, 10), (20, 5, 5)):
+        s1 = EpisodeSampler(cat_of, np.arange(C), N, K, Q)
+        s2 = EpisodeSampler(cat_of, np.arange(C), N, K, Q)
+        random.seed(5); torch.manual_seed(5)
+        s1.new_iterator()
+        want = [s1.next_batch(B) for _ in range(2)]
+        st1 = (random.getstate(), torch.get_rng_state())
+        random.seed(5); torch.manual_seed(5)
+        s2.new_iterator()
+        got = [s2.expand(s2.plan(B), device) for _ in range(2)]
+        assert random.getstate() == st1[0] and torch.equal(torch.get_rng_state(), st1[1])
+        for w, d in zip(want, got):
+            for k in w:
+                assert np.array_equal(w[k], d[k].cpu().numpy()), (N, K, Q, k)
+
+
+def device_loader_case(device):
+    """EpisodeLoader(device_sampler=True, prefetch=2) hands out the same batches and leaves the same generator
+    states as the synchronous all-host loader."""
+    import random
+    from fumi_b200.data.loader import EpisodeLoader
+    from fumi_b200.sampler import EpisodeSampler
+    rs = np.random.RandomState(3)
+    C, N, K, Q, B = 40, 5, 2, 6, 9
+    sizes = rs.randint(K + Q, K + Q + 30, size=C)
+    cat_of = np.repeat(np.arange(C), sizes)
+    rs.shuffle(cat_of)
+    feats = torch.zeros(len(cat_of), 4, device=device)
+    ref = []
+    for mode in ("host", "device"):
+        sampler = EpisodeSampler(cat_of, np.arange(C), N, K, Q, num_threads=2)
+        bank = FeatureBank(feats=feats, text=torch.zeros(C, 4, device=device), ids=sampler.ids, categories=np.arange(C))
+        loader = EpisodeLoader(bank, sampler, B, pin_memory=False, prefetch=0 if mode == "host" else 2,
+                               device_sampler=(mode == "device"))
+        random.seed(11); torch.manual_seed(12)
+        it = iter(loader)
+        for i in range(4):
+            b = next(it)
+            snap = (random.getstate(), torch.get_rng_state().clone())
+            cur = {k: torch.as_tensor(getattr(b, k)).cpu().numpy().copy()
+                   for k in ("sup_rows", "qry_rows", "sup_y", "qry_y", "sup_ids", "qry_ids", "head_class")}
+            if mode == "host":
+                ref.append((cur, snap))
+            else:
+                assert b.sup_rows.device.type == torch.device(device).type
+                for k, v in cur.items():
+                    assert np.array_equal(v, ref[i][0][k]), (i, k)
+                assert snap[0] == ref[i][1][0] and torch.equal(snap[1], ref[i][1][1])
+        loader.close()

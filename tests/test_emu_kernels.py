@@ -76,3 +76,16 @@ def test_am3():
 
 def test_dropout_masks():
     kc.dropout_case("cpu")
+
+
+@pytest.mark.parametrize("name,N,K,Qtrain", [("sampler_n5k5b4", 5, 5, 32), pytest.param("sampler_n20k5b2", 20, 5, 16, marks=full)])
+def test_device_sampler_golden(name, N, K, Qtrain):
+    kc.device_sampler_golden_case("cpu", name, N, K, Qtrain)
+
+
+def test_device_sampler_equals_host_sampler():
+    kc.device_sampler_vs_host_case("cpu", B=6)
+
+
+def test_device_loader_prefetch():
+    kc.device_loader_case("cpu")

@@ -75,6 +75,20 @@ def test_dropout_masks():
     kc.dropout_case(DEV)
 
 
+@pytest.mark.parametrize("name,N,K,Qtrain", [("sampler_n5k5b4", 5, 5, 32), ("sampler_n5k1b3", 5, 1, 32),
+                                              ("sampler_n10k5b2", 10, 5, 20), ("sampler_n20k5b2", 20, 5, 16)])
+def test_device_sampler_golden(name, N, K, Qtrain):
+    kc.device_sampler_golden_case("cuda", name, N, K, Qtrain)
+
+
+def test_device_sampler_equals_host_sampler():
+    kc.device_sampler_vs_host_case("cuda", B=64)
+
+
+def test_device_loader_prefetch():
+    kc.device_loader_case("cuda")
+
+
 def test_no_cpu_path():
     """The product refuses non-CUDA devices instead of falling back."""
     from fumi_b200 import _lib
