@@ -158,6 +158,21 @@ def cpu_reference_leg(wl, D, T, steps_k, warmup, budget_s, tasks_per_batch=4, se
 
 
 # ------------------------------------------------------------------------------------------ our arm
+def ncu_traffic(kernel, workload, tasks):
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch of `kernel`, from the committed `ncu --set full`
+    summary -- only when that capture was taken on this workload at this batch size (else None)."""
+    path = os.path.join(os.path.dirname(os.path.abspath(__file__)), "profiles", "r1_ncu_full_v7_summary.json")
+    try:
+        with open(path) as f:
+            d = json.load(f)
+        if d["workload"] != workload or int(d["tasks"]) != int(tasks):
+            return None, None
+        recs = d["kernels"][kernel]
+        return max(r["traffic_bytes"] for r in recs), "profiles/r1_ncu_full_v7_summary.json"
+    except (OSError, KeyError, ValueError):
+        return None, None
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -339,8 +354,9 @@ def main():
         top = max(kernels, key=lambda k: kernels[k]["ms_per_step"])
         dur = kernels[top]["ms_per_step"] / kernels[top]["calls_per_step"] * 1e-3
         ach = bytes_task * a.tasks / dur / 1e9
+        traffic, traffic_src = ncu_traffic(top, a.workload, a.tasks)
         roof = {"kernel": top, "bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
-                "traffic": None, "peak_source": peak_src, "launch_ms": dur * 1e3,
+                "traffic": traffic, "traffic_source": traffic_src, "peak_source": peak_src, "launch_ms": dur * 1e3,
                 "algorithmic_bytes_per_task": bytes_task,
                 "note": "achieved = SURVEY 8(d) bytes/task x tasks / launch time of the longest kernel; "
                         "fumi_gram is the kernel that actually streams those bytes (see by_kernel)"}

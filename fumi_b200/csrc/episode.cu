@@ -641,360 +641,8 @@ __device__ inline SmemM carve_m(float* p) {
     return s;
 }
 
-// H0 tile: Z0 = A + b0 - alpha * (G S) -> relu, dropout.  `Apre`: the projected rows (row stride lda_pre).
-template <int MT>
-__device__ __forceinline__ void mma_tile_h0(const EpiParams& P, const SmemM& s, int64_t task, const float* G,
-                                            bool use_s, int K8, const float* Apre, int lda_pre, int r0, int tr,
-                                            int pass) {
-    const int w = threadIdx.x >> 5;
-    float acc[MT][4][4];
-#pragma unroll
-    for (int i = 0; i < MT; ++i)
-#pragma unroll
-        for (int j = 0; j < 4; ++j)
-#pragma unroll
-            for (int q = 0; q < 4; ++q) acc[i][j][q] = 0.f;
-    if (use_s) warp_gemm_3xtf32<MT, 4, false, false>(G, kSG, s.sS + 32 * w, kSS, K8, 1.f, acc);
-    const float alpha = P.cfg.step_size, sc = dropout_scale(P.cfg);
-    const bool drop = P.cfg.dropout_p > 0.f;
-    const uint32_t thr = dropout_thr(P.cfg);
-    const uint32_t dbase = drop ? dropout_base(P.cfg, task, pass, 0) : 0u;
-    uint32_t bits = 0;
-    warp_tile_foreach<MT, 4>(acc, [&](int i, int hh, float& c) {
-        const int h = 32 * w + hh;
-        float v = 0.f;
-        if (i < tr) {
-            const float z = Apre[i * lda_pre + h] + s.b0s[h] - alpha * c;
-            if (drop && (hh & 1) == 0) bits = dropout_bits(dbase, r0 + i, h);
-            if (z > 0.f && (!drop || dropout_keep_bits(bits, h, thr))) v = z * sc;
-        }
-        s.h0t[i * kS0 + h] = v;
-    });
-}
-
-// H1 tile: Z1 = H0 W1^T + b1 -> relu, dropout
-template <int MT>
-__device__ __forceinline__ void mma_tile_h1(const EpiParams& P, const SmemM& s, int64_t task, int r0, int tr, int pass) {
-    const int w = threadIdx.x >> 5;
-    float acc[MT][1][4];
-#pragma unroll
-    for (int i = 0; i < MT; ++i)
-#pragma unroll
-        for (int q = 0; q < 4; ++q) acc[i][0][q] = 0.f;
-    warp_gemm_3xtf32<MT, 1, false, false>(s.h0t, kS0, s.w1t + 8 * w, kS1, kH0, 1.f, acc);
-    const float sc = dropout_scale(P.cfg);
-    const bool drop = P.cfg.dropout_p > 0.f;
-    const uint32_t thr = dropout_thr(P.cfg);
-    const uint32_t dbase = drop ? dropout_base(P.cfg, task, pass, 1) : 0u;
-    uint32_t bits = 0;
-    warp_tile_foreach<MT, 1>(acc, [&](int i, int oo, float& c) {
-        const int o = 8 * w + oo;
-        float v = 0.f;
-        if (i < tr) {
-            const float z = c + s.b1s[o];
-            if (drop && (oo & 1) == 0) bits = dropout_bits(dbase, r0 + i, o);
-            if (z > 0.f && (!drop || dropout_keep_bits(bits, o, thr))) v = z * sc;
-        }
-        s.h1t[i * kS1 + o] = v;
-    });
-}
-
-__device__ __forceinline__ void m_tile_logits(const EpiParams& P, const SmemM& s, int rows, int tr) {
-    const int N = P.cfg.num_ways;
-    for (int idx = threadIdx.x; idx < rows * N; idx += kThreads) {
-        const int i = idx / N, c = idx - i * N;
-        float l = 0.f;
-        if (i < tr) {
-            float l0 = s.hp[c * kHD + kH1], l1 = 0.f, l2 = 0.f, l3 = 0.f;      // 4 chains instead of one 64-long one
-#pragma unroll 4
-            for (int o = 0; o < kH1; o += 4) {
-                l0 = fmaf(s.h1t[i * kS1 + o], s.hp[c * kHD + o], l0);
-                l1 = fmaf(s.h1t[i * kS1 + o + 1], s.hp[c * kHD + o + 1], l1);
-                l2 = fmaf(s.h1t[i * kS1 + o + 2], s.hp[c * kHD + o + 2], l2);
-                l3 = fmaf(s.h1t[i * kS1 + o + 3], s.hp[c * kHD + o + 3], l3);
-            }
-            l = (l0 + l1) + (l2 + l3);
-        }
-        s.lt[i * kLS + c] = l;
-    }
-}
-
-template <int MT>
-__global__ void __launch_bounds__(kThreads, 1) episode_fwd_mma_kernel(EpiParams P) {
-    constexpr int RS = 16 * MT;                       // padded support rows
-    FUMI_DYN_SMEM(float, smem_raw);
-    const SmemM s = carve_m(smem_raw);
-    const fumi_episode_cfg& c = P.cfg;
-    const int tid = threadIdx.x, w = tid >> 5;
-    const int n = c.num_support, m = c.num_query, N = c.num_ways, steps = c.steps;
-    const int n8 = (n + 7) & ~7;
-    const float alpha = c.step_size;
-    const Layout L = make_layout(c);
-    const int o_ = tid & 63, kg_ = tid >> 6;
-    __shared__ float task_sum[2];
-    PhaseClock pc;
-    pc.start();
-
-    for (int i = 0; i < 32; ++i) s.sS[i * kSS + tid] = 0.f;         // pad rows of S stay zero for the whole kernel
-    for (int idx = tid; idx < 32 * kSG; idx += kThreads) { s.gS[idx] = 0.f; s.gQ[idx] = 0.f; }
-    __syncthreads();
-
-    for (int64_t b = blockIdx.x; b < P.B; b += gridDim.x) {
-        const int64_t task = c.task_offset + b;
-        float* slot = P.stash + (P.save ? b : int64_t(blockIdx.x)) * P.slot_floats;
-        // ---- task prologue: everything the inner loop needs is staged in shared memory once
-        // (global -> shared copies go through register batches: a store to shared memory may alias a later
-        //  global load as far as the compiler knows, which would serialise load latencies)
-        {
-            float v[16];
-#pragma unroll 1
-            for (int o0 = 0; o0 < kH1; o0 += 16) {               // w1 is [H1][H0] row-major; thread == k
-#pragma unroll
-                for (int q = 0; q < 16; ++q) v[q] = __ldg(&P.w1[(o0 + q) * kH0 + tid]);
-#pragma unroll
-                for (int q = 0; q < 16; ++q) s.w1t[tid * kS1 + o0 + q] = v[q];
-            }
-#pragma unroll 1
-            for (int i0 = 0; i0 < RS; i0 += 16) {
-#pragma unroll
-                for (int q = 0; q < 16; ++q)
-                    v[q] = (i0 + q < n) ? __ldg(&P.proj[__ldg(&P.sup_rows[b * n + i0 + q]) * kH0 + tid]) : 0.f;
-#pragma unroll
-                for (int q = 0; q < 16; ++q) s.sA[(i0 + q) * kH0 + tid] = v[q];
-            }
-        }
-        s.b0s[tid] = __ldg(&P.b0[tid]);
-        if (tid < kH1) s.b1s[tid] = __ldg(&P.b1[tid]);
-        for (int idx = tid; idx < N * kHD; idx += kThreads) {
-            const int cc = idx / kHD, o = idx - cc * kHD;
-            const int64_t r = P.head_rows ? __ldg(&P.head_rows[b * N + cc]) : cc;
-            s.hp[idx] = __ldg(&P.head_table[r * kHD + o]);
-        }
-        for (int idx = tid; idx < n * n; idx += kThreads) {
-            const int i = idx / n, j = idx - i * n;
-            s.gS[i * kSG + j] = __ldg(&P.gram[(b * int64_t(n + m) + i) * n + j]);
-        }
-        if (tid < 32) s.ysS[tid] = tid < n ? int(P.sup_y[b * n + tid]) : 0;
-        for (int idx = tid; idx < m; idx += kThreads) {
-            s.rowsQ[idx] = P.qry_rows[b * m + idx];
-            s.ysQ[idx] = int(P.qry_y[b * m + idx]);
-        }
-        if (tid == 0) { task_sum[0] = 0.f; task_sum[1] = 0.f; }
-        __syncthreads();
-        pc.mark(20);    // prologue
-
-        for (int st = 0; st < steps; ++st) {
-            float* rec = P.save ? slot + L.steps + int64_t(st) * L.per_step : nullptr;
-            for (int idx = tid; idx < N * kHD; idx += kThreads) s.dhp[idx] = 0.f;
-            mma_tile_h0<MT>(P, s, task, s.gS, st > 0, n8, s.sA, kH0, 0, n, st);
-            __syncthreads();
-            pc.mark(21);    // s: H0
-            mma_tile_h1<MT>(P, s, task, 0, n, st);
-            __syncthreads();
-            pc.mark(22);    // s: H1 (K=256)
-            m_tile_logits(P, s, RS, n);
-            __syncthreads();
-            pc.mark(23);    // s: logits
-            if (tid < RS) {                                    // dL = (softmax - onehot) / n
-                float* l = &s.lt[tid * kLS];
-                if (tid < n) {
-                    float mx, sum;
-                    row_softmax(l, N, mx, sum);
-                    const float inv = 1.f / sum, invn = 1.f / float(n);
-                    const int y = s.ysS[tid];
-                    for (int cc = 0; cc < N; ++cc) {
-                        const float p = expf(l[cc] - mx) * inv;
-                        l[cc] = (p - (cc == y ? 1.f : 0.f)) * invn;
-                    }
-                } else {
-                    for (int cc = 0; cc < N; ++cc) l[cc] = 0.f;
-                }
-            }
-            __syncthreads();
-            pc.mark(24);    // s: softmax
-            // head gradient; dZ1 (uses the pre-update head)
-            for (int idx = tid; idx < N * kHD; idx += kThreads) {
-                const int cc = idx / kHD, o = idx - cc * kHD;
-                float a = 0.f;
-                for (int i = 0; i < n; ++i) a = fmaf(s.lt[i * kLS + cc], o < kH1 ? s.h1t[i * kS1 + o] : 1.f, a);
-                s.dhp[idx] = a;
-            }
-            {
-                const float sc = dropout_scale(c);
-#pragma unroll
-                for (int ii = 0; ii < RS / 4; ++ii) {
-                    const int i = kg_ + 4 * ii;
-                    float dz = 0.f;
-                    if (i < n && s.h1t[i * kS1 + o_] > 0.f) {
-                        float dh = 0.f;
-                        for (int cc = 0; cc < N; ++cc) dh = fmaf(s.lt[i * kLS + cc], s.hp[cc * kHD + o_], dh);
-                        dz = dh * sc;
-                    }
-                    s.dz1t[i * kS1 + o_] = dz;
-                }
-            }
-            __syncthreads();
-            pc.mark(25);    // s: dhp, dZ1
-            float db1 = 0.f;
-            if (tid < kH1) for (int i = 0; i < n; ++i) db1 += s.dz1t[i * kS1 + tid];
-            // dZ0 = (dZ1 W1) * gate ;  S += dZ0 ;  db0 = column sums of dZ0
-            {
-                float acc[MT][4][4];
-#pragma unroll
-                for (int i = 0; i < MT; ++i)
-#pragma unroll
-                    for (int j = 0; j < 4; ++j)
-#pragma unroll
-                        for (int q = 0; q < 4; ++q) acc[i][j][q] = 0.f;
-                warp_gemm_3xtf32<MT, 4, false, true>(s.dz1t, kS1, s.w1t + 32 * w * kS1, kS1, kH1, 1.f, acc);
-                const float sc = dropout_scale(c);
-                float colsum[4][2];
-#pragma unroll
-                for (int j = 0; j < 4; ++j) colsum[j][0] = colsum[j][1] = 0.f;
-                warp_tile_foreach<MT, 4>(acc, [&](int i, int hh, float& cv) {
-                    const int h = 32 * w + hh;
-                    const float dz0 = (i < n && s.h0t[i * kS0 + h] > 0.f) ? cv * sc : 0.f;
-                    if (i < n) s.sS[i * kSS + h] = (st > 0 ? s.sS[i * kSS + h] : 0.f) + dz0;
-                    colsum[hh >> 3][hh & 1] += dz0;
-                });
-                const int lane = tid & 31;
-#pragma unroll
-                for (int j = 0; j < 4; ++j)
-#pragma unroll
-                    for (int q = 0; q < 2; ++q) {
-                        float v = colsum[j][q];
-                        v += __shfl_xor_sync(0xffffffffu, v, 4);
-                        v += __shfl_xor_sync(0xffffffffu, v, 8);
-                        v += __shfl_xor_sync(0xffffffffu, v, 16);
-                        if ((lane >> 2) == 0) s.db0s[32 * w + 8 * j + 2 * (lane & 3) + q] = v;
-                    }
-            }
-            if (rec) {                                          // records for the backward
-                for (int i = 0; i < n; ++i) rec[L.oH0 + int64_t(i) * kH0 + tid] = s.h0t[i * kS0 + tid];
-                for (int idx = tid; idx < n * kH1; idx += kThreads) {
-                    const int i = idx / kH1, o = idx - i * kH1;
-                    rec[L.oH1 + idx] = s.h1t[i * kS1 + o];
-                    rec[L.oDZ1 + idx] = s.dz1t[i * kS1 + o];
-                }
-                for (int idx = tid; idx < n * N; idx += kThreads) {
-                    const int i = idx / N, cc = idx - i * N;
-                    rec[L.oDL + idx] = s.lt[i * kLS + cc];
-                }
-                for (int idx = tid; idx < N * kHD; idx += kThreads) rec[L.oHP + idx] = s.hp[idx];
-            }
-            __syncthreads();                                    // everyone is done reading W1^T and the old head
-            pc.mark(26);    // s: dZ0 gemm, S update, stash
-            // W1 -= alpha * dZ1^T H0   (rows of W1^T owned by this warp: h in [32w, 32w+32))
-            {
-                float acc[2][8][4];
-#pragma unroll
-                for (int i = 0; i < 2; ++i)
-#pragma unroll
-                    for (int j = 0; j < 8; ++j)
-#pragma unroll
-                        for (int q = 0; q < 4; ++q) acc[i][j][q] = 0.f;
-                warp_gemm_3xtf32<2, 8, true, false>(s.h0t + 32 * w, kS0, s.dz1t, kS1, RS, 1.f, acc);
-                warp_tile_foreach<2, 8>(acc, [&](int hh, int o, float& cv) {
-                    s.w1t[(32 * w + hh) * kS1 + o] -= alpha * cv;
-                });
-            }
-            for (int idx = tid; idx < N * kHD; idx += kThreads) s.hp[idx] -= alpha * s.dhp[idx];
-            if (tid < kH1) s.b1s[tid] -= alpha * db1;
-            s.b0s[tid] -= alpha * s.db0s[tid];
-            __syncthreads();
-            pc.mark(27);    // s: W1 update gemm
-        }
-
-        // ---- query scoring, 32 rows per tile
-        for (int r0 = 0; r0 < m; r0 += 32) {
-            const int tr = min(32, m - r0);
-            {
-                float v[32];
-#pragma unroll
-                for (int i = 0; i < 32; ++i) v[i] = i < tr ? __ldg(&P.proj[s.rowsQ[r0 + i] * kH0 + tid]) : 0.f;
-                float gv[4];
-#pragma unroll
-                for (int q = 0; q < 4; ++q) {                      // 32 x n Gram tile: <= 4 elements per thread
-                    const int idx = tid + q * kThreads;
-                    const int i = idx / n, j = idx - i * n;
-                    gv[q] = (idx < 32 * n && i < tr) ? __ldg(&P.gram[(b * int64_t(n + m) + n + r0 + i) * n + j]) : 0.f;
-                }
-#pragma unroll
-                for (int i = 0; i < 32; ++i) s.h0t[i * kS0 + tid] = v[i];
-#pragma unroll
-                for (int q = 0; q < 4; ++q) {
-                    const int idx = tid + q * kThreads;
-                    const int i = idx / n, j = idx - i * n;
-                    if (idx < 32 * n) s.gQ[i * kSG + j] = gv[q];
-                }
-            }
-            __syncthreads();
-            pc.mark(28);    // q: loads
-            mma_tile_h0<2>(P, s, task, s.gQ, steps > 0, n8, s.h0t, kS0, r0, tr, steps);
-            __syncthreads();
-            pc.mark(29);    // q: H0
-            mma_tile_h1<2>(P, s, task, r0, tr, steps);
-            __syncthreads();
-            pc.mark(30);    // q: H1
-            m_tile_logits(P, s, 32, tr);
-            __syncthreads();
-            pc.mark(31);    // q: logits
-            if (P.save) {                                       // query activations for the backward
-                for (int i = 0; i < tr; ++i) slot[L.qH0 + int64_t(r0 + i) * kH0 + tid] = s.h0t[i * kS0 + tid];
-                for (int idx = tid; idx < tr * kH1; idx += kThreads) {
-                    const int i = idx / kH1, o = idx - i * kH1;
-                    slot[L.qH1 + int64_t(r0) * kH1 + idx] = s.h1t[i * kS1 + o];
-                }
-                for (int idx = tid; idx < tr * N; idx += kThreads) {
-                    const int i = idx / N, cc = idx - i * N;
-                    slot[L.qLG + int64_t(r0) * N + idx] = s.lt[i * kLS + cc];
-                }
-            }
-            if (tid < tr) {
-                const float* l = &s.lt[tid * kLS];
-                float mx, sum;
-                row_softmax(l, N, mx, sum);
-                int best = 0;
-                for (int cc = 1; cc < N; ++cc) if (l[cc] > l[best]) best = cc;   // first max (torch.max)
-                const int y = s.ysQ[r0 + tid];
-                s.rowv[tid] = (logf(sum) + mx) - l[y];
-                s.rowc[tid] = best == y ? 1.f : 0.f;
-                const int64_t q = b * m + r0 + tid;
-                P.preds[q] = best;
-                for (int cc = 0; cc < N; ++cc) P.logits[q * N + cc] = l[cc];
-            }
-            __syncthreads();
-            if (tid == 0) {
-                float a = task_sum[0], k = task_sum[1];
-                for (int i = 0; i < tr; ++i) { a += s.rowv[i]; k += s.rowc[i]; }
-                task_sum[0] = a; task_sum[1] = k;
-            }
-            pc.mark(32);    // q: stash, softmax, loss
-        }
-        __syncthreads();
-        if (tid == 0) {
-            P.task_loss[b] = task_sum[0] / float(m);
-            P.task_acc[b] = task_sum[1] / float(m);
-        }
-        if (P.save) {                                               // adapted state
-            for (int idx = tid; idx < kH0 * kH1; idx += kThreads) {
-                const int k = idx / kH1, o = idx - k * kH1;
-                slot[L.w1t + idx] = s.w1t[k * kS1 + o];
-            }
-            slot[L.b0 + tid] = s.b0s[tid];
-            if (tid < kH1) slot[L.b1 + tid] = s.b1s[tid];
-            for (int idx = tid; idx < N * kHD; idx += kThreads) slot[L.head + idx] = s.hp[idx];
-            float* Sout = slot + ((steps & 1) ? L.S1 : L.S0);      // final S where the backward expects it
-            for (int i = 0; i < n; ++i) Sout[int64_t(i) * kH0 + tid] = steps > 0 ? s.sS[i * kSS + tid] : 0.f;
-        }
-        __syncthreads();
-        pc.mark(33);    // epilogue (adapted state out)
-    }
-}
-
-// ------------------------------------------------------------------------------------ forward, 16 warps
-// Same algorithm as episode_fwd_mma_kernel on 512 threads: the phases are latency-bound with 2 warps per
-// scheduler (ncu: issue active 22-28 %, tensor pipe 20 %), so the work of every phase is split over 16 warps:
+// 512 threads: the phases are latency-bound with 2 warps per scheduler (an 8-warp version measured issue
+// active 22-28 %, tensor pipe 20 %), so the work of every phase is split over 16 warps:
 // warp w owns hidden units [16w, 16w+16) of the 256-wide ops and the (m tile w/8, n tile w%8) block of the
 // 64-wide op.  Launch bound 512 threads -> 128 registers per thread.
 constexpr int kThreads16 = 512;
@@ -1299,30 +947,35 @@ __global__ void __launch_bounds__(kThreads16, 1) episode_fwd_mma16_kernel(EpiPar
                     const int i = idx / kH1, o = idx - i * kH1;
                     slot[L.qH1 + int64_t(r0) * kH1 + idx] = s.h1t[i * kS1 + o];
                 }
-                for (int idx = tid; idx < tr * N; idx += NT_) {
-                    const int i = idx / N, cc = idx - i * N;
-                    slot[L.qLG + int64_t(r0) * N + idx] = s.lt[i * kLS + cc];
+            }
+            if (w == 0) {                                       // tr <= 32: one query row per lane of warp 0
+                float rv = 0.f, rc = 0.f;
+                if (lane < tr) {
+                    const float* l = &s.lt[lane * kLS];
+                    float mx, sum;
+                    row_softmax(l, N, mx, sum);
+                    int best = 0;
+                    for (int cc = 1; cc < N; ++cc) if (l[cc] > l[best]) best = cc;   // first max (torch.max)
+                    const int y = s.ysQ[r0 + lane];
+                    rv = (logf(sum) + mx) - l[y];
+                    rc = best == y ? 1.f : 0.f;
+                    const int64_t q = b * m + r0 + lane;
+                    P.preds[q] = best;
+                    for (int cc = 0; cc < N; ++cc) P.logits[q * N + cc] = l[cc];
+                    if (P.save) {                               // dL/dlogits of the row (unscaled) for the backward
+                        const float inv = 1.f / sum;
+                        float* dl = slot + L.qLG + int64_t(r0 + lane) * N;
+                        for (int cc = 0; cc < N; ++cc) dl[cc] = expf(l[cc] - mx) * inv - (cc == y ? 1.f : 0.f);
+                    }
                 }
+#pragma unroll
+                for (int off = 16; off >= 1; off >>= 1) {
+                    rv += __shfl_xor_sync(0xffffffffu, rv, off);
+                    rc += __shfl_xor_sync(0xffffffffu, rc, off);
+                }
+                if (lane == 0) { task_sum[0] += rv; task_sum[1] += rc; }
             }
-            if (tid < tr) {
-                const float* l = &s.lt[tid * kLS];
-                float mx, sum;
-                row_softmax(l, N, mx, sum);
-                int best = 0;
-                for (int cc = 1; cc < N; ++cc) if (l[cc] > l[best]) best = cc;   // first max (torch.max)
-                const int y = s.ysQ[r0 + tid];
-                s.rowv[tid] = (logf(sum) + mx) - l[y];
-                s.rowc[tid] = best == y ? 1.f : 0.f;
-                const int64_t q = b * m + r0 + tid;
-                P.preds[q] = best;
-                for (int cc = 0; cc < N; ++cc) P.logits[q * N + cc] = l[cc];
-            }
-            __syncthreads();
-            if (tid == 0) {
-                float a = task_sum[0], k = task_sum[1];
-                for (int i = 0; i < tr; ++i) { a += s.rowv[i]; k += s.rowc[i]; }
-                task_sum[0] = a; task_sum[1] = k;
-            }
+            __syncthreads();                                    // h0t / h1t / lt are rewritten by the next tile
             pc.mark(32);    // q: stash, softmax, loss
         }
         __syncthreads();
@@ -1397,484 +1050,8 @@ __device__ __forceinline__ void atomic_add2(float* addr, float a, float b) {
 #endif
 }
 
-// column sums of a warp's [16*MT x 32] slab held in MMA layout -> dst[32w + col] (+)=, one owner lane per column
-template <int MT>
-__device__ __forceinline__ void slab_colsum(float (&acc)[MT][4][4], float* dst, bool accumulate) {
-    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-#pragma unroll
-    for (int j = 0; j < 4; ++j)
-#pragma unroll
-        for (int q = 0; q < 2; ++q) {
-            float v = 0.f;
-#pragma unroll
-            for (int i = 0; i < MT; ++i) v += acc[i][j][q] + acc[i][j][q + 2];
-            v += __shfl_xor_sync(0xffffffffu, v, 4);
-            v += __shfl_xor_sync(0xffffffffu, v, 8);
-            v += __shfl_xor_sync(0xffffffffu, v, 16);
-            if ((lane >> 2) == 0) {
-                float* d = dst + 32 * w + 8 * j + 2 * (lane & 3) + q;
-                *d = accumulate ? *d + v : v;
-            }
-        }
-}
-
-__global__ void __launch_bounds__(kThreads, 1) episode_bwd_mma_kernel(EpiParams P) {
-    FUMI_DYN_SMEM(float, smem_raw);
-    const SmemB s = carve_b(smem_raw);
-    const fumi_episode_cfg& c = P.cfg;
-    const int tid = threadIdx.x, w = tid >> 5, lane = tid & 31;
-    const int n = c.num_support, m = c.num_query, N = c.num_ways, steps = c.steps;
-    const float alpha = c.step_size;
-    const Layout L = make_layout(c);
-    const int o_ = tid & 63, kg_ = tid >> 6;
-    const float sc = dropout_scale(c);
-    PhaseClock pc;
-    pc.start();
-
-    for (int idx = tid; idx < 32 * kSG; idx += kThreads) s.gS[idx] = 0.f;
-    for (int idx = tid; idx < 16 * kSG; idx += kThreads) s.gQ[idx] = 0.f;
-    __syncthreads();
-
-    for (int64_t b = blockIdx.x; b < P.B; b += gridDim.x) {
-        float* slot = P.stash + b * P.slot_floats;
-        float* aS = slot + L.S0;           // adjoint of S  [n][H0]
-        float* bZ = slot + L.S1;           // bar_Z0 rows of the current step [n][H0]
-        // ---- adapted state, zeroed adjoints
-        {
-            float v[16];
-#pragma unroll 1
-            for (int o0 = 0; o0 < kH1; o0 += 16) {
-#pragma unroll
-                for (int q = 0; q < 16; ++q) v[q] = __ldg(&slot[L.w1t + tid * kH1 + o0 + q]);
-#pragma unroll
-                for (int q = 0; q < 16; ++q) { s.w1t[tid * kS1 + o0 + q] = v[q]; s.aw1t[tid * kS1 + o0 + q] = 0.f; }
-            }
-        }
-        s.ab0s[tid] = 0.f;
-        if (tid < kH1) { s.b1s[tid] = slot[L.b1 + tid]; s.ab1[tid] = 0.f; }
-        for (int idx = tid; idx < N * kHD; idx += kThreads) { s.hp[idx] = slot[L.head + idx]; s.ahp[idx] = 0.f; }
-        for (int idx = tid; idx < n * n; idx += kThreads) {
-            const int i = idx / n, j = idx - i * n;
-            s.gS[i * kSG + j] = __ldg(&P.gram[(b * int64_t(n + m) + i) * n + j]);
-        }
-        for (int j = 0; j < n; ++j) aS[int64_t(j) * kH0 + tid] = 0.f;
-        __syncthreads();
-        pc.mark(0);     // prologue
-
-        // ---- query pass (activations from the forward's stash)
-        const float qscale = P.loss_scale / float(m);
-        float aSq[2][4][4];                  // Gq^T dZ0q summed over the query tiles (this warp's 32 columns)
-#pragma unroll
-        for (int i = 0; i < 2; ++i)
-#pragma unroll
-            for (int j = 0; j < 4; ++j)
-#pragma unroll
-                for (int q = 0; q < 4; ++q) aSq[i][j][q] = 0.f;
-        for (int r0 = 0; r0 < m; r0 += 16) {
-            const int tr = min(16, m - r0);
-            {
-                float v[16];
-#pragma unroll
-                for (int i = 0; i < 16; ++i) v[i] = i < tr ? __ldg(&slot[L.qH0 + int64_t(r0 + i) * kH0 + tid]) : 0.f;
-                float u[4], g2[2];
-#pragma unroll
-                for (int q = 0; q < 4; ++q) {
-                    const int idx = tid + q * kThreads;
-                    u[q] = idx < tr * kH1 ? __ldg(&slot[L.qH1 + int64_t(r0) * kH1 + idx]) : 0.f;
-                }
-#pragma unroll
-                for (int q = 0; q < 2; ++q) {
-                    const int idx = tid + q * kThreads;
-                    const int i = idx / n, j = idx - i * n;
-                    g2[q] = (idx < 16 * n && i < tr) ? __ldg(&P.gram[(b * int64_t(n + m) + n + r0 + i) * n + j]) : 0.f;
-                }
-#pragma unroll
-                for (int i = 0; i < 16; ++i) s.h0t[i * kS0 + tid] = v[i];
-#pragma unroll
-                for (int q = 0; q < 4; ++q) {
-                    const int idx = tid + q * kThreads;
-                    s.h1t[(idx / kH1) * kS1 + (idx % kH1)] = u[q];
-                }
-#pragma unroll
-                for (int q = 0; q < 2; ++q) {
-                    const int idx = tid + q * kThreads;
-                    if (idx < 16 * n) s.gQ[(idx / n) * kSG + (idx % n)] = g2[q];
-                }
-            }
-            for (int idx = tid; idx < 16 * N; idx += kThreads) {
-                const int i = idx / N, cc = idx - i * N;
-                s.rlt[i * kLS + cc] = i < tr ? __ldg(&slot[L.qLG + int64_t(r0) * N + idx]) : 0.f;
-            }
-            if (tid < 16) s.rows[tid] = tid < tr ? P.qry_rows[b * m + r0 + tid] : 0;
-            __syncthreads();
-            if (tid < 16) {
-                float* l = &s.lt[tid * kLS];
-                if (tid < tr) {
-                    for (int cc = 0; cc < N; ++cc) l[cc] = s.rlt[tid * kLS + cc];
-                    float mx, sum;
-                    row_softmax(l, N, mx, sum);
-                    const float inv = 1.f / sum;
-                    const int y = int(P.qry_y[b * m + r0 + tid]);
-                    for (int cc = 0; cc < N; ++cc) l[cc] = (expf(l[cc] - mx) * inv - (cc == y ? 1.f : 0.f)) * qscale;
-                } else {
-                    for (int cc = 0; cc < N; ++cc) l[cc] = 0.f;
-                }
-            }
-            __syncthreads();
-            pc.mark(1);     // q: loads + softmax
-            for (int idx = tid; idx < N * kHD; idx += kThreads) {              // a_head += dLq^T [H1q | 1]
-                const int cc = idx / kHD, o = idx - cc * kHD;
-                float a = 0.f;
-                for (int i = 0; i < tr; ++i) a = fmaf(s.lt[i * kLS + cc], o < kH1 ? s.h1t[i * kS1 + o] : 1.f, a);
-                s.ahp[idx] += a;
-            }
-#pragma unroll
-            for (int ii = 0; ii < 4; ++ii) {                                   // dZ1q
-                const int i = kg_ + 4 * ii;
-                float dz = 0.f;
-                if (i < tr && s.h1t[i * kS1 + o_] > 0.f) {
-                    float dh = 0.f;
-                    for (int cc = 0; cc < N; ++cc) dh = fmaf(s.lt[i * kLS + cc], s.hp[cc * kHD + o_], dh);
-                    dz = dh * sc;
-                }
-                s.dz1t[i * kS1 + o_] = dz;
-            }
-            __syncthreads();
-            pc.mark(2);     // q: a_head, dZ1q
-            if (tid < kH1) {
-                float a = 0.f;
-                for (int i = 0; i < tr; ++i) a += s.dz1t[i * kS1 + tid];
-                s.ab1[tid] += a;
-            }
-            {   // a_W1 += dZ1q^T H0q   (rows h of W1^T owned by this warp)
-                float acc[2][8][4];
-#pragma unroll
-                for (int i = 0; i < 2; ++i)
-#pragma unroll
-                    for (int j = 0; j < 8; ++j)
-#pragma unroll
-                        for (int q = 0; q < 4; ++q) acc[i][j][q] = 0.f;
-                warp_gemm_3xtf32<2, 8, true, false>(s.h0t + 32 * w, kS0, s.dz1t, kS1, 16, 1.f, acc);
-                warp_tile_foreach<2, 8>(acc, [&](int hh, int o, float& cv) { s.aw1t[(32 * w + hh) * kS1 + o] += cv; });
-            }
-            {   // dZ0q = (dZ1q W1) * gate  -> tt, d_proj, a_b0
-                float acc[1][4][4];
-#pragma unroll
-                for (int j = 0; j < 4; ++j)
-#pragma unroll
-                    for (int q = 0; q < 4; ++q) acc[0][j][q] = 0.f;
-                warp_gemm_3xtf32<1, 4, false, true>(s.dz1t, kS1, s.w1t + 32 * w * kS1, kS1, kH1, 1.f, acc);
-                warp_tile_foreach<1, 4>(acc, [&](int i, int hh, float& cv) {
-                    const int h = 32 * w + hh;
-                    cv = (i < tr && s.h0t[i * kS0 + h] > 0.f) ? cv * sc : 0.f;
-                    s.tt[i * kS0 + h] = cv;
-                });
-                const int g = lane >> 2, t = lane & 3;
-#pragma unroll
-                for (int j = 0; j < 4; ++j) {
-                    const int h = 32 * w + 8 * j + 2 * t;
-                    if (g < tr) atomic_add2(&P.d_proj[s.rows[g] * kH0 + h], acc[0][j][0], acc[0][j][1]);
-                    if (g + 8 < tr) atomic_add2(&P.d_proj[s.rows[g + 8] * kH0 + h], acc[0][j][2], acc[0][j][3]);
-                }
-                slab_colsum<1>(acc, s.ab0s, true);
-            }
-            __syncthreads();
-            pc.mark(3);     // q: a_W1 gemm, dZ0q gemm, atomics
-            if (steps > 0)     // a_S -= alpha * Gq^T dZ0q  (kept in registers until the last query tile)
-                warp_gemm_3xtf32<2, 4, true, false>(s.gQ, kSG, s.tt + 32 * w, kS0, 16, 1.f, aSq);
-            __syncthreads();
-            pc.mark(4);     // q: a_S gemm
-        }
-        if (steps > 0) {
-            warp_tile_foreach<2, 4>(aSq, [&](int j, int hh, float& cv) {
-                if (j < n) aS[int64_t(j) * kH0 + 32 * w + hh] = -alpha * cv;          // a_S starts from zero
-            });
-        }
-        __syncthreads();
-
-        // ---- inner steps in reverse
-        if (!c.first_order) {
-            for (int st = steps - 1; st >= 0; --st) {
-                const float* rec = slot + L.steps + int64_t(st) * L.per_step;
-                // head of this step (pre-update); undo W1_{s+1} = W1_s - alpha dZ1^T H0 with all rows at once:
-                // (h0t|tt) is a [32][kS0] buffer and (dz1t|rzh) a [32][kS1] buffer
-                for (int idx = tid; idx < N * kHD; idx += kThreads) { s.hp[idx] = rec[L.oHP + idx]; s.rhp[idx] = 0.f; }
-                if (tid < kH1) s.rb1[tid] = 0.f;
-                s.rb0s[tid] = 0.f;
-                s.gb0s[tid] = -alpha * s.ab0s[tid];
-                {
-                    float v[32];
-#pragma unroll
-                    for (int i = 0; i < 32; ++i) v[i] = i < n ? __ldg(&rec[L.oH0 + int64_t(i) * kH0 + tid]) : 0.f;
-                    float u[8];
-#pragma unroll
-                    for (int q = 0; q < 8; ++q) {
-                        const int idx = tid + q * kThreads;
-                        u[q] = idx < n * kH1 ? __ldg(&rec[L.oDZ1 + idx]) : 0.f;
-                    }
-#pragma unroll
-                    for (int i = 0; i < 32; ++i) s.h0t[i * kS0 + tid] = v[i];
-#pragma unroll
-                    for (int q = 0; q < 8; ++q) {
-                        const int idx = tid + q * kThreads;
-                        s.dz1t[(idx / kH1) * kS1 + (idx % kH1)] = u[q];
-                    }
-                }
-                __syncthreads();
-                {
-                    float acc[2][8][4];
-#pragma unroll
-                    for (int i = 0; i < 2; ++i)
-#pragma unroll
-                        for (int j = 0; j < 8; ++j)
-#pragma unroll
-                            for (int q = 0; q < 4; ++q) acc[i][j][q] = 0.f;
-                    warp_gemm_3xtf32<2, 8, true, false>(s.h0t + 32 * w, kS0, s.dz1t, kS1, 32, 1.f, acc);
-                    warp_tile_foreach<2, 8>(acc, [&](int hh, int o, float& cv) { s.w1t[(32 * w + hh) * kS1 + o] += alpha * cv; });
-                }
-                float rw[2][8][4];                       // this step's contribution to a_W1 (own rows), over both tiles
-#pragma unroll
-                for (int i = 0; i < 2; ++i)
-#pragma unroll
-                    for (int j = 0; j < 8; ++j)
-#pragma unroll
-                        for (int q = 0; q < 4; ++q) rw[i][j][q] = 0.f;
-                __syncthreads();
-                pc.mark(5);     // s: loads + undo W1
-
-                for (int r0 = 0; r0 < n; r0 += 16) {
-                    const int tr = min(16, n - r0);
-                    {
-                        float v[16], a2[16];
-#pragma unroll
-                        for (int i = 0; i < 16; ++i) {
-                            v[i] = i < tr ? __ldg(&rec[L.oH0 + int64_t(r0 + i) * kH0 + tid]) : 0.f;
-                            a2[i] = i < tr ? aS[int64_t(r0 + i) * kH0 + tid] : 0.f;
-                        }
-                        float u[4], d[4];
-#pragma unroll
-                        for (int q = 0; q < 4; ++q) {
-                            const int idx = tid + q * kThreads;
-                            u[q] = idx < tr * kH1 ? __ldg(&rec[L.oH1 + int64_t(r0) * kH1 + idx]) : 0.f;
-                            d[q] = idx < tr * kH1 ? __ldg(&rec[L.oDZ1 + int64_t(r0) * kH1 + idx]) : 0.f;
-                        }
-                        const float gb0 = s.gb0s[tid];
-#pragma unroll
-                        for (int i = 0; i < 16; ++i) {
-                            s.h0t[i * kS0 + tid] = v[i];
-                            s.tt[i * kS0 + tid] = (i < tr && v[i] > 0.f) ? (a2[i] + gb0) * sc : 0.f;      // (12r) r_dH0
-                        }
-#pragma unroll
-                        for (int q = 0; q < 4; ++q) {
-                            const int idx = tid + q * kThreads;
-                            s.h1t[(idx / kH1) * kS1 + (idx % kH1)] = u[q];
-                            s.dz1t[(idx / kH1) * kS1 + (idx % kH1)] = d[q];
-                        }
-                    }
-                    for (int idx = tid; idx < 16 * kLS; idx += kThreads) {
-                        const int i = idx / kLS, cc = idx - i * kLS;
-                        s.lt[idx] = (i < tr && cc < N) ? rec[L.oDL + int64_t(r0 + i) * N + cc] : 0.f;
-                    }
-                    if (tid < 16) {
-                        s.rows[tid] = tid < tr ? P.sup_rows[b * n + r0 + tid] : 0;
-                        s.ys[tid] = tid < tr ? int(P.sup_y[b * n + r0 + tid]) : 0;
-                    }
-                    __syncthreads();
-                    pc.mark(6);     // s: tile loads
-                    // (11r)+(10r)+(9r): r_dH1 = gate1 * (r_dH0 W1^T + H0 (g_W1)^T + g_b1),  g_W1 = -alpha a_W1
-                    {
-                        float acc[1][1][4] = {{{0.f, 0.f, 0.f, 0.f}}};
-                        warp_gemm_3xtf32<1, 1, false, false>(s.tt, kS0, s.w1t + 8 * w, kS1, kH0, 1.f, acc);
-                        warp_gemm_3xtf32<1, 1, false, false>(s.h0t, kS0, s.aw1t + 8 * w, kS1, kH0, -alpha, acc);
-                        warp_tile_foreach<1, 1>(acc, [&](int i, int oo, float& cv) {
-                            const int o = 8 * w + oo;
-                            s.rzh[i * kS1 + o] = (i < tr && s.h1t[i * kS1 + o] > 0.f) ? (cv - alpha * s.ab1[o]) * sc : 0.f;
-                        });
-                    }
-                    // r_W1 += dZ1^T r_dH0 ;  r_H0 = dZ1 g_W1 (kept in registers)
-                    warp_gemm_3xtf32<2, 8, true, false>(s.tt + 32 * w, kS0, s.dz1t, kS1, 16, 1.f, rw);
-                    float rh0[1][4][4];
-#pragma unroll
-                    for (int j = 0; j < 4; ++j)
-#pragma unroll
-                        for (int q = 0; q < 4; ++q) rh0[0][j][q] = 0.f;
-                    warp_gemm_3xtf32<1, 4, false, true>(s.dz1t, kS1, s.aw1t + 32 * w * kS1, kS1, kH1, -alpha, rh0);
-                    __syncthreads();
-                    pc.mark(7);     // s: r_dH1 gemms (K=256 x2), r_W1 gemm, r_H0 gemm
-                    // (8r)+(7r): r_dL = r_dH1 Wh^T + H1 (g_Wh)^T + g_bh ; r_head += dL^T r_dH1
-                    for (int idx = tid; idx < 16 * N; idx += kThreads) {
-                        const int i = idx / N, cc = idx - i * N;
-                        float a = 0.f;
-                        if (i < tr) {
-                            float a0 = -alpha * s.ahp[cc * kHD + kH1], a1 = 0.f, a2 = 0.f, a3 = 0.f;
-#pragma unroll 4
-                            for (int o = 0; o < kH1; o += 2) {
-                                a0 = fmaf(s.rzh[i * kS1 + o], s.hp[cc * kHD + o], a0);
-                                a1 = fmaf(s.h1t[i * kS1 + o], -alpha * s.ahp[cc * kHD + o], a1);
-                                a2 = fmaf(s.rzh[i * kS1 + o + 1], s.hp[cc * kHD + o + 1], a2);
-                                a3 = fmaf(s.h1t[i * kS1 + o + 1], -alpha * s.ahp[cc * kHD + o + 1], a3);
-                            }
-                            a = (a0 + a1) + (a2 + a3);
-                        }
-                        s.rlt[i * kLS + cc] = a;
-                    }
-                    for (int idx = tid; idx < N * kH1; idx += kThreads) {
-                        const int cc = idx / kH1, o = idx - cc * kH1;
-                        float a = 0.f;
-                        for (int i = 0; i < tr; ++i) a = fmaf(s.lt[i * kLS + cc], s.rzh[i * kS1 + o], a);
-                        s.rhp[cc * kHD + o] += a;
-                    }
-                    __syncthreads();
-                    pc.mark(8);     // s: r_dL, r_head (FMA)
-                    // (6r) r_L = P * (r_dL - <P, r_dL>) / n ; (7r) r_H1 = dL g_Wh  (overwrites rzh)
-                    if (tid < tr) {
-                        const int y = s.ys[tid];
-                        float dot = 0.f;
-                        for (int cc = 0; cc < N; ++cc) {
-                            const float p = s.lt[tid * kLS + cc] * float(n) + (cc == y ? 1.f : 0.f);
-                            dot = fmaf(p, s.rlt[tid * kLS + cc], dot);
-                        }
-                        for (int cc = 0; cc < N; ++cc) {
-                            const float p = s.lt[tid * kLS + cc] * float(n) + (cc == y ? 1.f : 0.f);
-                            s.rlt[tid * kLS + cc] = p * (s.rlt[tid * kLS + cc] - dot) / float(n);
-                        }
-                    }
-#pragma unroll
-                    for (int ii = 0; ii < 4; ++ii) {
-                        const int i = kg_ + 4 * ii;
-                        float a = 0.f;
-                        if (i < tr)
-                            for (int cc = 0; cc < N; ++cc) a = fmaf(s.lt[i * kLS + cc], -alpha * s.ahp[cc * kHD + o_], a);
-                        s.rzh[i * kS1 + o_] = a;
-                    }
-                    __syncthreads();
-                    pc.mark(9);     // s: softmax jacobian, r_H1
-                    // (5r) r_H1 += r_L Wh ; r_head += r_L^T [H1 | 1] ; (4r) r_Z1 = r_H1 * gate1
-#pragma unroll
-                    for (int ii = 0; ii < 4; ++ii) {
-                        const int i = kg_ + 4 * ii;
-                        float a = s.rzh[i * kS1 + o_];
-                        if (i < tr)
-                            for (int cc = 0; cc < N; ++cc) a = fmaf(s.rlt[i * kLS + cc], s.hp[cc * kHD + o_], a);
-                        s.rzh[i * kS1 + o_] = (i < tr && s.h1t[i * kS1 + o_] > 0.f) ? a * sc : 0.f;
-                    }
-                    for (int idx = tid; idx < N * kHD; idx += kThreads) {
-                        const int cc = idx / kHD, o = idx - cc * kHD;
-                        float a = 0.f;
-                        for (int i = 0; i < tr; ++i) a = fmaf(s.rlt[i * kLS + cc], o < kH1 ? s.h1t[i * kS1 + o] : 1.f, a);
-                        s.rhp[idx] += a;
-                    }
-                    __syncthreads();
-                    pc.mark(10);    // s: r_Z1, r_head
-                    // (3r) r_H0 += r_Z1 W1 ; r_W1 += r_Z1^T H0 ; r_b1 += sum r_Z1
-                    if (tid < kH1) {
-                        float a = 0.f;
-                        for (int i = 0; i < tr; ++i) a += s.rzh[i * kS1 + tid];
-                        s.rb1[tid] += a;
-                    }
-                    warp_gemm_3xtf32<1, 4, false, true>(s.rzh, kS1, s.w1t + 32 * w * kS1, kS1, kH1, 1.f, rh0);
-                    warp_gemm_3xtf32<2, 8, true, false>(s.h0t + 32 * w, kS0, s.rzh, kS1, 16, 1.f, rw);
-                    // (2r) bar_Z0 = r_H0 * gate0 ; (1r) a_A (d_proj), a_b0 ; bar_Z0 rows parked in the workspace
-                    {
-                        const int g = lane >> 2, t = lane & 3;
-#pragma unroll
-                        for (int j = 0; j < 4; ++j) {
-                            const int h = 32 * w + 8 * j + 2 * t;
-#pragma unroll
-                            for (int q = 0; q < 4; ++q) {
-                                const int i = g + (q >> 1) * 8;
-                                float& cv = rh0[0][j][q];
-                                cv = (i < tr && s.h0t[i * kS0 + h + (q & 1)] > 0.f) ? cv * sc : 0.f;
-                            }
-                            if (g < tr) {
-                                atomic_add2(&P.d_proj[s.rows[g] * kH0 + h], rh0[0][j][0], rh0[0][j][1]);
-                                bZ[int64_t(r0 + g) * kH0 + h] = rh0[0][j][0];
-                                bZ[int64_t(r0 + g) * kH0 + h + 1] = rh0[0][j][1];
-                            }
-                            if (g + 8 < tr) {
-                                atomic_add2(&P.d_proj[s.rows[g + 8] * kH0 + h], rh0[0][j][2], rh0[0][j][3]);
-                                bZ[int64_t(r0 + g + 8) * kH0 + h] = rh0[0][j][2];
-                                bZ[int64_t(r0 + g + 8) * kH0 + h + 1] = rh0[0][j][3];
-                            }
-                        }
-                        slab_colsum<1>(rh0, s.rb0s, true);
-                    }
-                    __syncthreads();
-                    pc.mark(11);    // s: r_H0 gemm, r_W1 gemm, bar_Z0, atomics
-                }
-                // ---- end of reversed step: fold the contributions into the adjoints; a_S -= alpha G bar_Z0
-                warp_tile_foreach<2, 8>(rw, [&](int hh, int o, float& cv) { s.aw1t[(32 * w + hh) * kS1 + o] += cv; });
-                for (int idx = tid; idx < N * kHD; idx += kThreads) s.ahp[idx] += s.rhp[idx];
-                if (tid < kH1) s.ab1[tid] += s.rb1[tid];
-                s.ab0s[tid] += s.rb0s[tid];
-                {
-                    float v[32];
-#pragma unroll
-                    for (int i = 0; i < 32; ++i) v[i] = i < n ? bZ[int64_t(i) * kH0 + tid] : 0.f;
-#pragma unroll
-                    for (int i = 0; i < 32; ++i) s.h0t[i * kS0 + tid] = v[i];
-                }
-                __syncthreads();
-                pc.mark(12);    // s: fold adjoints, reload bar_Z0
-                {
-                    float acc[2][4][4];
-#pragma unroll
-                    for (int i = 0; i < 2; ++i)
-#pragma unroll
-                        for (int j = 0; j < 4; ++j)
-#pragma unroll
-                            for (int q = 0; q < 4; ++q) acc[i][j][q] = 0.f;
-                    warp_gemm_3xtf32<2, 4, false, false>(s.gS, kSG, s.h0t + 32 * w, kS0, 32, 1.f, acc);
-                    float old[2][4][4];                              // batched read-modify-write of a_S
-                    {
-                        const int g = lane >> 2, t = lane & 3;
-#pragma unroll
-                        for (int i = 0; i < 2; ++i)
-#pragma unroll
-                            for (int j = 0; j < 4; ++j)
-#pragma unroll
-                                for (int q = 0; q < 4; q += 2) {
-                                    const int row = i * 16 + g + (q >> 1) * 8;
-                                    const float2 v = row < n ? *reinterpret_cast<const float2*>(
-                                                                   &aS[int64_t(row) * kH0 + 32 * w + j * 8 + 2 * t])
-                                                             : make_float2(0.f, 0.f);
-                                    old[i][j][q] = v.x; old[i][j][q + 1] = v.y;
-                                }
-#pragma unroll
-                        for (int i = 0; i < 2; ++i)
-#pragma unroll
-                            for (int j = 0; j < 4; ++j)
-#pragma unroll
-                                for (int q = 0; q < 4; q += 2) {
-                                    const int row = i * 16 + g + (q >> 1) * 8;
-                                    if (row < n)
-                                        *reinterpret_cast<float2*>(&aS[int64_t(row) * kH0 + 32 * w + j * 8 + 2 * t]) =
-                                            make_float2(old[i][j][q] - alpha * acc[i][j][q],
-                                                        old[i][j][q + 1] - alpha * acc[i][j][q + 1]);
-                                }
-                    }
-                }
-                __syncthreads();
-                pc.mark(13);    // s: a_S gemm
-            }
-        }
-
-        // ---- task epilogue: head gradient per task, shared-parameter gradients into this CTA's partials
-        for (int idx = tid; idx < N * kHD; idx += kThreads) P.d_head[b * N * kHD + idx] = s.ahp[idx];
-        float* pw = P.d_w1_parts + int64_t(blockIdx.x) * kH0 * kH1;
-        for (int idx = tid; idx < kH0 * kH1; idx += kThreads) {
-            const int o = idx / kH0, k = idx - o * kH0;                         // [H1][H0] like linear1.weight
-            pw[idx] += s.aw1t[k * kS1 + o];
-        }
-        P.d_b0_parts[int64_t(blockIdx.x) * kH0 + tid] += s.ab0s[tid];
-        if (tid < kH1) P.d_b1_parts[int64_t(blockIdx.x) * kH1 + tid] += s.ab1[tid];
-        __syncthreads();
-        pc.mark(14);    // epilogue
-    }
-}
-
 // ------------------------------------------------------------------------------------ backward, 16 warps
-// episode_bwd_mma_kernel on 512 threads (same shared-memory layout).  Warp w owns rows [16w, 16w+16) of the
+// 512 threads.  Warp w owns rows [16w, 16w+16) of the
 // W1^T-shaped adjoints, hidden units [16w, 16w+16) of the 256-wide ops, and in the 64-wide reductions over
 // the 256 hidden units the (n tile w%8, K half w/8) block; the two K halves meet in shared memory.
 template <int MT>
@@ -1921,14 +1098,16 @@ __global__ void __launch_bounds__(kThreads16, 1) episode_bwd_mma16_kernel(EpiPar
         float* aS = slot + L.S0;           // adjoint of S  [n][H0]
         float* bZ = slot + L.S1;           // bar_Z0 rows of the current step [n][H0]
         // ---- adapted state, zeroed adjoints
-        {
-            float v[16];
-#pragma unroll 1
-            for (int o0 = half * 32; o0 < half * 32 + 32; o0 += 16) {
+        {   // W1_S^T [H0][H1] from the stash: coalesced 16-byte loads, 8 per thread in flight
+            float4 v[8];
+            const float4* src = reinterpret_cast<const float4*>(slot + L.w1t);
 #pragma unroll
-                for (int q = 0; q < 16; ++q) v[q] = __ldg(&slot[L.w1t + col * kH1 + o0 + q]);
+            for (int q = 0; q < 8; ++q) v[q] = __ldg(&src[tid + q * NT_]);
 #pragma unroll
-                for (int q = 0; q < 16; ++q) { s.w1t[col * kS1 + o0 + q] = v[q]; s.aw1t[col * kS1 + o0 + q] = 0.f; }
+            for (int q = 0; q < 8; ++q) {
+                const int idx = tid + q * NT_, k = idx >> 4, o = (idx & 15) * 4;
+                *reinterpret_cast<float4*>(&s.w1t[k * kS1 + o]) = v[q];
+                *reinterpret_cast<float4*>(&s.aw1t[k * kS1 + o]) = make_float4(0.f, 0.f, 0.f, 0.f);
             }
         }
         if (tid < kH0) s.ab0s[tid] = 0.f;
@@ -1987,25 +1166,11 @@ __global__ void __launch_bounds__(kThreads16, 1) episode_bwd_mma16_kernel(EpiPar
                 s.h1t[(idx / kH1) * kS1 + (idx % kH1)] = pu[q];
             }
             if (tid < 16 * n) s.gQ[(tid / n) * kSG + (tid % n)] = pg;
-            if (tid < 16 * N) s.rlt[(tid / N) * kLS + (tid % N)] = pl;
+            if (tid < 16 * N) s.lt[(tid / N) * kLS + (tid % N)] = pl * qscale;     // dLq (softmax - onehot from the forward)
             if (tid < 16) { s.rows[tid] = prow; s.ys[tid] = py; }
             __syncthreads();
             if (r0 + 16 < m) q_load(r0 + 16);
-            if (tid < 16) {
-                float* l = &s.lt[tid * kLS];
-                if (tid < tr) {
-                    for (int cc = 0; cc < N; ++cc) l[cc] = s.rlt[tid * kLS + cc];
-                    float mx, sum;
-                    row_softmax(l, N, mx, sum);
-                    const float inv = 1.f / sum;
-                    const int y = s.ys[tid];
-                    for (int cc = 0; cc < N; ++cc) l[cc] = (expf(l[cc] - mx) * inv - (cc == y ? 1.f : 0.f)) * qscale;
-                } else {
-                    for (int cc = 0; cc < N; ++cc) l[cc] = 0.f;
-                }
-            }
-            __syncthreads();
-            pc.mark(1);     // q: loads + softmax
+            pc.mark(1);     // q: tile loads
             for (int idx = tid; idx < N * kHD; idx += NT_) {              // a_head += dLq^T [H1q | 1]
                 const int cc = idx / kHD, o = idx - cc * kHD;
                 float a = 0.f;
@@ -2790,22 +1955,12 @@ extern "C" int fumi_episode_fwd(const fumi_episode_cfg* cfg, int64_t B, const fl
     const bool use_mma = nk <= 32 && cfg->num_query <= kMaxQueryRows;
     if (use_mma) {
         const size_t smem = smem_m_floats() * sizeof(float);
-        static int warps = -1;
-        if (warps < 0) { const char* e = getenv("FUMI_FWD_WARPS"); warps = (e && atoi(e) == 8) ? 8 : 16; }
-        if (warps == 16) {
-            if (nk <= 16) {
-                FUMI_SET_SMEM_ATTR(episode_fwd_mma16_kernel<1>, smem);
-                FUMI_LAUNCH(episode_fwd_mma16_kernel<1>, grid, kThreads16, smem, stream, P);
-            } else {
-                FUMI_SET_SMEM_ATTR(episode_fwd_mma16_kernel<2>, smem);
-                FUMI_LAUNCH(episode_fwd_mma16_kernel<2>, grid, kThreads16, smem, stream, P);
-            }
-        } else if (nk <= 16) {
-            FUMI_SET_SMEM_ATTR(episode_fwd_mma_kernel<1>, smem);
-            FUMI_LAUNCH(episode_fwd_mma_kernel<1>, grid, kThreads, smem, stream, P);
+        if (nk <= 16) {
+            FUMI_SET_SMEM_ATTR(episode_fwd_mma16_kernel<1>, smem);
+            FUMI_LAUNCH(episode_fwd_mma16_kernel<1>, grid, kThreads16, smem, stream, P);
         } else {
-            FUMI_SET_SMEM_ATTR(episode_fwd_mma_kernel<2>, smem);
-            FUMI_LAUNCH(episode_fwd_mma_kernel<2>, grid, kThreads, smem, stream, P);
+            FUMI_SET_SMEM_ATTR(episode_fwd_mma16_kernel<2>, smem);
+            FUMI_LAUNCH(episode_fwd_mma16_kernel<2>, grid, kThreads16, smem, stream, P);
         }
     } else if (nk > 32) FUMI_FWD_CASE(32, true);
     else if (nk > 28) FUMI_FWD_CASE(32, false);
@@ -2842,16 +1997,9 @@ extern "C" int fumi_episode_bwd(const fumi_episode_cfg* cfg, int64_t B, const fl
     if (grid <= 0) return grid;
     if (cfg->num_support <= 32 && cfg->num_query <= kMaxQueryRows) {      // tensor-core path (pairs with fwd_mma)
         const size_t smem_b = smem_b_floats() * sizeof(float);
-        static int warps = -1;
-        if (warps < 0) { const char* e = getenv("FUMI_BWD_WARPS"); warps = (e && atoi(e) == 8) ? 8 : 16; }
-        if (warps == 16) {
-            FUMI_SET_SMEM_ATTR(episode_bwd_mma16_kernel, smem_b);
-            FUMI_LAUNCH(episode_bwd_mma16_kernel, grid, kThreads16, smem_b, stream, P);
-        } else {
-            FUMI_SET_SMEM_ATTR(episode_bwd_mma_kernel, smem_b);
-            FUMI_LAUNCH(episode_bwd_mma_kernel, grid, kThreads, smem_b, stream, P);
-        }
-        FUMI_CHECK_LAUNCH("episode_bwd_mma_kernel");
+        FUMI_SET_SMEM_ATTR(episode_bwd_mma16_kernel, smem_b);
+        FUMI_LAUNCH(episode_bwd_mma16_kernel, grid, kThreads16, smem_b, stream, P);
+        FUMI_CHECK_LAUNCH("episode_bwd_mma16_kernel");
         return FUMI_OK;
     }
     const size_t smem = smem_floats<kTRB, true>() * sizeof(float);
