@@ -719,6 +719,39 @@ __device__ __forceinline__ void m16_tile_logits(const EpiParams& P, const SmemM&
     }
 }
 
+// Logits and their softmax in one phase: one lane per (row, class), a row's N lanes in the same warp
+// (32 / N rows per warp), so the row statistics need only a warp barrier.  Every lane of a row recomputes
+// max / sum-of-exp (N <= 32 expf) and hands (row, class, logit, max, sum) to `sink`, which may overwrite
+// lt[row][class] -- all of the row's reads are complete by then.
+template <typename Sink>
+__device__ __forceinline__ void m16_tile_logits_softmax(const EpiParams& P, const SmemM& s, int rows, int tr, Sink sink) {
+    const int N = P.cfg.num_ways;
+    const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int rpw = 32 / N, li = lane / N, c = lane - li * N;
+    for (int rbase = w * rpw; rbase < rows; rbase += (kThreads16 / 32) * rpw) {      // uniform within a warp
+        const int i = rbase + li;
+        const bool act = li < rpw && i < rows;
+        float l = 0.f;
+        if (act && i < tr) {
+            float l0 = s.hp[c * kHD + kH1], l1 = 0.f, l2 = 0.f, l3 = 0.f;
+#pragma unroll 4
+            for (int o = 0; o < kH1; o += 4) {
+                l0 = fmaf(s.h1t[i * kS1 + o], s.hp[c * kHD + o], l0);
+                l1 = fmaf(s.h1t[i * kS1 + o + 1], s.hp[c * kHD + o + 1], l1);
+                l2 = fmaf(s.h1t[i * kS1 + o + 2], s.hp[c * kHD + o + 2], l2);
+                l3 = fmaf(s.h1t[i * kS1 + o + 3], s.hp[c * kHD + o + 3], l3);
+            }
+            l = (l0 + l1) + (l2 + l3);
+        }
+        if (act) s.lt[i * kLS + c] = l;
+        __syncwarp();
+        float mx = 0.f, sum = 1.f;
+        if (act && i < tr) row_softmax(&s.lt[i * kLS], N, mx, sum);
+        __syncwarp();
+        if (act) sink(i, c, l, mx, sum);
+    }
+}
+
 template <int MT>
 __global__ void __launch_bounds__(kThreads16, 1) episode_fwd_mma16_kernel(EpiParams P) {
     constexpr int RS = 16 * MT;                       // padded support rows
@@ -791,25 +824,16 @@ __global__ void __launch_bounds__(kThreads16, 1) episode_fwd_mma16_kernel(EpiPar
             mma16_tile_h1<MT>(P, s, task, 0, n, st);
             __syncthreads();
             pc.mark(22);    // s: H1 (K=256)
-            m16_tile_logits(P, s, RS, n);
-            __syncthreads();
-            pc.mark(23);    // s: logits
-            if (tid < RS) {                                    // dL = (softmax - onehot) / n
-                float* l = &s.lt[tid * kLS];
-                if (tid < n) {
-                    float mx, sum;
-                    row_softmax(l, N, mx, sum);
-                    const float inv = 1.f / sum, invn = 1.f / float(n);
-                    const int y = s.ysS[tid];
-                    for (int cc = 0; cc < N; ++cc) {
-                        const float p = expf(l[cc] - mx) * inv;
-                        l[cc] = (p - (cc == y ? 1.f : 0.f)) * invn;
-                    }
-                } else {
-                    for (int cc = 0; cc < N; ++cc) l[cc] = 0.f;
-                }
+            {                                                   // logits, then dL = (softmax - onehot) / n in place
+                const float invn = 1.f / float(n);
+                m16_tile_logits_softmax(P, s, RS, n, [&](int i, int cc, float l, float mx, float sum) {
+                    float dl = 0.f;
+                    if (i < n) dl = (expf(l - mx) * (1.f / sum) - (cc == s.ysS[i] ? 1.f : 0.f)) * invn;
+                    s.lt[i * kLS + cc] = dl;
+                });
             }
             __syncthreads();
+            pc.mark(23);    // s: logits + softmax
             pc.mark(24);    // s: softmax
             // head gradient; dZ1 (uses the pre-update head)
             for (int idx = tid; idx < N * kHD; idx += NT_) {
@@ -931,43 +955,8 @@ __global__ void __launch_bounds__(kThreads16, 1) episode_fwd_mma16_kernel(EpiPar
             }
             __syncthreads();
             if (r0 + 32 < m) q_load(r0 + 32);
-            pc.mark(28);    // q: loads
-            mma16_tile_h0<2>(P, s, task, s.gQ, steps > 0, n8, s.h0t, kS0, r0, tr, steps);
-            __syncthreads();
-            pc.mark(29);    // q: H0
-            mma16_tile_h1<2>(P, s, task, r0, tr, steps);
-            __syncthreads();
-            pc.mark(30);    // q: H1
-            m16_tile_logits(P, s, 32, tr);
-            __syncthreads();
-            pc.mark(31);    // q: logits
-            if (P.save) {                                       // query activations for the backward
-                for (int i = half; i < tr; i += 2) slot[L.qH0 + int64_t(r0 + i) * kH0 + col] = s.h0t[i * kS0 + col];
-                for (int idx = tid; idx < tr * kH1; idx += NT_) {
-                    const int i = idx / kH1, o = idx - i * kH1;
-                    slot[L.qH1 + int64_t(r0) * kH1 + idx] = s.h1t[i * kS1 + o];
-                }
-            }
-            if (w == 0) {                                       // tr <= 32: one query row per lane of warp 0
-                float rv = 0.f, rc = 0.f;
-                if (lane < tr) {
-                    const float* l = &s.lt[lane * kLS];
-                    float mx, sum;
-                    row_softmax(l, N, mx, sum);
-                    int best = 0;
-                    for (int cc = 1; cc < N; ++cc) if (l[cc] > l[best]) best = cc;   // first max (torch.max)
-                    const int y = s.ysQ[r0 + lane];
-                    rv = (logf(sum) + mx) - l[y];
-                    rc = best == y ? 1.f : 0.f;
-                    const int64_t q = b * m + r0 + lane;
-                    P.preds[q] = best;
-                    for (int cc = 0; cc < N; ++cc) P.logits[q * N + cc] = l[cc];
-                    if (P.save) {                               // dL/dlogits of the row (unscaled) for the backward
-                        const float inv = 1.f / sum;
-                        float* dl = slot + L.qLG + int64_t(r0 + lane) * N;
-                        for (int cc = 0; cc < N; ++cc) dl[cc] = expf(l[cc] - mx) * inv - (cc == y ? 1.f : 0.f);
-                    }
-                }
+            if (r0 > 0 && w == 0) {                             // loss / accuracy of the previous tile (rowv, rowc)
+                float rv = s.rowv[lane], rc = s.rowc[lane];
 #pragma unroll
                 for (int off = 16; off >= 1; off >>= 1) {
                     rv += __shfl_xor_sync(0xffffffffu, rv, off);
@@ -975,13 +964,55 @@ __global__ void __launch_bounds__(kThreads16, 1) episode_fwd_mma16_kernel(EpiPar
                 }
                 if (lane == 0) { task_sum[0] += rv; task_sum[1] += rc; }
             }
-            __syncthreads();                                    // h0t / h1t / lt are rewritten by the next tile
+            pc.mark(28);    // q: loads
+            mma16_tile_h0<2>(P, s, task, s.gQ, steps > 0, n8, s.h0t, kS0, r0, tr, steps);
+            __syncthreads();
+            pc.mark(29);    // q: H0
+            mma16_tile_h1<2>(P, s, task, r0, tr, steps);
+            __syncthreads();
+            pc.mark(30);    // q: H1
+            // logits + softmax on the (row, class) lanes; the other warps go straight to the stash copies
+            m16_tile_logits_softmax(P, s, 32, tr, [&](int i, int cc, float l, float mx, float sum) {
+                if (i >= tr) {
+                    if (cc == 0) { s.rowv[i] = 0.f; s.rowc[i] = 0.f; }
+                    return;
+                }
+                const int y = s.ysQ[r0 + i];
+                const int64_t q = b * m + r0 + i;
+                P.logits[q * N + cc] = l;
+                if (P.save)                                     // dL/dlogits (unscaled) for the backward
+                    slot[L.qLG + int64_t(r0 + i) * N + cc] = expf(l - mx) * (1.f / sum) - (cc == y ? 1.f : 0.f);
+                if (cc == 0) {
+                    const float* lr = &s.lt[i * kLS];
+                    int best = 0;
+                    for (int k = 1; k < N; ++k) if (lr[k] > lr[best]) best = k;      // first max (torch.max)
+                    s.rowv[i] = (logf(sum) + mx) - lr[y];
+                    s.rowc[i] = best == y ? 1.f : 0.f;
+                    P.preds[q] = best;
+                }
+            });
+            pc.mark(31);    // q: logits + softmax
+            if (P.save) {                                       // query activations for the backward
+                for (int i = half; i < tr; i += 2) slot[L.qH0 + int64_t(r0 + i) * kH0 + col] = s.h0t[i * kS0 + col];
+                for (int idx = tid; idx < tr * kH1; idx += NT_) {
+                    const int i = idx / kH1, o = idx - i * kH1;
+                    slot[L.qH1 + int64_t(r0) * kH1 + idx] = s.h1t[i * kS1 + o];
+                }
+            }
+            __syncthreads();                                    // h0t / h1t / lt / rowv are rewritten by the next tile
             pc.mark(32);    // q: stash, softmax, loss
         }
-        __syncthreads();
-        if (tid == 0) {
-            P.task_loss[b] = task_sum[0] / float(m);
-            P.task_acc[b] = task_sum[1] / float(m);
+        if (w == 0) {                                           // last tile's rows, then the task means
+            float rv = s.rowv[lane], rc = s.rowc[lane];
+#pragma unroll
+            for (int off = 16; off >= 1; off >>= 1) {
+                rv += __shfl_xor_sync(0xffffffffu, rv, off);
+                rc += __shfl_xor_sync(0xffffffffu, rc, off);
+            }
+            if (lane == 0) {
+                P.task_loss[b] = (task_sum[0] + rv) / float(m);
+                P.task_acc[b] = (task_sum[1] + rc) / float(m);
+            }
         }
         if (P.save) {                                               // adapted state
             for (int idx = tid; idx < kH0 * kH1; idx += NT_) {
@@ -1366,23 +1397,28 @@ __global__ void __launch_bounds__(kThreads16, 1) episode_bwd_mma16_kernel(EpiPar
                     __syncthreads();
                     pc.mark(7);     // s: r_dH1 gemms (K=256 x2), r_W1 gemm, r_H0 gemm
                     // (8r)+(7r): r_dL = r_dH1 Wh^T + H1 (g_Wh)^T + g_bh ; r_head += dL^T r_dH1
-                    for (int idx = tid; idx < 16 * N; idx += NT_) {
+                    // four lanes per (row, class): each sums 16 of the 64 hidden units, then two shuffles
+                    for (int idx4 = tid; idx4 < 64 * N; idx4 += NT_) {     // 64 N and NT_ are multiples of 32
+                        const int idx = idx4 >> 2, part = idx4 & 3;
                         const int i = idx / N, cc = idx - i * N;
-                        float a = 0.f;
+                        float a0 = 0.f, a1 = 0.f;
                         if (i < tr) {
-                            float a0 = -alpha * s.ahp[cc * kHD + kH1], a1 = 0.f, a2 = 0.f, a3 = 0.f;
-#pragma unroll 4
-                            for (int o = 0; o < kH1; o += 2) {
-                                a0 = fmaf(s.rzh[i * kS1 + o], s.hp[cc * kHD + o], a0);
-                                a1 = fmaf(s.h1t[i * kS1 + o], -alpha * s.ahp[cc * kHD + o], a1);
-                                a2 = fmaf(s.rzh[i * kS1 + o + 1], s.hp[cc * kHD + o + 1], a2);
-                                a3 = fmaf(s.h1t[i * kS1 + o + 1], -alpha * s.ahp[cc * kHD + o + 1], a3);
+                            const float* rz = &s.rzh[i * kS1 + 16 * part];
+                            const float* h1 = &s.h1t[i * kS1 + 16 * part];
+                            const float* wh = &s.hp[cc * kHD + 16 * part];
+                            const float* ah = &s.ahp[cc * kHD + 16 * part];
+#pragma unroll 8
+                            for (int o = 0; o < 16; ++o) {
+                                a0 = fmaf(rz[o], wh[o], a0);
+                                a1 = fmaf(h1[o], ah[o], a1);
                             }
-                            a = (a0 + a1) + (a2 + a3);
                         }
-                        s.rlt[i * kLS + cc] = a;
+                        float a = fmaf(-alpha, a1, a0);
+                        a += __shfl_xor_sync(0xffffffffu, a, 1);
+                        a += __shfl_xor_sync(0xffffffffu, a, 2);
+                        if (part == 0) s.rlt[i * kLS + cc] = i < tr ? a - alpha * s.ahp[cc * kHD + kH1] : 0.f;
                     }
-                    for (int idx = tid; idx < N * kH1; idx += NT_) {
+                    for (int idx = NT_ - 1 - tid; idx < N * kH1; idx += NT_) {    // from the other end of the block
                         const int cc = idx / kH1, o = idx - cc * kH1;
                         float a = 0.f;
                         for (int i = 0; i < tr; ++i) a = fmaf(s.lt[i * kLS + cc], s.rzh[i * kS1 + o], a);
@@ -1391,18 +1427,6 @@ __global__ void __launch_bounds__(kThreads16, 1) episode_bwd_mma16_kernel(EpiPar
                     __syncthreads();
                     pc.mark(8);     // s: r_dL, r_head (FMA)
                     // (6r) r_L = P * (r_dL - <P, r_dL>) / n ; (7r) r_H1 = dL g_Wh  (overwrites rzh)
-                    if (tid < tr) {
-                        const int y = s.ys[tid];
-                        float dot = 0.f;
-                        for (int cc = 0; cc < N; ++cc) {
-                            const float p = s.lt[tid * kLS + cc] * float(n) + (cc == y ? 1.f : 0.f);
-                            dot = fmaf(p, s.rlt[tid * kLS + cc], dot);
-                        }
-                        for (int cc = 0; cc < N; ++cc) {
-                            const float p = s.lt[tid * kLS + cc] * float(n) + (cc == y ? 1.f : 0.f);
-                            s.rlt[tid * kLS + cc] = p * (s.rlt[tid * kLS + cc] - dot) / float(n);
-                        }
-                    }
 #pragma unroll
                     for (int ii = 0; ii < 2; ++ii) {
                         const int i = kg_ + 8 * ii;
@@ -1410,6 +1434,24 @@ __global__ void __launch_bounds__(kThreads16, 1) episode_bwd_mma16_kernel(EpiPar
                         if (i < tr)
                             for (int cc = 0; cc < N; ++cc) a = fmaf(s.lt[i * kLS + cc], -alpha * s.ahp[cc * kHD + o_], a);
                         s.rzh[i * kS1 + o_] = a;
+                    }
+                    {   // one lane per (row, class), a row's N lanes in one warp (32 / N rows per warp): the row's
+                        // <P, r_dL> is recomputed by each of its lanes, and rlt is overwritten after a warp barrier
+                        const int rpw = 32 / N, li = lane / N, c0 = lane - li * N, i = w * rpw + li;
+                        const bool act = li < rpw && i < tr;
+                        float out = 0.f;
+                        if (act) {
+                            const int y = s.ys[i];
+                            float dot = 0.f;
+                            for (int cc = 0; cc < N; ++cc) {
+                                const float p = s.lt[i * kLS + cc] * float(n) + (cc == y ? 1.f : 0.f);
+                                dot = fmaf(p, s.rlt[i * kLS + cc], dot);
+                            }
+                            const float p = s.lt[i * kLS + c0] * float(n) + (c0 == y ? 1.f : 0.f);
+                            out = p * (s.rlt[i * kLS + c0] - dot) / float(n);
+                        }
+                        __syncwarp();
+                        if (act) s.rlt[i * kLS + c0] = out;
                     }
                     __syncthreads();
                     pc.mark(9);     // s: softmax jacobian, r_H1
