@@ -53,15 +53,46 @@ def peaks():
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md recipe)."""
+    """SM clock / throttle reasons of one GPU sampled DURING the timed region (B200_PROFILING.md clocks line):
+    NVML polled every 5 ms from a thread when pynvml is importable, else `nvidia-smi -lms 100`."""
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
          "clocks_event_reasons.sw_power_cap")
 
     def __init__(self, index):
         self.index, self.proc, self.lines = index, None, []
+        self.nvml, self.samples, self.stop_flag = None, [], threading.Event()
+
+    def _poll(self):
+        n = self.nvml
+        try:
+            h = n.nvmlDeviceGetHandleByIndex(self._nvml_index())
+            mx = n.nvmlDeviceGetMaxClockInfo(h, n.NVML_CLOCK_SM)
+            while not self.stop_flag.is_set():
+                self.samples.append((n.nvmlDeviceGetClockInfo(h, n.NVML_CLOCK_SM), mx,
+                                     n.nvmlDeviceGetCurrentClocksEventReasons(h)))
+                time.sleep(0.005)
+        except Exception as e:          # fall through to whatever was collected
+            self.err = repr(e)
+
+    def _nvml_index(self):
+        vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+        if vis:
+            ids = [v.strip() for v in vis.split(",") if v.strip()]
+            if self.index < len(ids) and ids[self.index].isdigit():
+                return int(ids[self.index])
+        return self.index
 
     def start(self):
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nvml = pynvml
+            self.thread = threading.Thread(target=self._poll, daemon=True)
+            self.thread.start()
+            return
+        except Exception:
+            self.nvml = None
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
                                           "-lms", "100", "-i", str(self.index)], stdout=subprocess.PIPE, text=True)
@@ -70,6 +101,19 @@ class ClockSampler:
             self.proc = None
 
     def stop(self):
+        if self.nvml is not None:
+            self.stop_flag.set()
+            self.thread.join(timeout=1.0)
+            n = self.nvml
+            bits = {"hw_slowdown": n.nvmlClocksEventReasonHwSlowdown,
+                    "hw_thermal_slowdown": n.nvmlClocksEventReasonHwThermalSlowdown,
+                    "sw_thermal_slowdown": n.nvmlClocksEventReasonSwThermalSlowdown,
+                    "sw_power_cap": n.nvmlClocksEventReasonSwPowerCap}
+            sm = [x[0] for x in self.samples]
+            reasons = sorted(nm for nm, bit in bits.items() if any(x[2] & bit for x in self.samples))
+            return {"sm_mhz": float(np.median(sm)) if sm else None,
+                    "sm_max_mhz": float(self.samples[0][1]) if sm else None, "samples": len(sm), "reasons": reasons,
+                    "source": "nvml"}
         if self.proc is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
         time.sleep(0.15)
@@ -88,7 +132,7 @@ class ClockSampler:
                 if v.lower().startswith("active"):
                     reasons.add(nm)
         return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "samples": len(sm), "reasons": sorted(reasons)}
+                "samples": len(sm), "reasons": sorted(reasons), "source": "nvidia-smi"}
 
 
 def make_args(model, N, K, Q, steps, train, device, D, T, tasks, dropout):

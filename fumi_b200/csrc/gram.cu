@@ -13,6 +13,7 @@
 // fp32-accurate split, accumulator restarted every 32 features).  Row stride 68 makes both fragment reads
 // bank-conflict free.
 #include <cstdint>
+#include <cstdlib>
 
 #include "../../include/fumi_b200.h"
 #include "common.cuh"
@@ -86,6 +87,11 @@ __global__ void __launch_bounds__(GT) gram_kernel(const float* __restrict__ feat
 
 int fumi_gram_tc(const float*, int64_t, int64_t, const int64_t*, const int64_t*, int64_t, int32_t, int32_t, float*, void*);
 
+#ifndef FUMI_EMU
+int fumi_gram_tc_launch(const float* feats, int64_t D, const int64_t* sup_rows, const int64_t* qry_rows, int64_t B,
+                        int32_t NK, int32_t NQ, float* gram, void* stream);     // gram_tc.cu (tcgen05)
+#endif
+
 extern "C" int fumi_gram(const float* feats, int64_t num_rows, int64_t D, const int64_t* sup_rows,
                          const int64_t* qry_rows, int64_t B, int32_t NK, int32_t NQ, float* gram, void* stream) {
     FUMI_CHECK_ARG(B >= 0 && NK >= 1 && NK <= kMaxSupport && NQ >= 0 && D >= 1 && num_rows >= 1, "bad shape");
@@ -93,6 +99,16 @@ extern "C" int fumi_gram(const float* feats, int64_t num_rows, int64_t D, const 
     FUMI_CHECK_ARG((uintptr_t(feats) & 15) == 0, "feature matrix must be 16-byte aligned");
     if (B == 0) return FUMI_OK;
     FUMI_CHECK_ARG(feats && sup_rows && (qry_rows || NQ == 0) && gram, "null pointer");
+#ifndef FUMI_EMU
+    {   // NK <= 32 and NK + NQ <= 192: tcgen05 kernel (FUMI_GRAM_TC=0 keeps the warp-level kernel, for A/B runs)
+        static int use_tc = -1;
+        if (use_tc < 0) { const char* e = getenv("FUMI_GRAM_TC"); use_tc = (e && atoi(e) == 0) ? 0 : 1; }
+        if (use_tc) {
+            const int rc = fumi_gram_tc_launch(feats, D, sup_rows, qry_rows, B, NK, NQ, gram, stream);
+            if (rc <= 0) return rc;
+        }
+    }
+#endif
     FUMI_CHECK_ARG(B <= 65535, "at most 65535 tasks per call");
     dim3 grid((unsigned)((NK + NQ + TI - 1) / TI), (unsigned)((NK + TJ - 1) / TJ), (unsigned)B);
     FUMI_LAUNCH(gram_kernel, grid, GT, 0, stream, feats, D, sup_rows, qry_rows, int(NK), int(NQ), gram);

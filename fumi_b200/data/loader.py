@@ -85,13 +85,27 @@ class EpisodeLoader:
         q = queue.Queue(maxsize=self.prefetch)
         stop = self._stop = threading.Event()
 
+        # device sampler on a CUDA bank: the plan upload and fumi_sampler_expand run on the loader's own stream from
+        # the prefetch thread, so they overlap the previous batch's kernels; the consumer's stream waits on an event.
+        dev = self.bank.feats.device
+        side = torch.cuda.Stream(dev) if (self.device_sampler and dev.type == "cuda") else None
+
         def worker():
             try:
+                if side is not None:
+                    torch.cuda.set_device(dev)
                 while not stop.is_set():
                     if self.device_sampler:
                         plan = self.sampler.empty_plan(self.batch_size, pin_memory=self.pin)
                         self.sampler.plan_states(self.batch_size, py, st, plan)
-                        item = (plan, None, py.copy(), st.copy())
+                        if side is not None:
+                            with torch.cuda.stream(side):
+                                batch = self._expand(plan)
+                                ev = torch.cuda.Event()
+                                ev.record(side)
+                            item = (batch, ev, py.copy(), st.copy())
+                        else:
+                            item = (plan, None, py.copy(), st.copy())
                     else:
                         ts, arrs = self._host_buffers()
                         self.sampler.next_batch_states(self.batch_size, py, st, arrs)
@@ -114,7 +128,14 @@ class EpisodeLoader:
                 ts, arrs, py_after, st_after = item
                 random.setstate((ver, tuple(int(x) for x in py_after), gauss))
                 _torch_state_set(st_after, raw)
-                yield self._expand(ts) if arrs is None else self._make(ts, arrs)
+                if isinstance(ts, EpisodeBatch):                 # expanded on the loader stream
+                    cur = torch.cuda.current_stream(dev)
+                    cur.wait_event(arrs)
+                    for t in (ts.sup_rows, ts.qry_rows, ts.sup_y, ts.qry_y, ts.sup_ids, ts.qry_ids, ts.head_class):
+                        t.record_stream(cur)
+                    yield ts
+                else:
+                    yield self._expand(ts) if arrs is None else self._make(ts, arrs)
         finally:
             stop.set()
 
