@@ -230,8 +230,8 @@ def main():
     ap.add_argument("--im_dim", type=int, default=2048)
     ap.add_argument("--text_dim", type=int, default=768)
     ap.add_argument("--dropout", type=float, default=0.25)
-    ap.add_argument("--precision", type=int, default=int(os.environ.get("FUMI_PRECISION", "1")),
-                    help="dense layers: 1 = tcgen05 3xTF32 (default), 0 = fp32 FMA")
+    ap.add_argument("--precision", type=int, default=int(os.environ.get("FUMI_PRECISION", "2")),
+                    help="dense layers: 2 = tcgen05 with fp16 hi/lo bank planes (default), 1 = tcgen05 3xTF32, 0 = fp32 FMA")
     ap.add_argument("--cpu_budget_s", type=float, default=15.0)
     ap.add_argument("--no_cpu_baseline", action="store_true")
     ap.add_argument("--no_kernel_pass", action="store_true")

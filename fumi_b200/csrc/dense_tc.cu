@@ -25,6 +25,7 @@
 // plain fp32); restarting the accumulator every stage keeps <= 4 significant truncations per partial sum.
 // Out-of-range rows / k are zero-filled by TMA, so M, N, K need no padding (leading dims: multiple of 4).
 #include <cuda.h>
+#include <cuda_fp16.h>
 #include <cuda_runtime.h>
 
 #include <cstdint>
@@ -54,7 +55,19 @@ struct TcParams {
     int act;
     int atomic;             // 1: atomicAdd partial tiles (split-K / accumulate); bias & act must be off
     int drain;              // k stages accumulated in one TMEM buffer before it is drained into registers
+    const float* a_absmax;  // f16x3 only: device scalars max|A|, max|B| that fixed the power-of-two plane scales
+    const float* b_absmax;
 };
+
+// f16x3 planes hold x * s with s = 2^(14 - e), 2^(e-1) <= max|x| < 2^e: the largest element lands in [2^13, 2^14),
+// the fp16 "lo" plane of typical elements stays normal, and the scale is undone exactly in the epilogue.
+__host__ __device__ __forceinline__ int f16_scale_exp(float amax) {
+    if (!(amax > 0.f) || !(amax < 3.0e38f)) return 0;
+    int e;
+    frexpf(amax, &e);
+    int k = 14 - e;
+    return k > 100 ? 100 : (k < -100 ? -100 : k);
+}
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return static_cast<uint32_t>(__cvta_generic_to_shared(p)); }
 
@@ -97,6 +110,15 @@ __device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t da, uint64_t
         "}\n" ::"r"(tmem_d), "l"(da), "l"(db), "r"(idesc), "r"(accum)
         : "memory");
 }
+__device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t da, uint64_t db, uint32_t idesc, uint32_t accum) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "setp.ne.b32 p, %4, 0;\n"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n"
+        "}\n" ::"r"(tmem_d), "l"(da), "l"(db), "r"(idesc), "r"(accum)
+        : "memory");
+}
 __device__ __forceinline__ void umma_commit(uint32_t bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
 }
@@ -107,7 +129,11 @@ __device__ __forceinline__ float act_f(float v, int act) {
     return v;
 }
 
-__global__ void __launch_bounds__(kThreadsTc, 1) gemm_tf32x3_kernel(const __grid_constant__ TcParams p) {
+// F16 = false: tf32 planes (fp32 containers, 32 k per 128-byte stage row, K = 8 per MMA);
+// F16 = true : fp16 planes (64 k per 128-byte stage row, K = 16 per MMA at twice the rate, half the bytes).
+// Stage geometry in bytes, descriptors and the k-step advance (32 B) are identical.
+template <bool F16>
+__global__ void __launch_bounds__(kThreadsTc, 1) gemm_x3_kernel(const __grid_constant__ TcParams p) {
     extern __shared__ uint8_t smem_dyn[];
     const uint32_t base = (smem_u32(smem_dyn) + 1023u) & ~1023u;          // SWIZZLE_128B atoms: 1024 B aligned
     const uint32_t bars = base + kStages * kStageBytes;     // full[2], empty[2], tmem_full[2], tmem_empty[2], tmem_ptr
@@ -144,7 +170,7 @@ __global__ void __launch_bounds__(kThreadsTc, 1) gemm_tf32x3_kernel(const __grid
                 mbar_wait(empty_bar + 8 * s, ph ^ 1);
                 const uint32_t st = base + s * kStageBytes;
                 mbar_expect_tx(full_bar + 8 * s, kStageBytes);
-                const int kc = (kt0 + it) * BK;
+                const int kc = (kt0 + it) * (F16 ? 2 * BK : BK);              // element coordinate of the stage
                 tma_load_2d(st, &p.a_hi, full_bar + 8 * s, kc, m0);
                 tma_load_2d(st + kABytes, &p.a_lo, full_bar + 8 * s, kc, m0);
                 tma_load_2d(st + 2 * kABytes, &p.b_hi, full_bar + 8 * s, kc, n0);
@@ -155,7 +181,12 @@ __global__ void __launch_bounds__(kThreadsTc, 1) gemm_tf32x3_kernel(const __grid
         // ===== MMA issuer =====
         if (lane == 0 && nk > 0) {
             // instruction descriptor (cute::UMMA::InstrDescriptor): D=f32, A=B=tf32, K-major both, N>>3, M>>4
-            const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | (uint32_t(BN >> 3) << 17) | (uint32_t(BM >> 4) << 24);
+            // (kind::f16: A = B = f16 is format 0)
+            const uint32_t idesc = (1u << 4) | (F16 ? 0u : ((2u << 7) | (2u << 10))) | (uint32_t(BN >> 3) << 17) |
+                                   (uint32_t(BM >> 4) << 24);
+            auto mma = [&](uint32_t td, uint64_t da, uint64_t db, uint32_t accum) {
+                if (F16) umma_f16(td, da, db, idesc, accum); else umma_tf32(td, da, db, idesc, accum);
+            };
             for (int it = 0; it < nk; ++it) {
                 const int s = it % kStages;
                 const uint32_t ph = (it / kStages) & 1;
@@ -171,14 +202,14 @@ __global__ void __launch_bounds__(kThreadsTc, 1) gemm_tf32x3_kernel(const __grid
                     const uint64_t ahi = umma_desc_sw128(st + k * 32), alo = umma_desc_sw128(st + kABytes + k * 32);
                     const uint64_t bhi = umma_desc_sw128(st + 2 * kABytes + k * 32);
                     const uint64_t blo = umma_desc_sw128(st + 2 * kABytes + kBBytes + k * 32);
-                    umma_tf32(td, alo, bhi, idesc, (k | sub) != 0);
-                    umma_tf32(td, ahi, blo, idesc, 1);
+                    mma(td, alo, bhi, (k | sub) != 0);
+                    mma(td, ahi, blo, 1);
                 }
 #pragma unroll
                 for (int k = 0; k < BK / 8; ++k) {
                     const uint64_t ahi = umma_desc_sw128(st + k * 32);
                     const uint64_t bhi = umma_desc_sw128(st + 2 * kABytes + k * 32);
-                    umma_tf32(td, ahi, bhi, idesc, 1);
+                    mma(td, ahi, bhi, 1);
                 }
                 umma_commit(empty_bar + 8 * s);        // frees the smem stage once these MMAs retire
                 if (sub == p.drain - 1 || it == nk - 1) umma_commit(tmem_full_bar + 8 * tb);   // partial sums complete
@@ -216,6 +247,12 @@ __global__ void __launch_bounds__(kThreadsTc, 1) gemm_tf32x3_kernel(const __grid
             asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
             __syncwarp();
             if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(tmem_empty_bar + 8 * tb) : "memory");
+        }
+        if (F16) {                                    // undo the plane scales (exact powers of two)
+            const float ia = ldexpf(1.f, -f16_scale_exp(p.a_absmax ? *p.a_absmax : 0.f));
+            const float ib = ldexpf(1.f, -f16_scale_exp(p.b_absmax ? *p.b_absmax : 0.f));
+#pragma unroll
+            for (int j = 0; j < 128; ++j) acc[j] = (acc[j] * ia) * ib;
         }
         if (nk > 0 && row < p.M) {
 #pragma unroll
@@ -304,22 +341,63 @@ EncodeTiledFn get_encode() {
     return fn;
 }
 
-// 2D fp32 row-major [rows, cols] with leading dimension ld (floats); box = [BK cols x box_rows]
-int make_map(CUtensorMap* m, const float* ptr, int64_t rows, int64_t cols, int64_t ld, int box_rows) {
+// 2D row-major [rows, cols] with leading dimension ld (elements); box = [128 bytes of columns x box_rows]
+int make_map(CUtensorMap* m, const void* ptr, int64_t rows, int64_t cols, int64_t ld, int box_rows, bool f16) {
     EncodeTiledFn enc = get_encode();
     if (!enc) { fumi_set_error("cuTensorMapEncodeTiled is not available from the driver"); return FUMI_ERR_CUDA; }
+    const int esz = f16 ? 2 : 4;
     cuuint64_t dims[2] = {cuuint64_t(cols), cuuint64_t(rows)};
-    cuuint64_t strides[1] = {cuuint64_t(ld) * 4};
-    cuuint32_t box[2] = {cuuint32_t(BK), cuuint32_t(box_rows)};
+    cuuint64_t strides[1] = {cuuint64_t(ld) * esz};
+    cuuint32_t box[2] = {cuuint32_t(128 / esz), cuuint32_t(box_rows)};
     cuuint32_t estr[2] = {1, 1};
-    CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(ptr), dims, strides, box, estr,
-                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    CUresult r = enc(m, f16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<void*>(ptr), dims,
+                     strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                     CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) {
         fumi_set_error("cuTensorMapEncodeTiled failed with CUresult " + std::to_string(int(r)));
         return FUMI_ERR_CUDA;
     }
     return FUMI_OK;
+}
+
+// max |x| over a buffer, as the bit pattern of a non-negative float (ordered like an unsigned integer)
+__global__ void absmax_kernel(const float* __restrict__ x, int64_t n, unsigned int* __restrict__ out) {
+    float m = 0.f;
+    for (int64_t i = int64_t(blockIdx.x) * blockDim.x + threadIdx.x; i < n; i += int64_t(gridDim.x) * blockDim.x)
+        m = fmaxf(m, fabsf(x[i]));
+#pragma unroll
+    for (int off = 16; off >= 1; off >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, off));
+    if ((threadIdx.x & 31) == 0 && m > 0.f) atomicMax(out, __float_as_uint(m));
+}
+
+__device__ __forceinline__ void split_f16(float v, __half& hi, __half& lo) {
+    hi = __float2half_rn(v);
+    lo = __float2half_rn(v - __half2float(hi));
+}
+
+// x -> fp16 planes of x * 2^k (k from the device scalar max|x|): hi = fp16(xs), lo = fp16(xs - hi)
+__global__ void split_f16_kernel(const float* __restrict__ x, __half* __restrict__ hi, __half* __restrict__ lo, int64_t n,
+                                 const float* __restrict__ absmax) {
+    const float sc = ldexpf(1.f, f16_scale_exp(*absmax));
+    for (int64_t i = int64_t(blockIdx.x) * blockDim.x + threadIdx.x; i < n; i += int64_t(gridDim.x) * blockDim.x)
+        split_f16(x[i] * sc, hi[i], lo[i]);
+}
+
+// x[R,Ccols] -> hiT / loT [Ccols, ldt] fp16 (transposed, scaled, split), 32x32 tiles through shared memory
+__global__ void transpose_split_f16_kernel(const float* __restrict__ x, __half* __restrict__ hiT, __half* __restrict__ loT,
+                                           int64_t R, int64_t Ccols, int64_t ldt, const float* __restrict__ absmax) {
+    __shared__ float tile[32][33];
+    const float sc = ldexpf(1.f, f16_scale_exp(*absmax));
+    const int64_t r0 = int64_t(blockIdx.x) * 32, c0 = int64_t(blockIdx.y) * 32;
+    for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+        const int64_t r = r0 + i, c = c0 + threadIdx.x;
+        tile[i][threadIdx.x] = (r < R && c < Ccols) ? x[r * Ccols + c] : 0.f;
+    }
+    __syncthreads();
+    for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+        const int64_t c = c0 + i, r = r0 + threadIdx.x;
+        if (c < Ccols && r < ldt) split_f16(r < R ? tile[threadIdx.x][i] * sc : 0.f, hiT[c * ldt + r], loT[c * ldt + r]);
+    }
 }
 
 }  // namespace
@@ -346,24 +424,27 @@ extern "C" int fumi_transpose_split_tf32(const float* x, float* hiT, float* loT,
     return FUMI_OK;
 }
 
-extern "C" int fumi_gemm_tf32x3(const float* a_hi, const float* a_lo, const float* b_hi, const float* b_lo,
-                                const float* bias, float* c, int64_t M, int64_t N, int64_t K, int64_t lda, int64_t ldb,
-                                int64_t ldc, int32_t act, int32_t accumulate, int32_t split_k, void* stream) {
+namespace {
+int launch_gemm_x3(bool f16, const void* a_hi, const void* a_lo, const void* b_hi, const void* b_lo, const float* a_absmax,
+                   const float* b_absmax, const float* bias, float* c, int64_t M, int64_t N, int64_t K, int64_t lda,
+                   int64_t ldb, int64_t ldc, int32_t act, int32_t accumulate, int32_t split_k, void* stream) {
     FUMI_CHECK_ARG(M >= 1 && N >= 1 && K >= 1, "bad shape");
     FUMI_CHECK_ARG(a_hi && a_lo && b_hi && b_lo && c, "null pointer");
-    FUMI_CHECK_ARG(lda >= K && ldb >= K && ldc >= N && (lda & 3) == 0 && (ldb & 3) == 0,
-                   "leading dimensions must cover K / N and be multiples of 4 floats (TMA 16-byte strides)");
+    const int al = f16 ? 8 : 4;            // elements per 16 bytes
+    FUMI_CHECK_ARG(lda >= K && ldb >= K && ldc >= N && lda % al == 0 && ldb % al == 0,
+                   "leading dimensions must cover K / N and be multiples of 16 bytes (TMA strides)");
     FUMI_CHECK_ARG(act >= 0 && act <= 3, "act must be 0..3");
     FUMI_CHECK_ARG((uintptr_t(a_hi) | uintptr_t(a_lo) | uintptr_t(b_hi) | uintptr_t(b_lo)) % 16 == 0,
                    "operand planes must be 16-byte aligned");
     TcParams p;
     std::memset(&p, 0, sizeof(p));
     int rc;
-    if ((rc = make_map(&p.a_hi, a_hi, M, K, lda, BM)) != FUMI_OK) return rc;
-    if ((rc = make_map(&p.a_lo, a_lo, M, K, lda, BM)) != FUMI_OK) return rc;
-    if ((rc = make_map(&p.b_hi, b_hi, N, K, ldb, BN)) != FUMI_OK) return rc;
-    if ((rc = make_map(&p.b_lo, b_lo, N, K, ldb, BN)) != FUMI_OK) return rc;
+    if ((rc = make_map(&p.a_hi, a_hi, M, K, lda, BM, f16)) != FUMI_OK) return rc;
+    if ((rc = make_map(&p.a_lo, a_lo, M, K, lda, BM, f16)) != FUMI_OK) return rc;
+    if ((rc = make_map(&p.b_hi, b_hi, N, K, ldb, BN, f16)) != FUMI_OK) return rc;
+    if ((rc = make_map(&p.b_lo, b_lo, N, K, ldb, BN, f16)) != FUMI_OK) return rc;
     p.C = c; p.bias = bias; p.M = M; p.N = N; p.ldc = ldc; p.act = act;
+    p.a_absmax = a_absmax; p.b_absmax = b_absmax;
     {   // stages per TMEM drain: 1 = best accuracy (<= 4 truncating adds per partial sum), more = fewer drains
         static int drain = -1;
         if (drain < 0) {
@@ -372,9 +453,10 @@ extern "C" int fumi_gemm_tf32x3(const float* a_hi, const float* a_lo, const floa
             if (drain < 1) drain = 1;
             if (drain > 8) drain = 8;
         }
-        p.drain = drain;
+        p.drain = f16 ? (drain + 1) / 2 : drain;         // an f16 stage holds twice the k
     }
-    p.k_tiles = int((K + BK - 1) / BK);
+    const int kstage = f16 ? 2 * BK : BK;
+    p.k_tiles = int((K + kstage - 1) / kstage);
     const int64_t tiles = ((M + BM - 1) / BM) * ((N + BN - 1) / BN);
     int splits = split_k;
     if (splits <= 0 && (bias != nullptr || act != 0)) splits = 1;     // fused epilogue needs whole-K tiles
@@ -397,14 +479,70 @@ extern "C" int fumi_gemm_tf32x3(const float* a_hi, const float* a_lo, const floa
     }
     static bool attr_done = false;
     if (!attr_done) {
-        cudaError_t e = cudaFuncSetAttribute(gemm_tf32x3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(kSmemBytes));
-        if (e != cudaSuccess) return fumi_cuda_fail(e, "cudaFuncSetAttribute(gemm_tf32x3)");
+        cudaError_t e = cudaFuncSetAttribute(gemm_x3_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(kSmemBytes));
+        if (e == cudaSuccess)
+            e = cudaFuncSetAttribute(gemm_x3_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(kSmemBytes));
+        if (e != cudaSuccess) return fumi_cuda_fail(e, "cudaFuncSetAttribute(gemm_x3)");
         attr_done = true;
     }
     dim3 grid((unsigned)((M + BM - 1) / BM), (unsigned)((N + BN - 1) / BN), (unsigned)splits);
     FUMI_CHECK_ARG(grid.y <= 65535 && grid.z <= 65535, "grid too large");
-    gemm_tf32x3_kernel<<<grid, kThreadsTc, kSmemBytes, (cudaStream_t)stream>>>(p);
-    FUMI_CHECK_LAUNCH("gemm_tf32x3_kernel");
+    if (f16) gemm_x3_kernel<true><<<grid, kThreadsTc, kSmemBytes, (cudaStream_t)stream>>>(p);
+    else gemm_x3_kernel<false><<<grid, kThreadsTc, kSmemBytes, (cudaStream_t)stream>>>(p);
+    FUMI_CHECK_LAUNCH("gemm_x3_kernel");
+    return FUMI_OK;
+}
+}  // namespace
+
+extern "C" int fumi_gemm_tf32x3(const float* a_hi, const float* a_lo, const float* b_hi, const float* b_lo,
+                                const float* bias, float* c, int64_t M, int64_t N, int64_t K, int64_t lda, int64_t ldb,
+                                int64_t ldc, int32_t act, int32_t accumulate, int32_t split_k, void* stream) {
+    return launch_gemm_x3(false, a_hi, a_lo, b_hi, b_lo, nullptr, nullptr, bias, c, M, N, K, lda, ldb, ldc, act, accumulate,
+                          split_k, stream);
+}
+
+extern "C" int fumi_gemm_f16x3(const void* a_hi, const void* a_lo, const void* b_hi, const void* b_lo,
+                               const float* a_absmax, const float* b_absmax, const float* bias, float* c, int64_t M,
+                               int64_t N, int64_t K, int64_t lda, int64_t ldb, int64_t ldc, int32_t act,
+                               int32_t accumulate, int32_t split_k, void* stream) {
+    FUMI_CHECK_ARG(a_absmax && b_absmax, "null scale pointer");
+    return launch_gemm_x3(true, a_hi, a_lo, b_hi, b_lo, a_absmax, b_absmax, bias, c, M, N, K, lda, ldb, ldc, act, accumulate,
+                          split_k, stream);
+}
+
+extern "C" int fumi_absmax(const float* x, int64_t n, float* out, void* stream) {
+    FUMI_CHECK_ARG(n >= 0 && out && (x || n == 0), "bad argument");
+    cudaError_t e = cudaMemsetAsync(out, 0, 4, (cudaStream_t)stream);
+    if (e != cudaSuccess) return fumi_cuda_fail(e, "cudaMemsetAsync");
+    if (n == 0) return FUMI_OK;
+    int64_t blocks = (n + 1023) / 1024;
+    if (blocks > 148 * 8) blocks = 148 * 8;
+    absmax_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(x, n, reinterpret_cast<unsigned int*>(out));
+    FUMI_CHECK_LAUNCH("absmax_kernel");
+    return FUMI_OK;
+}
+
+extern "C" int fumi_split_f16(const float* x, const float* absmax, void* hi, void* lo, int64_t n, void* stream) {
+    FUMI_CHECK_ARG(n >= 0, "n < 0");
+    if (n == 0) return FUMI_OK;
+    FUMI_CHECK_ARG(x && absmax && hi && lo, "null pointer");
+    int64_t blocks = (n + 255) / 256;
+    if (blocks > 148 * 16) blocks = 148 * 16;
+    split_f16_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(x, static_cast<__half*>(hi), static_cast<__half*>(lo), n,
+                                                                         absmax);
+    FUMI_CHECK_LAUNCH("split_f16_kernel");
+    return FUMI_OK;
+}
+
+extern "C" int fumi_transpose_split_f16(const float* x, const float* absmax, void* hiT, void* loT, int64_t R, int64_t C,
+                                        int64_t ldt, void* stream) {
+    FUMI_CHECK_ARG(R >= 1 && C >= 1 && ldt >= R && (ldt & 7) == 0, "need ldt >= R and ldt % 8 == 0");
+    FUMI_CHECK_ARG(x && absmax && hiT && loT, "null pointer");
+    dim3 grid((unsigned)((ldt + 31) / 32), (unsigned)((C + 31) / 32));
+    FUMI_CHECK_ARG(grid.y <= 65535, "too many columns");
+    transpose_split_f16_kernel<<<grid, dim3(32, 8), 0, (cudaStream_t)stream>>>(x, static_cast<__half*>(hiT),
+                                                                               static_cast<__half*>(loT), R, C, ldt, absmax);
+    FUMI_CHECK_LAUNCH("transpose_split_f16_kernel");
     return FUMI_OK;
 }
 

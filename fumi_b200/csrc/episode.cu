@@ -699,26 +699,6 @@ __device__ __forceinline__ void mma16_tile_h1(const EpiParams& P, const SmemM& s
     });
 }
 
-__device__ __forceinline__ void m16_tile_logits(const EpiParams& P, const SmemM& s, int rows, int tr) {
-    const int N = P.cfg.num_ways;
-    for (int idx = threadIdx.x; idx < rows * N; idx += kThreads16) {
-        const int i = idx / N, c = idx - i * N;
-        float l = 0.f;
-        if (i < tr) {
-            float l0 = s.hp[c * kHD + kH1], l1 = 0.f, l2 = 0.f, l3 = 0.f;
-#pragma unroll 4
-            for (int o = 0; o < kH1; o += 4) {
-                l0 = fmaf(s.h1t[i * kS1 + o], s.hp[c * kHD + o], l0);
-                l1 = fmaf(s.h1t[i * kS1 + o + 1], s.hp[c * kHD + o + 1], l1);
-                l2 = fmaf(s.h1t[i * kS1 + o + 2], s.hp[c * kHD + o + 2], l2);
-                l3 = fmaf(s.h1t[i * kS1 + o + 3], s.hp[c * kHD + o + 3], l3);
-            }
-            l = (l0 + l1) + (l2 + l3);
-        }
-        s.lt[i * kLS + c] = l;
-    }
-}
-
 // Logits and their softmax in one phase: one lane per (row, class), a row's N lanes in the same warp
 // (32 / N rows per warp), so the row statistics need only a warp barrier.  Every lane of a row recomputes
 // max / sum-of-exp (N <= 32 expf) and hands (row, class, logit, max, sum) to `sink`, which may overwrite

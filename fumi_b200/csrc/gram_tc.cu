@@ -46,15 +46,19 @@
 namespace {
 
 constexpr int kRows = 192;                       // rows per task: tile 0 = rows 0-127, tile 1 = rows 128-191
-constexpr int kBK = 32;                          // features per stage = 128 bytes per row
+template <bool F16> struct GramCfg {              // F16: fp16 (hi, lo) bank planes, 64 features per 128-byte stage row
+    static constexpr int kFeat = F16 ? 64 : 32;                  // features per stage
+    static constexpr int kRingSlots = F16 ? 4 : 6;               // staging ring of gathered row pieces
+    static constexpr int kAhead = F16 ? 2 : 4;                   // stages of cp.async in flight (96 KB either way)
+    static constexpr uint32_t kRingSlot = 192u * 128u * (F16 ? 2u : 1u);      // 24 KB per plane
+    static constexpr int kDrain = F16 ? 1 : 2;                   // stages (64 features) per TMEM accumulator
+    static constexpr uint32_t kSmem = 3u * 2u * 4096u + kRingSlots * kRingSlot + 1024 + 256;
+};
+constexpr int kBK = 32;                          // 32-bit words per stage row = 128 bytes
 constexpr int kStagesG = 3;                      // A stages in TMEM / B stages in shared memory
-constexpr int kDrain = 2;                        // stages accumulated in one TMEM buffer
 constexpr uint32_t kBPlane = 32 * kBK * 4;       // 4 KB: 32 support rows x 128 B
 constexpr uint32_t kBStage = 2 * kBPlane;        // hi + lo
 constexpr int kThreadsG = 12 * 32;               // warps 0-5 loaders, 6 MMA, 7 idle, 8-11 drain
-constexpr int kRingSlots = 6, kAhead = 4;        // staging ring of raw row pieces; stages of cp.async in flight
-constexpr uint32_t kRingSlot = kRows * kBK * 4;  // 24 KB
-constexpr uint32_t kSmemBytesG = kStagesG * kBStage + kRingSlots * kRingSlot + 1024 + 256;
 constexpr int kTmemCols = 512;
 constexpr uint32_t kAccCols = 128, kAStageCols = 128;
 
@@ -92,6 +96,15 @@ __device__ __forceinline__ void umma_tf32_ts(uint32_t tmem_d, uint32_t tmem_a, u
         "}\n" ::"r"(tmem_d), "r"(tmem_a), "l"(db), "r"(idesc), "r"(accum)
         : "memory");
 }
+__device__ __forceinline__ void umma_f16_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t db, uint32_t idesc, uint32_t accum) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "setp.ne.b32 p, %4, 0;\n"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n"
+        "}\n" ::"r"(tmem_d), "r"(tmem_a), "l"(db), "r"(idesc), "r"(accum)
+        : "memory");
+}
 __device__ __forceinline__ void tmem_st32(uint32_t taddr, const uint32_t (&v)[32]) {
     asm volatile(
         "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], "
@@ -119,7 +132,9 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
 }
 
 struct GramTcParams {
-    const float* feats;
+    const void* feats;        // fp32 bank, or the fp16 hi plane
+    const void* feats_lo;     // fp16 lo plane (F16 only)
+    const float* absmax;      // device scalar that fixed the fp16 plane scale (F16 only)
     int64_t D;
     const int64_t* sup_rows;
     const int64_t* qry_rows;
@@ -129,7 +144,20 @@ struct GramTcParams {
     int dbg;      // diagnostics (FUMI_GRAM_DBG): 1 skip the MMAs, 2 skip the gather, 4 skip the TMEM stores
 };
 
+__host__ __device__ __forceinline__ int gram_f16_scale_exp(float amax) {      // = f16_scale_exp of dense_tc.cu
+    if (!(amax > 0.f) || !(amax < 3.0e38f)) return 0;
+    int e;
+    frexpf(amax, &e);
+    const int k = 14 - e;
+    return k > 100 ? 100 : (k < -100 ? -100 : k);
+}
+
+template <bool F16>
 __global__ void __launch_bounds__(kThreadsG, 1) gram_tc_kernel(const GramTcParams p) {
+    using Cfg = GramCfg<F16>;
+    constexpr int kRingSlots = Cfg::kRingSlots, kAhead = Cfg::kAhead, kDrain = Cfg::kDrain;
+    constexpr uint32_t kRingSlot = Cfg::kRingSlot;
+    constexpr int kEsz = F16 ? 2 : 4;
     extern __shared__ uint8_t smem_dyn[];
     const uint32_t base = (smem_u32(smem_dyn) + 1023u) & ~1023u;
     uint8_t* base_ptr = smem_dyn + (base - smem_u32(smem_dyn));
@@ -141,7 +169,7 @@ __global__ void __launch_bounds__(kThreadsG, 1) gram_tc_kernel(const GramTcParam
     const int rows = p.NK + p.NQ;
     const bool two_tiles = rows > 128;
     const int n_loader_warps = two_tiles ? 6 : 4;
-    const int k_stages = int(p.D / kBK);                                   // stages per task
+    const int k_stages = int(p.D / Cfg::kFeat);                            // stages per task
     const int64_t my_tasks = p.B > blockIdx.x ? (p.B - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
     const int64_t total = my_tasks * k_stages;                             // stages this CTA runs
 
@@ -176,7 +204,9 @@ __global__ void __launch_bounds__(kThreadsG, 1) gram_tc_kernel(const GramTcParam
         const uint32_t a_lane = uint32_t((r & 127) & ~31) << 16;
         const uint32_t a_col0 = kAccCols + uint32_t(tile) * 64u;
         const uint32_t sw = uint32_t(r & 7);                     // swizzle phase of row r
-        const float* rowp[8];
+        int64_t rowoff[8];                                       // byte offset of (row, chunk c) in a bank plane
+        const uint8_t* plane_hi = static_cast<const uint8_t*>(p.feats);
+        const uint8_t* plane_lo = static_cast<const uint8_t*>(p.feats_lo);
         int64_t gi = 0, bi = blockIdx.x;                         // issue side: stage, its task, its k chunk
         int kci = 0;
         auto task_rows = [&](int64_t b) {
@@ -184,7 +214,7 @@ __global__ void __launch_bounds__(kThreadsG, 1) gram_tc_kernel(const GramTcParam
             for (int j = 0; j < 8; ++j) {
                 const int rg = rg0 + rstep * j;
                 const int64_t row = rg < p.NK ? p.sup_rows[b * p.NK + rg] : (rg < rows ? p.qry_rows[b * p.NQ + (rg - p.NK)] : 0);
-                rowp[j] = p.feats + row * p.D + c * 4;
+                rowoff[j] = row * p.D * kEsz + c * 16;
             }
         };
         auto issue = [&]() {                                     // cp.async of stage gi
@@ -193,10 +223,14 @@ __global__ void __launch_bounds__(kThreadsG, 1) gram_tc_kernel(const GramTcParam
 #pragma unroll
                 for (int j = 0; j < 8; ++j) {
                     const int rg = rg0 + rstep * j;
-                    if (rg < rows)
+                    if (rg < rows) {
+                        const uint32_t d = dst + uint32_t(rg) * 128u + uint32_t((c ^ (rg & 7)) << 4);
                         asm volatile("cp.async.cg.shared.global [%0], [%1], 16;"
-                                     ::"r"(dst + uint32_t(rg) * 128u + uint32_t((c ^ (rg & 7)) << 4)), "l"(rowp[j] + kci * kBK)
-                                     : "memory");
+                                     ::"r"(d), "l"(plane_hi + rowoff[j] + int64_t(kci) * 128) : "memory");
+                        if (F16)
+                            asm volatile("cp.async.cg.shared.global [%0], [%1], 16;"
+                                         ::"r"(d + kRingSlot / 2), "l"(plane_lo + rowoff[j] + int64_t(kci) * 128) : "memory");
+                    }
                 }
                 if (++kci == k_stages) {
                     kci = 0;
@@ -207,8 +241,11 @@ __global__ void __launch_bounds__(kThreadsG, 1) gram_tc_kernel(const GramTcParam
             asm volatile("cp.async.commit_group;" ::: "memory");
             ++gi;
         };
-        auto process = [&](float4 (&v)[8], int64_t g) {          // stage g: registers -> TMEM (and B planes)
+        auto process = [&](const uint8_t* src, int64_t g) {      // stage g: staging ring -> TMEM (and B planes)
             const int s = int(g % kStagesG);
+            float4 v[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) v[j] = *reinterpret_cast<const float4*>(src + ((uint32_t(j) ^ sw) << 4));
             mbar_wait(empty_bar + 8 * s, (uint32_t(g / kStagesG) & 1) ^ 1);
             uint32_t u[32];
 #pragma unroll
@@ -217,17 +254,26 @@ __global__ void __launch_bounds__(kThreadsG, 1) gram_tc_kernel(const GramTcParam
                 u[4 * j + 2] = __float_as_uint(v[j].z); u[4 * j + 3] = __float_as_uint(v[j].w);
             }
             const uint32_t ta = tmem_base + a_lane + a_col0 + uint32_t(s) * kAStageCols;
-            if (!(p.dbg & 4)) tmem_st32(ta, u);                  // hi plane: the raw bits
+            if (!(p.dbg & 4)) tmem_st32(ta, u);                  // hi plane (fp32: the raw bits)
             uint8_t* bst = base_ptr + s * kBStage;
             if (warp == 0) {
 #pragma unroll
                 for (int j = 0; j < 8; ++j)
                     *reinterpret_cast<float4*>(bst + r * 128 + ((uint32_t(j) ^ sw) << 4)) = v[j];
             }
+            if (F16) {                                           // the lo plane was gathered too
 #pragma unroll
-            for (int i = 0; i < 32; ++i) {
-                const float x = __uint_as_float(u[i]);
-                u[i] = __float_as_uint(x - __uint_as_float(u[i] & 0xFFFFE000u));
+                for (int j = 0; j < 8; ++j) {
+                    v[j] = *reinterpret_cast<const float4*>(src + kRingSlot / 2 + ((uint32_t(j) ^ sw) << 4));
+                    u[4 * j] = __float_as_uint(v[j].x); u[4 * j + 1] = __float_as_uint(v[j].y);
+                    u[4 * j + 2] = __float_as_uint(v[j].z); u[4 * j + 3] = __float_as_uint(v[j].w);
+                }
+            } else {
+#pragma unroll
+                for (int i = 0; i < 32; ++i) {
+                    const float x = __uint_as_float(u[i]);
+                    u[i] = __float_as_uint(x - __uint_as_float(u[i] & 0xFFFFE000u));
+                }
             }
             if (!(p.dbg & 4)) tmem_st32(ta + 32, u);             // lo plane
             if (warp == 0) {
@@ -253,17 +299,17 @@ __global__ void __launch_bounds__(kThreadsG, 1) gram_tc_kernel(const GramTcParam
                 issue();
                 asm volatile("cp.async.wait_group %0;" ::"n"(kAhead) : "memory");   // this thread's pieces of stage g
                 asm volatile("bar.sync 1, %0;" ::"r"(LT) : "memory");               // ... and everyone else's
-                const uint8_t* src = base_ptr + kStagesG * kBStage + uint32_t(g % kRingSlots) * kRingSlot + r * 128;
-                float4 v[8];
-#pragma unroll
-                for (int j = 0; j < 8; ++j) v[j] = *reinterpret_cast<const float4*>(src + ((uint32_t(j) ^ sw) << 4));
-                process(v, g);
+                process(base_ptr + kStagesG * kBStage + uint32_t(g % kRingSlots) * kRingSlot + r * 128, g);
             }
         }
     } else if (warp == 6) {
         // ===================== MMA issuer =====================
         if (lane == 0) {
-            const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | (uint32_t(32 >> 3) << 17) | (uint32_t(128 >> 4) << 24);
+            const uint32_t idesc = (1u << 4) | (F16 ? 0u : ((2u << 7) | (2u << 10))) | (uint32_t(32 >> 3) << 17) |
+                                   (uint32_t(128 >> 4) << 24);
+            auto mma = [&](uint32_t td, uint32_t ta, uint64_t db, uint32_t accum) {
+                if (F16) umma_f16_ts(td, ta, db, idesc, accum); else umma_tf32_ts(td, ta, db, idesc, accum);
+            };
             for (int64_t g = 0; g < total; ++g) {
                 const int s = int(g % kStagesG);
                 const int64_t grp = g / kDrain;
@@ -281,11 +327,11 @@ __global__ void __launch_bounds__(kThreadsG, 1) gram_tc_kernel(const GramTcParam
                     const uint32_t ahi = tmem_base + kAccCols + uint32_t(s) * kAStageCols + uint32_t(t) * 64u, alo = ahi + 32;
 #pragma unroll
                     for (int k = 0; k < kBK / 8; ++k) {          // small cross products first
-                        umma_tf32_ts(td, alo + 8 * k, umma_desc_sw128(bhi + k * 32), idesc, (k | sub) != 0);
-                        umma_tf32_ts(td, ahi + 8 * k, umma_desc_sw128(blo + k * 32), idesc, 1);
+                        mma(td, alo + 8 * k, umma_desc_sw128(bhi + k * 32), (k | sub) != 0);
+                        mma(td, ahi + 8 * k, umma_desc_sw128(blo + k * 32), 1);
                     }
 #pragma unroll
-                    for (int k = 0; k < kBK / 8; ++k) umma_tf32_ts(td, ahi + 8 * k, umma_desc_sw128(bhi + k * 32), idesc, 1);
+                    for (int k = 0; k < kBK / 8; ++k) mma(td, ahi + 8 * k, umma_desc_sw128(bhi + k * 32), 1);
                 }
                 umma_commit(empty_bar + 8 * s);                  // A stage (TMEM) and B stage (smem) are free once these retire
                 if (sub == kDrain - 1 || g == total - 1) umma_commit(tmem_full_bar + 8 * tb);
@@ -321,6 +367,11 @@ __global__ void __launch_bounds__(kThreadsG, 1) gram_tc_kernel(const GramTcParam
                 __syncwarp();
                 if (lane == 0) mbar_arrive(tmem_empty_bar + 8 * tb);
             }
+            if (F16) {                                           // undo the plane scale (squared): exact powers of two
+                const float inv = ldexpf(1.f, -gram_f16_scale_exp(*p.absmax));
+#pragma unroll
+                for (int j = 0; j < 32; ++j) { acc0[j] = (acc0[j] * inv) * inv; acc1[j] = (acc1[j] * inv) * inv; }
+            }
             float* g = p.gram + b * int64_t(rows) * p.NK;
             const int r0 = q * 32 + lane;
             if (r0 < rows) {
@@ -345,26 +396,51 @@ __global__ void __launch_bounds__(kThreadsG, 1) gram_tc_kernel(const GramTcParam
 
 }  // namespace
 
-// Returns FUMI_OK when the launch was made, 1 when the shape is outside this kernel (caller falls back to the
-// warp-level kernel of gram.cu), < 0 on error.
-int fumi_gram_tc_launch(const float* feats, int64_t D, const int64_t* sup_rows, const int64_t* qry_rows, int64_t B,
-                        int32_t NK, int32_t NQ, float* gram, void* stream) {
-    if (NK > 32 || NK + NQ > kRows || D % (kBK * kDrain) != 0) return 1;
+namespace {
+template <bool F16>
+int launch_gram_tc(const GramTcParams& p, void* stream) {
     int dev = 0, sms = 0;
     if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess)
         return fumi_cuda_fail(cudaGetLastError(), "fumi_gram (device query)");
     static bool attr_done = false;
     if (!attr_done) {
-        cudaError_t e = cudaFuncSetAttribute(gram_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(kSmemBytesG));
+        cudaError_t e = cudaFuncSetAttribute(gram_tc_kernel<F16>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                             int(GramCfg<F16>::kSmem));
         if (e != cudaSuccess) return fumi_cuda_fail(e, "cudaFuncSetAttribute(gram_tc_kernel)");
         attr_done = true;
     }
-    static int dbg = -1;
-    if (dbg < 0) { const char* e = getenv("FUMI_GRAM_DBG"); dbg = e ? atoi(e) : 0; }
-    GramTcParams p{feats, D, sup_rows, qry_rows, B, NK, NQ, gram, dbg};
-    const unsigned grid = unsigned(B < sms ? B : sms);
-    gram_tc_kernel<<<grid, kThreadsG, kSmemBytesG, (cudaStream_t)stream>>>(p);
+    const unsigned grid = unsigned(p.B < sms ? p.B : sms);
+    gram_tc_kernel<F16><<<grid, kThreadsG, GramCfg<F16>::kSmem, (cudaStream_t)stream>>>(p);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return fumi_cuda_fail(e, "gram_tc_kernel");
     return FUMI_OK;
+}
+int gram_dbg() {
+    static int dbg = -1;
+    if (dbg < 0) { const char* e = getenv("FUMI_GRAM_DBG"); dbg = e ? atoi(e) : 0; }
+    return dbg;
+}
+}  // namespace
+
+// Returns FUMI_OK when the launch was made, 1 when the shape is outside this kernel (caller falls back to the
+// warp-level kernel of gram.cu), < 0 on error.
+int fumi_gram_tc_launch(const float* feats, int64_t D, const int64_t* sup_rows, const int64_t* qry_rows, int64_t B,
+                        int32_t NK, int32_t NQ, float* gram, void* stream) {
+    if (NK > 32 || NK + NQ > kRows || D % 64 != 0) return 1;
+    GramTcParams p{feats, nullptr, nullptr, D, sup_rows, qry_rows, B, NK, NQ, gram, gram_dbg()};
+    return launch_gram_tc<false>(p, stream);
+}
+
+// fp16 (hi, lo) bank planes (fumi_split_f16): half the MMAs per feature (K = 16), no split arithmetic in the kernel
+extern "C" int fumi_gram_f16(const void* feats_hi, const void* feats_lo, const float* absmax, int64_t num_rows, int64_t D,
+                             const int64_t* sup_rows, const int64_t* qry_rows, int64_t B, int32_t NK, int32_t NQ,
+                             float* gram, void* stream) {
+    FUMI_CHECK_ARG(B >= 0 && NK >= 1 && NK <= 32 && NQ >= 0 && NK + NQ <= kRows && num_rows >= 1,
+                   "fp16-plane Gram kernel: NK <= 32 and NK + NQ <= 192");
+    FUMI_CHECK_ARG(D >= 64 && D % 64 == 0, "feature dim must be a multiple of 64");
+    if (B == 0) return FUMI_OK;
+    FUMI_CHECK_ARG(feats_hi && feats_lo && absmax && sup_rows && (qry_rows || NQ == 0) && gram, "null pointer");
+    FUMI_CHECK_ARG((uintptr_t(feats_hi) | uintptr_t(feats_lo)) % 16 == 0, "planes must be 16-byte aligned");
+    GramTcParams p{feats_hi, feats_lo, absmax, D, sup_rows, qry_rows, B, NK, NQ, gram, gram_dbg()};
+    return launch_gram_tc<true>(p, stream);
 }

@@ -46,8 +46,9 @@ class EpisodeEngine:
             raise _lib.FumiError(f"fumi_b200 runs on CUDA devices only (got {self.device}); there is no CPU path")
         self.L = _lib.lib()
         if precision is None:            # default: tensor cores (the host emulation used by CPU tests has none)
-            precision = 0 if _lib.is_emulation() else 1
-        self.precision = precision       # dense layers: 0 fp32 FMA, 1 tcgen05 3xTF32
+            precision = 0 if _lib.is_emulation() else 2
+        # dense layers: 0 fp32 FMA; 1 tcgen05 3xTF32; 2 = 1 + the two bank-sized contractions on fp16 hi/lo planes
+        self.precision = precision
         self.launches = 0                # kernels launched through this engine (bench: gpu_launches)
         self.profile = None              # dict name -> [cuda event pairs] while bench.py profiles kernels
 
@@ -128,6 +129,58 @@ class EpisodeEngine:
         self.launches += 1
         return out
 
+    # ---- tcgen05 3 x fp16 path (precision 2): scaled fp16 (hi, lo) planes + the device scalar max|x| --------
+    def absmax(self, x):
+        out = torch.empty(1, dtype=torch.float32, device=x.device)
+        self._call("fumi_absmax", self.L.fumi_absmax, _lib.ptr(x), x.numel(), _lib.ptr(out), self._stream())
+        self.launches += 1
+        return out
+
+    def split_f16(self, x):
+        x = x.contiguous()
+        am = self.absmax(x)
+        hi = torch.empty(x.shape, dtype=torch.float16, device=x.device)
+        lo = torch.empty_like(hi)
+        self._call("fumi_split_f16", self.L.fumi_split_f16, _lib.ptr(x), _lib.ptr(am), _lib.ptr(hi), _lib.ptr(lo),
+                   x.numel(), self._stream())
+        self.launches += 1
+        return hi, lo, am
+
+    def transpose_split_f16(self, x):
+        """x [R,C] -> (hiT, loT, absmax), planes [C, ldt] fp16 with ldt = R rounded up to 64."""
+        x = x.contiguous()
+        R, Cc = x.shape
+        ldt = (R + 63) // 64 * 64
+        am = self.absmax(x)
+        hiT = torch.empty((Cc, ldt), dtype=torch.float16, device=x.device)
+        loT = torch.empty_like(hiT)
+        self._call("fumi_transpose_split_f16", self.L.fumi_transpose_split_f16, _lib.ptr(x), _lib.ptr(am), _lib.ptr(hiT),
+                   _lib.ptr(loT), R, Cc, ldt, self._stream())
+        self.launches += 1
+        return hiT, loT, am
+
+    def gemm_f16(self, a, b, bias=None, act=0, out=None, accumulate=False, split_k=0, K=None):
+        """out[M,N] (=|+=) act(A . B^T + bias); a, b = (hi, lo, absmax) from split_f16 / transpose_split_f16."""
+        M, lda = a[0].shape
+        N, ldb = b[0].shape
+        K = min(lda, ldb) if K is None else K
+        if out is None:
+            out = self._new(M, N)
+        self._call("fumi_gemm_f16x3", self.L.fumi_gemm_f16x3, _lib.ptr(a[0]), _lib.ptr(a[1]), _lib.ptr(b[0]),
+                   _lib.ptr(b[1]), _lib.ptr(a[2]), _lib.ptr(b[2]), _lib.ptr(bias), _lib.ptr(out), M, N, K, lda, ldb,
+                   out.stride(0), act, int(accumulate), split_k, self._stream())
+        self.launches += 1
+        return out
+
+    def _feat_planes16(self, feats, bank, transposed):
+        key = "_f16T" if transposed else "_f16"
+        fn = self.transpose_split_f16 if transposed else self.split_f16
+        if bank is not None:
+            if getattr(bank, key, None) is None:
+                setattr(bank, key, fn(feats))
+            return getattr(bank, key)
+        return fn(feats)
+
     def _feat_planes(self, feats, bank):
         """(hi, lo) of the feature matrix; cached on the FeatureBank (static data, split once)."""
         if bank is not None:
@@ -145,24 +198,35 @@ class EpisodeEngine:
 
     def project_rows(self, feats, bank, w0):
         """proj = X W0^T (first image layer over every feature row, no bias)."""
-        if self.precision == 1:
+        if self.precision == 2 and feats.shape[1] % 8 == 0:
+            return self.gemm_f16(self._feat_planes16(feats, bank, False), self.split_f16(w0))
+        if self.precision >= 1:
             return self.gemm_tc(self._feat_planes(feats, bank), self.split_tf32(w0))
         return self.linear_fwd(feats, w0, None, act=0, precision=0)
 
     def wgrad_rows(self, d_proj, feats, bank, dw0):
         """dW0 = d_proj^T X."""
-        if self.precision == 1:
+        if self.precision == 2:
+            R = d_proj.shape[0]
+            self.gemm_f16(self.transpose_split_f16(d_proj), self._feat_planes16(feats, bank, True), out=dw0, K=R)
+        elif self.precision >= 1:
             R = d_proj.shape[0]
             self.gemm_tc(self.transpose_split_tf32(d_proj), self._feat_planes_T(feats, bank), out=dw0, K=R)
         else:
             self.linear_wgrad(d_proj, feats, dw0, precision=0)
 
-    def gram(self, feats, sup_rows, qry_rows):
+    def gram(self, feats, sup_rows, qry_rows, bank=None):
         B, NK = sup_rows.shape
         NQ = qry_rows.shape[1]
         g = self._new(B, NK + NQ, NK)
-        self._call("fumi_gram", self.L.fumi_gram, _lib.ptr(feats), feats.shape[0], feats.shape[1], _lib.ptr(sup_rows),
-                                    _lib.ptr(qry_rows), B, NK, NQ, _lib.ptr(g), self._stream())
+        D = feats.shape[1]
+        if self.precision == 2 and NK <= 32 and NK + NQ <= 192 and D % 64 == 0:      # fp16 bank planes (split once)
+            hi, lo, am = self._feat_planes16(feats, bank, False)
+            self._call("fumi_gram", self.L.fumi_gram_f16, _lib.ptr(hi), _lib.ptr(lo), _lib.ptr(am), feats.shape[0], D,
+                       _lib.ptr(sup_rows), _lib.ptr(qry_rows), B, NK, NQ, _lib.ptr(g), self._stream())
+        else:
+            self._call("fumi_gram", self.L.fumi_gram, _lib.ptr(feats), feats.shape[0], D, _lib.ptr(sup_rows),
+                       _lib.ptr(qry_rows), B, NK, NQ, _lib.ptr(g), self._stream())
         self.launches += 1
         return g
 
@@ -280,7 +344,7 @@ class EpisodeEngine:
     def hypernet(self, model, text_rows, keep=False):
         """hyper_net(text): Linear-ReLU-Linear(-Tanh)  (fumi.py:70-107,109-113)."""
         l0, l2 = model.hyper_net[0], model.hyper_net[2]
-        if self.precision == 1 and text_rows.shape[1] % 4 == 0:
+        if self.precision >= 1 and text_rows.shape[1] % 4 == 0:
             u = self.gemm_tc(self.split_tf32(text_rows), self.split_tf32(l0.weight), bias=l0.bias, act=1)
         else:
             u = self.linear_fwd(text_rows, l0.weight, l0.bias, act=1, precision=0)
@@ -313,7 +377,7 @@ class EpisodeEngine:
                             task_offset=rank * B, save=train or return_state)
         hp_table, u = self.hypernet(model, text_rows, keep=True)
         proj = self.project_rows(feats, eb.bank, lin0.weight)
-        gram = self.gram(feats, eb.sup_rows, eb.qry_rows)
+        gram = self.gram(feats, eb.sup_rows, eb.qry_rows, bank=eb.bank)
         out = self.episode_fwd(cfg, proj, eb, gram, lin0.bias, lin1.weight, lin1.bias, hp_table, head_rows)
         la = self.loss_acc(out["task_loss"], out["task_acc"])
         res = dict(loss_acc=la, preds=out["preds"], logits=out["logits"], qry_y=eb.qry_y, task_loss=out["task_loss"],
@@ -354,7 +418,7 @@ class EpisodeEngine:
         cfg = self.make_cfg(N, NK, NQ, steps, step_size, first_order=first_order, save=train or return_state)
         head_table = torch.cat([fin.weight, fin.bias.unsqueeze(1)], 1).contiguous()      # [N, 65]
         proj = self.project_rows(feats, eb.bank, lin0.weight)
-        gram = self.gram(feats, eb.sup_rows, eb.qry_rows)
+        gram = self.gram(feats, eb.sup_rows, eb.qry_rows, bank=eb.bank)
         out = self.episode_fwd(cfg, proj, eb, gram, lin0.bias, lin1.weight, lin1.bias, head_table, None)
         la = self.loss_acc(out["task_loss"], out["task_acc"])
         res = dict(loss_acc=la, preds=out["preds"], logits=out["logits"], qry_y=eb.qry_y, cfg=cfg,
@@ -386,7 +450,7 @@ class EpisodeEngine:
         else:
             eb, feats, text_rows, class_rows = self.unpack(batch, N, want_text=True)
         P = model.prototype_dim
-        if self.precision == 1:
+        if self.precision >= 1:
             emb = self.gemm_tc(self._feat_planes(feats, eb.bank), self.split_tf32(model.image_encoder.weight),
                                bias=model.image_encoder.bias)
         else:

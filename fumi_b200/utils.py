@@ -93,8 +93,9 @@ def parser():
     # additions of this implementation (no reference flag is renamed)
     p.add_argument("--tasks_per_batch", type=int, default=None,
                    help="tasks per meta-batch for the batched engine (overrides --batch_size)")
-    p.add_argument("--precision", type=int, default=1, choices=[0, 1],
-                   help="dense layers: 1 tcgen05 3xTF32 tensor cores (default), 0 fp32 FMA")
+    p.add_argument("--precision", type=int, default=2, choices=[0, 1, 2],
+                   help="dense layers: 2 (default) tcgen05, bank-sized contractions + Gram on fp16 hi/lo planes, the rest "
+                        "3xTF32; 1 tcgen05 3xTF32 everywhere; 0 fp32 FMA")
     p.add_argument("--synthetic", action="store_true",
                    help="use the synthetic iNat-Anim-shaped banks instead of --data_dir")
     return p
@@ -119,7 +120,7 @@ def init_model(args, dictionary, watch=True):
                         prototype_dim=args.prototype_dim, dropout=args.dropout, fine_tune=args.fine_tune,
                         dictionary=dictionary, pooling_strat=args.pooling_strat, lamda_fixed=args.lamda_fixed)
     model.to(args.device)
-    model._get_engine(args.device).precision = int(getattr(args, "precision", 1))
+    model._get_engine(args.device).precision = int(getattr(args, "precision", 2))
     if hasattr(model, "dropout_base_seed") or args.model == "fumi":
         model.dropout_base_seed = int(getattr(args, "seed", 0))
     return model

@@ -111,6 +111,26 @@ int fumi_gemm_tf32x3(const float* a_hi, const float* a_lo, const float* b_hi, co
                      void* stream);
 
 /* ------------------------------------------------------------------------------------------
+ * tcgen05 "3 x fp16" contraction: same contract as fumi_gemm_tf32x3 on fp16 operand planes --
+ * half the bytes per element pair (hi + lo = 4 B) and K = 16 per MMA at twice the tf32 rate.  The
+ * planes hold x * 2^k with k chosen from the DEVICE scalar max|x| (fumi_absmax) so that the largest
+ * element lands in [2^13, 2^14); the epilogue undoes both scales exactly.  Used for the two
+ * bank-sized contractions (im_net.linear0 over the feature bank, fumi.py:215, and its weight gradient,
+ * fumi.py:192); the static bank is split once.
+ *   fumi_absmax(x, n, out)                 out[0] = max |x[i]|   (device scalar, stream-ordered)
+ *   fumi_split_f16 / _transpose_split_f16  fp32 -> fp16 (hi, lo) planes, row-major / transposed [C, ldt], ldt % 8 == 0
+ *   fumi_gemm_f16x3                        C (=|+=) act(A . B^T + bias); lda / ldb in fp16 elements, % 8 == 0
+ * ---------------------------------------------------------------------------------------- */
+int fumi_absmax(const float* x, int64_t n, float* out, void* stream);
+int fumi_split_f16(const float* x, const float* absmax, void* hi, void* lo, int64_t n, void* stream);
+int fumi_transpose_split_f16(const float* x, const float* absmax, void* hiT, void* loT, int64_t R, int64_t C,
+                             int64_t ldt, void* stream);
+int fumi_gemm_f16x3(const void* a_hi, const void* a_lo, const void* b_hi, const void* b_lo,
+                    const float* a_absmax, const float* b_absmax, const float* bias, float* c,
+                    int64_t M, int64_t N, int64_t K, int64_t lda, int64_t ldb, int64_t ldc,
+                    int32_t act, int32_t accumulate, int32_t split_k, void* stream);
+
+/* ------------------------------------------------------------------------------------------
  * Episode Gram blocks (the HBM-bound gather of the path).
  * gram[b, i, j] = <feats[row(b,i)], feats[sup_rows[b,j]]>, i over the NK support rows then the NQ
  * query rows of task b.  Each sampled feature row is read from HBM once per task.
@@ -122,6 +142,11 @@ int fumi_gemm_tf32x3(const float* a_hi, const float* a_lo, const float* b_hi, co
 int fumi_gram(const float* feats, int64_t num_rows, int64_t D,
               const int64_t* sup_rows, const int64_t* qry_rows,
               int64_t B, int32_t NK, int32_t NQ, float* gram, void* stream);
+/* Same blocks from the bank's fp16 (hi, lo) planes (fumi_split_f16 + its absmax scalar): tcgen05 kind::f16,
+ * K = 16 per MMA, no split arithmetic in the kernel.  NK <= 32, NK + NQ <= 192, D % 64 == 0 (else use fumi_gram). */
+int fumi_gram_f16(const void* feats_hi, const void* feats_lo, const float* absmax, int64_t num_rows, int64_t D,
+                  const int64_t* sup_rows, const int64_t* qry_rows, int64_t B, int32_t NK, int32_t NQ,
+                  float* gram, void* stream);
 
 /* ------------------------------------------------------------------------------------------
  * Fused inner loop + query scoring   (fumi.py:148-185, maml.py:158-183)

@@ -76,3 +76,15 @@ extern "C" int fumi_transpose_split_tf32(const float*, float*, float*, int64_t, 
 extern "C" int fumi_gemm_tf32x3(const float*, const float*, const float*, const float*, const float*, float*, int64_t,
                                 int64_t, int64_t, int64_t, int64_t, int64_t, int32_t, int32_t, int32_t, void*) {
     g_last_error = "tcgen05 path is not emulated"; return FUMI_ERR_UNSUPPORTED; }
+extern "C" int fumi_absmax(const float*, int64_t, float*, void*) {
+    g_last_error = "tcgen05 path is not emulated"; return FUMI_ERR_UNSUPPORTED; }
+extern "C" int fumi_split_f16(const float*, const float*, void*, void*, int64_t, void*) {
+    g_last_error = "tcgen05 path is not emulated"; return FUMI_ERR_UNSUPPORTED; }
+extern "C" int fumi_transpose_split_f16(const float*, const float*, void*, void*, int64_t, int64_t, int64_t, void*) {
+    g_last_error = "tcgen05 path is not emulated"; return FUMI_ERR_UNSUPPORTED; }
+extern "C" int fumi_gemm_f16x3(const void*, const void*, const void*, const void*, const float*, const float*, const float*,
+                               float*, int64_t, int64_t, int64_t, int64_t, int64_t, int64_t, int32_t, int32_t, int32_t, void*) {
+    g_last_error = "tcgen05 path is not emulated"; return FUMI_ERR_UNSUPPORTED; }
+extern "C" int fumi_gram_f16(const void*, const void*, const float*, int64_t, int64_t, const int64_t*, const int64_t*, int64_t,
+                             int32_t, int32_t, float*, void*) {
+    g_last_error = "tcgen05 path is not emulated"; return FUMI_ERR_UNSUPPORTED; }

@@ -112,6 +112,39 @@ def gemm_tc_case(device):
     assert relerr(got, x1.astype(np.float64).T @ x2.astype(np.float64)) < 2e-6
 
 
+def gemm_f16_case(device):
+    """tcgen05 3 x fp16 GEMM: fp32-level accuracy against fp64 on operands of very different magnitudes (the
+    power-of-two plane scales), ragged shapes, split-K, fused epilogue, transposed (weight-gradient) form."""
+    eng = engine_mod.EpisodeEngine(device, precision=2)
+    rs = np.random.RandomState(9)
+    t = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(device)
+    for (M, N, K, split, sa, sb) in [(128, 256, 64, 1, 1.0, 1.0), (403, 256, 768, 1, 3.0, 0.02), (1000, 64, 512, 1, 1e-6, 1e3),
+                                      (300, 65, 104, 1, 1.0, 1.0), (256, 2048, 5000, 0, 1e-5, 2.0), (256, 512, 4104, 7, 40.0, 1e-3),
+                                      (37, 300, 40, 1, 1.0, 1.0)]:
+        a = (rs.randn(M, K) * rs.uniform(0.1, 3, size=(M, 1)) * sa).astype(np.float32)
+        b = (rs.randn(N, K) / np.sqrt(K) * sb).astype(np.float32)
+        bias = (rs.randn(N) * sa * sb).astype(np.float32)
+        want = a.astype(np.float64) @ b.astype(np.float64).T
+        ap, bp = eng.split_f16(t(a)), eng.split_f16(t(b))
+        assert abs(float(ap[2].item()) - np.abs(a).max()) == 0.0
+        got = eng.gemm_f16(ap, bp, split_k=split).cpu().numpy()
+        err = relerr(got, want)
+        f32 = relerr(a @ b.T, want)
+        assert err < max(4 * f32, 2e-6), (M, N, K, split, err, f32)
+        if split == 1:
+            got = eng.gemm_f16(ap, bp, bias=t(bias), act=1).cpu().numpy()
+            assert relerr(got, np.maximum(want + bias, 0)) < max(4 * f32, 2e-6), (M, N, K, "bias+relu")
+        acc = eng.gemm_f16(ap, bp, split_k=split, out=torch.ones(M, N, device=device), accumulate=True).cpu().numpy()
+        assert relerr(acc - 1, want) < max(4 * f32, 1e-5) or relerr(acc, want + 1) < 2e-6, (M, N, K, "accumulate")
+    R, C1, C2 = 1234, 256, 512
+    x1, x2 = (rs.randn(R, C1) * 1e-4).astype(np.float32), np.maximum(rs.randn(R, C2), 0).astype(np.float32)
+    x1[rs.rand(R) < 0.5] = 0.0                                    # like d_proj: many untouched rows
+    got = eng.gemm_f16(eng.transpose_split_f16(t(x1)), eng.transpose_split_f16(t(x2)), K=R).cpu().numpy()
+    assert relerr(got, x1.astype(np.float64).T @ x2.astype(np.float64)) < 2e-6
+    z = eng.split_f16(torch.zeros(8, 64, device=device))          # all-zero operand: scale 1, no NaN
+    assert float(eng.gemm_f16(z, eng.split_f16(t(rs.randn(16, 64).astype(np.float32)))).abs().max()) == 0.0
+
+
 def fumi_train_case(device, name, via="dict", precision=0):
     g, bank = load_golden(name)
     N = argv_int(g, "--num_ways", 5)
@@ -313,18 +346,25 @@ def dense_case(device):
         assert relerr(dx, (dy.astype(np.float64) @ w) * (gate > 0)) < 1e-5
 
 
-def gram_case(device):
-    eng = engine_mod.EpisodeEngine(device)
+def gram_case(device, big=False):
     rs = np.random.RandomState(4)
-    for (R, D, B, NK, NQ) in [(300, 64, 3, 25, 40), (500, 132, 2, 100, 70), (64, 2048, 2, 5, 100)]:
-        feats = rs.randn(R, D).astype(np.float32)
-        sup, qry = rs.randint(0, R, size=(B, NK)), rs.randint(0, R, size=(B, NQ))
-        t = lambda a: torch.from_numpy(a).to(device)
-        g = eng.gram(t(feats), t(sup), t(qry)).cpu().numpy()
-        f64 = feats.astype(np.float64)
-        for b in range(B):
-            rows = np.concatenate([sup[b], qry[b]])
-            assert relerr(g[b], f64[rows] @ f64[sup[b]].T) < 1e-5
+    # tcgen05 path (NK <= 32, NK + NQ <= 192, D % 64 == 0): one and two row tiles, ragged tails, more tasks than
+    # SMs (persistent loop + stage ring across task boundaries), single task; everything else: warp-level kernel
+    shapes = [(300, 64, 3, 25, 40), (500, 132, 2, 100, 70), (64, 2048, 2, 5, 100)]
+    if big:      # GPU only (minutes under the host emulation)
+        shapes += [(700, 256, 331, 25, 160), (700, 128, 1, 32, 160), (700, 192, 5, 1, 7), (700, 64, 150, 7, 121),
+                   (300, 96, 3, 25, 40), (300, 64, 3, 25, 200)]
+    for precision in ((1, 2) if big else (None,)):       # 2: fp16 (hi, lo) bank planes, scaled by a power of two
+        eng = engine_mod.EpisodeEngine(device, precision=precision)
+        for (R, D, B, NK, NQ) in shapes:
+            feats = (rs.randn(R, D) * (37.0 if precision == 2 else 1.0)).astype(np.float32)
+            sup, qry = rs.randint(0, R, size=(B, NK)), rs.randint(0, R, size=(B, NQ))
+            t = lambda a: torch.from_numpy(a).to(device)
+            g = eng.gram(t(feats), t(sup), t(qry)).cpu().numpy()
+            f64 = feats.astype(np.float64)
+            for b in range(B):
+                rows = np.concatenate([sup[b], qry[b]])
+                assert relerr(g[b], f64[rows] @ f64[sup[b]].T) < 1e-5, (precision, R, D, B, NK, NQ, b)
 
 
 def adam_case(device):

@@ -26,13 +26,18 @@ def test_gemm_tcgen05_3xtf32():
     kc.gemm_tc_case(DEV)
 
 
+def test_gemm_tcgen05_3xf16():
+    kc.gemm_f16_case(DEV)
+
+
+@pytest.mark.parametrize("precision", [1, 2])
 @pytest.mark.parametrize("via", ["dict", "bank"])
-def test_fumi_train_tensor_core_dense(via):
-    kc.fumi_train_case(DEV, "fumi_train_n5k5_d512", via=via, precision=1)
+def test_fumi_train_tensor_core_dense(via, precision):
+    kc.fumi_train_case(DEV, "fumi_train_n5k5_d512", via=via, precision=precision)
 
 
 def test_gram():
-    kc.gram_case(DEV)
+    kc.gram_case(DEV, big=True)
 
 
 def test_adam():
