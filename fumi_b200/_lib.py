@@ -41,6 +41,7 @@ _SIGS = {
     "fumi_transpose_split_tf32": (C.c_int, [_P, _P, _P, _I64, _I64, _I64, _P]),
     "fumi_gemm_tf32x3": (C.c_int, [_P] * 6 + [_I64] * 6 + [_I32] * 3 + [_P]),
     "fumi_gram_f16": (C.c_int, [_P, _P, _P, _I64, _I64, _P, _P, _I64, _I32, _I32, _P, _P]),
+    "fumi_debug_gemm_f16": (C.c_int, [_P, _P, _I32, _I32, _I32, _I32, _P, _P]),
     "fumi_absmax": (C.c_int, [_P, _I64, _P, _P]),
     "fumi_split_f16": (C.c_int, [_P, _P, _P, _P, _I64, _P]),
     "fumi_transpose_split_f16": (C.c_int, [_P, _P, _P, _P, _I64, _I64, _I64, _P]),

@@ -18,6 +18,32 @@
 #ifdef FUMI_EMU
 #include "cuda_emu.h"
 #else
+#include <cuda_fp16.h>
+// ---- fp16 plane primitives (see warp_gemm_f16x3 below) ------------------------------------------------------
+typedef __half fumi_half;
+__device__ __forceinline__ fumi_half fumi_f2h(float x) { return __float2half_rn(x); }
+__device__ __forceinline__ float fumi_h2f(fumi_half h) { return __half2float(h); }
+__device__ __forceinline__ void fumi_ldsm4(uint32_t (&r)[4], const fumi_half* p) {
+    const uint32_t a = static_cast<uint32_t>(__cvta_generic_to_shared(p));
+    asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0,%1,%2,%3}, [%4];" : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(a));
+}
+__device__ __forceinline__ void fumi_ldsm4t(uint32_t (&r)[4], const fumi_half* p) {
+    const uint32_t a = static_cast<uint32_t>(__cvta_generic_to_shared(p));
+    asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0,%1,%2,%3}, [%4];" : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(a));
+}
+__device__ __forceinline__ void fumi_ldsm2(uint32_t (&r)[2], const fumi_half* p) {
+    const uint32_t a = static_cast<uint32_t>(__cvta_generic_to_shared(p));
+    asm volatile("ldmatrix.sync.aligned.m8n8.x2.shared.b16 {%0,%1}, [%2];" : "=r"(r[0]), "=r"(r[1]) : "r"(a));
+}
+__device__ __forceinline__ void fumi_ldsm2t(uint32_t (&r)[2], const fumi_half* p) {
+    const uint32_t a = static_cast<uint32_t>(__cvta_generic_to_shared(p));
+    asm volatile("ldmatrix.sync.aligned.m8n8.x2.trans.shared.b16 {%0,%1}, [%2];" : "=r"(r[0]), "=r"(r[1]) : "r"(a));
+}
+__device__ __forceinline__ void fumi_mma_f16(float (&c)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+    asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+                 : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+                 : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
 __device__ __forceinline__ void fumi_mma_tf32(float (&c)[4], const uint32_t (&a)[4], const uint32_t (&b)[2]) {
     asm volatile("mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
                  : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
@@ -137,3 +163,91 @@ __device__ __forceinline__ void warp_tile_foreach(float (&acc)[MT][NT][4], F f) 
             f(i * 16 + g + 8, j * 8 + 2 * t + 1, acc[i][j][3]);
         }
 }
+
+// ================================================================================================================
+// fp16 hi/lo PLANES: the operand matrices live in shared memory already split, x * 2^s = hi + lo with
+// hi = fp16(x 2^s), lo = fp16(x 2^s - hi) (22 significant bits; same bytes as one fp32 tile), so the inner loop is
+// ldmatrix + mma.m16n8k16 only: 3 MMAs per 16 k and no arithmetic, against 2 x (loads + LOP3/FADD splits + 3 MMAs)
+// on fp32 tiles.  Measured (tools/warp_gemm_bench.cu, 16 warps, 32x64x256): 2,231 vs 5,782 cycles per GEMM per SM,
+// 96 % of the fp16 tensor-pipe rate, relative error 2.3e-7 (tf32 split 3.9e-7, fp32 FMA chain 4.2e-7).
+//   acc[mt][nt][0..3] += (A 2^sa) . (B 2^sb): the caller multiplies by 2^-(sa+sb).
+//   A(m,k) = A[m*lda + k]  (ATRANS: A[k*lda + m]);   B(k,n) = B[k*ldb + n]  (BTRANS: B[n*ldb + k]);  lda / ldb in
+//   halves, rows 16-byte aligned and 16 bytes apart mod 128 (ld = cols + 8 for cols % 64 == 0) -> conflict-free.
+//   K % 16 == 0; the accumulator restarts every 64 k (the tensor core adds with truncation).
+template <int MT, int NT, bool ATRANS, bool BTRANS>
+__device__ __forceinline__ void warp_gemm_f16x3(const fumi_half* Ahi, const fumi_half* Alo, int lda, const fumi_half* Bhi,
+                                                const fumi_half* Blo, int ldb, int K, float (&acc)[MT][NT][4]) {
+    static_assert(NT == 1 || NT % 2 == 0, "n tiles come in pairs (ldmatrix.x4) or alone");
+    const int lane = threadIdx.x & 31;
+    const int l7 = lane & 7, b3 = (lane >> 3) & 1, b4 = lane >> 4;
+    // element offsets of this lane's ldmatrix row (relative to (m0 = 0 / n0 = 0, k = 0))
+    const int aoff = ATRANS ? (l7 + 8 * b4) * lda + 8 * b3 : (l7 + 8 * b3) * lda + 8 * b4;
+    const int boff = BTRANS ? (l7 + 8 * b4) * ldb + 8 * b3 : (l7 + 8 * b3) * ldb + 8 * b4;
+    const int boff1 = BTRANS ? l7 * ldb + 8 * b3 : (l7 + 8 * b3) * ldb;           // single n tile (x2): lanes 0-15 count
+    for (int k0 = 0; k0 < K; k0 += 64) {
+        float part[MT][NT][4];
+#pragma unroll
+        for (int i = 0; i < MT; ++i)
+#pragma unroll
+            for (int j = 0; j < NT; ++j)
+#pragma unroll
+                for (int q = 0; q < 4; ++q) part[i][j][q] = 0.f;
+#pragma unroll
+        for (int kk = 0; kk < 64; kk += 16) {
+            if (k0 + kk >= K) break;
+            const int k = k0 + kk;
+            uint32_t ah[MT][4], al[MT][4];
+#pragma unroll
+            for (int i = 0; i < MT; ++i) {
+                const int o = ATRANS ? k * lda + 16 * i + aoff : 16 * i * lda + k + aoff;
+                if (ATRANS) { fumi_ldsm4t(ah[i], Ahi + o); fumi_ldsm4t(al[i], Alo + o); }
+                else        { fumi_ldsm4(ah[i], Ahi + o);  fumi_ldsm4(al[i], Alo + o); }
+            }
+            if (NT == 1) {
+                uint32_t bh[2], bl[2];
+                const int o = BTRANS ? k + boff1 : k * ldb + boff1;
+                if (BTRANS) { fumi_ldsm2(bh, Bhi + o);  fumi_ldsm2(bl, Blo + o); }
+                else        { fumi_ldsm2t(bh, Bhi + o); fumi_ldsm2t(bl, Blo + o); }
+#pragma unroll
+                for (int i = 0; i < MT; ++i) {
+                    fumi_mma_f16(part[i][0], al[i], bh[0], bh[1]);
+                    fumi_mma_f16(part[i][0], ah[i], bl[0], bl[1]);
+                    fumi_mma_f16(part[i][0], ah[i], bh[0], bh[1]);
+                }
+            } else {
+#pragma unroll
+                for (int jp = 0; jp < NT / 2; ++jp) {
+                    uint32_t bh[4], bl[4];           // {b0, b1} of n tile 2 jp, {b0, b1} of n tile 2 jp + 1
+                    const int o = BTRANS ? 16 * jp * ldb + k + boff : k * ldb + 16 * jp + boff;
+                    if (BTRANS) { fumi_ldsm4(bh, Bhi + o);  fumi_ldsm4(bl, Blo + o); }
+                    else        { fumi_ldsm4t(bh, Bhi + o); fumi_ldsm4t(bl, Blo + o); }
+#pragma unroll
+                    for (int i = 0; i < MT; ++i) {
+#pragma unroll
+                        for (int h = 0; h < 2; ++h) {
+                            fumi_mma_f16(part[i][2 * jp + h], al[i], bh[2 * h], bh[2 * h + 1]);
+                            fumi_mma_f16(part[i][2 * jp + h], ah[i], bl[2 * h], bl[2 * h + 1]);
+                            fumi_mma_f16(part[i][2 * jp + h], ah[i], bh[2 * h], bh[2 * h + 1]);
+                        }
+                    }
+                }
+            }
+        }
+#pragma unroll
+        for (int i = 0; i < MT; ++i)
+#pragma unroll
+            for (int j = 0; j < NT; ++j)
+#pragma unroll
+                for (int q = 0; q < 4; ++q) acc[i][j][q] += part[i][j][q];
+    }
+}
+
+// power-of-two plane scale from max |x| (held as the bit pattern of a non-negative float): the largest element lands
+// in [2^13, 2^14).  Returns the exponent s (planes hold x 2^s).
+__device__ __forceinline__ int fumi_plane_exp(uint32_t absmax_bits) {
+    const int e = int(absmax_bits >> 23) - 126;              // |x| < 2^e  (0 and denormals: e <= -126)
+    if (absmax_bits == 0u) return 0;
+    const int s = 14 - e;
+    return s > 100 ? 100 : (s < -100 ? -100 : s);
+}
+__device__ __forceinline__ float fumi_exp2i(int s) { return __uint_as_float(uint32_t(127 + s) << 23); }   // 2^s, |s| <= 126

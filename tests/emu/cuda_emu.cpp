@@ -11,6 +11,7 @@ char* dyn_smem = nullptr;
 pthread_barrier_t g_barrier;
 pthread_barrier_t g_warp_barrier[64];
 WarpXchg g_xchg[64];
+const void* g_ptr_xchg[64][32];
 
 void launch_impl(const std::function<void()>& body, dim3 grid, dim3 block, size_t smem) {
     const unsigned nthreads = block.x * block.y * block.z;

@@ -132,6 +132,90 @@ static inline int __shfl_sync(unsigned, int v, int src_lane) {
     return r;
 }
 
+// ---- fp16 planes (warp_mma.cuh): a 16-bit storage type, ldmatrix and mma.m16n8k16.f16 --------------------------
+struct fumi_half { uint16_t bits; };
+static inline fumi_half fumi_f2h(float f) {                 // round to nearest even, like __float2half_rn
+    uint32_t x = __float_as_uint(f);
+    const uint32_t sign = (x >> 16) & 0x8000u;
+    x &= 0x7FFFFFFFu;
+    uint16_t h;
+    if (x >= 0x7F800000u) h = uint16_t(x > 0x7F800000u ? 0x7E00u : 0x7C00u);
+    else if (x >= 0x477FF000u) h = 0x7C00u;                  // rounds to >= 65520: inf
+    else if (x >= 0x38800000u) {                             // normal
+        const uint32_t mant = x & 0x7FFFFFu, e = (x >> 23) - 112u;
+        uint32_t v = (e << 10) | (mant >> 13);
+        const uint32_t rem = mant & 0x1FFFu;
+        if (rem > 0x1000u || (rem == 0x1000u && (v & 1u))) ++v;
+        h = uint16_t(v);
+    } else if (x >= 0x33000000u) {                           // subnormal
+        const uint32_t e = x >> 23, mant = (x & 0x7FFFFFu) | 0x800000u;
+        const uint32_t shift = 126u - e;                     // 14 .. 24
+        uint32_t v = mant >> shift;
+        const uint32_t rem = mant & ((1u << shift) - 1u), halfway = 1u << (shift - 1);
+        if (rem > halfway || (rem == halfway && (v & 1u))) ++v;
+        h = uint16_t(v);
+    } else h = 0;
+    return fumi_half{uint16_t(h | sign)};
+}
+static inline float fumi_h2f(fumi_half hh) {
+    const uint32_t h = hh.bits, sign = (h & 0x8000u) << 16, e = (h >> 10) & 0x1Fu, m = h & 0x3FFu;
+    if (e == 0) return __uint_as_float(sign) + (sign ? -1.f : 1.f) * float(m) * 5.9604644775390625e-8f;   // m * 2^-24
+    if (e == 31) return __uint_as_float(sign | 0x7F800000u | (m << 13));
+    return __uint_as_float(sign | ((e + 112u) << 23) | (m << 13));
+}
+static inline unsigned atomicMax(unsigned* addr, unsigned v) {
+    unsigned old = __atomic_load_n(addr, __ATOMIC_RELAXED);
+    while (old < v && !__atomic_compare_exchange_n(addr, &old, v, false, __ATOMIC_RELAXED, __ATOMIC_RELAXED)) {}
+    return old;
+}
+namespace fumi_emu { extern const void* g_ptr_xchg[64][32]; }
+// ldmatrix.x4: lane 8 i + r supplies the address of row r of 8x8 matrix i; lane (g, t) receives, per matrix, the pair
+// (row g, cols 2t, 2t+1) -- or with .trans the pair (rows 2t, 2t+1; col g).
+template <bool TRANS, int NMAT>
+static inline void fumi_emu_ldsm(uint32_t* r, const fumi_half* p) {
+    const int w = fumi_emu::t_threadIdx.x >> 5, lane = fumi_emu::t_threadIdx.x & 31, g = lane >> 2, t = lane & 3;
+    fumi_emu::g_ptr_xchg[w][lane] = p;
+    __syncwarp();
+    for (int i = 0; i < NMAT; ++i) {
+        uint16_t a, b;
+        if (TRANS) {
+            a = static_cast<const fumi_half*>(fumi_emu::g_ptr_xchg[w][8 * i + 2 * t])[g].bits;
+            b = static_cast<const fumi_half*>(fumi_emu::g_ptr_xchg[w][8 * i + 2 * t + 1])[g].bits;
+        } else {
+            const fumi_half* row = static_cast<const fumi_half*>(fumi_emu::g_ptr_xchg[w][8 * i + g]);
+            a = row[2 * t].bits;
+            b = row[2 * t + 1].bits;
+        }
+        r[i] = uint32_t(a) | (uint32_t(b) << 16);
+    }
+    __syncwarp();
+}
+static inline void fumi_ldsm4(uint32_t (&r)[4], const fumi_half* p) { fumi_emu_ldsm<false, 4>(r, p); }
+static inline void fumi_ldsm4t(uint32_t (&r)[4], const fumi_half* p) { fumi_emu_ldsm<true, 4>(r, p); }
+static inline void fumi_ldsm2(uint32_t (&r)[2], const fumi_half* p) { fumi_emu_ldsm<false, 2>(r, p); }
+static inline void fumi_ldsm2t(uint32_t (&r)[2], const fumi_half* p) { fumi_emu_ldsm<true, 2>(r, p); }
+static inline void fumi_mma_f16(float (&c)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+    const int w = fumi_emu::t_threadIdx.x >> 5, lane = fumi_emu::t_threadIdx.x & 31, g = lane >> 2, t = lane & 3;
+    fumi_emu::WarpXchg& x = fumi_emu::g_xchg[w];
+    for (int i = 0; i < 4; ++i) x.a[lane][i] = a[i];
+    x.b[lane][0] = b0;
+    x.b[lane][1] = b1;
+    __syncwarp();
+    auto half_of = [](uint32_t reg, int k) { return fumi_h2f(fumi_half{uint16_t(k & 1 ? reg >> 16 : reg & 0xFFFFu)}); };
+    // A(m,k): lane (m%8)*4 + (k%8)/2, reg (m>=8) + 2*(k>=8);  B(k,n): lane n*4 + (k%8)/2, reg (k>=8)
+    auto A = [&](int m, int k) { return half_of(x.a[(m & 7) * 4 + ((k & 7) >> 1)][(m >> 3) + 2 * (k >> 3)], k); };
+    auto B = [&](int k, int n) { return half_of(x.b[n * 4 + ((k & 7) >> 1)][k >> 3], k); };
+    const int rows[4] = {g, g, g + 8, g + 8}, cols[4] = {2 * t, 2 * t + 1, 2 * t, 2 * t + 1};
+    float out[4];
+    for (int q = 0; q < 4; ++q) {
+        float s = c[q];
+        for (int k = 0; k < 16; ++k) s += A(rows[q], k) * B(k, cols[q]);
+        out[q] = s;
+    }
+    __syncwarp();
+    for (int q = 0; q < 4; ++q) c[q] = out[q];
+}
+
 using std::max;
 using std::min;
 static inline long min(long a, long long b) { return a < b ? a : long(b); }

@@ -145,6 +145,25 @@ def gemm_f16_case(device):
     assert float(eng.gemm_f16(z, eng.split_f16(t(rs.randn(16, 64).astype(np.float32)))).abs().max()) == 0.0
 
 
+def warp_gemm_f16_case(device):
+    """The fp16 hi/lo plane warp GEMM (ldmatrix addressing, fragment order, plane scales) in every layout variant."""
+    import ctypes as C
+    from fumi_b200 import _lib
+    rs = np.random.RandomState(12)
+    L = _lib.lib()
+    stream = _lib.stream_ptr(torch.device(device)) if torch.device(device).type == "cuda" else None
+    for (M, N) in [(16, 8), (32, 16), (16, 64), (32, 8)]:
+        for K in (16, 48, 64):
+            for variant in range(4):
+                a = (rs.randn(M, K) * rs.uniform(1e-3, 30)).astype(np.float32)
+                b = (rs.randn(K, N) * rs.uniform(1e-4, 5)).astype(np.float32)
+                out = torch.full((M, N), float("nan"), device=device)
+                ta, tb = torch.from_numpy(a).to(device), torch.from_numpy(b).to(device)
+                _lib.check(L.fumi_debug_gemm_f16(_lib.ptr(ta), _lib.ptr(tb), variant, M, N, K, _lib.ptr(out), stream), "dbg")
+                want = a.astype(np.float64) @ b.astype(np.float64)
+                assert relerr(out.cpu().numpy(), want) < 2e-6, (M, N, K, variant, relerr(out.cpu().numpy(), want))
+
+
 def fumi_train_case(device, name, via="dict", precision=0):
     g, bank = load_golden(name)
     N = argv_int(g, "--num_ways", 5)

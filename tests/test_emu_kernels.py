@@ -32,6 +32,10 @@ def test_dense():
     kc.dense_case("cpu")
 
 
+def test_warp_gemm_f16_planes():
+    kc.warp_gemm_f16_case("cpu")
+
+
 def test_gram():
     kc.gram_case("cpu")
 

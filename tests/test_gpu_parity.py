@@ -36,6 +36,10 @@ def test_fumi_train_tensor_core_dense(via, precision):
     kc.fumi_train_case(DEV, "fumi_train_n5k5_d512", via=via, precision=precision)
 
 
+def test_warp_gemm_f16_planes():
+    kc.warp_gemm_f16_case(DEV)
+
+
 def test_gram():
     kc.gram_case(DEV, big=True)
 
