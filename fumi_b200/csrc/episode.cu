@@ -703,8 +703,8 @@ __device__ __forceinline__ void mma16_tile_h1(const EpiParams& P, const SmemM& s
 // (32 / N rows per warp), so the row statistics need only a warp barrier.  Every lane of a row recomputes
 // max / sum-of-exp (N <= 32 expf) and hands (row, class, logit, max, sum) to `sink`, which may overwrite
 // lt[row][class] -- all of the row's reads are complete by then.
-template <typename Sink>
-__device__ __forceinline__ void m16_tile_logits_softmax(const EpiParams& P, const SmemM& s, int rows, int tr, Sink sink) {
+template <typename SM, typename Sink>
+__device__ __forceinline__ void m16_tile_logits_softmax(const EpiParams& P, const SM& s, int rows, int tr, Sink sink) {
     const int N = P.cfg.num_ways;
     const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int rpw = 32 / N, li = lane / N, c = lane - li * N;
@@ -1007,6 +1007,531 @@ __global__ void __launch_bounds__(kThreads16, 1) episode_fwd_mma16_kernel(EpiPar
         }
         __syncthreads();
         pc.mark(33);    // epilogue (adapted state out)
+    }
+}
+
+// ------------------------------------------------------------------------------------ forward, fp16 planes
+// Same algorithm and launch shape as episode_fwd_mma16_kernel, but every GEMM operand lives in shared memory as
+// PRE-SPLIT fp16 hi/lo planes (x 2^s = hi + lo, 22 significant bits, the bytes of one fp32 tile): the inner loops
+// are ldmatrix + mma.m16n8k16 only (warp_gemm_f16x3; 2.6x the throughput of splitting fp32 fragments per use,
+// tools/warp_gemm_bench.cu).  A matrix is produced in registers, its max |x| goes through a shared-memory
+// atomicMax (one extra barrier), the power-of-two scale 2^s puts that max in [2^13, 2^14), and the planes are
+// written once; consumers undo the two scales exactly in their epilogues.  W1^T and S are updated in place by
+// reconstructing (hi + lo) 2^-s at the thread's own accumulator positions.  The projected rows A are not staged in
+// shared memory any more: each thread loads the 8-byte pieces at its own accumulator positions from `proj`.
+constexpr int kHW = kH1 + 8;      // half stride of W1^T [H0][H1] and dZ1 [rows][H1] planes
+constexpr int kHS = kH0 + 8;      // half stride of S / H0 [rows][H0] planes
+constexpr int kHG = 32 + 8;       // half stride of a Gram tile [rows][32] planes
+
+struct SmemF {
+    fumi_half *w1h, *w1l, *sh, *sl, *h0h, *h0l, *dzh, *dzl, *gsh, *gsl, *gqh, *gql;
+    float *h1t, *dz1t, *lt, *hp, *dhp, *b0s, *db0s, *b1s, *rowv, *rowc;
+    unsigned* mx;                  // max |x| slots, two per matrix (alternating productions)
+    long long *rowsQ, *rowsS;
+    int *ysQ, *ysS;
+};
+enum { MX_W1 = 0, MX_S = 2, MX_H0 = 4, MX_DZ = 6, MX_GS = 8, MX_GQ = 10, MX_COUNT = 12 };
+// lays the buffers out from `base` (16-byte aligned pieces) and returns the total size; base = nullptr sizes it
+__host__ __device__ inline size_t carve_f(char* base, SmemF& s) {
+    char* p = base;
+    auto take = [&](size_t bytes) { char* r = p; p += (bytes + 15) & ~size_t(15); return r; };
+    s.rowsQ = reinterpret_cast<long long*>(take(kMaxQueryRows * 8));
+    s.rowsS = reinterpret_cast<long long*>(take(32 * 8));
+    s.ysQ = reinterpret_cast<int*>(take(kMaxQueryRows * 4));
+    s.ysS = reinterpret_cast<int*>(take(32 * 4));
+    s.mx = reinterpret_cast<unsigned*>(take(16 * 4));
+    // everything from here on is zero-filled once per kernel (plane pads must be finite)
+    s.w1h = reinterpret_cast<fumi_half*>(take(kH0 * kHW * 2));  s.w1l = reinterpret_cast<fumi_half*>(take(kH0 * kHW * 2));
+    s.sh = reinterpret_cast<fumi_half*>(take(32 * kHS * 2));    s.sl = reinterpret_cast<fumi_half*>(take(32 * kHS * 2));
+    s.h0h = reinterpret_cast<fumi_half*>(take(32 * kHS * 2));   s.h0l = reinterpret_cast<fumi_half*>(take(32 * kHS * 2));
+    s.dzh = reinterpret_cast<fumi_half*>(take(32 * kHW * 2));   s.dzl = reinterpret_cast<fumi_half*>(take(32 * kHW * 2));
+    s.gsh = reinterpret_cast<fumi_half*>(take(32 * kHG * 2));   s.gsl = reinterpret_cast<fumi_half*>(take(32 * kHG * 2));
+    s.gqh = reinterpret_cast<fumi_half*>(take(32 * kHG * 2));   s.gql = reinterpret_cast<fumi_half*>(take(32 * kHG * 2));
+    s.h1t = reinterpret_cast<float*>(take(32 * kS1 * 4));
+    s.dz1t = reinterpret_cast<float*>(take(32 * kS1 * 4));
+    s.lt = reinterpret_cast<float*>(take(32 * kLS * 4));
+    s.hp = reinterpret_cast<float*>(take(kMaxWays * kHD * 4));
+    s.dhp = reinterpret_cast<float*>(take(kMaxWays * kHD * 4));
+    s.b0s = reinterpret_cast<float*>(take(kH0 * 4));
+    s.db0s = reinterpret_cast<float*>(take(kH0 * 4));
+    s.b1s = reinterpret_cast<float*>(take(kH1 * 4));
+    s.rowv = reinterpret_cast<float*>(take(32 * 4));
+    s.rowc = reinterpret_cast<float*>(take(32 * 4));
+    return size_t(p - base);
+}
+inline size_t smem_f_bytes() { SmemF t; return carve_f(nullptr, t); }
+
+// warp max of a non-negative value, then one shared-memory atomicMax per warp (bit pattern order == value order)
+__device__ __forceinline__ void block_max_push(unsigned* slot, float m) {
+#pragma unroll
+    for (int off = 16; off >= 1; off >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, off));
+    if ((threadIdx.x & 31) == 0 && m > 0.f) atomicMax(slot, __float_as_uint(m));
+}
+__device__ __forceinline__ void store_pair(fumi_half* hi, fumi_half* lo, int off, float a, float b, float scale) {
+    a *= scale; b *= scale;
+    const fumi_half ah = fumi_f2h(a), bh = fumi_f2h(b);
+    hi[off] = ah; hi[off + 1] = bh;
+    lo[off] = fumi_f2h(a - fumi_h2f(ah)); lo[off + 1] = fumi_f2h(b - fumi_h2f(bh));
+}
+__device__ __forceinline__ float plane_value(const fumi_half* hi, const fumi_half* lo, int off, float inv) {
+    return (fumi_h2f(hi[off]) + fumi_h2f(lo[off])) * inv;
+}
+
+template <int MT>
+__global__ void __launch_bounds__(kThreads16, 1) episode_fwd_f16_kernel(EpiParams P) {
+    constexpr int RS = 16 * MT;
+    constexpr int NT_ = kThreads16;
+    FUMI_DYN_SMEM(float, smem_raw);
+    SmemF s;
+    const size_t smem_total = carve_f(reinterpret_cast<char*>(smem_raw), s);
+    const fumi_episode_cfg& c = P.cfg;
+    const int tid = threadIdx.x, w = tid >> 5, lane = tid & 31, g = lane >> 2, t = lane & 3;
+    const int col = tid & 255, half = tid >> 8;
+    const int n = c.num_support, m = c.num_query, N = c.num_ways, steps = c.steps;
+    const float alpha = c.step_size;
+    const Layout L = make_layout(c);
+    const int o_ = tid & 63, kg_ = tid >> 6;
+    const float dsc = dropout_scale(c);
+    const bool drop = c.dropout_p > 0.f;
+    const uint32_t thr = dropout_thr(c);
+    __shared__ float task_sum[2];
+    PhaseClock pc;
+    pc.start();
+
+    // planes start as zeros: pad rows / columns that no phase writes must be finite
+    {
+        uint32_t* z = reinterpret_cast<uint32_t*>(s.w1h);
+        const int nz = int((reinterpret_cast<char*>(smem_raw) + smem_total - reinterpret_cast<char*>(s.w1h)) / 4);
+        for (int idx = tid; idx < nz; idx += NT_) z[idx] = 0u;
+    }
+    __syncthreads();
+
+    // the H0 epilogue shared by support steps and query tiles: acc (raw G.S product) -> activations in acc, planes
+    // written after a block-wide max.  rows: global bank rows of the tile's 32 rows (smem), gscale: 2^-(sG + sS)
+    auto h0_tile = [&](const fumi_half* gh, const fumi_half* gl, const long long* rows, int r0, int tr, bool use_s, float ginv,
+                       int pass, int64_t task, int prod) {
+        float2 ap[2][2][2];                                 // projected rows at this thread's accumulator positions
+#pragma unroll
+        for (int i = 0; i < 2; ++i)
+#pragma unroll
+            for (int j = 0; j < 2; ++j)
+#pragma unroll
+                for (int hq = 0; hq < 2; ++hq) {
+                    const int r = 16 * i + g + 8 * hq, h = 16 * w + 8 * j + 2 * t;
+                    ap[i][j][hq] = r < tr ? __ldg(reinterpret_cast<const float2*>(&P.proj[rows[r] * kH0 + h])) : make_float2(0.f, 0.f);
+                }
+        float acc[2][2][4];
+#pragma unroll
+        for (int i = 0; i < 2; ++i)
+#pragma unroll
+            for (int j = 0; j < 2; ++j)
+#pragma unroll
+                for (int q = 0; q < 4; ++q) acc[i][j][q] = 0.f;
+        if (use_s) warp_gemm_f16x3<2, 2, false, false>(gh, gl, kHG, s.sh + 16 * w, s.sl + 16 * w, kHS, 32, acc);
+        const uint32_t dbase = drop ? dropout_base(c, task, pass, 0) : 0u;
+        uint32_t bits = 0;
+        float mxv = 0.f;
+#pragma unroll
+        for (int i = 0; i < 2; ++i)
+#pragma unroll
+            for (int j = 0; j < 2; ++j)
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    const int r = 16 * i + g + 8 * (q >> 1), h = 16 * w + 8 * j + 2 * t + (q & 1);
+                    float v = 0.f;
+                    if (r < tr) {
+                        const float a = (q & 1) ? ap[i][j][q >> 1].y : ap[i][j][q >> 1].x;
+                        const float z = a + s.b0s[h] - (use_s ? alpha * (acc[i][j][q] * ginv) : 0.f);
+                        if (drop && (q & 1) == 0) bits = dropout_bits(dbase, r0 + r, h);
+                        if (z > 0.f && (!drop || dropout_keep_bits(bits, h, thr))) v = z * dsc;
+                    }
+                    acc[i][j][q] = v;
+                    mxv = fmaxf(mxv, v);
+                }
+        block_max_push(&s.mx[MX_H0 + (prod & 1)], mxv);
+        __syncthreads();
+        const float sc = fumi_exp2i(fumi_plane_exp(s.mx[MX_H0 + (prod & 1)]));
+#pragma unroll
+        for (int i = 0; i < 2; ++i)
+#pragma unroll
+            for (int j = 0; j < 2; ++j)
+#pragma unroll
+                for (int hq = 0; hq < 2; ++hq)
+                    store_pair(s.h0h, s.h0l, (16 * i + g + 8 * hq) * kHS + 16 * w + 8 * j + 2 * t, acc[i][j][2 * hq],
+                               acc[i][j][2 * hq + 1], sc);
+        if (tid == 0) s.mx[MX_H0 + ((prod + 1) & 1)] = 0u;
+        __syncthreads();
+    };
+    // H1 = relu(H0 W1^T + b1) (dropout) -> fp32 tile; warp (m tile w / 8, n tile w % 8)
+    auto h1_tile = [&](int r0, int tr, int mtiles, int pass, int64_t task, int prod_h0, int prod_w1) {
+        const int nt = w & 7, mt = w >> 3;
+        if (mt >= mtiles) return;
+        float acc[1][1][4] = {{{0.f, 0.f, 0.f, 0.f}}};
+        warp_gemm_f16x3<1, 1, false, false>(s.h0h + 16 * mt * kHS, s.h0l + 16 * mt * kHS, kHS, s.w1h + 8 * nt, s.w1l + 8 * nt, kHW,
+                                            kH0, acc);
+        const float inv = fumi_exp2i(-fumi_plane_exp(s.mx[MX_H0 + (prod_h0 & 1)])) *
+                          fumi_exp2i(-fumi_plane_exp(s.mx[MX_W1 + (prod_w1 & 1)]));
+        const uint32_t dbase = drop ? dropout_base(c, task, pass, 1) : 0u;
+        uint32_t bits = 0;
+        warp_tile_foreach<1, 1>(acc, [&](int ii, int oo, float& cv) {
+            const int i = 16 * mt + ii, o = 8 * nt + oo;
+            float v = 0.f;
+            if (i < tr) {
+                const float z = cv * inv + s.b1s[o];
+                if (drop && (oo & 1) == 0) bits = dropout_bits(dbase, r0 + i, o);
+                if (z > 0.f && (!drop || dropout_keep_bits(bits, o, thr))) v = z * dsc;
+            }
+            s.h1t[i * kS1 + o] = v;
+        });
+    };
+
+    for (int64_t b = blockIdx.x; b < P.B; b += gridDim.x) {
+        const int64_t task = c.task_offset + b;
+        float* slot = P.stash + (P.save ? b : int64_t(blockIdx.x)) * P.slot_floats;
+        int prod_w1 = 0, prod_s = 0, prod_h0 = 0, prod_dz = 0;            // productions so far (slot parity)
+        // ---- task prologue
+        if (tid < MX_COUNT) s.mx[tid] = 0u;
+        __syncthreads();
+        float w1v[32];                                                    // W1[o][h] for h = col, o in [32 half, 32 half + 32)
+        {
+            float mxv = 0.f;
+#pragma unroll
+            for (int q = 0; q < 32; ++q) {
+                w1v[q] = __ldg(&P.w1[(half * 32 + q) * kH0 + col]);
+                mxv = fmaxf(mxv, fabsf(w1v[q]));
+            }
+            block_max_push(&s.mx[MX_W1], mxv);
+        }
+        float gv[2];                                                      // support Gram block, <= 2 entries per thread
+        {
+            float mxv = 0.f;
+#pragma unroll
+            for (int q = 0; q < 2; ++q) {
+                const int idx = tid + q * NT_, i = idx >> 5, j = idx & 31;
+                gv[q] = (i < n && j < n) ? __ldg(&P.gram[(b * int64_t(n + m) + i) * n + j]) : 0.f;
+                mxv = fmaxf(mxv, fabsf(gv[q]));
+            }
+            block_max_push(&s.mx[MX_GS], mxv);
+        }
+        if (tid < kH0) s.b0s[tid] = __ldg(&P.b0[tid]);
+        if (tid < kH1) s.b1s[tid] = __ldg(&P.b1[tid]);
+        for (int idx = tid; idx < N * kHD; idx += NT_) {
+            const int cc = idx / kHD, o = idx - cc * kHD;
+            const int64_t r = P.head_rows ? __ldg(&P.head_rows[b * N + cc]) : cc;
+            s.hp[idx] = __ldg(&P.head_table[r * kHD + o]);
+        }
+        if (tid < 32) {
+            s.ysS[tid] = tid < n ? int(P.sup_y[b * n + tid]) : 0;
+            s.rowsS[tid] = tid < n ? P.sup_rows[b * n + tid] : 0;
+        }
+        for (int idx = tid; idx < m; idx += NT_) {
+            s.rowsQ[idx] = P.qry_rows[b * m + idx];
+            s.ysQ[idx] = int(P.qry_y[b * m + idx]);
+        }
+        if (tid == 0) { task_sum[0] = 0.f; task_sum[1] = 0.f; }
+        __syncthreads();
+        {
+            const float sc = fumi_exp2i(fumi_plane_exp(s.mx[MX_W1]));
+#pragma unroll
+            for (int q = 0; q < 32; ++q) {
+                const float v = w1v[q] * sc;
+                const fumi_half hh = fumi_f2h(v);
+                s.w1h[col * kHW + half * 32 + q] = hh;
+                s.w1l[col * kHW + half * 32 + q] = fumi_f2h(v - fumi_h2f(hh));
+            }
+            const float sg = fumi_exp2i(fumi_plane_exp(s.mx[MX_GS]));
+#pragma unroll
+            for (int q = 0; q < 2; ++q) {
+                const int idx = tid + q * NT_, i = idx >> 5, j = idx & 31;
+                const float v = gv[q] * sg;
+                const fumi_half hh = fumi_f2h(v);
+                s.gsh[i * kHG + j] = hh;
+                s.gsl[i * kHG + j] = fumi_f2h(v - fumi_h2f(hh));
+            }
+        }
+        __syncthreads();
+        pc.mark(20);    // prologue
+
+        for (int st = 0; st < steps; ++st) {
+            float* rec = P.save ? slot + L.steps + int64_t(st) * L.per_step : nullptr;
+            // ---- H0 = relu(A + b0 - alpha G S) (dropout): planes
+            {
+                const float ginv = st > 0 ? fumi_exp2i(-fumi_plane_exp(s.mx[MX_GS])) *
+                                                fumi_exp2i(-fumi_plane_exp(s.mx[MX_S + ((prod_s - 1) & 1)])) : 0.f;
+                h0_tile(s.gsh, s.gsl, s.rowsS, 0, n, st > 0, ginv, st, task, prod_h0);
+                ++prod_h0;
+            }
+            pc.mark(21);    // s: H0
+            h1_tile(0, n, MT, st, task, prod_h0 - 1, prod_w1);
+            __syncthreads();
+            pc.mark(22);    // s: H1 (K=256)
+            {
+                const float invn = 1.f / float(n);
+                m16_tile_logits_softmax(P, s, RS, n, [&](int i, int cc, float l, float mx, float sum) {
+                    float dl = 0.f;
+                    if (i < n) dl = (expf(l - mx) * (1.f / sum) - (cc == s.ysS[i] ? 1.f : 0.f)) * invn;
+                    s.lt[i * kLS + cc] = dl;
+                });
+            }
+            __syncthreads();
+            pc.mark(23);    // s: logits + softmax
+            // ---- head gradient; dZ1 (fp32 copy for the stash / column sums, planes for the two GEMMs)
+            for (int idx = tid; idx < N * kHD; idx += NT_) {
+                const int cc = idx / kHD, o = idx - cc * kHD;
+                float a = 0.f;
+                for (int i = 0; i < n; ++i) a = fmaf(s.lt[i * kLS + cc], o < kH1 ? s.h1t[i * kS1 + o] : 1.f, a);
+                s.dhp[idx] = a;
+            }
+            float dzv[4];
+            {
+                float mxv = 0.f;
+#pragma unroll
+                for (int ii = 0; ii < 4; ++ii) {
+                    const int i = kg_ + 8 * ii;
+                    float dz = 0.f;
+                    if (i < n && s.h1t[i * kS1 + o_] > 0.f) {
+                        float dh = 0.f;
+                        for (int cc = 0; cc < N; ++cc) dh = fmaf(s.lt[i * kLS + cc], s.hp[cc * kHD + o_], dh);
+                        dz = dh * dsc;
+                    }
+                    dzv[ii] = dz;
+                    s.dz1t[i * kS1 + o_] = dz;
+                    mxv = fmaxf(mxv, fabsf(dz));
+                }
+                block_max_push(&s.mx[MX_DZ + (prod_dz & 1)], mxv);
+            }
+            __syncthreads();
+            {
+                const float sc = fumi_exp2i(fumi_plane_exp(s.mx[MX_DZ + (prod_dz & 1)]));
+#pragma unroll
+                for (int ii = 0; ii < 4; ++ii) {
+                    const float v = dzv[ii] * sc;
+                    const fumi_half hh = fumi_f2h(v);
+                    s.dzh[(kg_ + 8 * ii) * kHW + o_] = hh;
+                    s.dzl[(kg_ + 8 * ii) * kHW + o_] = fumi_f2h(v - fumi_h2f(hh));
+                }
+                if (tid == 0) s.mx[MX_DZ + ((prod_dz + 1) & 1)] = 0u;
+                ++prod_dz;
+            }
+            __syncthreads();
+            pc.mark(25);    // s: dhp, dZ1
+            float db1 = 0.f;
+            if (tid < kH1) for (int i = 0; i < n; ++i) db1 += s.dz1t[i * kS1 + tid];
+            // ---- dZ0 = (dZ1 W1) * gate ;  S += dZ0 ;  db0 = column sums of dZ0
+            {
+                float acc[2][2][4];
+#pragma unroll
+                for (int i = 0; i < 2; ++i)
+#pragma unroll
+                    for (int j = 0; j < 2; ++j)
+#pragma unroll
+                        for (int q = 0; q < 4; ++q) acc[i][j][q] = 0.f;
+                warp_gemm_f16x3<2, 2, false, true>(s.dzh, s.dzl, kHW, s.w1h + 16 * w * kHW, s.w1l + 16 * w * kHW, kHW, kH1, acc);
+                const float inv = fumi_exp2i(-fumi_plane_exp(s.mx[MX_DZ + ((prod_dz - 1) & 1)])) *
+                                  fumi_exp2i(-fumi_plane_exp(s.mx[MX_W1 + (prod_w1 & 1)]));
+                const float sinv = st > 0 ? fumi_exp2i(-fumi_plane_exp(s.mx[MX_S + ((prod_s - 1) & 1)])) : 0.f;
+                float colsum[2][2] = {{0.f, 0.f}, {0.f, 0.f}};
+                float mxv = 0.f;
+#pragma unroll
+                for (int i = 0; i < 2; ++i)
+#pragma unroll
+                    for (int j = 0; j < 2; ++j)
+#pragma unroll
+                        for (int q = 0; q < 4; ++q) {
+                            const int r = 16 * i + g + 8 * (q >> 1), h = 16 * w + 8 * j + 2 * t + (q & 1);
+                            const int off = r * kHS + h;
+                            const bool on = r < n && (fumi_h2f(s.h0h[off]) > 0.f || fumi_h2f(s.h0l[off]) > 0.f);
+                            const float dz0 = on ? acc[i][j][q] * inv * dsc : 0.f;
+                            const float sv = (st > 0 && r < n ? plane_value(s.sh, s.sl, off, sinv) : 0.f) + dz0;
+                            colsum[j][q & 1] += dz0;
+                            acc[i][j][q] = sv;
+                            mxv = fmaxf(mxv, fabsf(sv));
+                        }
+                block_max_push(&s.mx[MX_S + (prod_s & 1)], mxv);
+#pragma unroll
+                for (int j = 0; j < 2; ++j)
+#pragma unroll
+                    for (int q = 0; q < 2; ++q) {
+                        float v = colsum[j][q];
+                        v += __shfl_xor_sync(0xffffffffu, v, 4);
+                        v += __shfl_xor_sync(0xffffffffu, v, 8);
+                        v += __shfl_xor_sync(0xffffffffu, v, 16);
+                        if ((lane >> 2) == 0) s.db0s[16 * w + 8 * j + 2 * (lane & 3) + q] = v;
+                    }
+                if (rec) {                                          // records for the backward (H0 from its planes)
+                    const float hinv = fumi_exp2i(-fumi_plane_exp(s.mx[MX_H0 + ((prod_h0 - 1) & 1)]));
+                    for (int i = half; i < n; i += 2) rec[L.oH0 + int64_t(i) * kH0 + col] = plane_value(s.h0h, s.h0l, i * kHS + col, hinv);
+                    for (int idx = tid; idx < n * kH1; idx += NT_) {
+                        const int i = idx / kH1, o = idx - i * kH1;
+                        rec[L.oH1 + idx] = s.h1t[i * kS1 + o];
+                        rec[L.oDZ1 + idx] = s.dz1t[i * kS1 + o];
+                    }
+                    for (int idx = tid; idx < n * N; idx += NT_) {
+                        const int i = idx / N, cc = idx - i * N;
+                        rec[L.oDL + idx] = s.lt[i * kLS + cc];
+                    }
+                    for (int idx = tid; idx < N * kHD; idx += NT_) rec[L.oHP + idx] = s.hp[idx];
+                }
+                __syncthreads();                                    // all reads of the old S planes are done
+                const float sc = fumi_exp2i(fumi_plane_exp(s.mx[MX_S + (prod_s & 1)]));
+#pragma unroll
+                for (int i = 0; i < 2; ++i)
+#pragma unroll
+                    for (int j = 0; j < 2; ++j)
+#pragma unroll
+                        for (int hq = 0; hq < 2; ++hq)
+                            store_pair(s.sh, s.sl, (16 * i + g + 8 * hq) * kHS + 16 * w + 8 * j + 2 * t, acc[i][j][2 * hq],
+                                       acc[i][j][2 * hq + 1], sc);
+                if (tid == 0) s.mx[MX_S + ((prod_s + 1) & 1)] = 0u;
+                ++prod_s;
+            }
+            pc.mark(26);    // s: dZ0 gemm, S update, stash
+            // ---- W1 -= alpha dZ1^T H0 (rows h of W1^T owned by this warp), in place on the planes
+            {
+                float acc[1][8][4];
+#pragma unroll
+                for (int j = 0; j < 8; ++j)
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) acc[0][j][q] = 0.f;
+                warp_gemm_f16x3<1, 8, true, false>(s.h0h + 16 * w, s.h0l + 16 * w, kHS, s.dzh, s.dzl, kHW, RS, acc);
+                const float inv = alpha * fumi_exp2i(-fumi_plane_exp(s.mx[MX_H0 + ((prod_h0 - 1) & 1)])) *
+                                  fumi_exp2i(-fumi_plane_exp(s.mx[MX_DZ + ((prod_dz - 1) & 1)]));
+                const float winv = fumi_exp2i(-fumi_plane_exp(s.mx[MX_W1 + (prod_w1 & 1)]));
+                float mxv = 0.f;
+                warp_tile_foreach<1, 8>(acc, [&](int hh, int o, float& cv) {
+                    cv = plane_value(s.w1h, s.w1l, (16 * w + hh) * kHW + o, winv) - cv * inv;
+                    mxv = fmaxf(mxv, fabsf(cv));
+                });
+                block_max_push(&s.mx[MX_W1 + ((prod_w1 + 1) & 1)], mxv);
+                __syncthreads();                                    // all reads of the old W1 planes are done
+                const float sc = fumi_exp2i(fumi_plane_exp(s.mx[MX_W1 + ((prod_w1 + 1) & 1)]));
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    store_pair(s.w1h, s.w1l, (16 * w + g) * kHW + 8 * j + 2 * t, acc[0][j][0], acc[0][j][1], sc);
+                    store_pair(s.w1h, s.w1l, (16 * w + g + 8) * kHW + 8 * j + 2 * t, acc[0][j][2], acc[0][j][3], sc);
+                }
+                if (tid == 0) s.mx[MX_W1 + (prod_w1 & 1)] = 0u;
+                ++prod_w1;
+            }
+            for (int idx = tid; idx < N * kHD; idx += NT_) s.hp[idx] -= alpha * s.dhp[idx];
+            if (tid < kH1) s.b1s[tid] -= alpha * db1;
+            if (tid < kH0) s.b0s[tid] -= alpha * s.db0s[tid];
+            __syncthreads();
+            pc.mark(27);    // s: W1 update gemm
+        }
+
+        // ---- query scoring, 32 rows per tile; the Gram tile of the next tile travels in registers, and its max is
+        // pushed one tile ahead so that its plane scale needs no barrier of its own
+        float qg[2];
+        int qtile = 0;
+        auto q_load = [&](int r0) {
+            const int tr = min(32, m - r0);
+            float mxv = 0.f;
+#pragma unroll
+            for (int q = 0; q < 2; ++q) {
+                const int idx = tid + q * NT_, i = idx >> 5, j = idx & 31;
+                qg[q] = (i < tr && j < n) ? __ldg(&P.gram[(b * int64_t(n + m) + n + r0 + i) * n + j]) : 0.f;
+                mxv = fmaxf(mxv, fabsf(qg[q]));
+            }
+            return mxv;
+        };
+        block_max_push(&s.mx[MX_GQ], q_load(0));
+        __syncthreads();
+        const float sinv_fin = steps > 0 ? fumi_exp2i(-fumi_plane_exp(s.mx[MX_S + ((prod_s - 1) & 1)])) : 0.f;
+        for (int r0 = 0; r0 < m; r0 += 32, ++qtile) {
+            const int tr = min(32, m - r0);
+            const int gexp = fumi_plane_exp(s.mx[MX_GQ + (qtile & 1)]);
+            {
+                const float sg = fumi_exp2i(gexp);
+#pragma unroll
+                for (int q = 0; q < 2; ++q) {
+                    const int idx = tid + q * NT_, i = idx >> 5, j = idx & 31;
+                    const float v = qg[q] * sg;
+                    const fumi_half hh = fumi_f2h(v);
+                    s.gqh[i * kHG + j] = hh;
+                    s.gql[i * kHG + j] = fumi_f2h(v - fumi_h2f(hh));
+                }
+            }
+            __syncthreads();
+            if (tid == 0) s.mx[MX_GQ + ((qtile + 1) & 1)] = 0u;  // read for the last time two tiles ago
+            if (r0 > 0 && w == 0) {                             // loss / accuracy of the previous tile (rowv, rowc)
+                float rv = s.rowv[lane], rc = s.rowc[lane];
+#pragma unroll
+                for (int off = 16; off >= 1; off >>= 1) {
+                    rv += __shfl_xor_sync(0xffffffffu, rv, off);
+                    rc += __shfl_xor_sync(0xffffffffu, rc, off);
+                }
+                if (lane == 0) { task_sum[0] += rv; task_sum[1] += rc; }
+            }
+            pc.mark(28);    // q: loads
+            h0_tile(s.gqh, s.gql, s.rowsQ + r0, r0, tr, steps > 0, fumi_exp2i(-gexp) * sinv_fin, steps, task, prod_h0);
+            ++prod_h0;
+            float nmx = 0.f;
+            if (r0 + 32 < m) nmx = q_load(r0 + 32);             // issued here, consumed at the end of the tile
+            pc.mark(29);    // q: H0
+            h1_tile(r0, tr, 2, steps, task, prod_h0 - 1, prod_w1);
+            __syncthreads();
+            pc.mark(30);    // q: H1
+            m16_tile_logits_softmax(P, s, 32, tr, [&](int i, int cc, float l, float mx, float sum) {
+                if (i >= tr) {
+                    if (cc == 0) { s.rowv[i] = 0.f; s.rowc[i] = 0.f; }
+                    return;
+                }
+                const int y = s.ysQ[r0 + i];
+                const int64_t q = b * m + r0 + i;
+                P.logits[q * N + cc] = l;
+                if (P.save)
+                    slot[L.qLG + int64_t(r0 + i) * N + cc] = expf(l - mx) * (1.f / sum) - (cc == y ? 1.f : 0.f);
+                if (cc == 0) {
+                    const float* lr = &s.lt[i * kLS];
+                    int best = 0;
+                    for (int k = 1; k < N; ++k) if (lr[k] > lr[best]) best = k;      // first max (torch.max)
+                    s.rowv[i] = (logf(sum) + mx) - lr[y];
+                    s.rowc[i] = best == y ? 1.f : 0.f;
+                    P.preds[q] = best;
+                }
+            });
+            pc.mark(31);    // q: logits + softmax
+            if (P.save) {
+                const float hinv = fumi_exp2i(-fumi_plane_exp(s.mx[MX_H0 + ((prod_h0 - 1) & 1)]));
+                for (int i = half; i < tr; i += 2)
+                    slot[L.qH0 + int64_t(r0 + i) * kH0 + col] = plane_value(s.h0h, s.h0l, i * kHS + col, hinv);
+                for (int idx = tid; idx < tr * kH1; idx += NT_) {
+                    const int i = idx / kH1, o = idx - i * kH1;
+                    slot[L.qH1 + int64_t(r0) * kH1 + idx] = s.h1t[i * kS1 + o];
+                }
+            }
+            if (r0 + 32 < m) block_max_push(&s.mx[MX_GQ + ((qtile + 1) & 1)], nmx);
+            __syncthreads();
+            pc.mark(32);    // q: stash, loss
+        }
+        if (w == 0) {
+            float rv = s.rowv[lane], rc = s.rowc[lane];
+#pragma unroll
+            for (int off = 16; off >= 1; off >>= 1) {
+                rv += __shfl_xor_sync(0xffffffffu, rv, off);
+                rc += __shfl_xor_sync(0xffffffffu, rc, off);
+            }
+            if (lane == 0) {
+                P.task_loss[b] = (task_sum[0] + rv) / float(m);
+                P.task_acc[b] = (task_sum[1] + rc) / float(m);
+            }
+        }
+        if (P.save) {                                               // adapted state (fp32, as the backward expects it)
+            const float winv = fumi_exp2i(-fumi_plane_exp(s.mx[MX_W1 + (prod_w1 & 1)]));
+            for (int idx = tid; idx < kH0 * kH1; idx += NT_) {
+                const int k = idx / kH1, o = idx - k * kH1;
+                slot[L.w1t + idx] = plane_value(s.w1h, s.w1l, k * kHW + o, winv);
+            }
+            if (tid < kH0) slot[L.b0 + tid] = s.b0s[tid];
+            if (tid < kH1) slot[L.b1 + tid] = s.b1s[tid];
+            for (int idx = tid; idx < N * kHD; idx += NT_) slot[L.head + idx] = s.hp[idx];
+            float* Sout = slot + ((steps & 1) ? L.S1 : L.S0);
+            for (int i = half; i < n; i += 2)
+                Sout[int64_t(i) * kH0 + col] = steps > 0 ? plane_value(s.sh, s.sl, i * kHS + col, sinv_fin) : 0.f;
+        }
+        __syncthreads();
+        pc.mark(33);    // epilogue
     }
 }
 
@@ -1975,7 +2500,18 @@ extern "C" int fumi_episode_fwd(const fumi_episode_cfg* cfg, int64_t B, const fl
         FUMI_LAUNCH(kern, grid, kThreads, smem, stream, P);                                                    \
     } while (0)
     const bool use_mma = nk <= 32 && cfg->num_query <= kMaxQueryRows;
-    if (use_mma) {
+    static int use_f16 = -1;          // FUMI_FWD_F16=0: the fp32-tile kernel (split per use), for A/B runs
+    if (use_f16 < 0) { const char* e = getenv("FUMI_FWD_F16"); use_f16 = (e && atoi(e) == 0) ? 0 : 1; }
+    if (use_mma && use_f16) {
+        const size_t smem = smem_f_bytes();
+        if (nk <= 16) {
+            FUMI_SET_SMEM_ATTR(episode_fwd_f16_kernel<1>, smem);
+            FUMI_LAUNCH(episode_fwd_f16_kernel<1>, grid, kThreads16, smem, stream, P);
+        } else {
+            FUMI_SET_SMEM_ATTR(episode_fwd_f16_kernel<2>, smem);
+            FUMI_LAUNCH(episode_fwd_f16_kernel<2>, grid, kThreads16, smem, stream, P);
+        }
+    } else if (use_mma) {
         const size_t smem = smem_m_floats() * sizeof(float);
         if (nk <= 16) {
             FUMI_SET_SMEM_ATTR(episode_fwd_mma16_kernel<1>, smem);
