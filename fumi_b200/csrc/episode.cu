@@ -1026,11 +1026,11 @@ constexpr int kHG = 32 + 8;       // half stride of a Gram tile [rows][32] plane
 struct SmemF {
     fumi_half *w1h, *w1l, *sh, *sl, *h0h, *h0l, *dzh, *dzl, *gsh, *gsl, *gqh, *gql;
     float *h1t, *dz1t, *lt, *hp, *dhp, *b0s, *db0s, *b1s, *rowv, *rowc;
-    unsigned* mx;                  // max |x| slots, two per matrix (alternating productions)
+    float* mx;                     // max |x| of each matrix: 16 per-warp partials per slot, two slots per matrix
     long long *rowsQ, *rowsS;
     int *ysQ, *ysS;
 };
-enum { MX_W1 = 0, MX_S = 2, MX_H0 = 4, MX_DZ = 6, MX_GS = 8, MX_GQ = 10, MX_COUNT = 12 };
+enum { MX_W1 = 0, MX_S = 2, MX_H0 = 4, MX_DZ = 6, MX_GS = 8, MX_GQ = 10, MX_COUNT = 12 };   // slot indices (x 16 floats)
 // lays the buffers out from `base` (16-byte aligned pieces) and returns the total size; base = nullptr sizes it
 __host__ __device__ inline size_t carve_f(char* base, SmemF& s) {
     char* p = base;
@@ -1039,7 +1039,7 @@ __host__ __device__ inline size_t carve_f(char* base, SmemF& s) {
     s.rowsS = reinterpret_cast<long long*>(take(32 * 8));
     s.ysQ = reinterpret_cast<int*>(take(kMaxQueryRows * 4));
     s.ysS = reinterpret_cast<int*>(take(32 * 4));
-    s.mx = reinterpret_cast<unsigned*>(take(16 * 4));
+    s.mx = reinterpret_cast<float*>(take(MX_COUNT * 16 * 4));
     // everything from here on is zero-filled once per kernel (plane pads must be finite)
     s.w1h = reinterpret_cast<fumi_half*>(take(kH0 * kHW * 2));  s.w1l = reinterpret_cast<fumi_half*>(take(kH0 * kHW * 2));
     s.sh = reinterpret_cast<fumi_half*>(take(32 * kHS * 2));    s.sl = reinterpret_cast<fumi_half*>(take(32 * kHS * 2));
@@ -1061,17 +1061,23 @@ __host__ __device__ inline size_t carve_f(char* base, SmemF& s) {
 }
 inline size_t smem_f_bytes() { SmemF t; return carve_f(nullptr, t); }
 
-// warp max of a non-negative value, then one shared-memory atomicMax per warp (bit pattern order == value order)
-__device__ __forceinline__ void block_max_push(unsigned* slot, float m) {
+// block-wide max of a non-negative value without atomics: every warp leaves its max in its own word of the slot
+// (all 16 words are rewritten by each production, so a slot needs no reset), readers reduce the 16 words after
+// the barrier that follows.
+__device__ __forceinline__ void block_max_push(float* slot, float m) {
 #pragma unroll
     for (int off = 16; off >= 1; off >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, off));
-    if ((threadIdx.x & 31) == 0 && m > 0.f) atomicMax(slot, __float_as_uint(m));
+    if ((threadIdx.x & 31) == 0) slot[threadIdx.x >> 5] = m;
+}
+__device__ __forceinline__ int block_max_exp(const float* slot) {          // plane exponent s for the slot's matrix
+    const float4 a = *reinterpret_cast<const float4*>(slot), b = *reinterpret_cast<const float4*>(slot + 4);
+    const float4 c = *reinterpret_cast<const float4*>(slot + 8), d = *reinterpret_cast<const float4*>(slot + 12);
+    const float m = fmaxf(fmaxf(fmaxf(fmaxf(a.x, a.y), fmaxf(a.z, a.w)), fmaxf(fmaxf(b.x, b.y), fmaxf(b.z, b.w))),
+                          fmaxf(fmaxf(fmaxf(c.x, c.y), fmaxf(c.z, c.w)), fmaxf(fmaxf(d.x, d.y), fmaxf(d.z, d.w))));
+    return fumi_plane_exp(__float_as_uint(m));
 }
 __device__ __forceinline__ void store_pair(fumi_half* hi, fumi_half* lo, int off, float a, float b, float scale) {
-    a *= scale; b *= scale;
-    const fumi_half ah = fumi_f2h(a), bh = fumi_f2h(b);
-    hi[off] = ah; hi[off + 1] = bh;
-    lo[off] = fumi_f2h(a - fumi_h2f(ah)); lo[off + 1] = fumi_f2h(b - fumi_h2f(bh));
+    fumi_plane_store2(hi, lo, off, a, b, scale);
 }
 __device__ __forceinline__ float plane_value(const fumi_half* hi, const fumi_half* lo, int off, float inv) {
     return (fumi_h2f(hi[off]) + fumi_h2f(lo[off])) * inv;
@@ -1097,6 +1103,7 @@ __global__ void __launch_bounds__(kThreads16, 1) episode_fwd_f16_kernel(EpiParam
     __shared__ float task_sum[2];
     PhaseClock pc;
     pc.start();
+    int e_w1 = 0, e_s = 0, e_h0 = 0, e_dz = 0, e_gs = 0;              // plane exponents of the current W1^T, S, H0, dZ1, G_support
 
     // planes start as zeros: pad rows / columns that no phase writes must be finite
     {
@@ -1108,9 +1115,9 @@ __global__ void __launch_bounds__(kThreads16, 1) episode_fwd_f16_kernel(EpiParam
 
     // the H0 epilogue shared by support steps and query tiles: acc (raw G.S product) -> activations in acc, planes
     // written after a block-wide max.  rows: global bank rows of the tile's 32 rows (smem), gscale: 2^-(sG + sS)
-    auto h0_tile = [&](const fumi_half* gh, const fumi_half* gl, const long long* rows, int r0, int tr, bool use_s, float ginv,
-                       int pass, int64_t task, int prod) {
-        float2 ap[2][2][2];                                 // projected rows at this thread's accumulator positions
+    // projected rows at this thread's accumulator positions, straight from `proj` (issued a phase ahead of their use)
+    float2 ap[2][2][2];
+    auto h0_load = [&](const long long* rows, int tr) {
 #pragma unroll
         for (int i = 0; i < 2; ++i)
 #pragma unroll
@@ -1120,6 +1127,9 @@ __global__ void __launch_bounds__(kThreads16, 1) episode_fwd_f16_kernel(EpiParam
                     const int r = 16 * i + g + 8 * hq, h = 16 * w + 8 * j + 2 * t;
                     ap[i][j][hq] = r < tr ? __ldg(reinterpret_cast<const float2*>(&P.proj[rows[r] * kH0 + h])) : make_float2(0.f, 0.f);
                 }
+    };
+    auto h0_tile = [&](const fumi_half* gh, const fumi_half* gl, int r0, int tr, bool use_s, float ginv, int pass, int64_t task,
+                       int prod) {
         float acc[2][2][4];
 #pragma unroll
         for (int i = 0; i < 2; ++i)
@@ -1148,9 +1158,10 @@ __global__ void __launch_bounds__(kThreads16, 1) episode_fwd_f16_kernel(EpiParam
                     acc[i][j][q] = v;
                     mxv = fmaxf(mxv, v);
                 }
-        block_max_push(&s.mx[MX_H0 + (prod & 1)], mxv);
+        block_max_push(s.mx + 16 * (MX_H0 + (prod & 1)), mxv);
         __syncthreads();
-        const float sc = fumi_exp2i(fumi_plane_exp(s.mx[MX_H0 + (prod & 1)]));
+        e_h0 = block_max_exp(s.mx + 16 * (MX_H0 + (prod & 1)));
+        const float sc = fumi_exp2i(e_h0);
 #pragma unroll
         for (int i = 0; i < 2; ++i)
 #pragma unroll
@@ -1159,7 +1170,6 @@ __global__ void __launch_bounds__(kThreads16, 1) episode_fwd_f16_kernel(EpiParam
                 for (int hq = 0; hq < 2; ++hq)
                     store_pair(s.h0h, s.h0l, (16 * i + g + 8 * hq) * kHS + 16 * w + 8 * j + 2 * t, acc[i][j][2 * hq],
                                acc[i][j][2 * hq + 1], sc);
-        if (tid == 0) s.mx[MX_H0 + ((prod + 1) & 1)] = 0u;
         __syncthreads();
     };
     // H1 = relu(H0 W1^T + b1) (dropout) -> fp32 tile; warp (m tile w / 8, n tile w % 8)
@@ -1169,8 +1179,7 @@ __global__ void __launch_bounds__(kThreads16, 1) episode_fwd_f16_kernel(EpiParam
         float acc[1][1][4] = {{{0.f, 0.f, 0.f, 0.f}}};
         warp_gemm_f16x3<1, 1, false, false>(s.h0h + 16 * mt * kHS, s.h0l + 16 * mt * kHS, kHS, s.w1h + 8 * nt, s.w1l + 8 * nt, kHW,
                                             kH0, acc);
-        const float inv = fumi_exp2i(-fumi_plane_exp(s.mx[MX_H0 + (prod_h0 & 1)])) *
-                          fumi_exp2i(-fumi_plane_exp(s.mx[MX_W1 + (prod_w1 & 1)]));
+        const float inv = fumi_exp2i(-e_h0) * fumi_exp2i(-e_w1);
         const uint32_t dbase = drop ? dropout_base(c, task, pass, 1) : 0u;
         uint32_t bits = 0;
         warp_tile_foreach<1, 1>(acc, [&](int ii, int oo, float& cv) {
@@ -1190,8 +1199,6 @@ __global__ void __launch_bounds__(kThreads16, 1) episode_fwd_f16_kernel(EpiParam
         float* slot = P.stash + (P.save ? b : int64_t(blockIdx.x)) * P.slot_floats;
         int prod_w1 = 0, prod_s = 0, prod_h0 = 0, prod_dz = 0;            // productions so far (slot parity)
         // ---- task prologue
-        if (tid < MX_COUNT) s.mx[tid] = 0u;
-        __syncthreads();
         float w1v[32];                                                    // W1[o][h] for h = col, o in [32 half, 32 half + 32)
         {
             float mxv = 0.f;
@@ -1200,7 +1207,7 @@ __global__ void __launch_bounds__(kThreads16, 1) episode_fwd_f16_kernel(EpiParam
                 w1v[q] = __ldg(&P.w1[(half * 32 + q) * kH0 + col]);
                 mxv = fmaxf(mxv, fabsf(w1v[q]));
             }
-            block_max_push(&s.mx[MX_W1], mxv);
+            block_max_push(s.mx + 16 * (MX_W1), mxv);
         }
         float gv[2];                                                      // support Gram block, <= 2 entries per thread
         {
@@ -1211,7 +1218,7 @@ __global__ void __launch_bounds__(kThreads16, 1) episode_fwd_f16_kernel(EpiParam
                 gv[q] = (i < n && j < n) ? __ldg(&P.gram[(b * int64_t(n + m) + i) * n + j]) : 0.f;
                 mxv = fmaxf(mxv, fabsf(gv[q]));
             }
-            block_max_push(&s.mx[MX_GS], mxv);
+            block_max_push(s.mx + 16 * (MX_GS), mxv);
         }
         if (tid < kH0) s.b0s[tid] = __ldg(&P.b0[tid]);
         if (tid < kH1) s.b1s[tid] = __ldg(&P.b1[tid]);
@@ -1231,15 +1238,24 @@ __global__ void __launch_bounds__(kThreads16, 1) episode_fwd_f16_kernel(EpiParam
         if (tid == 0) { task_sum[0] = 0.f; task_sum[1] = 0.f; }
         __syncthreads();
         {
-            const float sc = fumi_exp2i(fumi_plane_exp(s.mx[MX_W1]));
+            e_w1 = block_max_exp(s.mx + 16 * MX_W1);
+            const float sc = fumi_exp2i(e_w1);
 #pragma unroll
-            for (int q = 0; q < 32; ++q) {
-                const float v = w1v[q] * sc;
-                const fumi_half hh = fumi_f2h(v);
-                s.w1h[col * kHW + half * 32 + q] = hh;
-                s.w1l[col * kHW + half * 32 + q] = fumi_f2h(v - fumi_h2f(hh));
+            for (int q8 = 0; q8 < 4; ++q8) {                    // 8 halves = 16 bytes per store, rows 144 bytes apart
+                uint32_t ph[4], pl[4];
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    const float a = w1v[8 * q8 + 2 * q] * sc, bb = w1v[8 * q8 + 2 * q + 1] * sc;
+                    const fumi_half ah = fumi_f2h(a), bh = fumi_f2h(bb);
+                    const fumi_half al = fumi_f2h(a - fumi_h2f(ah)), bl = fumi_f2h(bb - fumi_h2f(bh));
+                    ph[q] = uint32_t(*reinterpret_cast<const uint16_t*>(&ah)) | (uint32_t(*reinterpret_cast<const uint16_t*>(&bh)) << 16);
+                    pl[q] = uint32_t(*reinterpret_cast<const uint16_t*>(&al)) | (uint32_t(*reinterpret_cast<const uint16_t*>(&bl)) << 16);
+                }
+                *reinterpret_cast<uint4*>(&s.w1h[col * kHW + half * 32 + 8 * q8]) = make_uint4(ph[0], ph[1], ph[2], ph[3]);
+                *reinterpret_cast<uint4*>(&s.w1l[col * kHW + half * 32 + 8 * q8]) = make_uint4(pl[0], pl[1], pl[2], pl[3]);
             }
-            const float sg = fumi_exp2i(fumi_plane_exp(s.mx[MX_GS]));
+            e_gs = block_max_exp(s.mx + 16 * MX_GS);
+            const float sg = fumi_exp2i(e_gs);
 #pragma unroll
             for (int q = 0; q < 2; ++q) {
                 const int idx = tid + q * NT_, i = idx >> 5, j = idx & 31;
@@ -1249,6 +1265,7 @@ __global__ void __launch_bounds__(kThreads16, 1) episode_fwd_f16_kernel(EpiParam
                 s.gsl[i * kHG + j] = fumi_f2h(v - fumi_h2f(hh));
             }
         }
+        if (steps > 0) h0_load(s.rowsS, n);
         __syncthreads();
         pc.mark(20);    // prologue
 
@@ -1256,9 +1273,8 @@ __global__ void __launch_bounds__(kThreads16, 1) episode_fwd_f16_kernel(EpiParam
             float* rec = P.save ? slot + L.steps + int64_t(st) * L.per_step : nullptr;
             // ---- H0 = relu(A + b0 - alpha G S) (dropout): planes
             {
-                const float ginv = st > 0 ? fumi_exp2i(-fumi_plane_exp(s.mx[MX_GS])) *
-                                                fumi_exp2i(-fumi_plane_exp(s.mx[MX_S + ((prod_s - 1) & 1)])) : 0.f;
-                h0_tile(s.gsh, s.gsl, s.rowsS, 0, n, st > 0, ginv, st, task, prod_h0);
+                const float ginv = st > 0 ? fumi_exp2i(-e_gs) * fumi_exp2i(-e_s) : 0.f;
+                h0_tile(s.gsh, s.gsl, 0, n, st > 0, ginv, st, task, prod_h0);
                 ++prod_h0;
             }
             pc.mark(21);    // s: H0
@@ -1298,11 +1314,12 @@ __global__ void __launch_bounds__(kThreads16, 1) episode_fwd_f16_kernel(EpiParam
                     s.dz1t[i * kS1 + o_] = dz;
                     mxv = fmaxf(mxv, fabsf(dz));
                 }
-                block_max_push(&s.mx[MX_DZ + (prod_dz & 1)], mxv);
+                block_max_push(s.mx + 16 * (MX_DZ + (prod_dz & 1)), mxv);
             }
             __syncthreads();
             {
-                const float sc = fumi_exp2i(fumi_plane_exp(s.mx[MX_DZ + (prod_dz & 1)]));
+                e_dz = block_max_exp(s.mx + 16 * (MX_DZ + (prod_dz & 1)));
+                const float sc = fumi_exp2i(e_dz);
 #pragma unroll
                 for (int ii = 0; ii < 4; ++ii) {
                     const float v = dzv[ii] * sc;
@@ -1310,7 +1327,6 @@ __global__ void __launch_bounds__(kThreads16, 1) episode_fwd_f16_kernel(EpiParam
                     s.dzh[(kg_ + 8 * ii) * kHW + o_] = hh;
                     s.dzl[(kg_ + 8 * ii) * kHW + o_] = fumi_f2h(v - fumi_h2f(hh));
                 }
-                if (tid == 0) s.mx[MX_DZ + ((prod_dz + 1) & 1)] = 0u;
                 ++prod_dz;
             }
             __syncthreads();
@@ -1327,9 +1343,8 @@ __global__ void __launch_bounds__(kThreads16, 1) episode_fwd_f16_kernel(EpiParam
 #pragma unroll
                         for (int q = 0; q < 4; ++q) acc[i][j][q] = 0.f;
                 warp_gemm_f16x3<2, 2, false, true>(s.dzh, s.dzl, kHW, s.w1h + 16 * w * kHW, s.w1l + 16 * w * kHW, kHW, kH1, acc);
-                const float inv = fumi_exp2i(-fumi_plane_exp(s.mx[MX_DZ + ((prod_dz - 1) & 1)])) *
-                                  fumi_exp2i(-fumi_plane_exp(s.mx[MX_W1 + (prod_w1 & 1)]));
-                const float sinv = st > 0 ? fumi_exp2i(-fumi_plane_exp(s.mx[MX_S + ((prod_s - 1) & 1)])) : 0.f;
+                const float inv = fumi_exp2i(-e_dz) * fumi_exp2i(-e_w1);
+                const float sinv = st > 0 ? fumi_exp2i(-e_s) : 0.f;
                 float colsum[2][2] = {{0.f, 0.f}, {0.f, 0.f}};
                 float mxv = 0.f;
 #pragma unroll
@@ -1337,17 +1352,20 @@ __global__ void __launch_bounds__(kThreads16, 1) episode_fwd_f16_kernel(EpiParam
 #pragma unroll
                     for (int j = 0; j < 2; ++j)
 #pragma unroll
-                        for (int q = 0; q < 4; ++q) {
-                            const int r = 16 * i + g + 8 * (q >> 1), h = 16 * w + 8 * j + 2 * t + (q & 1);
-                            const int off = r * kHS + h;
-                            const bool on = r < n && (fumi_h2f(s.h0h[off]) > 0.f || fumi_h2f(s.h0l[off]) > 0.f);
-                            const float dz0 = on ? acc[i][j][q] * inv * dsc : 0.f;
-                            const float sv = (st > 0 && r < n ? plane_value(s.sh, s.sl, off, sinv) : 0.f) + dz0;
-                            colsum[j][q & 1] += dz0;
-                            acc[i][j][q] = sv;
-                            mxv = fmaxf(mxv, fabsf(sv));
+                        for (int hq = 0; hq < 2; ++hq) {
+                            const int r = 16 * i + g + 8 * hq, off = r * kHS + 16 * w + 8 * j + 2 * t;
+                            float h0a, h0b, s0 = 0.f, s1 = 0.f;
+                            fumi_plane_load2(s.h0h, s.h0l, off, 1.f, h0a, h0b);                 // only the sign is used
+                            if (st > 0 && r < n) fumi_plane_load2(s.sh, s.sl, off, sinv, s0, s1);
+                            const float d0 = (r < n && h0a > 0.f) ? acc[i][j][2 * hq] * inv * dsc : 0.f;
+                            const float d1 = (r < n && h0b > 0.f) ? acc[i][j][2 * hq + 1] * inv * dsc : 0.f;
+                            colsum[j][0] += d0;
+                            colsum[j][1] += d1;
+                            acc[i][j][2 * hq] = s0 + d0;
+                            acc[i][j][2 * hq + 1] = s1 + d1;
+                            mxv = fmaxf(mxv, fmaxf(fabsf(s0 + d0), fabsf(s1 + d1)));
                         }
-                block_max_push(&s.mx[MX_S + (prod_s & 1)], mxv);
+                block_max_push(s.mx + 16 * (MX_S + (prod_s & 1)), mxv);
 #pragma unroll
                 for (int j = 0; j < 2; ++j)
 #pragma unroll
@@ -1359,8 +1377,12 @@ __global__ void __launch_bounds__(kThreads16, 1) episode_fwd_f16_kernel(EpiParam
                         if ((lane >> 2) == 0) s.db0s[16 * w + 8 * j + 2 * (lane & 3) + q] = v;
                     }
                 if (rec) {                                          // records for the backward (H0 from its planes)
-                    const float hinv = fumi_exp2i(-fumi_plane_exp(s.mx[MX_H0 + ((prod_h0 - 1) & 1)]));
-                    for (int i = half; i < n; i += 2) rec[L.oH0 + int64_t(i) * kH0 + col] = plane_value(s.h0h, s.h0l, i * kHS + col, hinv);
+                    const float hinv = fumi_exp2i(-e_h0);
+                    for (int i = tid >> 7; i < n; i += 4) {           // two columns per thread
+                        float a0, a1;
+                        fumi_plane_load2(s.h0h, s.h0l, i * kHS + 2 * (tid & 127), hinv, a0, a1);
+                        *reinterpret_cast<float2*>(&rec[L.oH0 + int64_t(i) * kH0 + 2 * (tid & 127)]) = make_float2(a0, a1);
+                    }
                     for (int idx = tid; idx < n * kH1; idx += NT_) {
                         const int i = idx / kH1, o = idx - i * kH1;
                         rec[L.oH1 + idx] = s.h1t[i * kS1 + o];
@@ -1373,7 +1395,8 @@ __global__ void __launch_bounds__(kThreads16, 1) episode_fwd_f16_kernel(EpiParam
                     for (int idx = tid; idx < N * kHD; idx += NT_) rec[L.oHP + idx] = s.hp[idx];
                 }
                 __syncthreads();                                    // all reads of the old S planes are done
-                const float sc = fumi_exp2i(fumi_plane_exp(s.mx[MX_S + (prod_s & 1)]));
+                e_s = block_max_exp(s.mx + 16 * (MX_S + (prod_s & 1)));
+                const float sc = fumi_exp2i(e_s);
 #pragma unroll
                 for (int i = 0; i < 2; ++i)
 #pragma unroll
@@ -1382,7 +1405,6 @@ __global__ void __launch_bounds__(kThreads16, 1) episode_fwd_f16_kernel(EpiParam
                         for (int hq = 0; hq < 2; ++hq)
                             store_pair(s.sh, s.sl, (16 * i + g + 8 * hq) * kHS + 16 * w + 8 * j + 2 * t, acc[i][j][2 * hq],
                                        acc[i][j][2 * hq + 1], sc);
-                if (tid == 0) s.mx[MX_S + ((prod_s + 1) & 1)] = 0u;
                 ++prod_s;
             }
             pc.mark(26);    // s: dZ0 gemm, S update, stash
@@ -1394,28 +1416,34 @@ __global__ void __launch_bounds__(kThreads16, 1) episode_fwd_f16_kernel(EpiParam
 #pragma unroll
                     for (int q = 0; q < 4; ++q) acc[0][j][q] = 0.f;
                 warp_gemm_f16x3<1, 8, true, false>(s.h0h + 16 * w, s.h0l + 16 * w, kHS, s.dzh, s.dzl, kHW, RS, acc);
-                const float inv = alpha * fumi_exp2i(-fumi_plane_exp(s.mx[MX_H0 + ((prod_h0 - 1) & 1)])) *
-                                  fumi_exp2i(-fumi_plane_exp(s.mx[MX_DZ + ((prod_dz - 1) & 1)]));
-                const float winv = fumi_exp2i(-fumi_plane_exp(s.mx[MX_W1 + (prod_w1 & 1)]));
+                const float inv = alpha * fumi_exp2i(-e_h0) * fumi_exp2i(-e_dz);
+                const float winv = fumi_exp2i(-e_w1);
                 float mxv = 0.f;
-                warp_tile_foreach<1, 8>(acc, [&](int hh, int o, float& cv) {
-                    cv = plane_value(s.w1h, s.w1l, (16 * w + hh) * kHW + o, winv) - cv * inv;
-                    mxv = fmaxf(mxv, fabsf(cv));
-                });
-                block_max_push(&s.mx[MX_W1 + ((prod_w1 + 1) & 1)], mxv);
+#pragma unroll
+                for (int j = 0; j < 8; ++j)
+#pragma unroll
+                    for (int hq = 0; hq < 2; ++hq) {
+                        float o0, o1;
+                        fumi_plane_load2(s.w1h, s.w1l, (16 * w + g + 8 * hq) * kHW + 8 * j + 2 * t, winv, o0, o1);
+                        acc[0][j][2 * hq] = o0 - acc[0][j][2 * hq] * inv;
+                        acc[0][j][2 * hq + 1] = o1 - acc[0][j][2 * hq + 1] * inv;
+                        mxv = fmaxf(mxv, fmaxf(fabsf(acc[0][j][2 * hq]), fabsf(acc[0][j][2 * hq + 1])));
+                    }
+                block_max_push(s.mx + 16 * (MX_W1 + ((prod_w1 + 1) & 1)), mxv);
                 __syncthreads();                                    // all reads of the old W1 planes are done
-                const float sc = fumi_exp2i(fumi_plane_exp(s.mx[MX_W1 + ((prod_w1 + 1) & 1)]));
+                e_w1 = block_max_exp(s.mx + 16 * (MX_W1 + ((prod_w1 + 1) & 1)));
+                const float sc = fumi_exp2i(e_w1);
 #pragma unroll
                 for (int j = 0; j < 8; ++j) {
                     store_pair(s.w1h, s.w1l, (16 * w + g) * kHW + 8 * j + 2 * t, acc[0][j][0], acc[0][j][1], sc);
                     store_pair(s.w1h, s.w1l, (16 * w + g + 8) * kHW + 8 * j + 2 * t, acc[0][j][2], acc[0][j][3], sc);
                 }
-                if (tid == 0) s.mx[MX_W1 + (prod_w1 & 1)] = 0u;
                 ++prod_w1;
             }
             for (int idx = tid; idx < N * kHD; idx += NT_) s.hp[idx] -= alpha * s.dhp[idx];
             if (tid < kH1) s.b1s[tid] -= alpha * db1;
             if (tid < kH0) s.b0s[tid] -= alpha * s.db0s[tid];
+            if (st + 1 < steps) h0_load(s.rowsS, n);            // the same rows every step; latency hides behind the barrier
             __syncthreads();
             pc.mark(27);    // s: W1 update gemm
         }
@@ -1424,23 +1452,22 @@ __global__ void __launch_bounds__(kThreads16, 1) episode_fwd_f16_kernel(EpiParam
         // pushed one tile ahead so that its plane scale needs no barrier of its own
         float qg[2];
         int qtile = 0;
-        auto q_load = [&](int r0) {
+        auto q_load = [&](int r0) {                              // loads only: the values are first touched a tile later
             const int tr = min(32, m - r0);
-            float mxv = 0.f;
 #pragma unroll
             for (int q = 0; q < 2; ++q) {
                 const int idx = tid + q * NT_, i = idx >> 5, j = idx & 31;
                 qg[q] = (i < tr && j < n) ? __ldg(&P.gram[(b * int64_t(n + m) + n + r0 + i) * n + j]) : 0.f;
-                mxv = fmaxf(mxv, fabsf(qg[q]));
             }
-            return mxv;
         };
-        block_max_push(&s.mx[MX_GQ], q_load(0));
+        q_load(0);
+        block_max_push(s.mx + 16 * MX_GQ, fmaxf(fabsf(qg[0]), fabsf(qg[1])));
+        h0_load(s.rowsQ, min(32, m));
         __syncthreads();
-        const float sinv_fin = steps > 0 ? fumi_exp2i(-fumi_plane_exp(s.mx[MX_S + ((prod_s - 1) & 1)])) : 0.f;
+        const float sinv_fin = steps > 0 ? fumi_exp2i(-e_s) : 0.f;
         for (int r0 = 0; r0 < m; r0 += 32, ++qtile) {
             const int tr = min(32, m - r0);
-            const int gexp = fumi_plane_exp(s.mx[MX_GQ + (qtile & 1)]);
+            const int gexp = block_max_exp(s.mx + 16 * (MX_GQ + (qtile & 1)));
             {
                 const float sg = fumi_exp2i(gexp);
 #pragma unroll
@@ -1453,7 +1480,6 @@ __global__ void __launch_bounds__(kThreads16, 1) episode_fwd_f16_kernel(EpiParam
                 }
             }
             __syncthreads();
-            if (tid == 0) s.mx[MX_GQ + ((qtile + 1) & 1)] = 0u;  // read for the last time two tiles ago
             if (r0 > 0 && w == 0) {                             // loss / accuracy of the previous tile (rowv, rowc)
                 float rv = s.rowv[lane], rc = s.rowc[lane];
 #pragma unroll
@@ -1464,10 +1490,10 @@ __global__ void __launch_bounds__(kThreads16, 1) episode_fwd_f16_kernel(EpiParam
                 if (lane == 0) { task_sum[0] += rv; task_sum[1] += rc; }
             }
             pc.mark(28);    // q: loads
-            h0_tile(s.gqh, s.gql, s.rowsQ + r0, r0, tr, steps > 0, fumi_exp2i(-gexp) * sinv_fin, steps, task, prod_h0);
+            h0_tile(s.gqh, s.gql, r0, tr, steps > 0, fumi_exp2i(-gexp) * sinv_fin, steps, task, prod_h0);
             ++prod_h0;
-            float nmx = 0.f;
-            if (r0 + 32 < m) nmx = q_load(r0 + 32);             // issued here, consumed at the end of the tile
+            if (r0 + 32 < m) h0_load(s.rowsQ + r0 + 32, min(32, m - r0 - 32));     // next tile's rows, a tile ahead
+            if (r0 + 32 < m) q_load(r0 + 32);                   // issued here, consumed at the end of the tile
             pc.mark(29);    // q: H0
             h1_tile(r0, tr, 2, steps, task, prod_h0 - 1, prod_w1);
             __syncthreads();
@@ -1493,15 +1519,18 @@ __global__ void __launch_bounds__(kThreads16, 1) episode_fwd_f16_kernel(EpiParam
             });
             pc.mark(31);    // q: logits + softmax
             if (P.save) {
-                const float hinv = fumi_exp2i(-fumi_plane_exp(s.mx[MX_H0 + ((prod_h0 - 1) & 1)]));
-                for (int i = half; i < tr; i += 2)
-                    slot[L.qH0 + int64_t(r0 + i) * kH0 + col] = plane_value(s.h0h, s.h0l, i * kHS + col, hinv);
+                const float hinv = fumi_exp2i(-e_h0);
+                for (int i = tid >> 7; i < tr; i += 4) {
+                    float a0, a1;
+                    fumi_plane_load2(s.h0h, s.h0l, i * kHS + 2 * (tid & 127), hinv, a0, a1);
+                    *reinterpret_cast<float2*>(&slot[L.qH0 + int64_t(r0 + i) * kH0 + 2 * (tid & 127)]) = make_float2(a0, a1);
+                }
                 for (int idx = tid; idx < tr * kH1; idx += NT_) {
                     const int i = idx / kH1, o = idx - i * kH1;
                     slot[L.qH1 + int64_t(r0) * kH1 + idx] = s.h1t[i * kS1 + o];
                 }
             }
-            if (r0 + 32 < m) block_max_push(&s.mx[MX_GQ + ((qtile + 1) & 1)], nmx);
+            if (r0 + 32 < m) block_max_push(s.mx + 16 * (MX_GQ + ((qtile + 1) & 1)), fmaxf(fabsf(qg[0]), fabsf(qg[1])));
             __syncthreads();
             pc.mark(32);    // q: stash, loss
         }
@@ -1518,7 +1547,7 @@ __global__ void __launch_bounds__(kThreads16, 1) episode_fwd_f16_kernel(EpiParam
             }
         }
         if (P.save) {                                               // adapted state (fp32, as the backward expects it)
-            const float winv = fumi_exp2i(-fumi_plane_exp(s.mx[MX_W1 + (prod_w1 & 1)]));
+            const float winv = fumi_exp2i(-e_w1);
             for (int idx = tid; idx < kH0 * kH1; idx += NT_) {
                 const int k = idx / kH1, o = idx - k * kH1;
                 slot[L.w1t + idx] = plane_value(s.w1h, s.w1l, k * kHW + o, winv);

@@ -184,14 +184,21 @@ __device__ __forceinline__ void warp_gemm_f16x3(const fumi_half* Ahi, const fumi
     const int aoff = ATRANS ? (l7 + 8 * b4) * lda + 8 * b3 : (l7 + 8 * b3) * lda + 8 * b4;
     const int boff = BTRANS ? (l7 + 8 * b4) * ldb + 8 * b3 : (l7 + 8 * b3) * ldb + 8 * b4;
     const int boff1 = BTRANS ? l7 * ldb + 8 * b3 : (l7 + 8 * b3) * ldb;           // single n tile (x2): lanes 0-15 count
+    // few tiles per warp: the three products of a tile go to separate accumulators (three independent MMA chains
+    // instead of one dependent chain of 3 K/16 MMAs -- the 64-wide layer has one tile per warp and was latency-bound)
+    constexpr bool kSplitAcc = MT * NT <= 2;
     for (int k0 = 0; k0 < K; k0 += 64) {
         float part[MT][NT][4];
+        float c1[kSplitAcc ? MT : 1][kSplitAcc ? NT : 1][4], c2[kSplitAcc ? MT : 1][kSplitAcc ? NT : 1][4];
 #pragma unroll
         for (int i = 0; i < MT; ++i)
 #pragma unroll
             for (int j = 0; j < NT; ++j)
 #pragma unroll
-                for (int q = 0; q < 4; ++q) part[i][j][q] = 0.f;
+                for (int q = 0; q < 4; ++q) {
+                    part[i][j][q] = 0.f;
+                    if (kSplitAcc) { c1[i][j][q] = 0.f; c2[i][j][q] = 0.f; }
+                }
 #pragma unroll
         for (int kk = 0; kk < 64; kk += 16) {
             if (k0 + kk >= K) break;
@@ -210,8 +217,8 @@ __device__ __forceinline__ void warp_gemm_f16x3(const fumi_half* Ahi, const fumi
                 else        { fumi_ldsm2t(bh, Bhi + o); fumi_ldsm2t(bl, Blo + o); }
 #pragma unroll
                 for (int i = 0; i < MT; ++i) {
-                    fumi_mma_f16(part[i][0], al[i], bh[0], bh[1]);
-                    fumi_mma_f16(part[i][0], ah[i], bl[0], bl[1]);
+                    fumi_mma_f16(kSplitAcc ? c1[i][0] : part[i][0], al[i], bh[0], bh[1]);
+                    fumi_mma_f16(kSplitAcc ? c2[i][0] : part[i][0], ah[i], bl[0], bl[1]);
                     fumi_mma_f16(part[i][0], ah[i], bh[0], bh[1]);
                 }
             } else {
@@ -225,8 +232,8 @@ __device__ __forceinline__ void warp_gemm_f16x3(const fumi_half* Ahi, const fumi
                     for (int i = 0; i < MT; ++i) {
 #pragma unroll
                         for (int h = 0; h < 2; ++h) {
-                            fumi_mma_f16(part[i][2 * jp + h], al[i], bh[2 * h], bh[2 * h + 1]);
-                            fumi_mma_f16(part[i][2 * jp + h], ah[i], bl[2 * h], bl[2 * h + 1]);
+                            fumi_mma_f16(kSplitAcc ? c1[i][2 * jp + h] : part[i][2 * jp + h], al[i], bh[2 * h], bh[2 * h + 1]);
+                            fumi_mma_f16(kSplitAcc ? c2[i][2 * jp + h] : part[i][2 * jp + h], ah[i], bl[2 * h], bl[2 * h + 1]);
                             fumi_mma_f16(part[i][2 * jp + h], ah[i], bh[2 * h], bh[2 * h + 1]);
                         }
                     }
@@ -238,7 +245,8 @@ __device__ __forceinline__ void warp_gemm_f16x3(const fumi_half* Ahi, const fumi
 #pragma unroll
             for (int j = 0; j < NT; ++j)
 #pragma unroll
-                for (int q = 0; q < 4; ++q) acc[i][j][q] += part[i][j][q];
+                for (int q = 0; q < 4; ++q)
+                    acc[i][j][q] += kSplitAcc ? part[i][j][q] + (c1[i][j][q] + c2[i][j][q]) : part[i][j][q];
     }
 }
 
@@ -251,3 +259,20 @@ __device__ __forceinline__ int fumi_plane_exp(uint32_t absmax_bits) {
     return s > 100 ? 100 : (s < -100 ? -100 : s);
 }
 __device__ __forceinline__ float fumi_exp2i(int s) { return __uint_as_float(uint32_t(127 + s) << 23); }   // 2^s, |s| <= 126
+
+// two adjacent plane elements with one 32-bit access each (off even, rows 16-byte aligned)
+__device__ __forceinline__ void fumi_plane_load2(const fumi_half* hi, const fumi_half* lo, int off, float inv, float& a, float& b) {
+    const uint32_t h = *reinterpret_cast<const uint32_t*>(hi + off), l = *reinterpret_cast<const uint32_t*>(lo + off);
+    fumi_half h0, h1, l0, l1;
+    *reinterpret_cast<uint16_t*>(&h0) = uint16_t(h & 0xFFFFu); *reinterpret_cast<uint16_t*>(&h1) = uint16_t(h >> 16);
+    *reinterpret_cast<uint16_t*>(&l0) = uint16_t(l & 0xFFFFu); *reinterpret_cast<uint16_t*>(&l1) = uint16_t(l >> 16);
+    a = (fumi_h2f(h0) + fumi_h2f(l0)) * inv;
+    b = (fumi_h2f(h1) + fumi_h2f(l1)) * inv;
+}
+__device__ __forceinline__ void fumi_plane_store2(fumi_half* hi, fumi_half* lo, int off, float a, float b, float scale) {
+    a *= scale; b *= scale;
+    const fumi_half ah = fumi_f2h(a), bh = fumi_f2h(b);
+    const fumi_half al = fumi_f2h(a - fumi_h2f(ah)), bl = fumi_f2h(b - fumi_h2f(bh));
+    *reinterpret_cast<uint32_t*>(hi + off) = uint32_t(*reinterpret_cast<const uint16_t*>(&ah)) | (uint32_t(*reinterpret_cast<const uint16_t*>(&bh)) << 16);
+    *reinterpret_cast<uint32_t*>(lo + off) = uint32_t(*reinterpret_cast<const uint16_t*>(&al)) | (uint32_t(*reinterpret_cast<const uint16_t*>(&bl)) << 16);
+}
