@@ -1120,6 +1120,7 @@ __global__ void __launch_bounds__(kThreads16, 1) episode_fwd_f16_kernel(EpiParam
     auto h0_load = [&](const long long* rows, int tr) {
 #pragma unroll
         for (int i = 0; i < 2; ++i)
+            if (i == 0 || tr > 16)
 #pragma unroll
             for (int j = 0; j < 2; ++j)
 #pragma unroll
@@ -1137,12 +1138,18 @@ __global__ void __launch_bounds__(kThreads16, 1) episode_fwd_f16_kernel(EpiParam
             for (int j = 0; j < 2; ++j)
 #pragma unroll
                 for (int q = 0; q < 4; ++q) acc[i][j][q] = 0.f;
-        if (use_s) warp_gemm_f16x3<2, 2, false, false>(gh, gl, kHG, s.sh + 16 * w, s.sl + 16 * w, kHS, 32, acc);
+        const bool two = tr > 16;                           // rows 16..31 in use (support: NK > 16; last query tile may be short)
+        if (use_s) {
+            if (two) warp_gemm_f16x3<2, 2, false, false>(gh, gl, kHG, s.sh + 16 * w, s.sl + 16 * w, kHS, 32, acc);
+            else warp_gemm_f16x3<1, 2, false, false>(gh, gl, kHG, s.sh + 16 * w, s.sl + 16 * w, kHS, MT == 1 ? 16 : 32,
+                                                     reinterpret_cast<float(&)[1][2][4]>(acc));
+        }
         const uint32_t dbase = drop ? dropout_base(c, task, pass, 0) : 0u;
         uint32_t bits = 0;
         float mxv = 0.f;
 #pragma unroll
         for (int i = 0; i < 2; ++i)
+            if (i == 0 || two)
 #pragma unroll
             for (int j = 0; j < 2; ++j)
 #pragma unroll
@@ -1164,6 +1171,7 @@ __global__ void __launch_bounds__(kThreads16, 1) episode_fwd_f16_kernel(EpiParam
         const float sc = fumi_exp2i(e_h0);
 #pragma unroll
         for (int i = 0; i < 2; ++i)
+            if (i == 0 || two)
 #pragma unroll
             for (int j = 0; j < 2; ++j)
 #pragma unroll
@@ -1342,13 +1350,14 @@ __global__ void __launch_bounds__(kThreads16, 1) episode_fwd_f16_kernel(EpiParam
                     for (int j = 0; j < 2; ++j)
 #pragma unroll
                         for (int q = 0; q < 4; ++q) acc[i][j][q] = 0.f;
-                warp_gemm_f16x3<2, 2, false, true>(s.dzh, s.dzl, kHW, s.w1h + 16 * w * kHW, s.w1l + 16 * w * kHW, kHW, kH1, acc);
+                warp_gemm_f16x3<MT, 2, false, true>(s.dzh, s.dzl, kHW, s.w1h + 16 * w * kHW, s.w1l + 16 * w * kHW, kHW, kH1,
+                                                    reinterpret_cast<float(&)[MT][2][4]>(acc));
                 const float inv = fumi_exp2i(-e_dz) * fumi_exp2i(-e_w1);
                 const float sinv = st > 0 ? fumi_exp2i(-e_s) : 0.f;
                 float colsum[2][2] = {{0.f, 0.f}, {0.f, 0.f}};
                 float mxv = 0.f;
 #pragma unroll
-                for (int i = 0; i < 2; ++i)
+                for (int i = 0; i < MT; ++i)
 #pragma unroll
                     for (int j = 0; j < 2; ++j)
 #pragma unroll
@@ -1398,7 +1407,7 @@ __global__ void __launch_bounds__(kThreads16, 1) episode_fwd_f16_kernel(EpiParam
                 e_s = block_max_exp(s.mx + 16 * (MX_S + (prod_s & 1)));
                 const float sc = fumi_exp2i(e_s);
 #pragma unroll
-                for (int i = 0; i < 2; ++i)
+                for (int i = 0; i < MT; ++i)                  // NK <= 16: rows 16..31 of the S planes stay zero
 #pragma unroll
                     for (int j = 0; j < 2; ++j)
 #pragma unroll

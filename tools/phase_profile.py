@@ -15,13 +15,13 @@ from fumi_b200.data.loader import EpisodeLoader  # noqa: E402
 from fumi_b200.data.synth import class_split, make_bank  # noqa: E402
 from fumi_b200.sampler import EpisodeSampler  # noqa: E402
 
-NAMES = {0: "bwd prologue", 1: "bwd q: loads+softmax", 2: "bwd q: a_head,dZ1q", 3: "bwd q: aW1/dZ0q gemms+atomics",
+NAMES = {0: "bwd prologue", 1: "bwd q: tile loads", 2: "bwd q: a_head,dZ1q", 3: "bwd q: aW1/dZ0q gemms+atomics",
          4: "bwd q: a_S gemm", 5: "bwd s: loads+undo W1", 6: "bwd s: tile loads", 7: "bwd s: r_dH1/r_W1/r_H0 gemms",
          8: "bwd s: r_dL,r_head", 9: "bwd s: jacobian,r_H1", 10: "bwd s: r_Z1,r_head", 11: "bwd s: r_H0/r_W1 gemms+atomics",
          12: "bwd s: fold+reload bZ", 13: "bwd s: a_S gemm", 14: "bwd epilogue",
-         20: "fwd prologue", 21: "fwd s: H0", 22: "fwd s: H1", 23: "fwd s: logits", 24: "fwd s: softmax",
+         20: "fwd prologue", 21: "fwd s: H0", 22: "fwd s: H1", 23: "fwd s: logits+softmax", 24: "fwd s: (unused)",
          25: "fwd s: dhp,dZ1", 26: "fwd s: dZ0 gemm,S,stash", 27: "fwd s: W1 update gemm", 28: "fwd q: loads",
-         29: "fwd q: H0", 30: "fwd q: H1", 31: "fwd q: logits", 32: "fwd q: stash,softmax,loss", 33: "fwd epilogue"}
+         29: "fwd q: H0", 30: "fwd q: H1", 31: "fwd q: logits+softmax", 32: "fwd q: stash, tile end", 33: "fwd epilogue"}
 
 
 def main():
