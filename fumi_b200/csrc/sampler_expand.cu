@@ -9,9 +9,11 @@
 //   lane 0        init_genrand(seed): 624-step serial recurrence into shared memory
 //   32 lanes      the MT19937 twist, 32 words at a time (reads complete before writes; word k needs
 //                 the old k+1 and k+397, or the new k-227, so ascending 32-word groups are safe)
+//   32 lanes      tempering of the 624 words into a second array (the serial loop below then costs a load,
+//                 a mask and a compare per draw; tempering inside it was 40 % of its instructions)
 //   lane 0        numpy's backward Fisher-Yates: j = masked-rejection draw <= i, swap perm[i], perm[j]
 //   32 lanes      the K+Q picks -> image id, bank row and label, int64, written to HBM
-// Serial chains of different warps overlap; a 4096x5 batch takes ~0.1 ms.
+// Serial chains of different warps overlap; the kernel time is set by the largest class of the batch.
 #include <cstdint>
 
 #include "../../include/fumi_b200.h"
@@ -31,8 +33,8 @@ __device__ __forceinline__ uint32_t mt_temper(uint32_t y) {
     return y;
 }
 
-// In-place regeneration of the 624 state words by one warp.
-__device__ __forceinline__ void mt_twist_warp(uint32_t* key, int lane) {
+// In-place regeneration of the 624 state words by one warp, then the tempered outputs into draws[].
+__device__ __forceinline__ void mt_twist_warp(uint32_t* key, uint32_t* draws, int lane) {
     for (int base = 0; base < kMT; base += 32) {
         const int k = base + lane;
         uint32_t v = 0;
@@ -41,7 +43,7 @@ __device__ __forceinline__ void mt_twist_warp(uint32_t* key, int lane) {
             v = key[k < kMT - 397 ? k + 397 : k - (kMT - 397)] ^ (y >> 1) ^ ((y & 1u) ? 0x9908b0dfu : 0u);
         }
         __syncwarp();
-        if (k < kMT) key[k] = v;
+        if (k < kMT) { key[k] = v; draws[k] = mt_temper(v); }
         __syncwarp();
     }
 }
@@ -57,8 +59,9 @@ sampler_expand_kernel(const int64_t* __restrict__ offsets, const int64_t* __rest
                       int64_t* __restrict__ sup_rows, int64_t* __restrict__ qry_rows) {
     FUMI_DYN_SMEM(uint32_t, smem);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    uint32_t* key = smem + warp * kMT;
-    PermT* perm = reinterpret_cast<PermT*>(smem + kWarps * kMT) + size_t(warp) * perm_stride;
+    uint32_t* key = smem + warp * (2 * kMT);
+    uint32_t* draws = key + kMT;
+    PermT* perm = reinterpret_cast<PermT*>(smem + kWarps * 2 * kMT) + size_t(warp) * perm_stride;
     const int64_t job = int64_t(blockIdx.x) * kWarps + warp;
     if (job >= jobs) return;                       // whole warp leaves together; no block-wide barrier below
 
@@ -75,7 +78,7 @@ sampler_expand_kernel(const int64_t* __restrict__ offsets, const int64_t* __rest
     }
     for (int i = lane; i < n; i += 32) perm[i] = PermT(i);
     __syncwarp();
-    mt_twist_warp(key, lane);
+    mt_twist_warp(key, draws, lane);
 
     int pos = 0;
     int i = n - 1;
@@ -84,8 +87,10 @@ sampler_expand_kernel(const int64_t* __restrict__ offsets, const int64_t* __rest
             // run until the shuffle ends or the 624 words are used up
             uint32_t mask = uint32_t(i);
             mask |= mask >> 1; mask |= mask >> 2; mask |= mask >> 4; mask |= mask >> 8; mask |= mask >> 16;
+            uint32_t d = draws[pos];
             while (i >= 1 && pos < kMT) {
-                const uint32_t v = mt_temper(key[pos++]) & mask;
+                const uint32_t v = d & mask;
+                d = draws[++pos];                  // next draw in flight (one word past the array is readable shared memory)
                 if (v <= uint32_t(i)) {            // accepted: j = v
                     const PermT t = perm[i];
                     perm[i] = perm[v];
@@ -99,7 +104,7 @@ sampler_expand_kernel(const int64_t* __restrict__ offsets, const int64_t* __rest
         if (i >= 1) {                              // state exhausted mid-shuffle: next 624 words
             pos = 0;
             __syncwarp();
-            mt_twist_warp(key, lane);
+            mt_twist_warp(key, draws, lane);
         }
     }
     __syncwarp();
@@ -134,8 +139,8 @@ extern "C" int fumi_sampler_expand(const int64_t* class_offsets, const int64_t* 
     const int64_t jobs = B * N;
     const bool wide = max_class_size > 65535;
     const int64_t stride = (max_class_size + 7) & ~int64_t(7);
-    const size_t smem = size_t(kWarps) * kMT * 4 + size_t(kWarps) * stride * (wide ? 4 : 2);
-    FUMI_CHECK_ARG(smem <= 227 * 1024, "class too large for the shared-memory permutation (max ~25k images per class)");
+    const size_t smem = size_t(kWarps) * 2 * kMT * 4 + size_t(kWarps) * stride * (wide ? 4 : 2);
+    FUMI_CHECK_ARG(smem <= 227 * 1024, "class too large for the shared-memory permutation (max ~22k images per class)");
     const unsigned grid = unsigned((jobs + kWarps - 1) / kWarps);
     if (wide) {
 #ifndef FUMI_EMU
