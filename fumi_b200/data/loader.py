@@ -28,8 +28,14 @@ class EpisodeLoader:
     `random` / torch generator states are set to what they were right after that batch was drawn, so the
     host program observes the same generator sequence as with the synchronous loader."""
 
-    def __init__(self, bank, sampler, batch_size, pin_memory=True, prefetch=0, device_sampler=None):
+    def __init__(self, bank, sampler, batch_size, pin_memory=True, prefetch=0, device_sampler=None, shard=None):
         self.bank, self.sampler, self.batch_size = bank, sampler, int(batch_size)
+        # shard = (rank, world): every rank draws the SAME global stream of `world * batch_size` tasks per step (so the
+        # sampled tasks are bit-identical to a single-process run with that meta-batch) and keeps tasks
+        # [rank * batch_size, (rank + 1) * batch_size) -- SURVEY.md 8(e).  The host-side plan then costs `world` times
+        # more per step (5.5 ms per 4096 tasks); the default (shard=None) lets each rank draw its own stream.
+        self.shard = None if shard is None else (int(shard[0]), int(shard[1]))
+        self._draw = self.batch_size * (self.shard[1] if self.shard else 1)
         self.pin = bool(pin_memory) and bank.feats.is_cuda
         self.prefetch = int(prefetch)
         # device_sampler: the host only advances the sequential generator streams (fumi_sampler_plan); the
@@ -39,14 +45,22 @@ class EpisodeLoader:
         self.dataset = sampler          # len(loader.dataset) parity is not meaningful for episodes
         self._stop = None
 
+    def _mine(self, t):
+        """This rank's slice of a [world * batch_size, ...] array / tensor."""
+        if self.shard is None:
+            return t
+        r, B = self.shard[0], self.batch_size
+        return t[r * B:(r + 1) * B]
+
     def _host_buffers(self):
-        N, K, Q, B = self.sampler.N, self.sampler.K, self.sampler.Q, self.batch_size
+        N, K, Q, B = self.sampler.N, self.sampler.K, self.sampler.Q, self._draw
         widths = dict(classes=N, label_perm=N, sup_ids=N * K, qry_ids=N * Q, sup_y=N * K, qry_y=N * Q,
                       head_class=N, sup_rows=N * K, qry_rows=N * Q)
         ts = {k: torch.empty((B, w), dtype=torch.int64, pin_memory=self.pin) for k, w in widths.items()}
         return ts, {k: t.numpy() for k, t in ts.items()}
 
     def _expand(self, plan):
+        plan = {k: self._mine(v) for k, v in plan.items()}
         d = self.sampler.expand(plan, self.bank.feats.device)
         host = {k: plan[k].numpy() for k in ("classes", "label_perm", "head_class")}
         return EpisodeBatch(bank=self.bank, sup_rows=d["sup_rows"], qry_rows=d["qry_rows"], sup_y=d["sup_y"],
@@ -55,14 +69,14 @@ class EpisodeLoader:
 
     def next_batch(self):
         if self.device_sampler:
-            return self._expand(self.sampler.plan(self.batch_size, pin_memory=self.pin))
+            return self._expand(self.sampler.plan(self._draw, pin_memory=self.pin))
         ts, arrs = self._host_buffers()
-        self.sampler.next_batch(self.batch_size, out=arrs)
-        return EpisodeBatch(bank=self.bank, sup_rows=ts["sup_rows"], qry_rows=ts["qry_rows"], sup_y=ts["sup_y"],
-                            qry_y=ts["qry_y"], sup_ids=arrs["sup_ids"], qry_ids=arrs["qry_ids"],
-                            head_class=ts["head_class"], host=arrs)
+        self.sampler.next_batch(self._draw, out=arrs)
+        return self._make(ts, arrs)
 
     def _make(self, ts, arrs):
+        ts = {k: self._mine(v) for k, v in ts.items()}
+        arrs = {k: self._mine(v) for k, v in arrs.items()}
         return EpisodeBatch(bank=self.bank, sup_rows=ts["sup_rows"], qry_rows=ts["qry_rows"], sup_y=ts["sup_y"],
                             qry_y=ts["qry_y"], sup_ids=arrs["sup_ids"], qry_ids=arrs["qry_ids"],
                             head_class=ts["head_class"], host=arrs)
@@ -96,8 +110,8 @@ class EpisodeLoader:
                     torch.cuda.set_device(dev)
                 while not stop.is_set():
                     if self.device_sampler:
-                        plan = self.sampler.empty_plan(self.batch_size, pin_memory=self.pin)
-                        self.sampler.plan_states(self.batch_size, py, st, plan)
+                        plan = self.sampler.empty_plan(self._draw, pin_memory=self.pin)
+                        self.sampler.plan_states(self._draw, py, st, plan)
                         if side is not None:
                             with torch.cuda.stream(side):
                                 batch = self._expand(plan)
@@ -108,7 +122,7 @@ class EpisodeLoader:
                             item = (plan, None, py.copy(), st.copy())
                     else:
                         ts, arrs = self._host_buffers()
-                        self.sampler.next_batch_states(self.batch_size, py, st, arrs)
+                        self.sampler.next_batch_states(self._draw, py, st, arrs)
                         item = (ts, arrs, py.copy(), st.copy())
                     while not stop.is_set():
                         try:

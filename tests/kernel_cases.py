@@ -495,3 +495,15 @@ def device_loader_case(device):
                     assert np.array_equal(v, ref[i][0][k]), (i, k)
                 assert snap[0] == ref[i][1][0] and torch.equal(snap[1], ref[i][1][1])
         loader.close()
+    # device sampler + shard=(r, W): slices of the W * B single-stream batch
+    W = 3
+    sampler = EpisodeSampler(cat_of, np.arange(C), N, K, Q, num_threads=2)
+    bank = FeatureBank(feats=feats, text=torch.zeros(C, 4, device=device), ids=sampler.ids, categories=np.arange(C))
+    random.seed(31); torch.manual_seed(32)
+    whole = next(iter(EpisodeLoader(bank, sampler, W * B, pin_memory=False, device_sampler=True)))
+    for r in range(W):
+        s2 = EpisodeSampler(cat_of, np.arange(C), N, K, Q, num_threads=2)
+        random.seed(31); torch.manual_seed(32)
+        part = next(iter(EpisodeLoader(bank, s2, B, pin_memory=False, device_sampler=True, shard=(r, W))))
+        for k in ("sup_rows", "qry_rows", "sup_y", "qry_y", "sup_ids", "qry_ids", "head_class"):
+            assert torch.equal(getattr(whole, k)[r * B:(r + 1) * B].cpu(), getattr(part, k).cpu()), (r, k)

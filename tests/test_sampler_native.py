@@ -127,3 +127,35 @@ def test_prefetching_loader_hands_out_the_same_stream_and_states():
                 assert snap[0] == ref_states[i][0]
                 assert torch.equal(snap[1], ref_states[i][1])
         loader.close()
+
+
+def test_sharded_loaders_draw_one_global_stream():
+    """EpisodeLoader(shard=(r, W)): the ranks' batches are the slices of the single-process batch of W * B tasks
+    (same global generator streams on every rank), with and without the prefetch thread."""
+    from fumi_b200.data.bank import FeatureBank
+    from fumi_b200.data.loader import EpisodeLoader
+    rs = np.random.RandomState(4)
+    C, N, K, Q, B, W = 30, 5, 2, 4, 3, 2
+    sizes = rs.randint(K + Q, K + Q + 20, size=C)
+    cat_of = np.repeat(np.arange(C), sizes)
+    rs.shuffle(cat_of)
+    feats = torch.zeros(len(cat_of), 4)
+
+    def run(batch, shard, prefetch):
+        sampler = EpisodeSampler(cat_of, np.arange(C), N, K, Q, num_threads=2)
+        bank = FeatureBank(feats=feats, text=torch.zeros(C, 4), ids=sampler.ids, categories=np.arange(C))
+        loader = EpisodeLoader(bank, sampler, batch, pin_memory=False, prefetch=prefetch, shard=shard)
+        random.seed(21); torch.manual_seed(22)
+        it = iter(loader)
+        out = [{k: np.asarray(v).copy() for k, v in next(it).host.items()} for _ in range(3)]
+        loader.close()
+        return out, random.getstate(), torch.get_rng_state().clone()
+
+    whole, py_w, t_w = run(W * B, None, 0)
+    for prefetch in (0, 2):
+        for r in range(W):
+            part, py_r, t_r = run(B, (r, W), prefetch)
+            for a, b in zip(whole, part):
+                for k in a:
+                    assert np.array_equal(a[k][r * B:(r + 1) * B], b[k]), (prefetch, r, k)
+            assert py_r == py_w and torch.equal(t_r, t_w)
