@@ -367,8 +367,8 @@ def main():
     for i in range(a.steps):
         b = next(e2e_it)
         if i == 0:
-            if dev_sampler:      # the plan: classes, label_perm, head_class (i64), perm_seed (u32), picks (i32)
-                h2d = a.tasks * N * (3 * 8 + 4 + 4 * (K + Q))
+            if dev_sampler:      # the plan: classes, label_perm, head_class (i64), perm_seed (u32), picks, job_order (i32)
+                h2d = a.tasks * N * (3 * 8 + 4 + 4 * (K + Q) + 4)
             else:
                 h2d = sum(t.numel() * 8 for t in (b.sup_rows, b.qry_rows, b.sup_y, b.qry_y, b.head_class))
             d2h = 8                                                     # loss + acc (fumi.py:195-196)

@@ -61,8 +61,8 @@ _SIGS = {
     "fumi_sampler_destroy": (None, [_P]),
     "fumi_sampler_new_iterator": (C.c_int, [_P, _P]),
     "fumi_sampler_next": (C.c_int, [_P, _I64] + [_P] * 11 + [_I32]),
-    "fumi_sampler_plan": (C.c_int, [_P, _I64] + [_P] * 7),
-    "fumi_sampler_expand": (C.c_int, [_P, _P, _I64, _P, _P, _P, _P, _I64, _I32, _I32, _I32] + [_P] * 7),
+    "fumi_sampler_plan": (C.c_int, [_P, _I64] + [_P] * 8),
+    "fumi_sampler_expand": (C.c_int, [_P, _P, _I64, _P, _P, _P, _P, _P, _I64, _I32, _I32, _I32] + [_P] * 7),
     "fumi_py_tuple_hash": (_I64, [_P, _I64]),
     "fumi_debug_phase_profile": (C.c_int, [C.c_int]),
     "fumi_debug_read_phases": (C.c_int, [_P]),

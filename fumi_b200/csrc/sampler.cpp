@@ -280,7 +280,7 @@ extern "C" int fumi_sampler_next(fumi_sampler* s, int64_t B, uint32_t* py_state,
 // Sequential streams only; the per (task, class) permutations run on the device (sampler_expand.cu).
 extern "C" int fumi_sampler_plan(fumi_sampler* s, int64_t B, uint32_t* py_state, uint32_t* torch_state,
                                  int64_t* classes, int64_t* label_perm, int64_t* head_class,
-                                 uint32_t* perm_seed, int32_t* picks) {
+                                 uint32_t* perm_seed, int32_t* picks, int32_t* job_order) {
     if (!s || B <= 0 || !py_state || !torch_state || !classes || !label_perm || !head_class || !perm_seed || !picks) {
         fumi_set_error("fumi_sampler_plan: null/empty argument");
         return FUMI_ERR_ARG;
@@ -326,6 +326,17 @@ extern "C" int fumi_sampler_plan(fumi_sampler* s, int64_t B, uint32_t* py_state,
             std::swap(lp[i], lp[i + z]);
         }
         for (int p = 0; p < N; ++p) head_class[b * N + lp[p]] = classes[b * N + p];
+    }
+    if (job_order) {
+        // device jobs (task, class) longest class first: a job's cost is its class size, and the expand kernel's time is
+        // otherwise set by a long job that happens to start last (counting sort, stable)
+        int64_t max_n = 0;
+        for (int64_t c = 0; c < s->C; ++c) max_n = std::max(max_n, s->offsets[c + 1] - s->offsets[c]);
+        std::vector<int32_t> start(size_t(max_n) + 2, 0);
+        for (int64_t j = 0; j < B * N; ++j) ++start[size_t(max_n - (s->offsets[classes[j] + 1] - s->offsets[classes[j]])) + 1];
+        for (size_t k = 1; k < start.size(); ++k) start[k] += start[k - 1];
+        for (int64_t j = 0; j < B * N; ++j)
+            job_order[start[size_t(max_n - (s->offsets[classes[j] + 1] - s->offsets[classes[j]]))]++] = int32_t(j);
     }
     return FUMI_OK;
 }

@@ -53,7 +53,7 @@ __global__ void __launch_bounds__(kWarps * 32)
 sampler_expand_kernel(const int64_t* __restrict__ offsets, const int64_t* __restrict__ ids, int perm_stride,
                       const int64_t* __restrict__ classes, const int64_t* __restrict__ label_perm,
                       const uint32_t* __restrict__ perm_seed, const int32_t* __restrict__ picks,
-                      int64_t jobs, int K, int Q,
+                      const int32_t* __restrict__ job_order, int64_t jobs, int K, int Q,
                       int64_t* __restrict__ sup_ids, int64_t* __restrict__ qry_ids,
                       int64_t* __restrict__ sup_y, int64_t* __restrict__ qry_y,
                       int64_t* __restrict__ sup_rows, int64_t* __restrict__ qry_rows) {
@@ -62,8 +62,9 @@ sampler_expand_kernel(const int64_t* __restrict__ offsets, const int64_t* __rest
     uint32_t* key = smem + warp * (2 * kMT);
     uint32_t* draws = key + kMT;
     PermT* perm = reinterpret_cast<PermT*>(smem + kWarps * 2 * kMT) + size_t(warp) * perm_stride;
-    const int64_t job = int64_t(blockIdx.x) * kWarps + warp;
-    if (job >= jobs) return;                       // whole warp leaves together; no block-wide barrier below
+    const int64_t slot = int64_t(blockIdx.x) * kWarps + warp;
+    if (slot >= jobs) return;                      // whole warp leaves together; no block-wide barrier below
+    const int64_t job = job_order ? job_order[slot] : slot;        // longest classes first when the plan says so
 
     const int64_t c = classes[job];
     const int64_t row0 = offsets[c];
@@ -129,8 +130,8 @@ sampler_expand_kernel(const int64_t* __restrict__ offsets, const int64_t* __rest
 
 extern "C" int fumi_sampler_expand(const int64_t* class_offsets, const int64_t* class_image_ids,
                                    int64_t max_class_size, const int64_t* classes, const int64_t* label_perm,
-                                   const uint32_t* perm_seed, const int32_t* picks, int64_t B, int32_t N,
-                                   int32_t K, int32_t Q, int64_t* sup_ids, int64_t* qry_ids, int64_t* sup_y,
+                                   const uint32_t* perm_seed, const int32_t* picks, const int32_t* job_order,
+                                   int64_t B, int32_t N, int32_t K, int32_t Q, int64_t* sup_ids, int64_t* qry_ids, int64_t* sup_y,
                                    int64_t* qry_y, int64_t* sup_rows, int64_t* qry_rows, void* stream) {
     FUMI_CHECK_ARG(B >= 0 && N > 0 && K > 0 && Q >= 0 && max_class_size >= K + Q, "bad sizes");
     if (B == 0) return FUMI_OK;
@@ -147,14 +148,14 @@ extern "C" int fumi_sampler_expand(const int64_t* class_offsets, const int64_t* 
         cudaFuncSetAttribute(sampler_expand_kernel<uint32_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem));
 #endif
         FUMI_LAUNCH(sampler_expand_kernel<uint32_t>, grid, kWarps * 32, smem, stream, class_offsets, class_image_ids,
-                    int(stride), classes, label_perm, perm_seed, picks, jobs, K, Q, sup_ids, qry_ids, sup_y, qry_y,
+                    int(stride), classes, label_perm, perm_seed, picks, job_order, jobs, K, Q, sup_ids, qry_ids, sup_y, qry_y,
                     sup_rows, qry_rows);
     } else {
 #ifndef FUMI_EMU
         cudaFuncSetAttribute(sampler_expand_kernel<uint16_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem));
 #endif
         FUMI_LAUNCH(sampler_expand_kernel<uint16_t>, grid, kWarps * 32, smem, stream, class_offsets, class_image_ids,
-                    int(stride), classes, label_perm, perm_seed, picks, jobs, K, Q, sup_ids, qry_ids, sup_y, qry_y,
+                    int(stride), classes, label_perm, perm_seed, picks, job_order, jobs, K, Q, sup_ids, qry_ids, sup_y, qry_y,
                     sup_rows, qry_rows);
     }
     FUMI_CHECK_LAUNCH("fumi_sampler_expand");

@@ -60,7 +60,7 @@ class EpisodeLoader:
         return ts, {k: t.numpy() for k, t in ts.items()}
 
     def _expand(self, plan):
-        plan = {k: self._mine(v) for k, v in plan.items()}
+        plan = {k: self._mine(v) for k, v in plan.items() if not (self.shard and k == "job_order")}   # global job ids
         d = self.sampler.expand(plan, self.bank.feats.device)
         host = {k: plan[k].numpy() for k in ("classes", "label_perm", "head_class")}
         return EpisodeBatch(bank=self.bank, sup_rows=d["sup_rows"], qry_rows=d["qry_rows"], sup_y=d["sup_y"],

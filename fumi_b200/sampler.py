@@ -106,7 +106,7 @@ class EpisodeSampler:
         mk = lambda shape, dt: torch.empty(shape, dtype=dt, pin_memory=pin_memory)
         return {"classes": mk((B, N), torch.int64), "label_perm": mk((B, N), torch.int64),
                 "head_class": mk((B, N), torch.int64), "perm_seed": mk((B, N), torch.int32),   # uint32 bits
-                "picks": mk((B, N, KQ), torch.int32)}
+                "picks": mk((B, N, KQ), torch.int32), "job_order": mk((B, N), torch.int32)}
 
     def plan_states(self, batch_size, py_state, torch_state, plan):
         """Sequential generator streams of one meta-batch on explicit states (thread-safe like
@@ -114,7 +114,7 @@ class EpisodeSampler:
         try:
             _lib.check(_lib.lib().fumi_sampler_plan(
                 self._h, int(batch_size), _lib.ptr(py_state), _lib.ptr(torch_state),
-                *[_lib.ptr(plan[k]) for k in ("classes", "label_perm", "head_class", "perm_seed", "picks")]),
+                *[_lib.ptr(plan[k]) for k in ("classes", "label_perm", "head_class", "perm_seed", "picks", "job_order")]),
                 "fumi_sampler_plan")
         except _lib.FumiError as e:
             if "smaller than the minimum" in str(e):
@@ -157,7 +157,7 @@ class EpisodeSampler:
         stream = _lib.stream_ptr(device) if device.type == "cuda" else None
         _lib.check(_lib.lib().fumi_sampler_expand(
             _lib.ptr(offsets), _lib.ptr(ids), int(np.diff(self.offsets).max()), _lib.ptr(d["classes"]),
-            _lib.ptr(d["label_perm"]), _lib.ptr(d["perm_seed"]), _lib.ptr(d["picks"]), B, N, K, Q,
+            _lib.ptr(d["label_perm"]), _lib.ptr(d["perm_seed"]), _lib.ptr(d["picks"]), _lib.ptr(d.get("job_order")), B, N, K, Q,
             *[_lib.ptr(out[k]) for k in ("sup_ids", "qry_ids", "sup_y", "qry_y", "sup_rows", "qry_rows")], stream),
             "fumi_sampler_expand")
         out.update(head_class=d["head_class"], classes=d["classes"], label_perm=d["label_perm"])

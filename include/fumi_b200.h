@@ -280,13 +280,15 @@ int fumi_sampler_next(fumi_sampler* s, int64_t B, uint32_t* py_state, uint32_t* 
  * sup_ids / qry_ids / sup_y / qry_y / sup_rows / qry_rows straight into HBM, so the index arrays the
  * episode kernels gather by never exist on the host.  class_offsets[C+1] / class_image_ids are the
  * device copies of the fumi_sampler_create tables; max_class_size = max_c n_c (sizes the shared
- * memory).  Bit-identical to fumi_sampler_next. */
+ * memory).  job_order (optional, from the plan) lists the (task, class) jobs longest class first: a job costs
+ * its class size, so this keeps a long job from starting last.  Bit-identical to fumi_sampler_next. */
 int fumi_sampler_plan(fumi_sampler* s, int64_t B, uint32_t* py_state, uint32_t* torch_state,
                       int64_t* classes, int64_t* label_perm, int64_t* head_class,
-                      uint32_t* perm_seed, int32_t* picks);
+                      uint32_t* perm_seed, int32_t* picks, int32_t* job_order /* [B,N] or NULL */);
 int fumi_sampler_expand(const int64_t* class_offsets, const int64_t* class_image_ids, int64_t max_class_size,
                         const int64_t* classes, const int64_t* label_perm, const uint32_t* perm_seed,
-                        const int32_t* picks, int64_t B, int32_t N, int32_t K, int32_t Q,
+                        const int32_t* picks, const int32_t* job_order /* or NULL */,
+                        int64_t B, int32_t N, int32_t K, int32_t Q,
                         int64_t* sup_ids, int64_t* qry_ids, int64_t* sup_y, int64_t* qry_y,
                         int64_t* sup_rows, int64_t* qry_rows, void* stream);
 /* CPython hash(tuple of small non-negative ints) -- exposed for tests. */
