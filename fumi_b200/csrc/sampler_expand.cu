@@ -13,7 +13,8 @@
 //                 a mask and a compare per draw; tempering inside it was 40 % of its instructions)
 //   lane 0        numpy's backward Fisher-Yates: j = masked-rejection draw <= i, swap perm[i], perm[j]
 //   32 lanes      the K+Q picks -> image id, bank row and label, int64, written to HBM
-// Serial chains of different warps overlap; the kernel time is set by the largest class of the batch.
+// Serial chains of different warps overlap; a job costs its class size, so the host plan hands the jobs over
+// longest class first (job_order) -- 0.36 ms for a 4096 x 5 batch.
 #include <cstdint>
 
 #include "../../include/fumi_b200.h"
