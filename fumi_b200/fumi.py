@@ -130,7 +130,9 @@ class FUMI(nn.Module):
         Returns (loss np 0-d f32, acc np 0-d f32, test_preds f32 [B,NQ] on device, test_targets i64)."""
         if task == "train":
             self.train()
-            self.zero_grad()
+            # optimizer.zero_grad() of the reference (fumi.py:190); FusedAdam keeps its flat gradient views alive (one
+            # memset), Module.zero_grad() would drop them and fall back to per-tensor Adam / all-reduce launches
+            (optimizer if hasattr(optimizer, "_flat") else self).zero_grad()
         else:
             self.eval()
         eng = self._get_engine(args.device)
