@@ -62,7 +62,7 @@ class EpisodeLoader:
     def _expand(self, plan):
         plan = {k: self._mine(v) for k, v in plan.items() if not (self.shard and k == "job_order")}   # global job ids
         d = self.sampler.expand(plan, self.bank.feats.device)
-        host = {k: plan[k].numpy() for k in ("classes", "label_perm", "head_class")}
+        host = {k: plan[k].numpy().copy() for k in ("classes", "label_perm", "head_class")}   # the plan buffer is reused
         return EpisodeBatch(bank=self.bank, sup_rows=d["sup_rows"], qry_rows=d["qry_rows"], sup_y=d["sup_y"],
                             qry_y=d["qry_y"], sup_ids=d["sup_ids"], qry_ids=d["qry_ids"],
                             head_class=d["head_class"], host=host)
@@ -104,13 +104,21 @@ class EpisodeLoader:
         dev = self.bank.feats.device
         side = torch.cuda.Stream(dev) if (self.device_sampler and dev.type == "cuda") else None
 
+        # pinned plan buffers are allocated once and reused round-robin: a pinned allocation in steady state
+        # (cudaHostAlloc) stalls every CUDA call of the process for milliseconds.  A buffer is rewritten prefetch + 2
+        # batches after its upload was enqueued, long after the consumer waited on that batch's event.
+        ring = [self.sampler.empty_plan(self._draw, pin_memory=self.pin) for _ in range(self.prefetch + 2)] \
+            if self.device_sampler else []
+
         def worker():
             try:
                 if side is not None:
                     torch.cuda.set_device(dev)
+                produced = 0
                 while not stop.is_set():
                     if self.device_sampler:
-                        plan = self.sampler.empty_plan(self._draw, pin_memory=self.pin)
+                        plan = ring[produced % len(ring)]
+                        produced += 1
                         self.sampler.plan_states(self._draw, py, st, plan)
                         if side is not None:
                             with torch.cuda.stream(side):
