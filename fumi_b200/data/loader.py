@@ -183,7 +183,7 @@ def load_arrays(args):
 
     On-disk layout accepted: <data_dir>/iNat-Anim/bank.npz with arrays feats [M,D] f32, text [C,T] f32
     (description embeddings, precomputed), cat_of [M] i64.  The reference's inat_anim.json +
-    image_embeddings_*.hdf5 pair (data.py:373-430) converts to it with tools in DESIGN.md "next"."""
+    image_embeddings_*.hdf5 pair (data.py:373-430) converts to it with `python -m fumi_b200.data.convert`."""
     if getattr(args, "synthetic", False):
         b = make_bank(num_images=int(os.environ.get("FUMI_SYNTH_IMAGES", INAT_ANIM_IMAGES)),
                       num_classes=int(os.environ.get("FUMI_SYNTH_CLASSES", INAT_ANIM_CLASSES)),
