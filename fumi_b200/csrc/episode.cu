@@ -303,8 +303,10 @@ __device__ inline void tile_logits(const EpiParams& P, const Smem& s, int tr) {
 // softmax statistics of row i (N <= 32): returns max, sum of exp, and fills e[] with exp(l - max)
 __device__ inline void row_softmax(const float* l, int N, float& mx, float& sum) {
     mx = l[0];
+#pragma unroll 1
     for (int c = 1; c < N; ++c) mx = fmaxf(mx, l[c]);
     sum = 0.f;
+#pragma unroll 1
     for (int c = 0; c < N; ++c) sum += expf(l[c] - mx);
 }
 
@@ -1145,7 +1147,13 @@ __global__ void __launch_bounds__(kThreads16, 1) episode_fwd_f16_kernel(EpiParam
                                                      reinterpret_cast<float(&)[1][2][4]>(acc));
         }
         const uint32_t dbase = drop ? dropout_base(c, task, pass, 0) : 0u;
-        uint32_t bits = 0;
+        const float gs = use_s ? alpha * ginv : 0.f;
+        float b0v[2][2];
+#pragma unroll
+        for (int j = 0; j < 2; ++j) {
+            b0v[j][0] = s.b0s[16 * w + 8 * j + 2 * t];
+            b0v[j][1] = s.b0s[16 * w + 8 * j + 2 * t + 1];
+        }
         float mxv = 0.f;
 #pragma unroll
         for (int i = 0; i < 2; ++i)
@@ -1153,17 +1161,20 @@ __global__ void __launch_bounds__(kThreads16, 1) episode_fwd_f16_kernel(EpiParam
 #pragma unroll
             for (int j = 0; j < 2; ++j)
 #pragma unroll
-                for (int q = 0; q < 4; ++q) {
-                    const int r = 16 * i + g + 8 * (q >> 1), h = 16 * w + 8 * j + 2 * t + (q & 1);
-                    float v = 0.f;
-                    if (r < tr) {
-                        const float a = (q & 1) ? ap[i][j][q >> 1].y : ap[i][j][q >> 1].x;
-                        const float z = a + s.b0s[h] - (use_s ? alpha * (acc[i][j][q] * ginv) : 0.f);
-                        if (drop && (q & 1) == 0) bits = dropout_bits(dbase, r0 + r, h);
-                        if (z > 0.f && (!drop || dropout_keep_bits(bits, h, thr))) v = z * dsc;
+                for (int hq = 0; hq < 2; ++hq) {                 // one column pair (h, h + 1) of row r
+                    const int r = 16 * i + g + 8 * hq, h = 16 * w + 8 * j + 2 * t;
+                    const float z0 = ap[i][j][hq].x + b0v[j][0] - gs * acc[i][j][2 * hq];
+                    const float z1 = ap[i][j][hq].y + b0v[j][1] - gs * acc[i][j][2 * hq + 1];
+                    bool k0 = r < tr && z0 > 0.f, k1 = r < tr && z1 > 0.f;
+                    if (drop) {
+                        const uint32_t bits = dropout_bits(dbase, r0 + r, h);
+                        k0 = k0 && (bits & 0xFFFFu) >= thr;
+                        k1 = k1 && (bits >> 16) >= thr;
                     }
-                    acc[i][j][q] = v;
-                    mxv = fmaxf(mxv, v);
+                    const float v0 = k0 ? z0 * dsc : 0.f, v1 = k1 ? z1 * dsc : 0.f;
+                    acc[i][j][2 * hq] = v0;
+                    acc[i][j][2 * hq + 1] = v1;
+                    mxv = fmaxf(mxv, fmaxf(v0, v1));
                 }
         block_max_push(s.mx + 16 * (MX_H0 + (prod & 1)), mxv);
         __syncthreads();
@@ -1303,6 +1314,7 @@ __global__ void __launch_bounds__(kThreads16, 1) episode_fwd_f16_kernel(EpiParam
             for (int idx = tid; idx < N * kHD; idx += NT_) {
                 const int cc = idx / kHD, o = idx - cc * kHD;
                 float a = 0.f;
+#pragma unroll 2
                 for (int i = 0; i < n; ++i) a = fmaf(s.lt[i * kLS + cc], o < kH1 ? s.h1t[i * kS1 + o] : 1.f, a);
                 s.dhp[idx] = a;
             }
@@ -1315,6 +1327,7 @@ __global__ void __launch_bounds__(kThreads16, 1) episode_fwd_f16_kernel(EpiParam
                     float dz = 0.f;
                     if (i < n && s.h1t[i * kS1 + o_] > 0.f) {
                         float dh = 0.f;
+#pragma unroll 1
                         for (int cc = 0; cc < N; ++cc) dh = fmaf(s.lt[i * kLS + cc], s.hp[cc * kHD + o_], dh);
                         dz = dh * dsc;
                     }
@@ -1520,6 +1533,7 @@ __global__ void __launch_bounds__(kThreads16, 1) episode_fwd_f16_kernel(EpiParam
                 if (cc == 0) {
                     const float* lr = &s.lt[i * kLS];
                     int best = 0;
+#pragma unroll 1
                     for (int k = 1; k < N; ++k) if (lr[k] > lr[best]) best = k;      // first max (torch.max)
                     s.rowv[i] = (logf(sum) + mx) - lr[y];
                     s.rowc[i] = best == y ? 1.f : 0.f;

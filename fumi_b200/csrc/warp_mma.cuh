@@ -187,6 +187,7 @@ __device__ __forceinline__ void warp_gemm_f16x3(const fumi_half* Ahi, const fumi
     // few tiles per warp: the three products of a tile go to separate accumulators (three independent MMA chains
     // instead of one dependent chain of 3 K/16 MMAs -- the 64-wide layer has one tile per warp and was latency-bound)
     constexpr bool kSplitAcc = MT * NT <= 2;
+#pragma unroll 1
     for (int k0 = 0; k0 < K; k0 += 64) {
         float part[MT][NT][4];
         float c1[kSplitAcc ? MT : 1][kSplitAcc ? NT : 1][4], c2[kSplitAcc ? MT : 1][kSplitAcc ? NT : 1][4];
