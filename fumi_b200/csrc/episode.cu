@@ -2124,9 +2124,16 @@ __global__ void __launch_bounds__(kThreads16, 1) episode_bwd_mma16_kernel(EpiPar
         // ---- task epilogue: head gradient per task, shared-parameter gradients into this CTA's partials
         for (int idx = tid; idx < N * kHD; idx += NT_) P.d_head[b * N * kHD + idx] = s.ahp[idx];
         float* pw = P.d_w1_parts + int64_t(blockIdx.x) * kH0 * kH1;
-        for (int idx = tid; idx < kH0 * kH1; idx += NT_) {
-            const int o = idx / kH0, k = idx - o * kH0;                         // [H1][H0] like linear1.weight
-            pw[idx] += s.aw1t[k * kS1 + o];
+#pragma unroll 1
+        for (int base = tid; base < kH0 * kH1; base += 8 * NT_) {               // 8 partial-sum loads in flight per thread
+            float gsum[8];
+#pragma unroll
+            for (int q = 0; q < 8; ++q) gsum[q] = pw[base + q * NT_];
+#pragma unroll
+            for (int q = 0; q < 8; ++q) {
+                const int idx = base + q * NT_, o = idx / kH0, k = idx - o * kH0;   // [H1][H0] like linear1.weight
+                pw[idx] = gsum[q] + s.aw1t[k * kS1 + o];
+            }
         }
         if (tid < kH0) P.d_b0_parts[int64_t(blockIdx.x) * kH0 + tid] += s.ab0s[tid];
         if (tid < kH1) P.d_b1_parts[int64_t(blockIdx.x) * kH1 + tid] += s.ab1[tid];
