@@ -1953,90 +1953,68 @@ __global__ void __launch_bounds__(kThreads16, 1) episode_bwd_mma16_kernel(EpiPar
                     }
                     __syncthreads();
                     pc.mark(7);     // s: r_dH1 gemms (K=256 x2), r_W1 gemm, r_H0 gemm
-                    // (8r)+(7r): r_dL = r_dH1 Wh^T + H1 (g_Wh)^T + g_bh ; r_head += dL^T r_dH1
-                    // four lanes per (row, class): each sums 16 of the 64 hidden units, then two shuffles
-                    for (int idx4 = tid; idx4 < 64 * N; idx4 += NT_) {     // 64 N and NT_ are multiples of 32
-                        const int idx = idx4 >> 2, part = idx4 & 3;
-                        const int i = idx / N, cc = idx - i * N;
-                        float a0 = 0.f, a1 = 0.f;
-                        if (i < tr) {
-                            const float* rz = &s.rzh[i * kS1 + 16 * part];
-                            const float* h1 = &s.h1t[i * kS1 + 16 * part];
-                            const float* wh = &s.hp[cc * kHD + 16 * part];
-                            const float* ah = &s.ahp[cc * kHD + 16 * part];
-#pragma unroll 8
-                            for (int o = 0; o < 16; ++o) {
-                                a0 = fmaf(rz[o], wh[o], a0);
-                                a1 = fmaf(h1[o], ah[o], a1);
-                            }
+                    // (8r)-(4r) for one row per warp, no block barrier in between: the chain
+                    //   r_dL = r_dH1 Wh^T + H1 (g_Wh)^T + g_bh -> r_L = P (r_dL - <P, r_dL>) / n ->
+                    //   r_H1 = dL g_Wh + r_L Wh -> r_Z1 = r_H1 * gate1
+                    // only couples the 64 hidden units and N classes of the same row.  Lane l owns hidden units l, l + 32
+                    // and (l < N) class l.  r_Z1 goes to dz1t (free since the GEMMs above); rzh keeps r_dH1 and rlt gets
+                    // r_L for the cross-row head sums of the next phase.
+                    {
+                        const int i = w;
+                        const bool arow = i < tr;
+                        const float rd0 = s.rzh[i * kS1 + lane], rd1 = s.rzh[i * kS1 + lane + 32];
+                        const float h10 = s.h1t[i * kS1 + lane], h11 = s.h1t[i * kS1 + lane + 32];
+                        float rdl = 0.f;                                    // r_dL of class `lane`
+                        float ra0 = 0.f, ra1 = 0.f;                         // r_H1 of the two hidden units
+#pragma unroll 1
+                        for (int cc = 0; cc < N; ++cc) {
+                            const float* wh = &s.hp[cc * kHD];
+                            const float* ah = &s.ahp[cc * kHD];
+                            float a = fmaf(rd0, wh[lane], rd1 * wh[lane + 32]) - alpha * fmaf(h10, ah[lane], h11 * ah[lane + 32]);
+#pragma unroll
+                            for (int off = 16; off >= 1; off >>= 1) a += __shfl_xor_sync(0xffffffffu, a, off);
+                            if (lane == cc) rdl = a - alpha * ah[kH1];
+                            const float dl = s.lt[i * kLS + cc];
+                            ra0 = fmaf(dl, -alpha * ah[lane], ra0);
+                            ra1 = fmaf(dl, -alpha * ah[lane + 32], ra1);
                         }
-                        float a = fmaf(-alpha, a1, a0);
-                        a += __shfl_xor_sync(0xffffffffu, a, 1);
-                        a += __shfl_xor_sync(0xffffffffu, a, 2);
-                        if (part == 0) s.rlt[i * kLS + cc] = i < tr ? a - alpha * s.ahp[cc * kHD + kH1] : 0.f;
-                    }
-                    for (int idx = NT_ - 1 - tid; idx < N * kH1; idx += NT_) {    // from the other end of the block
-                        const int cc = idx / kH1, o = idx - cc * kH1;
-                        float a = 0.f;
-                        for (int i = 0; i < tr; ++i) a = fmaf(s.lt[i * kLS + cc], s.rzh[i * kS1 + o], a);
-                        s.rhp[cc * kHD + o] += a;
+                        const float pl = (arow && lane < N) ? s.lt[i * kLS + lane] * float(n) + (lane == s.ys[i] ? 1.f : 0.f) : 0.f;
+                        float dot = pl * rdl;                               // <P, r_dL>
+#pragma unroll
+                        for (int off = 16; off >= 1; off >>= 1) dot += __shfl_xor_sync(0xffffffffu, dot, off);
+                        const float rl = pl * (rdl - dot) / float(n);       // r_L of class `lane`
+#pragma unroll 1
+                        for (int cc = 0; cc < N; ++cc) {
+                            const float rlc = __shfl_sync(0xffffffffu, rl, cc);
+                            ra0 = fmaf(rlc, s.hp[cc * kHD + lane], ra0);
+                            ra1 = fmaf(rlc, s.hp[cc * kHD + lane + 32], ra1);
+                        }
+                        if (lane < N) s.rlt[i * kLS + lane] = arow ? rl : 0.f;
+                        s.dz1t[i * kS1 + lane] = (arow && h10 > 0.f) ? ra0 * sc : 0.f;
+                        s.dz1t[i * kS1 + lane + 32] = (arow && h11 > 0.f) ? ra1 * sc : 0.f;
                     }
                     __syncthreads();
-                    pc.mark(8);     // s: r_dL, r_head (FMA)
-                    // (6r) r_L = P * (r_dL - <P, r_dL>) / n ; (7r) r_H1 = dL g_Wh  (overwrites rzh)
-#pragma unroll
-                    for (int ii = 0; ii < 2; ++ii) {
-                        const int i = kg_ + 8 * ii;
-                        float a = 0.f;
-                        if (i < tr)
-                            for (int cc = 0; cc < N; ++cc) a = fmaf(s.lt[i * kLS + cc], -alpha * s.ahp[cc * kHD + o_], a);
-                        s.rzh[i * kS1 + o_] = a;
-                    }
-                    {   // one lane per (row, class), a row's N lanes in one warp (32 / N rows per warp): the row's
-                        // <P, r_dL> is recomputed by each of its lanes, and rlt is overwritten after a warp barrier
-                        const int rpw = 32 / N, li = lane / N, c0 = lane - li * N, i = w * rpw + li;
-                        const bool act = li < rpw && i < tr;
-                        float out = 0.f;
-                        if (act) {
-                            const int y = s.ys[i];
-                            float dot = 0.f;
-                            for (int cc = 0; cc < N; ++cc) {
-                                const float p = s.lt[i * kLS + cc] * float(n) + (cc == y ? 1.f : 0.f);
-                                dot = fmaf(p, s.rlt[i * kLS + cc], dot);
-                            }
-                            const float p = s.lt[i * kLS + c0] * float(n) + (c0 == y ? 1.f : 0.f);
-                            out = p * (s.rlt[i * kLS + c0] - dot) / float(n);
-                        }
-                        __syncwarp();
-                        if (act) s.rlt[i * kLS + c0] = out;
-                    }
-                    __syncthreads();
-                    pc.mark(9);     // s: softmax jacobian, r_H1
-                    // (5r) r_H1 += r_L Wh ; r_head += r_L^T [H1 | 1] ; (4r) r_Z1 = r_H1 * gate1
-#pragma unroll
-                    for (int ii = 0; ii < 2; ++ii) {
-                        const int i = kg_ + 8 * ii;
-                        float a = s.rzh[i * kS1 + o_];
-                        if (i < tr)
-                            for (int cc = 0; cc < N; ++cc) a = fmaf(s.rlt[i * kLS + cc], s.hp[cc * kHD + o_], a);
-                        s.rzh[i * kS1 + o_] = (i < tr && s.h1t[i * kS1 + o_] > 0.f) ? a * sc : 0.f;
-                    }
+                    pc.mark(8);     // s: r_dL .. r_Z1 (one row per warp)
+                    // cross-row sums: r_head += dL^T r_dH1 + r_L^T [H1 | 1]
                     for (int idx = tid; idx < N * kHD; idx += NT_) {
                         const int cc = idx / kHD, o = idx - cc * kHD;
                         float a = 0.f;
-                        for (int i = 0; i < tr; ++i) a = fmaf(s.rlt[i * kLS + cc], o < kH1 ? s.h1t[i * kS1 + o] : 1.f, a);
+                        if (o < kH1) {
+                            for (int i = 0; i < tr; ++i)
+                                a = fmaf(s.lt[i * kLS + cc], s.rzh[i * kS1 + o], fmaf(s.rlt[i * kLS + cc], s.h1t[i * kS1 + o], a));
+                        } else {
+                            for (int i = 0; i < tr; ++i) a += s.rlt[i * kLS + cc];
+                        }
                         s.rhp[idx] += a;
                     }
-                    __syncthreads();
-                    pc.mark(10);    // s: r_Z1, r_head
                     // (3r) r_H0 += r_Z1 W1 ; r_W1 += r_Z1^T H0 ; r_b1 += sum r_Z1
                     if (tid < kH1) {
                         float a = 0.f;
-                        for (int i = 0; i < tr; ++i) a += s.rzh[i * kS1 + tid];
+                        for (int i = 0; i < tr; ++i) a += s.dz1t[i * kS1 + tid];
                         s.rb1[tid] += a;
                     }
-                    warp_gemm_3xtf32<1, 2, false, true>(s.rzh, kS1, s.w1t + 16 * w * kS1, kS1, kH1, 1.f, rh0);
-                    warp_gemm_3xtf32<1, 8, true, false, 0>(s.h0t + 16 * w, kS0, s.rzh, kS1, 16, 1.f, rw);
+                    warp_gemm_3xtf32<1, 2, false, true>(s.dz1t, kS1, s.w1t + 16 * w * kS1, kS1, kH1, 1.f, rh0);
+                    warp_gemm_3xtf32<1, 8, true, false, 0>(s.h0t + 16 * w, kS0, s.dz1t, kS1, 16, 1.f, rw);
                     // (2r) bar_Z0 = r_H0 * gate0 ; (1r) a_A (d_proj), a_b0 ; bar_Z0 rows parked in the workspace
                     {
                         const int g = lane >> 2, t = lane & 3;
