@@ -1717,6 +1717,11 @@ __global__ void __launch_bounds__(kThreads16, 1) episode_bwd_mma16_kernel(EpiPar
             for (int j = 0; j < 2; ++j)
 #pragma unroll
                 for (int q = 0; q < 4; ++q) aSq[i][j][q] = 0.f;
+        float aWq[1][8][4];                  // dZ1q^T H0q summed over the query tiles (this warp's 16 rows of W1^T)
+#pragma unroll
+        for (int j = 0; j < 8; ++j)
+#pragma unroll
+            for (int q = 0; q < 4; ++q) aWq[0][j][q] = 0.f;
         // software prefetch: the next tile's stash rows travel in registers while the current tile is processed
         float pv[8], pu[2], pg = 0.f, pl = 0.f;
         long long prow = 0;
@@ -1783,15 +1788,8 @@ __global__ void __launch_bounds__(kThreads16, 1) episode_bwd_mma16_kernel(EpiPar
                 for (int i = 0; i < tr; ++i) a += s.dz1t[i * kS1 + tid];
                 s.ab1[tid] += a;
             }
-            {   // a_W1 += dZ1q^T H0q   (rows h of W1^T owned by this warp)
-                float acc[1][8][4];
-#pragma unroll
-                for (int j = 0; j < 8; ++j)
-#pragma unroll
-                    for (int q = 0; q < 4; ++q) acc[0][j][q] = 0.f;
-                warp_gemm_3xtf32<1, 8, true, false, 0>(s.h0t + 16 * w, kS0, s.dz1t, kS1, 16, 1.f, acc);
-                warp_tile_foreach<1, 8>(acc, [&](int hh, int o, float& cv) { s.aw1t[(16 * w + hh) * kS1 + o] += cv; });
-            }
+            // a_W1 += dZ1q^T H0q   (rows h of W1^T owned by this warp): summed in registers over the query tiles
+            warp_gemm_3xtf32<1, 8, true, false, 0>(s.h0t + 16 * w, kS0, s.dz1t, kS1, 16, 1.f, aWq);
             {   // dZ0q = (dZ1q W1) * gate  -> tt, d_proj, a_b0
                 float acc[1][2][4];
 #pragma unroll
@@ -1825,6 +1823,7 @@ __global__ void __launch_bounds__(kThreads16, 1) episode_bwd_mma16_kernel(EpiPar
                 if (j < n) aS[int64_t(j) * kH0 + 16 * w + hh] = -alpha * cv;          // a_S starts from zero
             });
         }
+        warp_tile_foreach<1, 8>(aWq, [&](int hh, int o, float& cv) { s.aw1t[(16 * w + hh) * kS1 + o] = cv; });   // was zero
         __syncthreads();
 
         // ---- inner steps in reverse
