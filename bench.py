@@ -205,14 +205,14 @@ def cpu_reference_leg(wl, D, T, steps_k, warmup, budget_s, tasks_per_batch=4, se
 def ncu_traffic(kernel, workload, tasks):
     """dram__bytes_read.sum + dram__bytes_write.sum per launch of `kernel`, from the committed `ncu --set full`
     summary -- only when that capture was taken on this workload at this batch size (else None)."""
-    path = os.path.join(os.path.dirname(os.path.abspath(__file__)), "profiles", "r1_ncu_full_v16_summary.json")
+    path = os.path.join(os.path.dirname(os.path.abspath(__file__)), "profiles", "r1_ncu_full_v18_summary.json")
     try:
         with open(path) as f:
             d = json.load(f)
         if d["workload"] != workload or int(d["tasks"]) != int(tasks):
             return None, None
         recs = d["kernels"][kernel]
-        return max(r["traffic_bytes"] for r in recs), "profiles/r1_ncu_full_v16_summary.json"
+        return max(r["traffic_bytes"] for r in recs), "profiles/r1_ncu_full_v18_summary.json"
     except (OSError, KeyError, ValueError):
         return None, None
 
