@@ -359,7 +359,7 @@ def main():
         sampler_ms, expand_ms = (time.perf_counter() - t_s) * 1e3, None
     e2e_loader = EpisodeLoader(fb, sampler, a.tasks, prefetch=2, device_sampler=dev_sampler)
     e2e_it = iter(e2e_loader)
-    for i in range(2):
+    for i in range(max(2, a.warmup)):
         run_api(next(e2e_it))
     barrier()
     h2d = d2h = 0
