@@ -41,7 +41,6 @@ _SIGS = {
     "fumi_transpose_split_tf32": (C.c_int, [_P, _P, _P, _I64, _I64, _I64, _P]),
     "fumi_gemm_tf32x3": (C.c_int, [_P] * 6 + [_I64] * 6 + [_I32] * 3 + [_P]),
     "fumi_gram_f16": (C.c_int, [_P, _P, _P, _I64, _I64, _P, _P, _I64, _I32, _I32, _P, _P]),
-    "fumi_debug_gemm_f16": (C.c_int, [_P, _P, _I32, _I32, _I32, _I32, _P, _P]),
     "fumi_absmax": (C.c_int, [_P, _I64, _P, _P]),
     "fumi_split_f16": (C.c_int, [_P, _P, _P, _P, _I64, _P]),
     "fumi_transpose_split_f16": (C.c_int, [_P, _P, _P, _P, _I64, _I64, _I64, _P]),
@@ -70,25 +69,24 @@ _SIGS = {
 EXPORTED = tuple(_SIGS)
 
 
-_EMULATION = False
-
-
-def load(path, emulation=False):
-    """Bind a build of the C ABI.  `emulation=True` is for tests/emu (host emulation of the kernels,
-    test infrastructure only): the product never sets it."""
-    global _LIB, _EMULATION
+def load(path):
+    """Bind a build of the C ABI (every symbol of include/fumi_b200.h must be exported)."""
+    global _LIB
     L = C.CDLL(path)
     for name, (res, args) in _SIGS.items():
         fn = getattr(L, name)          # AttributeError if the library does not export it
         fn.restype, fn.argtypes = res, args
     if L.fumi_abi_version() != 1:
         raise FumiError("libfumi_b200.so ABI version mismatch")
-    _LIB, _EMULATION = L, bool(emulation)
+    _LIB = L
     return L
 
 
-def is_emulation():
-    return _EMULATION
+def require_cuda(device, what):
+    """There is no CPU path: every compute front-end calls this with its device."""
+    import torch
+    if torch.device(device).type != "cuda":
+        raise FumiError(f"{what} runs on CUDA devices only (got {device}); there is no CPU path")
 
 
 def lib():

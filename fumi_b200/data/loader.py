@@ -45,6 +45,11 @@ class EpisodeLoader:
         self.dataset = sampler          # len(loader.dataset) parity is not meaningful for episodes
         self._stop = None
 
+    def set_shard(self, rank, world):
+        """Switch to the global-stream mode (see `shard` above) before the first iterator is created."""
+        self.shard = (int(rank), int(world))
+        self._draw = self.batch_size * self.shard[1]
+
     def _mine(self, t):
         """This rank's slice of a [world * batch_size, ...] array / tensor."""
         if self.shard is None:

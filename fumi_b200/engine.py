@@ -26,6 +26,8 @@ from .data.bank import EpisodeBatch
 
 H0, H1 = 256, 64
 HD = H1 + 1
+# dense layers: 0 fp32 FMA; 1 tcgen05 3xTF32; 2 = 1 + the two bank-sized contractions and the Gram blocks on fp16 planes
+DEFAULT_PRECISION = 2
 
 
 def first_row_of_each_label(targets, num_ways):
@@ -42,13 +44,9 @@ def first_row_of_each_label(targets, num_ways):
 class EpisodeEngine:
     def __init__(self, device, precision=None):
         self.device = torch.device(device)
-        if self.device.type != "cuda" and not _lib.is_emulation():
-            raise _lib.FumiError(f"fumi_b200 runs on CUDA devices only (got {self.device}); there is no CPU path")
+        _lib.require_cuda(self.device, "fumi_b200.EpisodeEngine")
         self.L = _lib.lib()
-        if precision is None:            # default: tensor cores (the host emulation used by CPU tests has none)
-            precision = 0 if _lib.is_emulation() else 2
-        # dense layers: 0 fp32 FMA; 1 tcgen05 3xTF32; 2 = 1 + the two bank-sized contractions on fp16 hi/lo planes
-        self.precision = precision
+        self.precision = DEFAULT_PRECISION if precision is None else precision
         self.launches = 0                # kernels launched through this engine (bench: gpu_launches)
         self.profile = None              # dict name -> [cuda event pairs] while bench.py profiles kernels
 
@@ -326,19 +324,44 @@ class EpisodeEngine:
             return dist.get_world_size()
         return 1
 
-    def _allreduce_grads(self, params, loss_acc):
-        """Tasks are sharded across ranks: one sum all-reduce of the meta-gradient
-        (flat buffer when the optimizer provides one) + the two scalars."""
+    def _flat_grads(self, params):
+        """FusedAdam's flat gradient buffer [n gradients | loss, acc] when every p.grad still lives in it."""
+        opt = getattr(params[0], "_fumi_flat_opt", None) if params else None
+        return opt.flat_grad(params) if opt is not None else None
+
+    def _allreduce_begin(self, params, head):
+        """Multi-GPU outer step, part 1: the gradient bucket that is complete first -- the first
+        `head` floats of the flat buffer = dW0, 2 MB of the 3 MB -- is summed over ranks asynchronously while the
+        hypernetwork backward and the small reductions still run on the compute stream.  Returns the handle(s)."""
         if self._world() == 1:
+            return None
+        flat = self._flat_grads(params)
+        if flat is None or head <= 0:
+            return None
+        return (flat, head, dist.all_reduce(flat[:head], async_op=True))
+
+    def _allreduce_finish(self, params, loss_acc, pending):
+        """Part 2: [remaining gradients | loss, acc] in ONE all-reduce (the two scalars ride in the flat buffer's
+        tail); the per-tensor path is kept for optimizers without a flat buffer.  loss_acc becomes the mean."""
+        world = self._world()
+        if world == 1:
             return
-        flat = getattr(params[0], "_fumi_flat_grad", None)
-        if flat is not None and all(getattr(p, "_fumi_flat_grad", None) is flat for p in params):
-            dist.all_reduce(flat)
+        flat = self._flat_grads(params)
+        if flat is not None:
+            head = pending[1] if pending is not None else 0
+            flat[-2:].copy_(loss_acc)
+            w = dist.all_reduce(flat[head:], async_op=True)
+            if pending is not None:
+                pending[2].wait()
+            w.wait()
+            loss_acc.copy_(flat[-2:])
         else:
+            if pending is not None:
+                pending[2].wait()
             for p in params:
                 dist.all_reduce(p.grad)
-        dist.all_reduce(loss_acc)
-        loss_acc /= self._world()
+            dist.all_reduce(loss_acc)
+        loss_acc /= world
 
     # ------------------------------------------------------------------ FuMI
     def hypernet(self, model, text_rows, keep=False):
@@ -392,6 +415,8 @@ class EpisodeEngine:
         self.reduce_parts(pw1, P, self._grad(lin1.weight))
         self.reduce_parts(pb1, P, self._grad(lin1.bias))
         self.wgrad_rows(d_proj, feats, eb.bank, self._grad(lin0.weight))         # dW0 = d_proj^T X
+        params = [p for p in model.parameters() if p.requires_grad]
+        pending = self._allreduce_begin(params, lin0.weight.numel() if params[0] is lin0.weight else 0)
         d_hp = torch.zeros_like(hp_table)
         self._call("fumi_scatter_add_rows", self.L.fumi_scatter_add_rows, _lib.ptr(d_head), _lib.ptr(head_rows.reshape(-1)), B * N, HD,
                                                 _lib.ptr(d_hp), self._stream())
@@ -403,7 +428,7 @@ class EpisodeEngine:
         self.linear_wgrad(d_hp, u, self._grad(l2.weight), self._grad(l2.bias), precision=0)
         d_u = self.linear_dgrad(d_hp, l2.weight, gate=u)
         self.linear_wgrad(d_u, text_rows, self._grad(l0.weight), self._grad(l0.bias), precision=0)
-        self._allreduce_grads([p for p in model.parameters() if p.requires_grad], la)
+        self._allreduce_finish(params, la, pending)
         return res
 
     # ------------------------------------------------------------------ MAML
@@ -431,12 +456,14 @@ class EpisodeEngine:
         self.reduce_parts(pw1, P, self._grad(lin1.weight))
         self.reduce_parts(pb1, P, self._grad(lin1.bias))
         self.wgrad_rows(d_proj, feats, eb.bank, self._grad(lin0.weight))
+        params = list(model.parameters())
+        pending = self._allreduce_begin(params, lin0.weight.numel() if params[0] is lin0.weight else 0)
         d_fin = self._new(N * HD)
         self.reduce_parts(d_head.reshape(B, N * HD), B, d_fin)                   # shared head: sum over tasks
         d_fin = d_fin.view(N, HD)
         self._grad(fin.weight).copy_(d_fin[:, :H1])
         self._grad(fin.bias).copy_(d_fin[:, H1])
-        self._allreduce_grads(list(model.parameters()), la)
+        self._allreduce_finish(params, la, pending)
         return res
 
     # ------------------------------------------------------------------ AM3 (meta-test scoring)

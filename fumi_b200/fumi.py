@@ -182,8 +182,11 @@ def training_run(args, model, optimizer, train_loader, val_loader, max_test_batc
     except KeyboardInterrupt:
         pass
     best_file = os.path.join(utils.run_dir(args), "best.pth.tar")
-    if os.path.exists(best_file):                                  # fumi.py:296-297
+    if saved_best and os.path.exists(best_file):                   # fumi.py:296-297 (only a checkpoint of THIS run)
         model, _ = utils.load_checkpoint(model, opt, args.device, best_file)
+    if saved_best and torch.distributed.is_available() and torch.distributed.is_initialized():
+        for t in list(model.parameters()) + list(model.buffers()):   # rank 0 holds the checkpoint files
+            torch.distributed.broadcast(t.data, 0)
     return model
 
 

@@ -54,9 +54,11 @@ class PureImageNetwork(nn.Module):
 def evaluate(args, model, batch, optimizer, task="train"):
     """One meta-batch (maml.py:134-193).  Returns (loss np 0-d f32, acc np 0-d f32)."""
     model.train()                 # maml.py:143 (no dropout layers: no behavioural effect)
-    # FusedAdam.zero_grad keeps its flat gradient views alive (one memset); Module.zero_grad() would drop them and the
-    # step would fall back to per-tensor Adam / all-reduce launches
-    (optimizer if hasattr(optimizer, "_flat") else model).zero_grad()
+    if task == "train":
+        # optimizer.zero_grad() of maml.py:188.  Only on the train path: test_loop passes optimizer=None, and a
+        # Module.zero_grad() there would drop the gradients out of FusedAdam's flat buffer (the engine writes no
+        # gradient in test mode, so there is nothing to clear).
+        (optimizer if hasattr(optimizer, "_flat") else model).zero_grad()
     eng = model._get_engine(args.device)
     steps = args.num_train_adapt_steps if task == "train" else args.num_test_adapt_steps
     res = eng.maml_batch(model, batch, steps=steps, step_size=args.step_size, train=(task == "train"),

@@ -22,12 +22,13 @@ class FusedAdam(torch.optim.Optimizer):
             if not ps or not all(p.dtype == torch.float32 for p in ps):
                 continue
             dev = ps[0].device
-            if dev.type != "cuda" and not _lib.is_emulation():
-                raise _lib.FumiError("FusedAdam needs CUDA parameters (move the model to the device first, "
-                                     "as utils.init_model does); there is no CPU path")
+            _lib.require_cuda(dev, "FusedAdam (move the model to the device first, as utils.init_model does)")
             n = sum(p.numel() for p in ps)
             fp = torch.empty(n, dtype=torch.float32, device=dev)
-            fg = torch.zeros_like(fp)
+            # two extra floats behind the gradients carry [loss, acc] of the meta-batch, so that the multi-GPU outer
+            # step needs ONE all-reduce; the Adam kernel only sees the first n
+            fg_ext = torch.zeros(n + 2, dtype=torch.float32, device=dev)
+            fg = fg_ext[:n]
             fm = torch.zeros_like(fp)
             fv = torch.zeros_like(fp)
             off = 0
@@ -36,18 +37,34 @@ class FusedAdam(torch.optim.Optimizer):
                 fp[off:off + k].copy_(p.data.reshape(-1))
                 p.data = fp[off:off + k].view(p.shape)
                 p.grad = fg[off:off + k].view(p.shape)
-                p._fumi_flat_grad = fg
+                p._fumi_flat_opt = self
                 st = self.state[p]
                 st["step"] = torch.zeros((), dtype=torch.float32)
                 st["exp_avg"] = fm[off:off + k].view(p.shape)
                 st["exp_avg_sq"] = fv[off:off + k].view(p.shape)
                 off += k
-            self._flat[gi] = dict(p=fp, g=fg, m=fm, v=fv, params=ps, step=0)
+            self._flat[gi] = dict(p=fp, g=fg, g_ext=fg_ext, m=fm, v=fv, params=ps, step=0)
 
     def zero_grad(self, set_to_none=False):
-        """Keeps the flat gradient views alive (the engine overwrites every gradient each batch)."""
+        """One memset of the flat gradient buffer.  Gradients that were detached from it (Module.zero_grad(),
+        set_to_none, a foreign backward) are re-attached to their flat views, so the single-launch Adam step and
+        the single flat all-reduce stay valid."""
         for f in self._flat.values():
-            f["g"].zero_()
+            f["g_ext"].zero_()
+            off = 0
+            for p in f["params"]:
+                k = p.numel()
+                if p.grad is None or p.grad.data_ptr() != f["g"].data_ptr() + 4 * off:
+                    p.grad = f["g"][off:off + k].view(p.shape)
+                off += k
+
+    def flat_grad(self, params):
+        """The flat gradient buffer (n gradients + 2 scalars for [loss, acc]) if every gradient of `params` still
+        lives in it, in order; else None."""
+        for f in self._flat.values():
+            if len(f["params"]) == len(params) and all(a is b for a, b in zip(f["params"], params)):
+                return f["g_ext"] if self._is_flat(f) else None
+        return None
 
     def _is_flat(self, f):
         off = 0
@@ -79,6 +96,11 @@ class FusedAdam(torch.optim.Optimizer):
                                             f["p"].numel(), *args, step, int(group["decoupled"]), stream),
                            "fumi_adam_step")
             else:       # views were replaced (e.g. load_state_dict / zero_grad(set_to_none)): per-tensor launches
+                if not getattr(self, "_warned_unflat", False):
+                    import warnings
+                    warnings.warn("FusedAdam: parameter/gradient/moment views left the flat buffers; falling back to "
+                                  "one Adam launch per tensor (call FusedAdam.zero_grad() to re-attach gradients)")
+                    self._warned_unflat = True
                 for p in f["params"]:
                     if p.grad is None:
                         continue

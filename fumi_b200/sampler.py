@@ -146,9 +146,7 @@ class EpisodeSampler:
         Returns dict(sup_ids, qry_ids, sup_y, qry_y, sup_rows, qry_rows, head_class, classes, label_perm)
         of device tensors -- bit-identical to next_batch()."""
         device = torch.device(device)
-        if device.type != "cuda" and not _lib.is_emulation():
-            raise RuntimeError("EpisodeSampler.expand needs a CUDA device (no CPU fallback; use next_batch for "
-                               "host-resident indices)")
+        _lib.require_cuda(device, "EpisodeSampler.expand (use next_batch for host-resident indices)")
         offsets, ids = self.device_tables(device)
         d = {k: v.to(device, non_blocking=True) for k, v in plan.items()}
         B, N, K, Q = d["classes"].shape[0], self.N, self.K, self.Q

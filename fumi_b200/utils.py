@@ -7,6 +7,7 @@ batched engine), --precision and --synthetic.  wandb is optional and never on th
 import argparse
 import os
 import shutil
+import time
 
 import numpy as np
 import torch
@@ -101,8 +102,9 @@ def parser():
     return p
 
 
-def init_model(args, dictionary, watch=True):
-    """utils.py:232-274 (CLIP is outside the episodic path: SURVEY.md section 2 row 9)."""
+def build_model(args, dictionary=None):
+    """The nn.Module of utils.py:232-266, constructed on the CPU exactly as the reference constructs it (same
+    layer creation order, so the same torch.manual_seed gives bit-identical initial weights)."""
     if args.model == "maml":
         model = maml.PureImageNetwork(im_embed_dim=args.im_emb_dim, n_way=args.num_ways, hidden_dims=args.im_hid_dim)
     elif args.model == "fumi":
@@ -119,6 +121,12 @@ def init_model(args, dictionary, watch=True):
                         text_emb_dim=args.text_emb_dim, text_hid_dim=args.text_hid_dim,
                         prototype_dim=args.prototype_dim, dropout=args.dropout, fine_tune=args.fine_tune,
                         dictionary=dictionary, pooling_strat=args.pooling_strat, lamda_fixed=args.lamda_fixed)
+    return model
+
+
+def init_model(args, dictionary, watch=True):
+    """utils.py:232-274 (CLIP is outside the episodic path: SURVEY.md section 2 row 9)."""
+    model = build_model(args, dictionary)
     model.to(args.device)
     model._get_engine(args.device).precision = int(getattr(args, "precision", 2))
     if hasattr(model, "dropout_base_seed") or args.model == "fumi":
@@ -133,10 +141,12 @@ def init_optim(args, model):
         return FusedAdam(params, lr=args.lr, weight_decay=args.weight_decay)
     if args.optim == "SGD":
         return torch.optim.SGD(params=params, lr=args.lr, weight_decay=args.weight_decay, momentum=args.momentum)
+    # the reference builds transformers.AdamW(params, lr) (utils.py:11,286-294), whose defaults are
+    # weight_decay=0.0, eps=1e-6, betas=(0.9, 0.999), correct_bias=True -- not torch.optim.AdamW's 1e-2 / 1e-8
     if args.optim == "adamw":
-        return FusedAdam(params, lr=args.lr, weight_decay=1e-2, decoupled=True)      # torch AdamW default wd
+        return FusedAdam(params, lr=args.lr, weight_decay=0.0, eps=1e-6, decoupled=True)
     if args.optim == "adamw_lin_schedule":
-        opt = FusedAdam(params, lr=args.lr, weight_decay=1e-2, decoupled=True)
+        opt = FusedAdam(params, lr=args.lr, weight_decay=0.0, eps=1e-6, decoupled=True)
         warm, total = args.num_warmup_steps, args.epochs
 
         def lr_lambda(step):                     # transformers.get_linear_schedule_with_warmup
@@ -147,70 +157,44 @@ def init_optim(args, model):
     raise NotImplementedError()
 
 
-# ---- AM3 prototype maths kept for API parity (plain torch; the hot path uses fumi_am3_score) ----------
-def get_num_samples(targets, num_classes, dtype=None):
-    batch_size = targets.size(0)
-    with torch.no_grad():
-        ones = torch.ones_like(targets, dtype=dtype)
-        num_samples = ones.new_zeros((batch_size, num_classes))
-        num_samples.scatter_add_(1, targets, ones)
-    return num_samples
-
-
-def get_prototypes(im_embeddings, text_embeddings, lamdas, targets, num_classes):
-    """utils.py:331-376."""
-    batch_size, embedding_size = im_embeddings.size(0), im_embeddings.size(-1)
-    num_samples = get_num_samples(targets, num_classes, dtype=im_embeddings.dtype).unsqueeze(-1)
-    num_samples = torch.max(num_samples, torch.ones_like(num_samples))
-    indices = targets.unsqueeze(-1).expand_as(im_embeddings)
-    im_prototypes = im_embeddings.new_zeros((batch_size, num_classes, embedding_size))
-    im_prototypes.scatter_add_(1, indices, im_embeddings).div_(num_samples)
-    text_prototypes = text_embeddings.new_zeros((batch_size, num_classes, embedding_size))
-    text_prototypes.scatter_add_(1, indices, text_embeddings).div_(num_samples)
-    lamdas_per_class = lamdas.new_zeros((batch_size, num_classes, 1))
-    lamdas_per_class.scatter_add_(1, targets.unsqueeze(-1), lamdas).div_(num_samples)
-    return lamdas_per_class * im_prototypes + (1 - lamdas_per_class) * text_prototypes
-
-
-def prototypical_loss(prototypes, embeddings, targets, **kwargs):
-    """utils.py:390-402."""
-    sq = torch.sum((prototypes.unsqueeze(2) - embeddings.unsqueeze(1)) ** 2, dim=-1)
-    return torch.nn.functional.cross_entropy(-sq, targets, **kwargs)
-
-
-def get_preds(prototypes, embeddings, targets):
-    """utils.py:302-328."""
-    from sklearn.metrics import accuracy_score, precision_recall_fscore_support
-    sq = torch.sum((prototypes.unsqueeze(1) - embeddings.unsqueeze(2)) ** 2, dim=-1)
-    _, preds = torch.min(sq, dim=-1)
-    preds = preds.detach().cpu().numpy()
-    flat_preds, flat_targets = np.reshape(preds, -1), np.reshape(targets.detach().cpu().numpy(), -1)
-    acc = accuracy_score(flat_targets, flat_preds)
-    prec, rec, f1, _ = precision_recall_fscore_support(flat_targets, flat_preds, average="macro")
-    return preds, acc, f1, prec, rec
-
-
 # ---- logging / checkpoints -----------------------------------------------------------------------
 def run_dir(args=None):
-    """wandb.run.dir when a run is active (utils.py:412), else <log_dir>/run."""
+    """wandb.run.dir when a run is active (utils.py:412); else a directory unique to this run,
+    <log_dir>/run-<pid>-<start time>, remembered on `args` (the reference's wandb.run.dir is unique per run, so a
+    run never sees another run's best.pth.tar)."""
     if wandb is not None and getattr(wandb, "run", None) is not None:
         return wandb.run.dir
-    d = os.path.join(getattr(args, "log_dir", "./results") if args is not None else "./results", "run")
+    d = getattr(args, "_run_dir", None) if args is not None else None
+    if d is None:
+        base = getattr(args, "log_dir", "./results") if args is not None else "./results"
+        d = os.path.join(base, f"run-{os.getpid()}-{int(time.time() * 1000)}")
+        if args is not None:
+            args._run_dir = d
     os.makedirs(d, exist_ok=True)
     return d
 
 
+def is_main_process():
+    """Rank 0 of a torchrun launch (or the only process): the one that logs and writes checkpoints."""
+    import torch.distributed as dist
+    return not (dist.is_available() and dist.is_initialized()) or dist.get_rank() == 0
+
+
 def log(metrics, step=None):
+    if not is_main_process():
+        return
     if wandb is not None and getattr(wandb, "run", None) is not None:
         wandb.log(metrics, step=step)
 
 
 def args_dict(args):
-    return {k: (str(v) if isinstance(v, torch.device) else v) for k, v in vars(args).items()}
+    return {k: (str(v) if isinstance(v, torch.device) else v) for k, v in vars(args).items() if not k.startswith("_")}
 
 
 def save_checkpoint(checkpoint_dict, is_best, args=None):
     """utils.py:406-419: same dict schema {batch_idx, state_dict, best_loss, optimizer, args}."""
+    if not is_main_process():          # ranks hold identical parameters after the all-reduced step: rank 0 writes
+        return
     d = run_dir(args)
     checkpoint_file = os.path.join(d, "ckpt.pth.tar")
     best_file = os.path.join(d, "best.pth.tar")
@@ -229,8 +213,16 @@ def load_checkpoint(model, optimizer, device, checkpoint_file):
             raise RuntimeError(f"Error(s) in loading state_dict: key mismatch {sorted(missing)}")
         for k, v in checkpoint["state_dict"].items():
             own[k].copy_(v)
-    if optimizer is not None and "optimizer" in checkpoint:
+    if optimizer is not None and "optimizer" in checkpoint and not hasattr(optimizer, "_flat"):
+        optimizer.load_state_dict(checkpoint["optimizer"])          # utils.py:436 (SGD and other torch optimizers)
+    elif optimizer is not None and "optimizer" in checkpoint:
+        # FusedAdam: copy the state INTO the flat moment buffers (load_state_dict would replace the views) and
+        # restore the hyper-parameters of every group
         sd = checkpoint["optimizer"]
+        for grp, saved in zip(optimizer.param_groups, sd.get("param_groups", [])):
+            for k, v in saved.items():
+                if k != "params":
+                    grp[k] = v
         for pid, st in sd.get("state", {}).items():
             p = optimizer.param_groups[0]["params"][pid] if isinstance(pid, int) else None
             if p is None or p not in optimizer.state:

@@ -299,10 +299,6 @@ int64_t fumi_py_tuple_hash(const int64_t* items, int64_t n);
  * CTAs by thread 0 of each.  fumi_debug_phase_profile(1) zeroes and enables them, (0) disables;
  * fumi_debug_read_phases copies the 64 counters to a HOST array (phase ids: csrc/episode.cu pc.mark).
  * ---------------------------------------------------------------------------------------- */
-/* one warp, out[M][N] = A[M][K] . B[K][N] through the fp16 hi/lo plane primitive of the episode kernels
- * (csrc/warp_mma.cuh warp_gemm_f16x3); variant bit 0: B staged as [n][k], bit 1: A staged as [k][m]. */
-int fumi_debug_gemm_f16(const float* A, const float* B, int32_t variant, int32_t M, int32_t N, int32_t K,
-                        float* out, void* stream);
 int fumi_debug_phase_profile(int enable);
 int fumi_debug_read_phases(unsigned long long* out64);
 

@@ -1,12 +1,15 @@
-// Diagnostics (no reference counterpart): one warp runs warp_gemm_f16x3 (csrc/warp_mma.cuh) on a small problem in
+// TEST INFRASTRUCTURE (not part of libfumi_b200.so / the public header): one warp runs warp_gemm_f16x3 (csrc/warp_mma.cuh) on a small problem in
 // every operand-layout variant, so the fp16-plane primitive (ldmatrix addressing, fragment order, plane scaling)
 // is tested on its own -- on the GPU and under the host emulation -- before the episode kernels depend on it.
 #include <cstdint>
 
 #include "../../include/fumi_b200.h"
-#include "common.cuh"
-#include "launch.cuh"
-#include "warp_mma.cuh"
+#include "../../fumi_b200/csrc/common.cuh"
+#include "../../fumi_b200/csrc/launch.cuh"
+#include "../../fumi_b200/csrc/warp_mma.cuh"
+
+extern "C" int fumi_debug_gemm_f16(const float* A, const float* B, int32_t variant, int32_t M, int32_t N, int32_t K,
+                                   float* out, void* stream);
 
 namespace {
 

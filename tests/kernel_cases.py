@@ -147,10 +147,17 @@ def gemm_f16_case(device):
 
 def warp_gemm_f16_case(device):
     """The fp16 hi/lo plane warp GEMM (ldmatrix addressing, fragment order, plane scales) in every layout variant."""
-    import ctypes as C
     from fumi_b200 import _lib
     rs = np.random.RandomState(12)
-    L = _lib.lib()
+    if torch.device(device).type == "cuda":
+        import build_test_kernels            # test-only sm_100a kernels (tests/csrc), not part of libfumi_b200.so
+        L = build_test_kernels.load()
+    else:
+        import ctypes
+        import build_emu                     # the emulation build carries the same test kernel
+        L = ctypes.CDLL(build_emu.build())
+        L.fumi_debug_gemm_f16.restype = ctypes.c_int
+        L.fumi_debug_gemm_f16.argtypes = [ctypes.c_void_p] * 2 + [ctypes.c_int32] * 4 + [ctypes.c_void_p] * 2
     stream = _lib.stream_ptr(torch.device(device)) if torch.device(device).type == "cuda" else None
     for (M, N) in [(16, 8), (32, 16), (16, 64), (32, 8)]:
         for K in (16, 48, 64):
@@ -292,6 +299,34 @@ def maml_case(device, name):
             assert np.abs(p.detach().cpu().numpy() - pre).max() <= 1.01 * float(g["lr"]) + 1e-7
             big = np.abs(g["grad:" + k] + float(g["wd"]) * pre) > 1e-5
             assert np.abs(p.detach().cpu().numpy() - ref)[big].max() <= 1e-6, k
+
+
+def maml_test_then_train_case(device, name="maml_train_n5k5_d512"):
+    """A test-mode call with optimizer=None (test_loop, which training_run runs first and every eval_freq) must not
+    detach the gradients from FusedAdam's flat buffer: the next train step still fills the flat buffer (the one the
+    multi-GPU all-reduce sums) and steps with a single fused launch."""
+    g, bank = load_golden(name)
+    model = _load(maml_mod.PureImageNetwork(im_embed_dim=bank.feats.shape[1], n_way=5, hidden_dims=[256, 64]),
+                  params_of(g), device)
+    opt = FusedAdam(model.parameters(), lr=float(g["lr"]), weight_decay=float(g["wd"]))
+    args, batch = _args(g, device), _torchmeta_batch(g, bank)
+    maml_mod.evaluate(args, model, batch, None, task="test")
+    f = opt._flat[0]
+    assert opt._is_flat(f), "test-mode evaluate detached the gradients from the flat buffer"
+    maml_mod.evaluate(args, model, batch, opt, task="train")
+    assert opt._is_flat(f)
+    eng = model._get_engine(device)
+    assert eng._flat_grads(list(model.parameters())) is f["g_ext"]
+    off = 0
+    for k, p in model.named_parameters():                       # the flat buffer holds the real gradients
+        got = f["g"][off:off + p.numel()].view(p.shape).cpu().numpy()
+        assert relerr(got, g["grad:" + k]) < 2e-4, k
+        off += p.numel()
+    # a foreign zero_grad (Module.zero_grad sets p.grad = None) is repaired by the next FusedAdam.zero_grad
+    model.zero_grad()
+    assert not opt._is_flat(f)
+    opt.zero_grad()
+    assert opt._is_flat(f)
 
 
 def am3_case(device, name="am3_test_n10k5_d512"):

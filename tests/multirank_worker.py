@@ -15,9 +15,8 @@ def main():
     rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
     device = sys.argv[1]
     if device == "cpu":
-        from fumi_b200 import _lib
-        import build_emu
-        _lib.load(build_emu.build(), emulation=True)
+        import inject
+        inject.enable()
         dist.init_process_group("gloo", rank=rank, world_size=world)
     else:
         torch.cuda.set_device(rank)

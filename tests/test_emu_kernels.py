@@ -21,11 +21,9 @@ full = pytest.mark.skipif(os.environ.get("FUMI_EMU_FULL") != "1", reason="set FU
 
 @pytest.fixture(scope="module", autouse=True)
 def emu_lib():
-    import build_emu
-    saved = (_lib._LIB, _lib._EMULATION)
-    _lib.load(build_emu.build(), emulation=True)
-    yield
-    _lib._LIB, _lib._EMULATION = saved
+    import inject
+    with inject.emulation():
+        yield
 
 
 def test_dense():
@@ -42,6 +40,10 @@ def test_gram():
 
 def test_adam():
     kc.adam_case("cpu")
+
+
+def test_maml_test_then_train_keeps_flat_gradients():
+    kc.maml_test_then_train_case("cpu")
 
 
 @pytest.mark.parametrize("via", ["dict", pytest.param("bank", marks=full)])

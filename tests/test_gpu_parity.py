@@ -13,8 +13,10 @@ DEV = "cuda:0"
 @pytest.fixture(scope="module", autouse=True)
 def real_library():
     from fumi_b200 import _lib
-    assert not _lib.is_emulation(), "GPU tests must run on the CUDA build of libfumi_b200.so"
-    assert _lib.lib().fumi_device_sm_count() > 0
+    from fumi_b200 import build
+    L = _lib.lib()
+    assert L._name == build.LIB, "GPU tests must run on the CUDA build of libfumi_b200.so"
+    assert L.fumi_device_sm_count() > 0
     yield
 
 
@@ -38,6 +40,10 @@ def test_fumi_train_tensor_core_dense(via, precision):
 
 def test_warp_gemm_f16_planes():
     kc.warp_gemm_f16_case(DEV)
+
+
+def test_maml_test_then_train_keeps_flat_gradients():
+    kc.maml_test_then_train_case(DEV)
 
 
 def test_gram():
