@@ -24,7 +24,8 @@ class EpisodeCfg(C.Structure):
 
 
 class StashLayout(C.Structure):
-    _fields_ = [(n, C.c_int64) for n in ("per_task", "S", "w1t", "b0", "b1", "head", "steps", "per_step")]
+    _fields_ = [(n, C.c_int64) for n in ("per_task", "S", "w1t", "b0", "b1", "head", "steps", "per_step",
+                                         "format", "rec_h1", "rec_exp", "rec_h0_hi", "rec_h0_lo")]
 
 
 _P = C.c_void_p

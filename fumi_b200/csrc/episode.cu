@@ -27,71 +27,11 @@
 #include "launch.cuh"
 #include "warp_mma.cuh"
 
+#include "episode_common.cuh"
+
+using namespace fumi_epi;
+
 namespace {
-
-constexpr int kThreads = 256;
-constexpr int kW1S = kH1 + 1;        // padded row stride of W1^T in shared memory (bank-conflict free)
-constexpr int kGS = kMaxSupport + 4; // row stride of the Gram tile in shared memory
-constexpr int kLS = kMaxWays;        // row stride of the logits tile
-
-struct EpiParams {
-    fumi_episode_cfg cfg;
-    int64_t B;
-    const float* proj;
-    const int64_t* sup_rows;
-    const int64_t* qry_rows;
-    const int64_t* sup_y;
-    const int64_t* qry_y;
-    const float* gram;
-    const float* b0;
-    const float* w1;
-    const float* b1;
-    const float* head_table;
-    const int64_t* head_rows;
-    float* logits;
-    int64_t* preds;
-    float* task_loss;
-    float* task_acc;
-    float* stash;
-    int save;              // 1: per-task stash with step records (backward / parity dumps); 0: per-CTA scratch
-    int64_t slot_floats;
-    // backward only
-    float loss_scale;
-    float* d_proj;
-    float* d_head;
-    float* d_b0_parts;
-    float* d_w1_parts;
-    float* d_b1_parts;
-};
-
-struct Layout {
-    int64_t per_task, S0, S1, w1t, b0, b1, head, steps, per_step, oH0, oH1, oDZ1, oDL, oHP, qH0, qH1, qLG;
-};
-
-__host__ __device__ inline Layout make_layout(const fumi_episode_cfg& c) {
-    Layout L;
-    const int64_t n = c.num_support, N = c.num_ways;
-    L.S0 = 0;
-    L.S1 = n * kH0;
-    L.w1t = 2 * n * kH0;
-    L.b0 = L.w1t + int64_t(kH0) * kH1;
-    L.b1 = L.b0 + kH0;
-    L.head = L.b1 + kH1;
-    L.steps = L.head + ((N * kHD + 3) / 4) * 4;
-    L.oH0 = 0;
-    L.oH1 = n * kH0;
-    L.oDZ1 = L.oH1 + n * kH1;
-    L.oDL = L.oDZ1 + n * kH1;
-    L.oHP = L.oDL + ((n * N + 3) / 4) * 4;
-    L.per_step = L.oHP + ((N * kHD + 3) / 4) * 4;
-    // query activations of the final forward (tensor-core path: the backward does not recompute them)
-    const int64_t mq = c.num_query;
-    L.qH0 = L.steps + int64_t(c.steps) * L.per_step;
-    L.qH1 = L.qH0 + mq * kH0;
-    L.qLG = L.qH1 + mq * kH1;
-    L.per_task = L.qLG + ((mq * N + 3) / 4) * 4;
-    return L;
-}
 
 // Shared-memory carve-up (floats).  Buffers hold TR = max(support tile, query tile) rows.
 struct Smem {
@@ -163,21 +103,6 @@ __device__ inline Smem carve(float* base) {
     s.sS = p; p += TRC * kH0;
     s.sA = p; p += TRC * kH0;
     return s;
-}
-
-__device__ inline float dropout_scale(const fumi_episode_cfg& c) {
-    return c.dropout_p > 0.f ? 1.f / (1.f - c.dropout_p) : 1.f;
-}
-// one 32-bit hash per (row, column pair): even column -> low 16 bits, odd column -> high 16 bits
-__device__ inline uint32_t dropout_base(const fumi_episode_cfg& c, int64_t task, int pass, int layer) {
-    return fumi_mask_base(c.dropout_seed, uint64_t(task), uint32_t(pass), uint32_t(layer));
-}
-__device__ inline uint32_t dropout_bits(uint32_t base, int row, int col) {
-    return fumi_mask_pair(base, uint32_t(row), uint32_t(col));
-}
-__device__ inline uint32_t dropout_thr(const fumi_episode_cfg& c) { return uint32_t(c.dropout_p * 65536.f); }
-__device__ inline bool dropout_keep_bits(uint32_t bits, int col, uint32_t thr) {
-    return ((col & 1) ? (bits >> 16) : (bits & 0xFFFFu)) >= thr;
 }
 
 // ---- tile loaders -----------------------------------------------------------------------------
@@ -578,133 +503,13 @@ __global__ void __launch_bounds__(kThreads, 1) episode_fwd_kernel(EpiParams P) {
 // mma.sync tiles (warp_mma.cuh) on the fp32 tiles in shared memory.  MT = 1 for NK <= 16, else 2
 // (rows padded with zeros to 16*MT).  Warp w of 8 owns hidden units [32w, 32w+32) of the 256-wide ops and
 // output units [8w, 8w+8) of the 64-wide op.  Query rows go through in tiles of 32.
-// Phase profiler (diagnostics only; enabled by fumi_debug_phase_profile(1)): thread 0 of each CTA adds the SM
-// cycles between consecutive marks to g_phase[id]; read back with fumi_debug_read_phases.
-__device__ unsigned long long g_phase[64];
-__device__ int g_phase_on = 0;
-struct PhaseClock {
-    long long last;
-    bool on;
-    __device__ __forceinline__ void start() {
-#ifndef FUMI_EMU
-        on = g_phase_on != 0 && threadIdx.x == 0;
-        if (on) last = clock64();
-#else
-        on = false; last = 0;
-#endif
-    }
-    __device__ __forceinline__ void mark(int id) {
-#ifndef FUMI_EMU
-        if (on) {
-            const long long t = clock64();
-            atomicAdd(&g_phase[id], (unsigned long long)(t - last));
-            last = t;
-        }
-#endif
-    }
-};
 
-constexpr int kS0 = kH0 + 4;     // row stride of [rows][H0] tiles (A operand: conflict-free fragment loads)
-constexpr int kS1 = kH1 + 4;     // row stride of [rows][H1] tiles and of W1^T [H0][H1]
-constexpr int kSS = kH0 + 8;     // row stride of S (B operand, k = row)
-constexpr int kSG = 36;          // row stride of a Gram tile with up to 32 columns
-constexpr int kMaxQueryRows = 640;
-
-struct SmemM {
-    float *w1t, *h0t, *h1t, *dz1t, *lt, *gS, *gQ, *sS, *sA, *hp, *dhp, *b0s, *db0s, *b1s, *rowv, *rowc;
-    long long* rowsQ;
-    int *ysQ, *ysS;
-};
-__host__ __device__ inline size_t smem_m_floats() {
-    return size_t(kH0) * kS1 + 32 * kS0 + 2 * 32 * kS1 + 32 * kLS + 2 * 32 * kSG + 32 * kSS + 32 * kH0 +
-           2 * kMaxWays * kHD + 2 * kH0 + kH1 + 64 + 2 * kMaxQueryRows + kMaxQueryRows + 32 + 16;
-}
-__device__ inline SmemM carve_m(float* p) {
-    SmemM s;
-    s.rowsQ = reinterpret_cast<long long*>(p); p += 2 * kMaxQueryRows;
-    s.w1t = p; p += kH0 * kS1;
-    s.h0t = p; p += 32 * kS0;
-    s.h1t = p; p += 32 * kS1;
-    s.dz1t = p; p += 32 * kS1;
-    s.lt = p; p += 32 * kLS;
-    s.gS = p; p += 32 * kSG;
-    s.gQ = p; p += 32 * kSG;
-    s.sS = p; p += 32 * kSS;
-    s.sA = p; p += 32 * kH0;
-    s.hp = p; p += kMaxWays * kHD;
-    s.dhp = p; p += kMaxWays * kHD;
-    s.b0s = p; p += kH0;
-    s.db0s = p; p += kH0;
-    s.b1s = p; p += kH1;
-    s.rowv = p; p += 32;
-    s.rowc = p; p += 32;
-    s.ysQ = reinterpret_cast<int*>(p); p += kMaxQueryRows;
-    s.ysS = reinterpret_cast<int*>(p); p += 32;
-    return s;
-}
 
 // 512 threads: the phases are latency-bound with 2 warps per scheduler (an 8-warp version measured issue
 // active 22-28 %, tensor pipe 20 %), so the work of every phase is split over 16 warps:
 // warp w owns hidden units [16w, 16w+16) of the 256-wide ops and the (m tile w/8, n tile w%8) block of the
 // 64-wide op.  Launch bound 512 threads -> 128 registers per thread.
-constexpr int kThreads16 = 512;
 
-template <int MT>
-__device__ __forceinline__ void mma16_tile_h0(const EpiParams& P, const SmemM& s, int64_t task, const float* G, bool use_s,
-                                              int K8, const float* Apre, int lda_pre, int r0, int tr, int pass) {
-    const int w = threadIdx.x >> 5;
-    float acc[MT][2][4];
-#pragma unroll
-    for (int i = 0; i < MT; ++i)
-#pragma unroll
-        for (int j = 0; j < 2; ++j)
-#pragma unroll
-            for (int q = 0; q < 4; ++q) acc[i][j][q] = 0.f;
-    if (use_s) warp_gemm_3xtf32<MT, 2, false, false>(G, kSG, s.sS + 16 * w, kSS, K8, 1.f, acc);
-    const float alpha = P.cfg.step_size, sc = dropout_scale(P.cfg);
-    const bool drop = P.cfg.dropout_p > 0.f;
-    const uint32_t thr = dropout_thr(P.cfg);
-    const uint32_t dbase = drop ? dropout_base(P.cfg, task, pass, 0) : 0u;
-    uint32_t bits = 0;
-    warp_tile_foreach<MT, 2>(acc, [&](int i, int hh, float& c) {
-        const int h = 16 * w + hh;
-        float v = 0.f;
-        if (i < tr) {
-            const float z = Apre[i * lda_pre + h] + s.b0s[h] - alpha * c;
-            if (drop && (hh & 1) == 0) bits = dropout_bits(dbase, r0 + i, h);
-            if (z > 0.f && (!drop || dropout_keep_bits(bits, h, thr))) v = z * sc;
-        }
-        s.h0t[i * kS0 + h] = v;
-    });
-}
-
-template <int MT>
-__device__ __forceinline__ void mma16_tile_h1(const EpiParams& P, const SmemM& s, int64_t task, int r0, int tr, int pass) {
-    const int w = threadIdx.x >> 5, nt = w & 7, mt = w >> 3;
-    if (mt >= MT) return;                                   // NK <= 16: one m tile, warps 8..15 have no block
-    float acc[1][1][4] = {{{0.f, 0.f, 0.f, 0.f}}};
-    warp_gemm_3xtf32<1, 1, false, false>(s.h0t + 16 * mt * kS0, kS0, s.w1t + 8 * nt, kS1, kH0, 1.f, acc);
-    const float sc = dropout_scale(P.cfg);
-    const bool drop = P.cfg.dropout_p > 0.f;
-    const uint32_t thr = dropout_thr(P.cfg);
-    const uint32_t dbase = drop ? dropout_base(P.cfg, task, pass, 1) : 0u;
-    uint32_t bits = 0;
-    warp_tile_foreach<1, 1>(acc, [&](int ii, int oo, float& c) {
-        const int i = 16 * mt + ii, o = 8 * nt + oo;
-        float v = 0.f;
-        if (i < tr) {
-            const float z = c + s.b1s[o];
-            if (drop && (oo & 1) == 0) bits = dropout_bits(dbase, r0 + i, o);
-            if (z > 0.f && (!drop || dropout_keep_bits(bits, o, thr))) v = z * sc;
-        }
-        s.h1t[i * kS1 + o] = v;
-    });
-}
-
-// Logits and their softmax in one phase: one lane per (row, class), a row's N lanes in the same warp
-// (32 / N rows per warp), so the row statistics need only a warp barrier.  Every lane of a row recomputes
-// max / sum-of-exp (N <= 32 expf) and hands (row, class, logit, max, sum) to `sink`, which may overwrite
-// lt[row][class] -- all of the row's reads are complete by then.
 template <typename SM, typename Sink>
 __device__ __forceinline__ void m16_tile_logits_softmax(const EpiParams& P, const SM& s, int rows, int tr, Sink sink) {
     const int N = P.cfg.num_ways;
@@ -734,284 +539,6 @@ __device__ __forceinline__ void m16_tile_logits_softmax(const EpiParams& P, cons
     }
 }
 
-template <int MT>
-__global__ void __launch_bounds__(kThreads16, 1) episode_fwd_mma16_kernel(EpiParams P) {
-    constexpr int RS = 16 * MT;                       // padded support rows
-    constexpr int NT_ = kThreads16;
-    FUMI_DYN_SMEM(float, smem_raw);
-    const SmemM s = carve_m(smem_raw);
-    const fumi_episode_cfg& c = P.cfg;
-    const int tid = threadIdx.x, w = tid >> 5, lane = tid & 31;
-    const int col = tid & 255, half = tid >> 8;       // column-wise copies: two threads per column, rows split
-    const int n = c.num_support, m = c.num_query, N = c.num_ways, steps = c.steps;
-    const int n8 = (n + 7) & ~7;
-    const float alpha = c.step_size;
-    const Layout L = make_layout(c);
-    const int o_ = tid & 63, kg_ = tid >> 6;          // 8 row groups x 64 outputs
-    __shared__ float task_sum[2];
-    PhaseClock pc;
-    pc.start();
-
-    for (int idx = tid; idx < 32 * kSS; idx += NT_) s.sS[idx] = 0.f;     // pad rows of S stay zero for the whole kernel
-    for (int idx = tid; idx < 32 * kSG; idx += NT_) { s.gS[idx] = 0.f; s.gQ[idx] = 0.f; }
-    __syncthreads();
-
-    for (int64_t b = blockIdx.x; b < P.B; b += gridDim.x) {
-        const int64_t task = c.task_offset + b;
-        float* slot = P.stash + (P.save ? b : int64_t(blockIdx.x)) * P.slot_floats;
-        // ---- task prologue: everything the inner loop needs is staged in shared memory once
-        {
-            float v[16];
-#pragma unroll 1
-            for (int o0 = half * 32; o0 < half * 32 + 32; o0 += 16) {     // w1 is [H1][H0] row-major; thread == (k, half)
-#pragma unroll
-                for (int q = 0; q < 16; ++q) v[q] = __ldg(&P.w1[(o0 + q) * kH0 + col]);
-#pragma unroll
-                for (int q = 0; q < 16; ++q) s.w1t[col * kS1 + o0 + q] = v[q];
-            }
-            constexpr int RH = RS / 2;                                    // rows per half
-#pragma unroll
-            for (int q = 0; q < RH; ++q) {
-                const int i = half * RH + q;
-                v[q] = i < n ? __ldg(&P.proj[__ldg(&P.sup_rows[b * n + i]) * kH0 + col]) : 0.f;
-            }
-#pragma unroll
-            for (int q = 0; q < RH; ++q) s.sA[(half * RH + q) * kH0 + col] = v[q];
-        }
-        if (tid < kH0) s.b0s[tid] = __ldg(&P.b0[tid]);
-        if (tid < kH1) s.b1s[tid] = __ldg(&P.b1[tid]);
-        for (int idx = tid; idx < N * kHD; idx += NT_) {
-            const int cc = idx / kHD, o = idx - cc * kHD;
-            const int64_t r = P.head_rows ? __ldg(&P.head_rows[b * N + cc]) : cc;
-            s.hp[idx] = __ldg(&P.head_table[r * kHD + o]);
-        }
-        for (int idx = tid; idx < n * n; idx += NT_) {
-            const int i = idx / n, j = idx - i * n;
-            s.gS[i * kSG + j] = __ldg(&P.gram[(b * int64_t(n + m) + i) * n + j]);
-        }
-        if (tid < 32) s.ysS[tid] = tid < n ? int(P.sup_y[b * n + tid]) : 0;
-        for (int idx = tid; idx < m; idx += NT_) {
-            s.rowsQ[idx] = P.qry_rows[b * m + idx];
-            s.ysQ[idx] = int(P.qry_y[b * m + idx]);
-        }
-        if (tid == 0) { task_sum[0] = 0.f; task_sum[1] = 0.f; }
-        __syncthreads();
-        pc.mark(20);    // prologue
-
-        for (int st = 0; st < steps; ++st) {
-            float* rec = P.save ? slot + L.steps + int64_t(st) * L.per_step : nullptr;
-            mma16_tile_h0<MT>(P, s, task, s.gS, st > 0, n8, s.sA, kH0, 0, n, st);
-            __syncthreads();
-            pc.mark(21);    // s: H0
-            mma16_tile_h1<MT>(P, s, task, 0, n, st);
-            __syncthreads();
-            pc.mark(22);    // s: H1 (K=256)
-            {                                                   // logits, then dL = (softmax - onehot) / n in place
-                const float invn = 1.f / float(n);
-                m16_tile_logits_softmax(P, s, RS, n, [&](int i, int cc, float l, float mx, float sum) {
-                    float dl = 0.f;
-                    if (i < n) dl = (expf(l - mx) * (1.f / sum) - (cc == s.ysS[i] ? 1.f : 0.f)) * invn;
-                    s.lt[i * kLS + cc] = dl;
-                });
-            }
-            __syncthreads();
-            pc.mark(23);    // s: logits + softmax
-            pc.mark(24);    // s: softmax
-            // head gradient; dZ1 (uses the pre-update head)
-            for (int idx = tid; idx < N * kHD; idx += NT_) {
-                const int cc = idx / kHD, o = idx - cc * kHD;
-                float a = 0.f;
-                for (int i = 0; i < n; ++i) a = fmaf(s.lt[i * kLS + cc], o < kH1 ? s.h1t[i * kS1 + o] : 1.f, a);
-                s.dhp[idx] = a;
-            }
-            {
-                const float sc = dropout_scale(c);
-#pragma unroll
-                for (int ii = 0; ii < RS / 8; ++ii) {
-                    const int i = kg_ + 8 * ii;
-                    float dz = 0.f;
-                    if (i < n && s.h1t[i * kS1 + o_] > 0.f) {
-                        float dh = 0.f;
-                        for (int cc = 0; cc < N; ++cc) dh = fmaf(s.lt[i * kLS + cc], s.hp[cc * kHD + o_], dh);
-                        dz = dh * sc;
-                    }
-                    s.dz1t[i * kS1 + o_] = dz;
-                }
-            }
-            __syncthreads();
-            pc.mark(25);    // s: dhp, dZ1
-            float db1 = 0.f;
-            if (tid < kH1) for (int i = 0; i < n; ++i) db1 += s.dz1t[i * kS1 + tid];
-            // dZ0 = (dZ1 W1) * gate ;  S += dZ0 ;  db0 = column sums of dZ0
-            {
-                float acc[MT][2][4];
-#pragma unroll
-                for (int i = 0; i < MT; ++i)
-#pragma unroll
-                    for (int j = 0; j < 2; ++j)
-#pragma unroll
-                        for (int q = 0; q < 4; ++q) acc[i][j][q] = 0.f;
-                warp_gemm_3xtf32<MT, 2, false, true>(s.dz1t, kS1, s.w1t + 16 * w * kS1, kS1, kH1, 1.f, acc);
-                const float sc = dropout_scale(c);
-                float colsum[2][2];
-#pragma unroll
-                for (int j = 0; j < 2; ++j) colsum[j][0] = colsum[j][1] = 0.f;
-                warp_tile_foreach<MT, 2>(acc, [&](int i, int hh, float& cv) {
-                    const int h = 16 * w + hh;
-                    const float dz0 = (i < n && s.h0t[i * kS0 + h] > 0.f) ? cv * sc : 0.f;
-                    if (i < n) s.sS[i * kSS + h] = (st > 0 ? s.sS[i * kSS + h] : 0.f) + dz0;
-                    colsum[hh >> 3][hh & 1] += dz0;
-                });
-#pragma unroll
-                for (int j = 0; j < 2; ++j)
-#pragma unroll
-                    for (int q = 0; q < 2; ++q) {
-                        float v = colsum[j][q];
-                        v += __shfl_xor_sync(0xffffffffu, v, 4);
-                        v += __shfl_xor_sync(0xffffffffu, v, 8);
-                        v += __shfl_xor_sync(0xffffffffu, v, 16);
-                        if ((lane >> 2) == 0) s.db0s[16 * w + 8 * j + 2 * (lane & 3) + q] = v;
-                    }
-            }
-            if (rec) {                                          // records for the backward
-                for (int i = half; i < n; i += 2) rec[L.oH0 + int64_t(i) * kH0 + col] = s.h0t[i * kS0 + col];
-                for (int idx = tid; idx < n * kH1; idx += NT_) {
-                    const int i = idx / kH1, o = idx - i * kH1;
-                    rec[L.oH1 + idx] = s.h1t[i * kS1 + o];
-                    rec[L.oDZ1 + idx] = s.dz1t[i * kS1 + o];
-                }
-                for (int idx = tid; idx < n * N; idx += NT_) {
-                    const int i = idx / N, cc = idx - i * N;
-                    rec[L.oDL + idx] = s.lt[i * kLS + cc];
-                }
-                for (int idx = tid; idx < N * kHD; idx += NT_) rec[L.oHP + idx] = s.hp[idx];
-            }
-            __syncthreads();                                    // everyone is done reading W1^T and the old head
-            pc.mark(26);    // s: dZ0 gemm, S update, stash
-            // W1 -= alpha * dZ1^T H0   (rows of W1^T owned by this warp: h in [16w, 16w+16))
-            {
-                float acc[1][8][4];
-#pragma unroll
-                for (int j = 0; j < 8; ++j)
-#pragma unroll
-                    for (int q = 0; q < 4; ++q) acc[0][j][q] = 0.f;
-                warp_gemm_3xtf32<1, 8, true, false>(s.h0t + 16 * w, kS0, s.dz1t, kS1, RS, 1.f, acc);
-                warp_tile_foreach<1, 8>(acc, [&](int hh, int o, float& cv) {
-                    s.w1t[(16 * w + hh) * kS1 + o] -= alpha * cv;
-                });
-            }
-            for (int idx = tid; idx < N * kHD; idx += NT_) s.hp[idx] -= alpha * s.dhp[idx];
-            if (tid < kH1) s.b1s[tid] -= alpha * db1;
-            if (tid < kH0) s.b0s[tid] -= alpha * s.db0s[tid];
-            __syncthreads();
-            pc.mark(27);    // s: W1 update gemm
-        }
-
-        // ---- query scoring, 32 rows per tile
-        // software prefetch: the next query tile's projected rows / Gram rows travel in registers
-        float qv[16], qg[2];
-        auto q_load = [&](int r0) {
-            const int tr = min(32, m - r0);
-#pragma unroll
-            for (int q = 0; q < 16; ++q) {
-                const int i = half * 16 + q;
-                qv[q] = i < tr ? __ldg(&P.proj[s.rowsQ[r0 + i] * kH0 + col]) : 0.f;
-            }
-#pragma unroll
-            for (int q = 0; q < 2; ++q) {                      // 32 x n Gram tile: <= 2 elements per thread
-                const int idx = tid + q * NT_;
-                const int i = idx / n, j = idx - i * n;
-                qg[q] = (idx < 32 * n && i < tr) ? __ldg(&P.gram[(b * int64_t(n + m) + n + r0 + i) * n + j]) : 0.f;
-            }
-        };
-        q_load(0);
-        for (int r0 = 0; r0 < m; r0 += 32) {
-            const int tr = min(32, m - r0);
-#pragma unroll
-            for (int q = 0; q < 16; ++q) s.h0t[(half * 16 + q) * kS0 + col] = qv[q];
-#pragma unroll
-            for (int q = 0; q < 2; ++q) {
-                const int idx = tid + q * NT_;
-                const int i = idx / n, j = idx - i * n;
-                if (idx < 32 * n) s.gQ[i * kSG + j] = qg[q];
-            }
-            __syncthreads();
-            if (r0 + 32 < m) q_load(r0 + 32);
-            if (r0 > 0 && w == 0) {                             // loss / accuracy of the previous tile (rowv, rowc)
-                float rv = s.rowv[lane], rc = s.rowc[lane];
-#pragma unroll
-                for (int off = 16; off >= 1; off >>= 1) {
-                    rv += __shfl_xor_sync(0xffffffffu, rv, off);
-                    rc += __shfl_xor_sync(0xffffffffu, rc, off);
-                }
-                if (lane == 0) { task_sum[0] += rv; task_sum[1] += rc; }
-            }
-            pc.mark(28);    // q: loads
-            mma16_tile_h0<2>(P, s, task, s.gQ, steps > 0, n8, s.h0t, kS0, r0, tr, steps);
-            __syncthreads();
-            pc.mark(29);    // q: H0
-            mma16_tile_h1<2>(P, s, task, r0, tr, steps);
-            __syncthreads();
-            pc.mark(30);    // q: H1
-            // logits + softmax on the (row, class) lanes; the other warps go straight to the stash copies
-            m16_tile_logits_softmax(P, s, 32, tr, [&](int i, int cc, float l, float mx, float sum) {
-                if (i >= tr) {
-                    if (cc == 0) { s.rowv[i] = 0.f; s.rowc[i] = 0.f; }
-                    return;
-                }
-                const int y = s.ysQ[r0 + i];
-                const int64_t q = b * m + r0 + i;
-                P.logits[q * N + cc] = l;
-                if (P.save)                                     // dL/dlogits (unscaled) for the backward
-                    slot[L.qLG + int64_t(r0 + i) * N + cc] = expf(l - mx) * (1.f / sum) - (cc == y ? 1.f : 0.f);
-                if (cc == 0) {
-                    const float* lr = &s.lt[i * kLS];
-                    int best = 0;
-                    for (int k = 1; k < N; ++k) if (lr[k] > lr[best]) best = k;      // first max (torch.max)
-                    s.rowv[i] = (logf(sum) + mx) - lr[y];
-                    s.rowc[i] = best == y ? 1.f : 0.f;
-                    P.preds[q] = best;
-                }
-            });
-            pc.mark(31);    // q: logits + softmax
-            if (P.save) {                                       // query activations for the backward
-                for (int i = half; i < tr; i += 2) slot[L.qH0 + int64_t(r0 + i) * kH0 + col] = s.h0t[i * kS0 + col];
-                for (int idx = tid; idx < tr * kH1; idx += NT_) {
-                    const int i = idx / kH1, o = idx - i * kH1;
-                    slot[L.qH1 + int64_t(r0) * kH1 + idx] = s.h1t[i * kS1 + o];
-                }
-            }
-            __syncthreads();                                    // h0t / h1t / lt / rowv are rewritten by the next tile
-            pc.mark(32);    // q: stash, softmax, loss
-        }
-        if (w == 0) {                                           // last tile's rows, then the task means
-            float rv = s.rowv[lane], rc = s.rowc[lane];
-#pragma unroll
-            for (int off = 16; off >= 1; off >>= 1) {
-                rv += __shfl_xor_sync(0xffffffffu, rv, off);
-                rc += __shfl_xor_sync(0xffffffffu, rc, off);
-            }
-            if (lane == 0) {
-                P.task_loss[b] = (task_sum[0] + rv) / float(m);
-                P.task_acc[b] = (task_sum[1] + rc) / float(m);
-            }
-        }
-        if (P.save) {                                               // adapted state
-            for (int idx = tid; idx < kH0 * kH1; idx += NT_) {
-                const int k = idx / kH1, o = idx - k * kH1;
-                slot[L.w1t + idx] = s.w1t[k * kS1 + o];
-            }
-            if (tid < kH0) slot[L.b0 + tid] = s.b0s[tid];
-            if (tid < kH1) slot[L.b1 + tid] = s.b1s[tid];
-            for (int idx = tid; idx < N * kHD; idx += NT_) slot[L.head + idx] = s.hp[idx];
-            float* Sout = slot + ((steps & 1) ? L.S1 : L.S0);      // final S where the backward expects it
-            for (int i = half; i < n; i += 2) Sout[int64_t(i) * kH0 + col] = steps > 0 ? s.sS[i * kSS + col] : 0.f;
-        }
-        __syncthreads();
-        pc.mark(33);    // epilogue (adapted state out)
-    }
-}
-
 // ------------------------------------------------------------------------------------ forward, fp16 planes
 // Same algorithm and launch shape as episode_fwd_mma16_kernel, but every GEMM operand lives in shared memory as
 // PRE-SPLIT fp16 hi/lo planes (x 2^s = hi + lo, 22 significant bits, the bytes of one fp32 tile): the inner loops
@@ -1021,9 +548,6 @@ __global__ void __launch_bounds__(kThreads16, 1) episode_fwd_mma16_kernel(EpiPar
 // written once; consumers undo the two scales exactly in their epilogues.  W1^T and S are updated in place by
 // reconstructing (hi + lo) 2^-s at the thread's own accumulator positions.  The projected rows A are not staged in
 // shared memory any more: each thread loads the 8-byte pieces at its own accumulator positions from `proj`.
-constexpr int kHW = kH1 + 8;      // half stride of W1^T [H0][H1] and dZ1 [rows][H1] planes
-constexpr int kHS = kH0 + 8;      // half stride of S / H0 [rows][H0] planes
-constexpr int kHG = 32 + 8;       // half stride of a Gram tile [rows][32] planes
 
 struct SmemF {
     fumi_half *w1h, *w1l, *sh, *sl, *h0h, *h0l, *dzh, *dzl, *gsh, *gsl, *gqh, *gql;
@@ -1063,27 +587,6 @@ __host__ __device__ inline size_t carve_f(char* base, SmemF& s) {
 }
 inline size_t smem_f_bytes() { SmemF t; return carve_f(nullptr, t); }
 
-// block-wide max of a non-negative value without atomics: every warp leaves its max in its own word of the slot
-// (all 16 words are rewritten by each production, so a slot needs no reset), readers reduce the 16 words after
-// the barrier that follows.
-__device__ __forceinline__ void block_max_push(float* slot, float m) {
-#pragma unroll
-    for (int off = 16; off >= 1; off >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, off));
-    if ((threadIdx.x & 31) == 0) slot[threadIdx.x >> 5] = m;
-}
-__device__ __forceinline__ int block_max_exp(const float* slot) {          // plane exponent s for the slot's matrix
-    const float4 a = *reinterpret_cast<const float4*>(slot), b = *reinterpret_cast<const float4*>(slot + 4);
-    const float4 c = *reinterpret_cast<const float4*>(slot + 8), d = *reinterpret_cast<const float4*>(slot + 12);
-    const float m = fmaxf(fmaxf(fmaxf(fmaxf(a.x, a.y), fmaxf(a.z, a.w)), fmaxf(fmaxf(b.x, b.y), fmaxf(b.z, b.w))),
-                          fmaxf(fmaxf(fmaxf(c.x, c.y), fmaxf(c.z, c.w)), fmaxf(fmaxf(d.x, d.y), fmaxf(d.z, d.w))));
-    return fumi_plane_exp(__float_as_uint(m));
-}
-__device__ __forceinline__ void store_pair(fumi_half* hi, fumi_half* lo, int off, float a, float b, float scale) {
-    fumi_plane_store2(hi, lo, off, a, b, scale);
-}
-__device__ __forceinline__ float plane_value(const fumi_half* hi, const fumi_half* lo, int off, float inv) {
-    return (fumi_h2f(hi[off]) + fumi_h2f(lo[off])) * inv;
-}
 
 template <int MT>
 __global__ void __launch_bounds__(kThreads16, 1) episode_fwd_f16_kernel(EpiParams P) {
@@ -1104,7 +607,7 @@ __global__ void __launch_bounds__(kThreads16, 1) episode_fwd_f16_kernel(EpiParam
     const uint32_t thr = dropout_thr(c);
     __shared__ float task_sum[2];
     PhaseClock pc;
-    pc.start();
+    pc.start(P.phase);
     int e_w1 = 0, e_s = 0, e_h0 = 0, e_dz = 0, e_gs = 0;              // plane exponents of the current W1^T, S, H0, dZ1, G_support
 
     // planes start as zeros: pad rows / columns that no phase writes must be finite
@@ -1629,14 +1132,6 @@ __device__ inline SmemB carve_b(float* p) {
     return s;
 }
 
-__device__ __forceinline__ void atomic_add2(float* addr, float a, float b) {
-#ifdef FUMI_EMU
-    atomicAdd(addr, a);
-    atomicAdd(addr + 1, b);
-#else
-    asm volatile("red.global.add.v2.f32 [%0], {%1, %2};" ::"l"(addr), "f"(a), "f"(b) : "memory");
-#endif
-}
 
 // ------------------------------------------------------------------------------------ backward, 16 warps
 // 512 threads.  Warp w owns rows [16w, 16w+16) of the
@@ -1675,7 +1170,7 @@ __global__ void __launch_bounds__(kThreads16, 1) episode_bwd_mma16_kernel(EpiPar
     const int o_ = tid & 63, kg_ = tid >> 6;          // 8 row groups x 64 outputs
     const float sc = dropout_scale(c);
     PhaseClock pc;
-    pc.start();
+    pc.start(P.phase);
 
     for (int idx = tid; idx < 32 * kSG; idx += NT_) s.gS[idx] = 0.f;
     for (int idx = tid; idx < 16 * kSG; idx += NT_) s.gQ[idx] = 0.f;
@@ -2482,15 +1977,37 @@ constexpr int kTRB = 16;   // backward rows per tile (two W1-sized buffers live 
 
 }  // namespace
 
+// v1 (the round-1 kernels: fp16-plane forward, 3xTF32 backward) stays selectable for A/B runs while FUMI_EPISODE_V1=1
+static bool use_v1() {
+    static int v1 = -1;
+    if (v1 < 0) { const char* e = getenv("FUMI_EPISODE_V1"); v1 = (e && atoi(e) != 0) ? 1 : 0; }
+    return v1 != 0;
+}
+// 2: fp16-plane kernels with plane-format step records; 1: v1 tensor-core kernels; 0: fp32 FMA kernels (NK > 32)
+static int episode_path(const fumi_episode_cfg& c) {
+    const bool small = c.num_support <= 32;
+    if (small && !use_v1() && episode_f16_supported(c)) return 2;
+    if (small && c.num_query <= kMaxQueryRows) return 1;
+    return 0;
+}
+
 extern "C" int64_t fumi_episode_stash_floats(const fumi_episode_cfg* cfg) {
     if (check_cfg(cfg) != FUMI_OK) return FUMI_ERR_ARG;
-    return make_layout(*cfg).per_task;
+    return episode_path(*cfg) == 2 ? make_layout_f(*cfg).per_task : make_layout(*cfg).per_task;
 }
 
 extern "C" int fumi_stash_layout(const fumi_episode_cfg* cfg, fumi_stash_layout_t* out) {
     int rc = check_cfg(cfg);
     if (rc != FUMI_OK) return rc;
     FUMI_CHECK_ARG(out != nullptr, "out is null");
+    if (episode_path(*cfg) == 2) {
+        const LayoutF F = make_layout_f(*cfg);
+        out->per_task = F.per_task; out->S = F.S; out->w1t = F.w1t; out->b0 = F.b0; out->b1 = F.b1; out->head = F.head;
+        out->steps = F.steps; out->per_step = F.per_step;
+        out->format = 1;
+        out->rec_h1 = F.oH1; out->rec_exp = F.oEXP; out->rec_h0_hi = F.oH0h; out->rec_h0_lo = F.oH0l;
+        return FUMI_OK;
+    }
     const Layout L = make_layout(*cfg);
     out->per_task = L.per_task;
     out->S = (cfg->steps & 1) ? L.S1 : L.S0;
@@ -2500,6 +2017,8 @@ extern "C" int fumi_stash_layout(const fumi_episode_cfg* cfg, fumi_stash_layout_
     out->head = L.head;
     out->steps = L.steps;
     out->per_step = L.per_step;
+    out->format = 0;
+    out->rec_h1 = L.oH1; out->rec_exp = -1; out->rec_h0_hi = L.oH0; out->rec_h0_lo = -1;
     return FUMI_OK;
 }
 
@@ -2535,10 +2054,13 @@ extern "C" int fumi_episode_fwd(const fumi_episode_cfg* cfg, int64_t B, const fl
         FUMI_SET_SMEM_ATTR(kern, smem);                                                                        \
         FUMI_LAUNCH(kern, grid, kThreads, smem, stream, P);                                                    \
     } while (0)
-    const bool use_mma = nk <= 32 && cfg->num_query <= kMaxQueryRows;
-    static int use_f16 = -1;          // FUMI_FWD_F16=0: the fp32-tile kernel (split per use), for A/B runs
-    if (use_f16 < 0) { const char* e = getenv("FUMI_FWD_F16"); use_f16 = (e && atoi(e) == 0) ? 0 : 1; }
-    if (use_mma && use_f16) {
+    const int path = episode_path(*cfg);
+    const bool use_mma = path == 1;
+    P.phase = episode_phase_counters();
+    if (path == 2) {
+        P.slot_floats = make_layout_f(*cfg).per_task;
+        return launch_episode_fwd_f16(P, grid, stream);
+    } else if (use_mma) {
         const size_t smem = smem_f_bytes();
         if (nk <= 16) {
             FUMI_SET_SMEM_ATTR(episode_fwd_f16_kernel<1>, smem);
@@ -2546,15 +2068,6 @@ extern "C" int fumi_episode_fwd(const fumi_episode_cfg* cfg, int64_t B, const fl
         } else {
             FUMI_SET_SMEM_ATTR(episode_fwd_f16_kernel<2>, smem);
             FUMI_LAUNCH(episode_fwd_f16_kernel<2>, grid, kThreads16, smem, stream, P);
-        }
-    } else if (use_mma) {
-        const size_t smem = smem_m_floats() * sizeof(float);
-        if (nk <= 16) {
-            FUMI_SET_SMEM_ATTR(episode_fwd_mma16_kernel<1>, smem);
-            FUMI_LAUNCH(episode_fwd_mma16_kernel<1>, grid, kThreads16, smem, stream, P);
-        } else {
-            FUMI_SET_SMEM_ATTR(episode_fwd_mma16_kernel<2>, smem);
-            FUMI_LAUNCH(episode_fwd_mma16_kernel<2>, grid, kThreads16, smem, stream, P);
         }
     } else if (nk > 32) FUMI_FWD_CASE(32, true);
     else if (nk > 28) FUMI_FWD_CASE(32, false);
@@ -2589,7 +2102,12 @@ extern "C" int fumi_episode_bwd(const fumi_episode_cfg* cfg, int64_t B, const fl
     P.d_b0_parts = d_b0_parts; P.d_w1_parts = d_w1_parts; P.d_b1_parts = d_b1_parts;
     const int grid = grid_for(B);
     if (grid <= 0) return grid;
-    if (cfg->num_support <= 32 && cfg->num_query <= kMaxQueryRows) {      // tensor-core path (pairs with fwd_mma)
+    P.phase = episode_phase_counters();
+    if (episode_path(*cfg) == 2) {
+        P.slot_floats = make_layout_f(*cfg).per_task;
+        return launch_episode_bwd_f16(P, grid, stream);
+    }
+    if (episode_path(*cfg) == 1) {      // v1 tensor-core path (pairs with episode_fwd_f16_kernel)
         const size_t smem_b = smem_b_floats() * sizeof(float);
         FUMI_SET_SMEM_ATTR(episode_bwd_mma16_kernel, smem_b);
         FUMI_LAUNCH(episode_bwd_mma16_kernel, grid, kThreads16, smem_b, stream, P);
@@ -2611,18 +2129,27 @@ extern "C" int fumi_episode_bwd(const fumi_episode_cfg* cfg, int64_t B, const fl
 }
 
 // ---- diagnostics (not part of the reference-facing surface): per-phase SM-cycle counters of the episode kernels
+static unsigned long long* g_phase_dev = nullptr;
+static bool g_phase_on = false;
+namespace fumi_epi {
+unsigned long long* episode_phase_counters() { return g_phase_on ? g_phase_dev : nullptr; }
+}
 extern "C" int fumi_debug_phase_profile(int enable) {
 #ifndef FUMI_EMU
-    unsigned long long zeros[64] = {0};
-    cudaError_t e = cudaMemcpyToSymbol(g_phase, zeros, sizeof(zeros));
-    if (e == cudaSuccess) e = cudaMemcpyToSymbol(g_phase_on, &enable, sizeof(int));
+    if (!g_phase_dev) {
+        cudaError_t e = cudaMalloc(&g_phase_dev, sizeof(unsigned long long) * 64);
+        if (e != cudaSuccess) return fumi_cuda_fail(e, "fumi_debug_phase_profile");
+    }
+    cudaError_t e = cudaMemset(g_phase_dev, 0, sizeof(unsigned long long) * 64);
     if (e != cudaSuccess) return fumi_cuda_fail(e, "fumi_debug_phase_profile");
 #endif
+    g_phase_on = enable != 0;
     return FUMI_OK;
 }
 extern "C" int fumi_debug_read_phases(unsigned long long* out64 /* HOST, 64 entries */) {
 #ifndef FUMI_EMU
-    cudaError_t e = cudaMemcpyFromSymbol(out64, g_phase, sizeof(unsigned long long) * 64);
+    if (!g_phase_dev) { for (int i = 0; i < 64; ++i) out64[i] = 0; return FUMI_OK; }
+    cudaError_t e = cudaMemcpy(out64, g_phase_dev, sizeof(unsigned long long) * 64, cudaMemcpyDeviceToHost);
     if (e != cudaSuccess) return fumi_cuda_fail(e, "fumi_debug_read_phases");
 #else
     for (int i = 0; i < 64; ++i) out64[i] = 0;

@@ -1,0 +1,688 @@
+// Fused inner loop + query scoring on fp16 hi/lo operand planes, NK <= 32 (fumi/models/fumi.py:148-185,
+// fumi/models/maml.py:158-183).  One persistent CTA of 16 warps walks a task; warp w owns hidden units
+// [16w, 16w+16) of the 256-wide layer.
+//
+// What shapes the kernel is the dependency structure of one SGD step in the Gram form:
+//     (a) H0 = act(A + b0 - alpha G S)          columns h of H0 need columns h of S            -> warp-local
+//     (b) Z1 = H0 W1^T                          contracts over all 256 hidden units              -> block-wide
+//     (c) logits, softmax, dL, dZ1              couples the 64 units / N classes of ONE row      -> one row per warp
+//     (d) dZ0 = (dZ1 W1) * gate ; S += dZ0      columns h need rows h of W1^T                    -> warp-local
+//     (e) W1 -= alpha dZ1^T H0                  rows h of W1^T need columns h of H0              -> warp-local
+// so a step costs THREE block barriers (before b, before c, before d); (d) -> (e) -> (a of the next step) is one
+// uninterrupted stream of 120 MMAs per warp with no block synchronisation.  Every GEMM operand lives in shared
+// memory as pre-split fp16 planes x 2^e = hi + lo (warp_mma.cuh: ldmatrix + 3 x mma.m16n8k16 per 16 k, fp32-grade
+// accuracy).  Plane exponents of matrices that all warps consume (H0, dZ1, W1^T, the query Gram tiles) are LAGGED:
+// a production is written with the exponent derived from the previous production's max (target 2^8, i.e. 8
+// binades of headroom; the new max travels through 16 per-warp words and is read after the barrier that follows
+// anyway), which removes the "exchange the max, then write" barrier per matrix.  A matrix growing more than 250x
+// between two consecutive inner steps would overflow fp16: the task's loss is then reported as NaN (the inner
+// loop has diverged); shrinking only costs precision gracefully.  S and b0 are warp-private (exact scales, registers).
+//
+// In train mode the step records are stashed as the planes themselves (LayoutF): the backward copies them into its
+// operand tiles with no conversion.
+#include "episode_common.cuh"
+
+namespace fumi_epi {
+namespace {
+
+enum { FX_W1 = 0, FX_H0 = 2, FX_DZ = 4, FX_GQ = 6, FX_GS = 8, FX_HP = 9, FX_COUNT = 10 };   // x 16 floats (two parities)
+
+struct SmemV {
+    fumi_half *w1h, *w1l, *sh, *sl, *h0h, *h0l, *dzh, *dzl, *gsh, *gsl, *gqh, *gql;
+    float *z1p, *h1t, *dz1t, *lt, *hp, *dhp, *b1s, *mx, *red;
+    int* ysS;
+};
+__host__ __device__ inline size_t carve_v(char* base, SmemV& s, int N) {
+    char* p = base;
+    auto take = [&](size_t bytes) { char* r = p; p += (bytes + 15) & ~size_t(15); return r; };
+    s.ysS = reinterpret_cast<int*>(take(32 * 4));
+    s.mx = reinterpret_cast<float*>(take(FX_COUNT * 16 * 4));
+    s.red = reinterpret_cast<float*>(take(2 * 16 * 4));
+    // zero-filled once per kernel from here (plane pads must be finite)
+    s.w1h = reinterpret_cast<fumi_half*>(take(kH0 * kHW * 2));  s.w1l = reinterpret_cast<fumi_half*>(take(kH0 * kHW * 2));
+    s.sh = reinterpret_cast<fumi_half*>(take(32 * kHS * 2));    s.sl = reinterpret_cast<fumi_half*>(take(32 * kHS * 2));
+    s.h0h = reinterpret_cast<fumi_half*>(take(32 * kHS * 2));   s.h0l = reinterpret_cast<fumi_half*>(take(32 * kHS * 2));
+    s.dzh = reinterpret_cast<fumi_half*>(take(32 * kHW * 2));   s.dzl = reinterpret_cast<fumi_half*>(take(32 * kHW * 2));
+    s.gsh = reinterpret_cast<fumi_half*>(take(32 * kHG * 2));   s.gsl = reinterpret_cast<fumi_half*>(take(32 * kHG * 2));
+    s.gqh = reinterpret_cast<fumi_half*>(take(2 * 32 * kHG * 2)); s.gql = reinterpret_cast<fumi_half*>(take(2 * 32 * kHG * 2));
+    s.z1p = reinterpret_cast<float*>(take(32 * kS1 * 4));
+    s.h1t = reinterpret_cast<float*>(take(32 * kS1 * 4));
+    s.dz1t = reinterpret_cast<float*>(take(32 * kS1 * 4));
+    s.lt = reinterpret_cast<float*>(take(32 * kLS * 4));
+    s.hp = reinterpret_cast<float*>(take(size_t(N) * kHD * 4));
+    s.dhp = reinterpret_cast<float*>(take(size_t(N) * kHD * 4));
+    s.b1s = reinterpret_cast<float*>(take(kH1 * 4));
+    return size_t(p - base);
+}
+
+template <int MT>
+__global__ void __launch_bounds__(kThreads16, 1) episode_fwd_v2_kernel(EpiParams P) {
+    constexpr int RS = 16 * MT;
+    constexpr int NT_ = kThreads16;
+    FUMI_DYN_SMEM(float, smem_raw);
+    const fumi_episode_cfg& c = P.cfg;
+    SmemV s;
+    const size_t smem_total = carve_v(reinterpret_cast<char*>(smem_raw), s, c.num_ways);
+    const int tid = threadIdx.x, w = tid >> 5, lane = tid & 31, g = lane >> 2, t = lane & 3;
+    const int n = c.num_support, m = c.num_query, N = c.num_ways, steps = c.steps;
+    const float alpha = c.step_size;
+    const LayoutF L = make_layout_f(c);
+    const float dsc = dropout_scale(c);
+    const bool drop = c.dropout_p > 0.f;
+    const uint32_t thr = dropout_thr(c);
+    const int hc = 16 * w + 2 * t;                       // this thread's column pairs: hc + 8 j + {0, 1}
+    PhaseClock pc;
+    pc.start(P.phase);
+
+    {   // planes start as zeros: pad rows / columns that no phase writes must be finite
+        uint32_t* z = reinterpret_cast<uint32_t*>(s.w1h);
+        const int nz = int((reinterpret_cast<char*>(s.z1p) - reinterpret_cast<char*>(s.w1h)) / 4);
+        for (int idx = tid; idx < nz; idx += NT_) z[idx] = 0u;
+        (void)smem_total;
+    }
+    __syncthreads();
+
+    for (int64_t b = blockIdx.x; b < P.B; b += gridDim.x) {
+        const int64_t task = c.task_offset + b;
+        float* slot = P.save ? P.stash + b * P.slot_floats : nullptr;
+        bool bad = false;                                 // a lagged plane exponent overflowed fp16
+        int e_w1, e_h0 = 0, e_dz, e_gs, e_gq, e_s = 0;
+        int e_h0n = 0, e_dzn = 0, e_w1n = 0, e_gqn = 0;   // exponents for the NEXT production (from the last observed max)
+        int par_h0 = 0, par_dz = 0, par_w1 = 0, par_gq = 0;
+
+        // ------------------------------------------------------------------ prologue
+        float w1v[32];                                    // W1[o][h], h = tid & 255, o in [32 half, 32 half + 32)
+        const int col = tid & 255, half = tid >> 8;
+        {
+            float mxv = 0.f;
+#pragma unroll
+            for (int q = 0; q < 32; ++q) {
+                w1v[q] = __ldg(&P.w1[(half * 32 + q) * kH0 + col]);
+                mxv = fmaxf(mxv, fabsf(w1v[q]));
+            }
+            block_max_push(s.mx + 16 * FX_W1, mxv);
+        }
+        float gv[2];                                      // support Gram block
+        {
+            float mxv = 0.f;
+#pragma unroll
+            for (int q = 0; q < 2; ++q) {
+                const int idx = tid + q * NT_, i = idx >> 5, j = idx & 31;
+                gv[q] = (i < n && j < n) ? __ldg(&P.gram[(b * int64_t(n + m) + i) * n + j]) : 0.f;
+                mxv = fmaxf(mxv, fabsf(gv[q]));
+            }
+            block_max_push(s.mx + 16 * FX_GS, mxv);
+        }
+        {
+            float mxv = 0.f;
+            for (int idx = tid; idx < N * kHD; idx += NT_) {
+                const int cc = idx / kHD, o = idx - cc * kHD;
+                const int64_t r = P.head_rows ? __ldg(&P.head_rows[b * N + cc]) : cc;
+                const float v = __ldg(&P.head_table[r * kHD + o]);
+                s.hp[idx] = v;
+                if (o < kH1) mxv = fmaxf(mxv, fabsf(v));
+            }
+            block_max_push(s.mx + 16 * FX_HP, mxv);
+        }
+        if (tid < kH1) s.b1s[tid] = __ldg(&P.b1[tid]);
+        if (tid < 32) s.ysS[tid] = tid < n ? int(P.sup_y[b * n + tid]) : 0;
+        float b0r[2][2];                                  // adapted linear0.bias at this thread's columns (warp-private)
+#pragma unroll
+        for (int j = 0; j < 2; ++j) {
+            b0r[j][0] = __ldg(&P.b0[hc + 8 * j]);
+            b0r[j][1] = __ldg(&P.b0[hc + 8 * j + 1]);
+        }
+        float Sr[MT][2][4];                               // S = sum of dZ0 so far at this thread's positions (fp32 master)
+#pragma unroll
+        for (int i = 0; i < MT; ++i)
+#pragma unroll
+            for (int j = 0; j < 2; ++j)
+#pragma unroll
+                for (int q = 0; q < 4; ++q) Sr[i][j][q] = 0.f;
+        uint32_t gate0 = 0u;                              // ReLU/dropout gates of H0 at this thread's 16 positions
+
+        // projected rows at this thread's accumulator positions, straight from `proj`
+        float2 ap[2][2][2];
+        auto h0_load = [&](const int64_t* rows, int tr, int mt) {
+#pragma unroll
+            for (int i = 0; i < 2; ++i)
+                if (i < mt)
+#pragma unroll
+                for (int hq = 0; hq < 2; ++hq) {
+                    const int r = 16 * i + g + 8 * hq;
+                    const int64_t row = r < tr ? __ldg(&rows[r]) : -1;
+#pragma unroll
+                    for (int j = 0; j < 2; ++j)
+                        ap[i][j][hq] = row >= 0 ? __ldg(reinterpret_cast<const float2*>(&P.proj[row * kH0 + hc + 8 * j]))
+                                                : make_float2(0.f, 0.f);
+                }
+        };
+        // H0 epilogue shared by support steps and query tiles: acc = raw G.S product (scaled) -> activations written as
+        // planes with the lagged exponent e_h0n; returns the gates.  mt: m tiles in use (support: MT, query: 2)
+        auto h0_finish = [&](float (&acc)[2][2][4], int mt, int r0, int tr, float gs, int pass) -> uint32_t {
+            const uint32_t dbase = drop ? dropout_base(c, task, pass, 0) : 0u;
+            const float sc = fumi_exp2i(e_h0n);
+            uint32_t gates = 0u;
+            float mxv = 0.f;
+#pragma unroll
+            for (int i = 0; i < 2; ++i)
+                if (i < mt)
+#pragma unroll
+                for (int j = 0; j < 2; ++j)
+#pragma unroll
+                    for (int hq = 0; hq < 2; ++hq) {
+                        const int r = 16 * i + g + 8 * hq, h = hc + 8 * j;
+                        const float z0 = ap[i][j][hq].x + b0r[j][0] - gs * acc[i][j][2 * hq];
+                        const float z1 = ap[i][j][hq].y + b0r[j][1] - gs * acc[i][j][2 * hq + 1];
+                        bool k0 = r < tr && z0 > 0.f, k1 = r < tr && z1 > 0.f;
+                        if (drop) {
+                            const uint32_t bits = dropout_bits(dbase, r0 + r, h);
+                            k0 = k0 && (bits & 0xFFFFu) >= thr;
+                            k1 = k1 && (bits >> 16) >= thr;
+                        }
+                        const float v0 = k0 ? z0 * dsc : 0.f, v1 = k1 ? z1 * dsc : 0.f;
+                        gates |= (uint32_t(k0) | (uint32_t(k1) << 1)) << (2 * (4 * i + 2 * j + hq));
+                        mxv = fmaxf(mxv, fmaxf(v0, v1));
+                        st_planes2(s.h0h, s.h0l, r * kHS + h, v0, v1, sc);
+                    }
+            block_max_push(s.mx + 16 * (FX_H0 + par_h0), mxv);
+            return gates;
+        };
+        // bookkeeping after the barrier that follows a production: the exponent just used becomes current, the observed
+        // max gives the next one
+#define FUMI_ADOPT(cur, next, par, slot_id)                                     \
+        do {                                                                    \
+            const float mx__ = slot_max(s.mx + 16 * ((slot_id) + (par)));       \
+            cur = next;                                                         \
+            bad = bad || plane_overflow(mx__, cur);                             \
+            if (mx__ > 0.f) next = fumi_plane_exp_t(__float_as_uint(mx__), kTarget); \
+            par ^= 1;                                                           \
+        } while (0)
+
+        // step 0's H0 has no G.S term: its values (and max) are known before the first barrier
+        float hv[2][2][4];
+#pragma unroll
+        for (int i = 0; i < 2; ++i)
+#pragma unroll
+            for (int j = 0; j < 2; ++j)
+#pragma unroll
+                for (int q = 0; q < 4; ++q) hv[i][j][q] = 0.f;
+        if (steps > 0) {
+            h0_load(P.sup_rows + b * n, n, MT);
+            const uint32_t dbase = drop ? dropout_base(c, task, 0, 0) : 0u;
+            float mxv = 0.f;
+#pragma unroll
+            for (int i = 0; i < MT; ++i)
+#pragma unroll
+                for (int j = 0; j < 2; ++j)
+#pragma unroll
+                    for (int hq = 0; hq < 2; ++hq) {
+                        const int r = 16 * i + g + 8 * hq, h = hc + 8 * j;
+                        const float z0 = ap[i][j][hq].x + b0r[j][0], z1 = ap[i][j][hq].y + b0r[j][1];
+                        bool k0 = r < n && z0 > 0.f, k1 = r < n && z1 > 0.f;
+                        if (drop) {
+                            const uint32_t bits = dropout_bits(dbase, r, h);
+                            k0 = k0 && (bits & 0xFFFFu) >= thr;
+                            k1 = k1 && (bits >> 16) >= thr;
+                        }
+                        hv[i][j][2 * hq] = k0 ? z0 * dsc : 0.f;
+                        hv[i][j][2 * hq + 1] = k1 ? z1 * dsc : 0.f;
+                        gate0 |= (uint32_t(k0) | (uint32_t(k1) << 1)) << (2 * (4 * i + 2 * j + hq));
+                        mxv = fmaxf(mxv, fmaxf(hv[i][j][2 * hq], hv[i][j][2 * hq + 1]));
+                    }
+            block_max_push(s.mx + 16 * FX_H0, mxv);
+        }
+        __syncthreads();                                  // P1: maxes of W1, G, hp, H0(step 0)
+        {
+            const float mw = slot_max(s.mx + 16 * FX_W1), mg = slot_max(s.mx + 16 * FX_GS), mh = slot_max(s.mx + 16 * FX_HP);
+            e_w1 = e_w1n = fumi_plane_exp_t(__float_as_uint(mw), kTarget);
+            e_gs = fumi_plane_exp_t(__float_as_uint(mg), kTarget);
+            e_gqn = e_gq = e_gs;                          // query Gram tiles: same magnitude class as the support block
+            // |dZ1| <= dsc * sum_c |dL_c| |hp_c| <= dsc * (2 / n) * max |hp|: bound for the first production
+            e_dz = e_dzn = fumi_plane_exp_t(__float_as_uint(fmaxf(mh * dsc * 2.f / float(n), 1e-30f)), kTarget);
+            par_w1 = 1;
+            if (steps > 0) {
+                const float m0 = slot_max(s.mx + 16 * FX_H0);
+                e_h0 = e_h0n = fumi_plane_exp_t(__float_as_uint(m0), kTarget);
+                par_h0 = 1;
+            }
+            const float sc = fumi_exp2i(e_w1);
+#pragma unroll
+            for (int q8 = 0; q8 < 4; ++q8) {              // 8 halves = 16 bytes per store
+                uint32_t ph[4], pl[4];
+#pragma unroll
+                for (int q = 0; q < 4; ++q) fumi_split2(w1v[8 * q8 + 2 * q] * sc, w1v[8 * q8 + 2 * q + 1] * sc, ph[q], pl[q]);
+                *reinterpret_cast<uint4*>(&s.w1h[col * kHW + half * 32 + 8 * q8]) = make_uint4(ph[0], ph[1], ph[2], ph[3]);
+                *reinterpret_cast<uint4*>(&s.w1l[col * kHW + half * 32 + 8 * q8]) = make_uint4(pl[0], pl[1], pl[2], pl[3]);
+            }
+            const float sg = fumi_exp2i(e_gs);
+#pragma unroll
+            for (int q = 0; q < 2; ++q) {
+                const int idx = tid + q * NT_, i = idx >> 5, j = idx & 31;
+                st_plane1(s.gsh, s.gsl, i * kHG + j, gv[q], sg);
+            }
+            if (steps > 0) {
+                const float sh0 = fumi_exp2i(e_h0);
+#pragma unroll
+                for (int i = 0; i < MT; ++i)
+#pragma unroll
+                    for (int j = 0; j < 2; ++j)
+#pragma unroll
+                        for (int hq = 0; hq < 2; ++hq)
+                            st_planes2(s.h0h, s.h0l, (16 * i + g + 8 * hq) * kHS + hc + 8 * j, hv[i][j][2 * hq],
+                                       hv[i][j][2 * hq + 1], sh0);
+            }
+        }
+        pc.mark(20);
+        float loss_sum = 0.f, corr_sum = 0.f;             // query loss / correct predictions of this warp's rows (lane 0)
+
+        // ------------------------------------------------------------------ row-per-warp pieces
+        // H1 of row i (lane owns units lane, lane + 32) from the Z1 partial sums, bias, ReLU, dropout
+        auto h1_row = [&](int i, int grow, int parts, int pass, float& h1a, float& h1b) {
+            float za = s.z1p[i * kS1 + lane] + s.b1s[lane], zb = s.z1p[i * kS1 + lane + 32] + s.b1s[lane + 32];
+            if (parts == 2) { za += s.z1p[(16 + i) * kS1 + lane]; zb += s.z1p[(16 + i) * kS1 + lane + 32]; }
+            bool ka = za > 0.f, kb = zb > 0.f;
+            if (drop) {
+                const uint32_t dbase = dropout_base(c, task, pass, 1);
+                ka = ka && dropout_keep_bits(dropout_bits(dbase, grow, lane), lane, thr);
+                kb = kb && dropout_keep_bits(dropout_bits(dbase, grow, lane + 32), lane + 32, thr);
+            }
+            h1a = ka ? za * dsc : 0.f;
+            h1b = kb ? zb * dsc : 0.f;
+        };
+        // logit of class `lane` (lanes >= N: 0)
+        auto logits_row = [&](float h1a, float h1b) -> float {
+            float lg = 0.f;
+#pragma unroll 1
+            for (int cc = 0; cc < N; ++cc) {
+                const float p = warp_sum(fmaf(h1a, s.hp[cc * kHD + lane], h1b * s.hp[cc * kHD + lane + 32]));
+                if (lane == cc) lg = p + s.hp[cc * kHD + kH1];
+            }
+            return lg;
+        };
+        // Z1 partial sums of the block-wide layer: warp (w >> 3, w & 7).  parts == 1: m tile w >> 3, all K;
+        // parts == 2 (16 rows): m tile 0, K half w >> 3.  Stored unscaled in z1p[(16 (w >> 3) + row)][o].
+        auto z1_gemm = [&](int parts, int mtiles) {
+            const int nt = w & 7, hi8 = w >> 3;
+            if (parts == 1 && hi8 >= mtiles) return;
+            float acc[1][1][4] = {{{0.f, 0.f, 0.f, 0.f}}};
+            const int mrow = parts == 1 ? 16 * hi8 : 0, k0 = parts == 1 ? 0 : 128 * hi8;
+            warp_gemm_f16x3<1, 1, false, false>(s.h0h + mrow * kHS + k0, s.h0l + mrow * kHS + k0, kHS, s.w1h + k0 * kHW + 8 * nt,
+                                                s.w1l + k0 * kHW + 8 * nt, kHW, parts == 1 ? kH0 : 128, acc);
+            const float inv = fumi_exp2i(-e_h0) * fumi_exp2i(-e_w1);
+            float* dst = s.z1p + (16 * hi8 + g) * kS1 + 8 * nt + 2 * t;
+            *reinterpret_cast<float2*>(dst) = make_float2(acc[0][0][0] * inv, acc[0][0][1] * inv);
+            *reinterpret_cast<float2*>(dst + 8 * kS1) = make_float2(acc[0][0][2] * inv, acc[0][0][3] * inv);
+        };
+
+        // ------------------------------------------------------------------ inner steps
+        for (int st = 0; st < steps; ++st) {
+            float* rec = slot ? slot + L.steps + int64_t(st) * L.per_step : nullptr;
+            __syncthreads();                              // B1: H0 planes, W1 planes, b1 / head of this step
+            if (st > 0) {
+                FUMI_ADOPT(e_h0, e_h0n, par_h0, FX_H0);
+                FUMI_ADOPT(e_w1, e_w1n, par_w1, FX_W1);
+            }
+            pc.mark(21);
+            z1_gemm(MT == 1 ? 2 : 1, MT);
+            __syncthreads();                              // B2: Z1 partial sums
+            pc.mark(22);
+            // ---- (c) one row per warp: H1, logits, softmax, dL, dZ1 (planes with the lagged exponent)
+            {
+                const float invn = 1.f / float(n), sc = fumi_exp2i(e_dzn);
+                float mxv = 0.f;
+#pragma unroll 1
+                for (int i = w; i < RS; i += 16) {
+                    if (i >= n) break;                    // warp-uniform; pad rows of the planes stay zero
+                    float h1a, h1b;
+                    h1_row(i, i, MT == 1 ? 2 : 1, st, h1a, h1b);
+                    s.h1t[i * kS1 + lane] = h1a;
+                    s.h1t[i * kS1 + lane + 32] = h1b;
+                    const float lg = logits_row(h1a, h1b);
+                    const float mxl = warp_max(lane < N ? lg : -3.0e38f);
+                    const float ex = lane < N ? expf(lg - mxl) : 0.f;
+                    const float sum = warp_sum(ex);
+                    const float dl = lane < N ? (ex * (1.f / sum) - (lane == s.ysS[i] ? 1.f : 0.f)) * invn : 0.f;
+                    if (lane < N) s.lt[i * kLS + lane] = dl;
+                    float da = 0.f, db = 0.f;
+#pragma unroll 1
+                    for (int cc = 0; cc < N; ++cc) {
+                        const float dlc = __shfl_sync(0xffffffffu, dl, cc);
+                        da = fmaf(dlc, s.hp[cc * kHD + lane], da);
+                        db = fmaf(dlc, s.hp[cc * kHD + lane + 32], db);
+                    }
+                    da = h1a > 0.f ? da * dsc : 0.f;
+                    db = h1b > 0.f ? db * dsc : 0.f;
+                    s.dz1t[i * kS1 + lane] = da;
+                    s.dz1t[i * kS1 + lane + 32] = db;
+                    st_plane1(s.dzh, s.dzl, i * kHW + lane, da, sc);
+                    st_plane1(s.dzh, s.dzl, i * kHW + lane + 32, db, sc);
+                    mxv = fmaxf(mxv, fmaxf(fabsf(da), fabsf(db)));
+                }
+                mxv = warp_max(mxv);
+                if (lane == 0) s.mx[16 * (FX_DZ + par_dz) + w] = mxv;
+            }
+            if (rec) {                                    // H0 planes of this step: stable between B1 and B3
+                for (int idx = tid; idx < n * 32; idx += NT_) {         // 16-byte pieces: 32 per row and plane
+                    const int i = idx >> 5, q = idx & 31;
+                    reinterpret_cast<uint4*>(rec + L.oH0h)[idx] = *reinterpret_cast<const uint4*>(&s.h0h[i * kHS + 8 * q]);
+                    reinterpret_cast<uint4*>(rec + L.oH0l)[idx] = *reinterpret_cast<const uint4*>(&s.h0l[i * kHS + 8 * q]);
+                }
+            }
+            __syncthreads();                              // B3: dZ1 planes, dL, H1
+            FUMI_ADOPT(e_dz, e_dzn, par_dz, FX_DZ);
+            pc.mark(23);
+            // ---- small updates by the first threads: head, b1 (their results are first read after the next B1)
+            for (int idx = tid; idx < N * kHD; idx += NT_) {
+                const int cc = idx / kHD, o = idx - cc * kHD;
+                float a = 0.f;
+#pragma unroll 2
+                for (int i = 0; i < n; ++i) a = fmaf(s.lt[i * kLS + cc], o < kH1 ? s.h1t[i * kS1 + o] : 1.f, a);
+                s.dhp[idx] = a;
+            }
+            // ---- (d) dZ0 = (dZ1 W1) * gate ; S += dZ0 ; b0 -= alpha colsum(dZ0): warp-local
+            {
+                float acc[MT][2][4];
+#pragma unroll
+                for (int i = 0; i < MT; ++i)
+#pragma unroll
+                    for (int j = 0; j < 2; ++j)
+#pragma unroll
+                        for (int q = 0; q < 4; ++q) acc[i][j][q] = 0.f;
+                warp_gemm_f16x3<MT, 2, false, true>(s.dzh, s.dzl, kHW, s.w1h + 16 * w * kHW, s.w1l + 16 * w * kHW, kHW, kH1, acc);
+                const float inv = fumi_exp2i(-e_dz) * fumi_exp2i(-e_w1) * dsc;
+                float colsum[2][2] = {{0.f, 0.f}, {0.f, 0.f}};
+                float mxv = 0.f;
+#pragma unroll
+                for (int i = 0; i < MT; ++i)
+#pragma unroll
+                    for (int j = 0; j < 2; ++j)
+#pragma unroll
+                        for (int hq = 0; hq < 2; ++hq) {
+                            const uint32_t gt = gate0 >> (2 * (4 * i + 2 * j + hq));
+                            const float d0 = (gt & 1u) ? acc[i][j][2 * hq] * inv : 0.f;
+                            const float d1 = (gt & 2u) ? acc[i][j][2 * hq + 1] * inv : 0.f;
+                            colsum[j][0] += d0;
+                            colsum[j][1] += d1;
+                            Sr[i][j][2 * hq] += d0;
+                            Sr[i][j][2 * hq + 1] += d1;
+                            mxv = fmaxf(mxv, fmaxf(fabsf(Sr[i][j][2 * hq]), fabsf(Sr[i][j][2 * hq + 1])));
+                        }
+                mxv = warp_max(mxv);
+                e_s = fumi_plane_exp(__float_as_uint(mxv));                   // exact: S is this warp's own operand
+                const float ssc = fumi_exp2i(e_s);
+#pragma unroll
+                for (int i = 0; i < MT; ++i)
+#pragma unroll
+                    for (int j = 0; j < 2; ++j)
+#pragma unroll
+                        for (int hq = 0; hq < 2; ++hq)
+                            st_planes2(s.sh, s.sl, (16 * i + g + 8 * hq) * kHS + hc + 8 * j, Sr[i][j][2 * hq], Sr[i][j][2 * hq + 1], ssc);
+#pragma unroll
+                for (int j = 0; j < 2; ++j)
+#pragma unroll
+                    for (int q = 0; q < 2; ++q) {
+                        float v = colsum[j][q];
+                        v += __shfl_xor_sync(0xffffffffu, v, 4);
+                        v += __shfl_xor_sync(0xffffffffu, v, 8);
+                        v += __shfl_xor_sync(0xffffffffu, v, 16);
+                        b0r[j][q] -= alpha * v;
+                    }
+            }
+            pc.mark(24);
+            // ---- (e) W1 -= alpha dZ1^T H0 on this warp's rows of W1^T, in place on the planes (lagged exponent)
+            {
+                float acc[1][8][4];
+#pragma unroll
+                for (int j = 0; j < 8; ++j)
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) acc[0][j][q] = 0.f;
+                warp_gemm_f16x3<1, 8, true, false>(s.h0h + 16 * w, s.h0l + 16 * w, kHS, s.dzh, s.dzl, kHW, RS, acc);
+                const float inv = alpha * fumi_exp2i(-e_h0) * fumi_exp2i(-e_dz);
+                const float winv = fumi_exp2i(-e_w1), wsc = fumi_exp2i(e_w1n);
+                float mxv = 0.f;
+#pragma unroll
+                for (int j = 0; j < 8; ++j)
+#pragma unroll
+                    for (int hq = 0; hq < 2; ++hq) {
+                        const int off = (16 * w + g + 8 * hq) * kHW + 8 * j + 2 * t;
+                        float o0, o1;
+                        ld_planes2(s.w1h, s.w1l, off, winv, o0, o1);
+                        o0 -= acc[0][j][2 * hq] * inv;
+                        o1 -= acc[0][j][2 * hq + 1] * inv;
+                        mxv = fmaxf(mxv, fmaxf(fabsf(o0), fabsf(o1)));
+                        st_planes2(s.w1h, s.w1l, off, o0, o1, wsc);
+                    }
+                block_max_push(s.mx + 16 * (FX_W1 + par_w1), mxv);
+            }
+            pc.mark(25);
+            // ---- step records (dZ1 planes, H1, dL, head before its update), then the head / b1 updates
+            if (rec) {
+                for (int idx = tid; idx < n * 8; idx += NT_) {          // 16-byte pieces: 8 per row and plane
+                    const int i = idx >> 3, q = idx & 7;
+                    reinterpret_cast<uint4*>(rec + L.oDZh)[idx] = *reinterpret_cast<const uint4*>(&s.dzh[i * kHW + 8 * q]);
+                    reinterpret_cast<uint4*>(rec + L.oDZl)[idx] = *reinterpret_cast<const uint4*>(&s.dzl[i * kHW + 8 * q]);
+                }
+                for (int idx = tid; idx < n * kH1; idx += NT_) rec[L.oH1 + idx] = s.h1t[(idx >> 6) * kS1 + (idx & 63)];
+                for (int idx = tid; idx < n * N; idx += NT_) {
+                    const int i = idx / N, cc = idx - i * N;
+                    rec[L.oDL + idx] = s.lt[i * kLS + cc];
+                }
+                if (tid == 0) {
+                    reinterpret_cast<int*>(rec + L.oEXP)[0] = e_h0;
+                    reinterpret_cast<int*>(rec + L.oEXP)[1] = e_dz;
+                }
+            }
+            for (int idx = tid; idx < N * kHD; idx += NT_) {            // the thread that computed dhp[idx] above
+                if (rec) rec[L.oHP + idx] = s.hp[idx];
+                s.hp[idx] -= alpha * s.dhp[idx];
+            }
+            if (tid < kH1) {
+                float db1 = 0.f;
+                for (int i = 0; i < n; ++i) db1 += s.dz1t[i * kS1 + tid];
+                s.b1s[tid] -= alpha * db1;
+            }
+            // ---- (a) of the next step: H0 = act(A + b0 - alpha G S), warp-local (S, b0 are this warp's own)
+            if (st + 1 < steps) {
+                float acc[2][2][4];
+#pragma unroll
+                for (int i = 0; i < 2; ++i)
+#pragma unroll
+                    for (int j = 0; j < 2; ++j)
+#pragma unroll
+                        for (int q = 0; q < 4; ++q) acc[i][j][q] = 0.f;
+                __syncwarp();                             // this warp's S planes are complete
+                warp_gemm_f16x3<MT, 2, false, false>(s.gsh, s.gsl, kHG, s.sh + 16 * w, s.sl + 16 * w, kHS, RS,
+                                                     reinterpret_cast<float(&)[MT][2][4]>(acc));
+                gate0 = h0_finish(acc, MT, 0, n, alpha * fumi_exp2i(-e_gs) * fumi_exp2i(-e_s), st + 1);
+            }
+            pc.mark(26);
+        }
+
+        // ------------------------------------------------------------------ query scoring, 32 rows per tile
+        // Tile t: [Z0q GEMM on this warp's columns -> H0q planes] B [Z1q partial sums; Gram planes of tile t+1] B
+        // [one row per warp: H1q, logits, softmax, loss, argmax].  The Gram rows of tile t+1 / t+2 and the projected
+        // rows of tile t+1 travel in registers.
+        const int64_t* qrows = P.qry_rows + b * m;
+        float qg[2];
+        auto q_load = [&](int r0) {
+            const int tr = min(32, m - r0);
+#pragma unroll
+            for (int q = 0; q < 2; ++q) {
+                const int idx = tid + q * NT_, i = idx >> 5, j = idx & 31;
+                qg[q] = (i < tr && j < n) ? __ldg(&P.gram[(b * int64_t(n + m) + n + r0 + i) * n + j]) : 0.f;
+            }
+        };
+        auto q_planes = [&](int buf) {                    // qg -> Gram planes of buffer `buf` (lagged exponent e_gqn)
+            const float sg = fumi_exp2i(e_gqn);
+#pragma unroll
+            for (int q = 0; q < 2; ++q) {
+                const int idx = tid + q * NT_, i = idx >> 5, j = idx & 31;
+                st_plane1(s.gqh + buf * 32 * kHG, s.gql + buf * 32 * kHG, i * kHG + j, qg[q], sg);
+            }
+            block_max_push(s.mx + 16 * (FX_GQ + par_gq), fmaxf(fabsf(qg[0]), fabsf(qg[1])));
+        };
+        q_load(0);
+        h0_load(qrows, min(32, m), 2);
+        if (steps == 0) {                                 // no H0 yet: bound |H0q| by dsc (max |A| + max |b0|) of tile 0
+            float mxv = 0.f;
+#pragma unroll
+            for (int i = 0; i < 2; ++i)
+#pragma unroll
+                for (int j = 0; j < 2; ++j)
+#pragma unroll
+                    for (int hq = 0; hq < 2; ++hq)
+                        mxv = fmaxf(mxv, fmaxf(fabsf(ap[i][j][hq].x + b0r[j][0]), fabsf(ap[i][j][hq].y + b0r[j][1])) * dsc);
+            block_max_push(s.mx + 16 * FX_H0, mxv);
+        }
+        q_planes(0);
+        __syncthreads();                                  // QB0: Gram planes of tile 0 (and the last step's W1 / head / b1)
+        if (steps > 0) FUMI_ADOPT(e_w1, e_w1n, par_w1, FX_W1);
+        else { e_h0n = fumi_plane_exp_t(__float_as_uint(fmaxf(slot_max(s.mx + 16 * FX_H0), 1e-30f)), kTarget); par_h0 = 1; }
+        FUMI_ADOPT(e_gq, e_gqn, par_gq, FX_GQ);
+        if (32 < m) q_load(32);
+        const float sinv = steps > 0 ? fumi_exp2i(-e_s) : 0.f;
+        int qtile = 0;
+        for (int r0 = 0; r0 < m; r0 += 32, ++qtile) {
+            const int tr = min(32, m - r0);
+            {
+                float acc[2][2][4];
+#pragma unroll
+                for (int i = 0; i < 2; ++i)
+#pragma unroll
+                    for (int j = 0; j < 2; ++j)
+#pragma unroll
+                        for (int q = 0; q < 4; ++q) acc[i][j][q] = 0.f;
+                const int buf = qtile & 1;
+                if (steps > 0)
+                    warp_gemm_f16x3<2, 2, false, false>(s.gqh + buf * 32 * kHG, s.gql + buf * 32 * kHG, kHG, s.sh + 16 * w,
+                                                        s.sl + 16 * w, kHS, RS, acc);
+                h0_finish(acc, 2, r0, tr, steps > 0 ? alpha * fumi_exp2i(-e_gq) * sinv : 0.f, steps);
+            }
+            if (r0 + 32 < m) h0_load(qrows + r0 + 32, min(32, m - r0 - 32), 2);      // next tile's rows, a tile ahead
+            __syncthreads();                              // QB1: H0q planes
+            FUMI_ADOPT(e_h0, e_h0n, par_h0, FX_H0);
+            pc.mark(28);
+            if (r0 + 32 < m) q_planes((qtile + 1) & 1);   // Gram planes of the next tile into the other buffer
+            if (slot) {
+                if (tid == 0) reinterpret_cast<int*>(slot + L.qEXP)[qtile] = e_h0;
+                for (int idx = tid; idx < tr * 32; idx += NT_) {
+                    const int i = idx >> 5, q = idx & 31;
+                    reinterpret_cast<uint4*>(slot + L.qH0h)[int64_t(r0) * 32 + idx] = *reinterpret_cast<const uint4*>(&s.h0h[i * kHS + 8 * q]);
+                    reinterpret_cast<uint4*>(slot + L.qH0l)[int64_t(r0) * 32 + idx] = *reinterpret_cast<const uint4*>(&s.h0l[i * kHS + 8 * q]);
+                }
+            }
+            z1_gemm(1, 2);
+            __syncthreads();                              // QB2: Z1q partial sums, next Gram planes
+            if (r0 + 32 < m) FUMI_ADOPT(e_gq, e_gqn, par_gq, FX_GQ);
+            if (r0 + 64 < m) q_load(r0 + 64);
+            pc.mark(29);
+#pragma unroll 1
+            for (int i = w; i < 32; i += 16) {
+                if (i >= tr) break;
+                float h1a, h1b;
+                h1_row(i, r0 + i, 1, steps, h1a, h1b);
+                const float lg = logits_row(h1a, h1b);
+                const int64_t q = b * m + r0 + i;
+                const int y = int(__ldg(&P.qry_y[q]));
+                const float mxl = warp_max(lane < N ? lg : -3.0e38f);
+                const float ex = lane < N ? expf(lg - mxl) : 0.f;
+                const float sum = warp_sum(ex);
+                if (lane < N) P.logits[q * N + lane] = lg;
+                if (slot) {
+                    slot[L.qH1 + int64_t(r0 + i) * kH1 + lane] = h1a;
+                    slot[L.qH1 + int64_t(r0 + i) * kH1 + lane + 32] = h1b;
+                    if (lane < N) slot[L.qLG + int64_t(r0 + i) * N + lane] = ex * (1.f / sum) - (lane == y ? 1.f : 0.f);
+                }
+                // argmax with ties to the lowest index (torch.max, fumi.py:180)
+                float bv = lane < N ? lg : -3.0e38f;
+                int bi = lane;
+#pragma unroll
+                for (int off = 16; off >= 1; off >>= 1) {
+                    const float ov = __shfl_xor_sync(0xffffffffu, bv, off);
+                    const int oi = __shfl_xor_sync(0xffffffffu, bi, off);
+                    if (ov > bv || (ov == bv && oi < bi)) { bv = ov; bi = oi; }
+                }
+                const float ly = __shfl_sync(0xffffffffu, lg, y);
+                if (lane == 0) {
+                    P.preds[q] = bi;
+                    loss_sum += (logf(sum) + mxl) - ly;
+                    corr_sum += bi == y ? 1.f : 0.f;
+                }
+            }
+            pc.mark(30);
+        }
+        // ------------------------------------------------------------------ task epilogue
+        if (lane == 0) { s.red[w] = loss_sum; s.red[16 + w] = corr_sum; }
+        if (slot) {                                       // adapted state (fp32): parity dumps, backward prologue
+            const float winv = fumi_exp2i(-e_w1);
+            for (int idx = tid; idx < kH0 * kH1 / 2; idx += NT_) {
+                const int k = idx >> 5, o = (idx & 31) * 2;
+                float a0, a1;
+                ld_planes2(s.w1h, s.w1l, k * kHW + o, winv, a0, a1);
+                *reinterpret_cast<float2*>(&slot[L.w1t + k * kH1 + o]) = make_float2(a0, a1);
+            }
+            if (g == 0) {
+#pragma unroll
+                for (int j = 0; j < 2; ++j)
+                    *reinterpret_cast<float2*>(&slot[L.b0 + hc + 8 * j]) = make_float2(b0r[j][0], b0r[j][1]);
+            }
+            if (tid < kH1) slot[L.b1 + tid] = s.b1s[tid];
+            for (int idx = tid; idx < N * kHD; idx += NT_) slot[L.head + idx] = s.hp[idx];
+#pragma unroll
+            for (int i = 0; i < MT; ++i)
+#pragma unroll
+                for (int j = 0; j < 2; ++j)
+#pragma unroll
+                    for (int hq = 0; hq < 2; ++hq) {
+                        const int r = 16 * i + g + 8 * hq;
+                        if (r < n)
+                            *reinterpret_cast<float2*>(&slot[L.S + int64_t(r) * kH0 + hc + 8 * j]) =
+                                make_float2(Sr[i][j][2 * hq], Sr[i][j][2 * hq + 1]);
+                    }
+        }
+        __syncthreads();
+        if (tid == 0) {
+            float ls = 0.f, cs = 0.f;
+            for (int q = 0; q < 16; ++q) { ls += s.red[q]; cs += s.red[16 + q]; }
+            P.task_loss[b] = bad ? __uint_as_float(0x7FC00000u) : ls / float(m);
+            P.task_acc[b] = cs / float(m);
+        }
+        pc.mark(33);
+    }
+#undef FUMI_ADOPT
+}
+
+size_t smem_v_bytes(int N) { SmemV t; return carve_v(nullptr, t, N); }
+
+}  // namespace
+
+bool episode_f16_supported(const fumi_episode_cfg& c) {
+    // both kernels size their head buffers by N; the backward's two W1-shaped plane pairs leave room for N <= 12
+    return c.num_support <= 32 && c.num_ways <= 12 && smem_v_bytes(c.num_ways) <= 227 * 1024;
+}
+
+int launch_episode_fwd_f16(const EpiParams& P, int grid, void* stream) {
+    const size_t smem = smem_v_bytes(P.cfg.num_ways);
+#ifndef FUMI_EMU
+#define FUMI_SMEM_ATTR(kern)                                                                                       \
+    do {                                                                                                            \
+        cudaError_t e__ = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem));       \
+        if (e__ != cudaSuccess) return fumi_cuda_fail(e__, "cudaFuncSetAttribute(episode_fwd_v2_kernel)");          \
+    } while (0)
+#else
+#define FUMI_SMEM_ATTR(kern) ((void)0)
+#endif
+    if (P.cfg.num_support <= 16) {
+        FUMI_SMEM_ATTR(episode_fwd_v2_kernel<1>);
+        FUMI_LAUNCH(episode_fwd_v2_kernel<1>, grid, kThreads16, smem, stream, P);
+    } else {
+        FUMI_SMEM_ATTR(episode_fwd_v2_kernel<2>);
+        FUMI_LAUNCH(episode_fwd_v2_kernel<2>, grid, kThreads16, smem, stream, P);
+    }
+#undef FUMI_SMEM_ATTR
+    FUMI_CHECK_LAUNCH("episode_fwd_v2_kernel");
+    return FUMI_OK;
+}
+
+}  // namespace fumi_epi

@@ -17,6 +17,18 @@
 
 #ifdef FUMI_EMU
 #include "cuda_emu.h"
+static inline void fumi_split2(float a, float b, uint32_t& hi, uint32_t& lo) {
+    const fumi_half ah = fumi_f2h(a), bh = fumi_f2h(b);
+    const fumi_half al = fumi_f2h(a - fumi_h2f(ah)), bl = fumi_f2h(b - fumi_h2f(bh));
+    hi = uint32_t(ah.bits) | (uint32_t(bh.bits) << 16);
+    lo = uint32_t(al.bits) | (uint32_t(bl.bits) << 16);
+}
+static inline void fumi_join2(uint32_t hi, uint32_t lo, float& a, float& b) {
+    a = fumi_h2f(fumi_half{uint16_t(hi & 0xFFFFu)}) + fumi_h2f(fumi_half{uint16_t(lo & 0xFFFFu)});
+    b = fumi_h2f(fumi_half{uint16_t(hi >> 16)}) + fumi_h2f(fumi_half{uint16_t(lo >> 16)});
+}
+static inline void fumi_cp_async16(void* smem_dst, const void* gmem_src) { std::memcpy(smem_dst, gmem_src, 16); }
+static inline void fumi_cp_async_wait() {}
 #else
 #include <cuda_fp16.h>
 // ---- fp16 plane primitives (see warp_gemm_f16x3 below) ------------------------------------------------------
@@ -53,6 +65,29 @@ __device__ __forceinline__ uint32_t fumi_tf32_hi(float x) {
     uint32_t h;
     asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(h) : "f"(x));
     return h;
+}
+// 16-byte asynchronous global -> shared copy (LDGSTS) and the wait for all copies of this thread
+__device__ __forceinline__ void fumi_cp_async16(void* smem_dst, const void* gmem_src) {
+    const uint32_t d = static_cast<uint32_t>(__cvta_generic_to_shared(smem_dst));
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d), "l"(gmem_src) : "memory");
+}
+__device__ __forceinline__ void fumi_cp_async_wait() {
+    asm volatile("cp.async.commit_group;\ncp.async.wait_group 0;" ::: "memory");
+}
+// (a, b) -> packed fp16 pairs hi = (fp16(a), fp16(b)) and lo = (fp16(a - hi.x), fp16(b - hi.y)): one F2FP per pair
+__device__ __forceinline__ void fumi_split2(float a, float b, uint32_t& hi, uint32_t& lo) {
+    const __half2 h = __floats2half2_rn(a, b);
+    const float2 hf = __half22float2(h);
+    const __half2 l = __floats2half2_rn(a - hf.x, b - hf.y);
+    hi = *reinterpret_cast<const uint32_t*>(&h);
+    lo = *reinterpret_cast<const uint32_t*>(&l);
+}
+// packed (hi, lo) pairs -> (a, b) = hi + lo  (unscaled)
+__device__ __forceinline__ void fumi_join2(uint32_t hi, uint32_t lo, float& a, float& b) {
+    const float2 hf = __half22float2(*reinterpret_cast<const __half2*>(&hi));
+    const float2 lf = __half22float2(*reinterpret_cast<const __half2*>(&lo));
+    a = hf.x + lf.x;
+    b = hf.y + lf.y;
 }
 #endif
 
@@ -257,6 +292,13 @@ __device__ __forceinline__ int fumi_plane_exp(uint32_t absmax_bits) {
     const int e = int(absmax_bits >> 23) - 126;              // |x| < 2^e  (0 and denormals: e <= -126)
     if (absmax_bits == 0u) return 0;
     const int s = 14 - e;
+    return s > 100 ? 100 : (s < -100 ? -100 : s);
+}
+// same with the tracked max landing in [2^(target-1), 2^target): planes written with a LAGGED exponent (the one
+// derived from the previous production of the same matrix) keep 16 - target binades of headroom before fp16 overflow
+__device__ __forceinline__ int fumi_plane_exp_t(uint32_t absmax_bits, int target) {
+    if (absmax_bits == 0u) return 0;
+    const int s = target - (int(absmax_bits >> 23) - 126);
     return s > 100 ? 100 : (s < -100 ? -100 : s);
 }
 __device__ __forceinline__ float fumi_exp2i(int s) { return __uint_as_float(uint32_t(127 + s) << 23); }   // 2^s, |s| <= 126

@@ -177,6 +177,15 @@ typedef struct {
     int64_t head;       /* [N,HD]   adapted head                             */
     int64_t steps;      /* start of the per-step activation records          */
     int64_t per_step;
+    /* per-step record, offsets relative to the record (4-byte words).  format 0: H0 [NK,H0] and H1 [NK,H1] as fp32.
+     * format 1 (NK <= 32, the tensor-core kernels): H1 fp32; H0 as the forward's fp16 operand planes -- hi and lo
+     * [NK,H0] halves with H0 = (hi + lo) * 2^-e, e = ((int32*)record)[rec_exp] -- which the backward copies straight
+     * into its tiles. */
+    int64_t format;
+    int64_t rec_h1;
+    int64_t rec_exp;    /* -1 in format 0 */
+    int64_t rec_h0_hi;  /* format 0: the fp32 H0 block */
+    int64_t rec_h0_lo;  /* -1 in format 0 */
 } fumi_stash_layout_t;
 int fumi_stash_layout(const fumi_episode_cfg* cfg, fumi_stash_layout_t* out /* HOST */);
 

@@ -124,6 +124,16 @@ static inline float __shfl_xor_sync(unsigned, float v, int lane_mask) {
     return r;
 }
 
+static inline int __shfl_xor_sync(unsigned, int v, int lane_mask) {
+    const int w = fumi_emu::t_threadIdx.x >> 5, lane = fumi_emu::t_threadIdx.x & 31;
+    fumi_emu::WarpXchg& x = fumi_emu::g_xchg[w];
+    x.a[lane][0] = uint32_t(v);
+    __syncwarp();
+    const int r = int(x.a[lane ^ lane_mask][0]);
+    __syncwarp();
+    return r;
+}
+
 static inline float __shfl_sync(unsigned, float v, int src_lane) {
     const int w = fumi_emu::t_threadIdx.x >> 5, lane = fumi_emu::t_threadIdx.x & 31;
     fumi_emu::WarpXchg& x = fumi_emu::g_xchg[w];

@@ -64,6 +64,19 @@ def make_fumi(g, bank, params, device, dropout=0.0):
     return _load(m, params, device)
 
 
+def step_gates(rec, lay, NK):
+    """(H0 > 0 [NK,256], H1 > 0 [NK,64]) of one step record of the stash (fumi_stash_layout): fp32 activations
+    (format 0) or, on the tensor-core path, H0 as the forward's fp16 hi/lo operand planes (format 1)."""
+    h1 = rec[lay.rec_h1:lay.rec_h1 + NK * 64].reshape(NK, 64)
+    if lay.format == 0:
+        h0 = rec[lay.rec_h0_hi:lay.rec_h0_hi + NK * 256].reshape(NK, 256)
+    else:
+        hi = rec[lay.rec_h0_hi:lay.rec_h0_hi + NK * 128].view(np.float16).reshape(NK, 256).astype(np.float32)
+        lo = rec[lay.rec_h0_lo:lay.rec_h0_lo + NK * 128].view(np.float16).reshape(NK, 256).astype(np.float32)
+        h0 = hi + lo                       # times 2^-e (e = rec.view(int32)[lay.rec_exp]): irrelevant for the sign
+    return h0 > 0, h1 > 0
+
+
 def check_adapted(res, g, eng, bank, N):
     """Adapted head / W1 / biases and the materialised W0 rows against the reference's."""
     lay = eng.stash_layout(res["cfg"])
@@ -253,8 +266,8 @@ def fumi_test_case(device, name, via="dict"):
     st = res["stash"].cpu().numpy().reshape(B, lay.per_task)
     gates = []
     for b in range(B):
-        recs = [st[b, lay.steps + s * lay.per_step:] for s in range(steps)]
-        gates.append([(r[:NK * 256].reshape(NK, 256) > 0, r[NK * 256:NK * 320].reshape(NK, 64) > 0) for r in recs])
+        recs = [st[b, lay.steps + s * lay.per_step:lay.steps + (s + 1) * lay.per_step] for s in range(steps)]
+        gates.append([step_gates(r, lay, NK) for r in recs])
     fb = flat_batch(g, bank, 5)
     o64 = episode_np.fumi_batch(params, fb, float(g["alpha"]), steps, dtype=np.float64, relu_gates=gates)
     logits = res["logits"].cpu().numpy()
