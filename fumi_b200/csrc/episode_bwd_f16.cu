@@ -25,14 +25,16 @@ struct SmemW {
     fumi_half *w1h, *w1l, *awh, *awl, *h0h, *h0l, *dzh, *dzl, *rzh, *rzl, *gsh, *gsl;
     fumi_half *h0bh, *h0bl, *bzh, *bzl, *gqh, *gql;       // query pass only: aliases of the a_W1 plane region
     float *h1t, *rzp, *lt, *rlt, *hp, *ahp, *rhp, *b1s, *ab1, *rb1, *mx;
-    long long* rows;
-    int* ys;
+    long long *rows, *srows;
+    int *ys, *sys;
 };
 __host__ __device__ inline size_t carve_w(char* base, SmemW& s, int N) {
     char* p = base;
     auto take = [&](size_t bytes) { char* r = p; p += (bytes + 15) & ~size_t(15); return r; };
     s.rows = reinterpret_cast<long long*>(take(32 * 8));
     s.ys = reinterpret_cast<int*>(take(32 * 4));
+    s.srows = reinterpret_cast<long long*>(take(32 * 8));
+    s.sys = reinterpret_cast<int*>(take(32 * 4));
     s.mx = reinterpret_cast<float*>(take(BX_COUNT * 16 * 4));
     // zero-filled once per kernel from here
     s.w1h = reinterpret_cast<fumi_half*>(take(kH0 * kHW * 2));  s.w1l = reinterpret_cast<fumi_half*>(take(kH0 * kHW * 2));
@@ -69,14 +71,15 @@ __device__ __forceinline__ uint32_t plane_gates2(const fumi_half* hi, const fumi
     return uint32_t((v & 0x7FFFu) != 0u) | (uint32_t((v & 0x7FFF0000u) != 0u) << 1);
 }
 
-template <int MT>
+// MT: 16-row tiles of the support set; kNC: compile-time class count (>= N; head buffers zero-padded to kNC rows)
+template <int MT, int kNC>
 __global__ void __launch_bounds__(kThreads16, 1) episode_bwd_v2_kernel(EpiParams P) {
     constexpr int RS = 16 * MT;
     constexpr int NT_ = kThreads16;
     FUMI_DYN_SMEM(float, smem_raw);
     const fumi_episode_cfg& c = P.cfg;
     SmemW s;
-    carve_w(reinterpret_cast<char*>(smem_raw), s, c.num_ways);
+    carve_w(reinterpret_cast<char*>(smem_raw), s, kNC);
     const int tid = threadIdx.x, w = tid >> 5, lane = tid & 31, g = lane >> 2, t = lane & 3;
     const int n = c.num_support, m = c.num_query, N = c.num_ways, steps = c.steps;
     const float alpha = c.step_size;
@@ -86,10 +89,11 @@ __global__ void __launch_bounds__(kThreads16, 1) episode_bwd_v2_kernel(EpiParams
     PhaseClock pc;
     pc.start(P.phase);
 
-    {
+    {   // planes (pads must be finite) and the dL tiles (columns N .. of inert classes must read as zero)
         uint32_t* z = reinterpret_cast<uint32_t*>(s.w1h);
         const int nz = int((reinterpret_cast<char*>(s.h1t) - reinterpret_cast<char*>(s.w1h)) / 4);
         for (int idx = tid; idx < nz; idx += NT_) z[idx] = 0u;
+        for (int idx = tid; idx < 32 * kLB; idx += NT_) s.lt[idx] = 0.f;
     }
     __syncthreads();
 
@@ -134,8 +138,8 @@ __global__ void __launch_bounds__(kThreads16, 1) episode_bwd_v2_kernel(EpiParams
         }
         {
             float mxv = 0.f;
-            for (int idx = tid; idx < N * kHD; idx += NT_) {
-                const float v = slot[L.head + idx];
+            for (int idx = tid; idx < kNC * kHD; idx += NT_) {
+                const float v = idx < N * kHD ? slot[L.head + idx] : 0.f;      // rows N .. kNC-1: inert classes
                 s.hp[idx] = v;
                 s.ahp[idx] = 0.f;
                 if (idx % kHD < kH1) mxv = fmaxf(mxv, fabsf(v));
@@ -143,6 +147,10 @@ __global__ void __launch_bounds__(kThreads16, 1) episode_bwd_v2_kernel(EpiParams
             block_max_push(s.mx + 16 * BX_HP, mxv);
         }
         if (tid < kH1) { s.b1s[tid] = slot[L.b1 + tid]; s.ab1[tid] = 0.f; }
+        if (tid < 32) {
+            s.srows[tid] = tid < n ? P.sup_rows[b * n + tid] : 0;
+            s.sys[tid] = tid < n ? int(P.sup_y[b * n + tid]) : 0;
+        }
         float aS[2][2][4];                                // adjoint of S at this thread's positions (rows x own columns)
         float wacc[8][4];                                 // adjoint of W1^T rows [16w, 16w+16): query pass sum, then per step
         float ab0r[2][2] = {{0.f, 0.f}, {0.f, 0.f}};      // adjoint of b0 at this thread's columns
@@ -257,14 +265,14 @@ __global__ void __launch_bounds__(kThreads16, 1) episode_bwd_v2_kernel(EpiParams
             {
                 const float scd = fumi_exp2i(e_dzn);
                 float mxv = 0.f;
-#pragma unroll 1
-                for (int i = w; i < 32; i += 16) {
+#pragma unroll
+                for (int rr = 0; rr < 2; ++rr) {
+                    const int i = w + 16 * rr;
                     float da = 0.f, db = 0.f;
                     if (i < tr) {
-                        const float dl = lane < N ? s.lt[i * kLB + lane] : 0.f;
-#pragma unroll 1
-                        for (int cc = 0; cc < N; ++cc) {
-                            const float dlc = __shfl_sync(0xffffffffu, dl, cc);
+#pragma unroll
+                        for (int cc = 0; cc < kNC; ++cc) {            // inert classes: zero head rows
+                            const float dlc = s.lt[i * kLB + cc];
                             da = fmaf(dlc, s.hp[cc * kHD + lane], da);
                             db = fmaf(dlc, s.hp[cc * kHD + lane + 32], db);
                         }
@@ -284,10 +292,17 @@ __global__ void __launch_bounds__(kThreads16, 1) episode_bwd_v2_kernel(EpiParams
             // a_head += dLq^T [H1q | 1] ; a_b1 += column sums of dZ1q   (first threads)
             for (int idx = tid; idx < N * kHD; idx += NT_) {
                 const int cc = idx / kHD, o = idx - cc * kHD;
-                float a = 0.f;
-#pragma unroll 2
-                for (int i = 0; i < tr; ++i) a = fmaf(s.lt[i * kLB + cc], o < kH1 ? s.h1t[i * kS1 + o] : 1.f, a);
-                s.ahp[idx] += a;
+                const float* hcol = o < kH1 ? s.h1t + o : nullptr;
+                float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+                int i = 0;
+                for (; i + 4 <= tr; i += 4) {
+                    a0 = fmaf(s.lt[i * kLB + cc], hcol ? hcol[i * kS1] : 1.f, a0);
+                    a1 = fmaf(s.lt[(i + 1) * kLB + cc], hcol ? hcol[(i + 1) * kS1] : 1.f, a1);
+                    a2 = fmaf(s.lt[(i + 2) * kLB + cc], hcol ? hcol[(i + 2) * kS1] : 1.f, a2);
+                    a3 = fmaf(s.lt[(i + 3) * kLB + cc], hcol ? hcol[(i + 3) * kS1] : 1.f, a3);
+                }
+                for (; i < tr; ++i) a0 = fmaf(s.lt[i * kLB + cc], hcol ? hcol[i * kS1] : 1.f, a0);
+                s.ahp[idx] += (a0 + a1) + (a2 + a3);
             }
             if (tid >= NT_ - kH1) {                       // the last two warps: the first ones carry the head sums
                 const int o = tid - (NT_ - kH1);
@@ -408,6 +423,11 @@ __global__ void __launch_bounds__(kThreads16, 1) episode_bwd_v2_kernel(EpiParams
         if (!c.first_order && steps > 0) {
             bool tt_first = true, rz_first = true;
             // step records -> shared memory: H0 planes of all rows into (h0 | tt) = h0h rows 0..31, dZ1 planes, head
+            // One step's records -> shared memory, issued a whole step ahead (cp.async; the small dL / head blocks travel in
+            // registers and are stored at the start of the step): H0 planes of all rows into (h0 | tt) = h0h rows 0..31,
+            // dZ1 planes, H1.
+            float dl_pref = 0.f, hp_pref[2] = {0.f, 0.f};
+            int ex_pref[2] = {0, 0};
             auto s_issue = [&](int st) {
                 const float* rec = slot + L.steps + int64_t(st) * L.per_step;
                 const uint4* sh = reinterpret_cast<const uint4*>(rec + L.oH0h);
@@ -434,41 +454,44 @@ __global__ void __launch_bounds__(kThreads16, 1) episode_bwd_v2_kernel(EpiParams
                         *reinterpret_cast<uint4*>(s.dzl + i * kHW + 8 * q) = make_uint4(0u, 0u, 0u, 0u);
                     }
                 }
-            };
-            // rows [r0, r0 + 16) of a step: H1, dL tiles, labels, rows; for the second tile also its H0 planes -> rows 0..15
-            auto t_issue = [&](int st, int r0, bool reload_h0) {
-                const float* rec = slot + L.steps + int64_t(st) * L.per_step;
-                const int tr = min(16, n - r0);
-                if (reload_h0) {
-                    const uint4* sh = reinterpret_cast<const uint4*>(rec + L.oH0h) + r0 * 32;
-                    const uint4* sl = reinterpret_cast<const uint4*>(rec + L.oH0l) + r0 * 32;
-                    for (int idx = tid; idx < 16 * 32; idx += NT_) {
-                        const int i = idx >> 5, q = idx & 31;
-                        if (i < tr) {
-                            fumi_cp_async16(s.h0h + i * kHS + 8 * q, sh + idx);
-                            fumi_cp_async16(s.h0l + i * kHS + 8 * q, sl + idx);
-                        } else {
-                            *reinterpret_cast<uint4*>(s.h0h + i * kHS + 8 * q) = make_uint4(0u, 0u, 0u, 0u);
-                            *reinterpret_cast<uint4*>(s.h0l + i * kHS + 8 * q) = make_uint4(0u, 0u, 0u, 0u);
-                        }
-                    }
+                const uint4* h1 = reinterpret_cast<const uint4*>(rec + L.oH1);
+                for (int idx = tid; idx < RS * 16; idx += NT_) {          // H1 [n][64] fp32: 16 pieces per row
+                    const int i = idx >> 4, q = idx & 15;
+                    if (i < n) fumi_cp_async16(s.h1t + i * kS1 + 4 * q, h1 + idx);
+                    else *reinterpret_cast<uint4*>(s.h1t + i * kS1 + 4 * q) = make_uint4(0u, 0u, 0u, 0u);
                 }
-                for (int idx = tid; idx < 16 * kH1; idx += NT_)
-                    s.h1t[(idx >> 6) * kS1 + (idx & 63)] = idx < tr * kH1 ? __ldg(&rec[L.oH1 + r0 * kH1 + idx]) : 0.f;
-                if (tid < 16 * N) s.lt[(tid / N) * kLB + (tid % N)] = tid < tr * N ? __ldg(&rec[L.oDL + r0 * N + tid]) : 0.f;
-                if (tid < 16) {
-                    s.rows[tid] = tid < tr ? P.sup_rows[b * n + r0 + tid] : 0;
-                    s.ys[tid] = tid < tr ? int(P.sup_y[b * n + r0 + tid]) : 0;
+                ex_pref[0] = __ldg(reinterpret_cast<const int*>(rec + L.oEXP));
+                ex_pref[1] = __ldg(reinterpret_cast<const int*>(rec + L.oEXP) + 1);
+                dl_pref = tid < n * N ? __ldg(&rec[L.oDL + tid]) : 0.f;
+#pragma unroll
+                for (int q = 0; q < 2; ++q) hp_pref[q] = tid + q * NT_ < N * kHD ? __ldg(&rec[L.oHP + tid + q * NT_]) : 0.f;
+            };
+            // second row tile of a step: its H0 planes (rows 16..31 of the records, L2-resident since s_issue) replace the
+            // first tile's in rows 0..15
+            auto t_reload = [&](int st) {
+                const float* rec = slot + L.steps + int64_t(st) * L.per_step;
+                const uint4* sh = reinterpret_cast<const uint4*>(rec + L.oH0h) + 16 * 32;
+                const uint4* sl = reinterpret_cast<const uint4*>(rec + L.oH0l) + 16 * 32;
+                for (int idx = tid; idx < 16 * 32; idx += NT_) {
+                    const int i = idx >> 5, q = idx & 31;
+                    if (i < n - 16) {
+                        fumi_cp_async16(s.h0h + i * kHS + 8 * q, sh + idx);
+                        fumi_cp_async16(s.h0l + i * kHS + 8 * q, sl + idx);
+                    } else {
+                        *reinterpret_cast<uint4*>(s.h0h + i * kHS + 8 * q) = make_uint4(0u, 0u, 0u, 0u);
+                        *reinterpret_cast<uint4*>(s.h0l + i * kHS + 8 * q) = make_uint4(0u, 0u, 0u, 0u);
+                    }
                 }
             };
             s_issue(steps - 1);
             for (int st = steps - 1; st >= 0; --st) {
-                const float* rec = slot + L.steps + int64_t(st) * L.per_step;
-                for (int idx = tid; idx < N * kHD; idx += NT_) { s.hp[idx] = rec[L.oHP + idx]; s.rhp[idx] = 0.f; }
+#pragma unroll
+                for (int q = 0; q < 2; ++q)
+                    if (tid + q * NT_ < N * kHD) { s.hp[tid + q * NT_] = hp_pref[q]; s.rhp[tid + q * NT_] = 0.f; }   // rows >= N stay 0
+                if (tid < n * N) s.lt[(tid / N) * kLB + (tid % N)] = dl_pref;
                 if (tid < kH1) s.rb1[tid] = 0.f;
-                e_h0 = reinterpret_cast<const int*>(rec + L.oEXP)[0];
-                const int e_dzs = reinterpret_cast<const int*>(rec + L.oEXP)[1];
-                t_issue(st, 0, false);
+                e_h0 = ex_pref[0];
+                const int e_dzs = ex_pref[1];
                 // both row tiles of a step see the adjoint of S as it was BEFORE the step: the second tile's rows are
                 // snapshotted here, the a_S updates of the first tile then go straight into aS
                 float aS1[2][4];
@@ -516,7 +539,7 @@ __global__ void __launch_bounds__(kThreads16, 1) episode_bwd_v2_kernel(EpiParams
                 for (int r0 = 0; r0 < n; r0 += 16) {
                     const int tr = min(16, n - r0), ti = r0 >> 4;
                     if (r0 > 0) {                          // second tile: its H0 planes replace the first tile's
-                        t_issue(st, r0, true);
+                        t_reload(st);
                         fumi_cp_async_wait();
                         __syncthreads();
                     }
@@ -603,31 +626,42 @@ __global__ void __launch_bounds__(kThreads16, 1) episode_bwd_v2_kernel(EpiParams
                     {
                         const int i = w;
                         const bool arow = i < tr;
-                        const float h10 = s.h1t[i * kS1 + lane], h11 = s.h1t[i * kS1 + lane + 32];
+                        const float h10 = s.h1t[(r0 + i) * kS1 + lane], h11 = s.h1t[(r0 + i) * kS1 + lane + 32];
                         float rd0 = s.rzp[i * kS1 + lane] + s.rzp[(16 + i) * kS1 + lane] - alpha * s.ab1[lane];
                         float rd1 = s.rzp[i * kS1 + lane + 32] + s.rzp[(16 + i) * kS1 + lane + 32] - alpha * s.ab1[lane + 32];
                         rd0 = (arow && h10 > 0.f) ? rd0 * sc : 0.f;           // r_dH1
                         rd1 = (arow && h11 > 0.f) ? rd1 * sc : 0.f;
-                        float rdl = 0.f, ra0 = 0.f, ra1 = 0.f;
-#pragma unroll 1
-                        for (int cc = 0; cc < N; ++cc) {
+                        // r_dL of every class in every lane: N partial sums, one interleaved butterfly
+                        float rdl[kNC];
+#pragma unroll
+                        for (int cc = 0; cc < kNC; ++cc) {
                             const float* wh = &s.hp[cc * kHD];
                             const float* ah = &s.ahp[cc * kHD];
-                            const float a = warp_sum(fmaf(rd0, wh[lane], rd1 * wh[lane + 32]) -
-                                                     alpha * fmaf(h10, ah[lane], h11 * ah[lane + 32]));
-                            if (lane == cc) rdl = a - alpha * ah[kH1];
-                            const float dl = s.lt[i * kLB + cc];
-                            ra0 = fmaf(dl, -alpha * ah[lane], ra0);
-                            ra1 = fmaf(dl, -alpha * ah[lane + 32], ra1);
+                            rdl[cc] = fmaf(rd0, wh[lane], rd1 * wh[lane + 32]) - alpha * fmaf(h10, ah[lane], h11 * ah[lane + 32]);
                         }
-                        const float pl_ = (arow && lane < N) ? s.lt[i * kLB + lane] * float(n) + (lane == s.ys[i] ? 1.f : 0.f) : 0.f;
-                        const float dot = warp_sum(pl_ * rdl);
-                        const float rl = pl_ * (rdl - dot) / float(n);
-#pragma unroll 1
-                        for (int cc = 0; cc < N; ++cc) {
-                            const float rlc = __shfl_sync(0xffffffffu, rl, cc);
-                            ra0 = fmaf(rlc, s.hp[cc * kHD + lane], ra0);
-                            ra1 = fmaf(rlc, s.hp[cc * kHD + lane + 32], ra1);
+#pragma unroll
+                        for (int off = 16; off >= 1; off >>= 1)
+#pragma unroll
+                            for (int cc = 0; cc < kNC; ++cc) rdl[cc] += __shfl_xor_sync(0xffffffffu, rdl[cc], off);
+                        const int y = s.sys[r0 + i];
+                        const float fn = float(n), invn = 1.f / fn;
+                        float dlr[kNC];                    // dL of the row (zero for inert classes and pad rows)
+                        float dot = 0.f;                   // <P, r_dL> with P = softmax = n dL + onehot
+#pragma unroll
+                        for (int cc = 0; cc < kNC; ++cc) {
+                            dlr[cc] = (arow && cc < N) ? s.lt[(r0 + i) * kLB + cc] : 0.f;
+                            rdl[cc] -= alpha * s.ahp[cc * kHD + kH1];
+                            const float pc_ = arow ? fmaf(dlr[cc], fn, cc == y ? 1.f : 0.f) : 0.f;
+                            dot = fmaf(pc_, rdl[cc], dot);
+                        }
+                        float ra0 = 0.f, ra1 = 0.f, rl = 0.f;
+#pragma unroll
+                        for (int cc = 0; cc < kNC; ++cc) {
+                            const float pc_ = arow ? fmaf(dlr[cc], fn, cc == y ? 1.f : 0.f) : 0.f;
+                            const float rlc = pc_ * (rdl[cc] - dot) * invn;                 // r_L of class cc
+                            if (lane == cc) rl = rlc;
+                            ra0 = fmaf(dlr[cc], -alpha * s.ahp[cc * kHD + lane], fmaf(rlc, s.hp[cc * kHD + lane], ra0));
+                            ra1 = fmaf(dlr[cc], -alpha * s.ahp[cc * kHD + lane + 32], fmaf(rlc, s.hp[cc * kHD + lane + 32], ra1));
                         }
                         if (lane < N) s.rlt[i * kLB + lane] = arow ? rl : 0.f;
                         s.rzp[i * kS1 + lane] = rd0;                           // r_dH1 for the head sums
@@ -651,14 +685,19 @@ __global__ void __launch_bounds__(kThreads16, 1) episode_bwd_v2_kernel(EpiParams
                     // ---- cross-row sums (first threads): r_head += dL^T r_dH1 + r_L^T [H1 | 1] ;  r_b1 += sum r_Z1
                     for (int idx = tid; idx < N * kHD; idx += NT_) {
                         const int cc = idx / kHD, o = idx - cc * kHD;
-                        float a = 0.f;
+                        float a0 = 0.f, a1 = 0.f;          // two independent chains over the rows
                         if (o < kH1) {
-                            for (int i = 0; i < tr; ++i)
-                                a = fmaf(s.lt[i * kLB + cc], s.rzp[i * kS1 + o], fmaf(s.rlt[i * kLB + cc], s.h1t[i * kS1 + o], a));
+                            int i = 0;
+                            for (; i + 2 <= tr; i += 2) {
+                                a0 = fmaf(s.lt[(r0 + i) * kLB + cc], s.rzp[i * kS1 + o], fmaf(s.rlt[i * kLB + cc], s.h1t[(r0 + i) * kS1 + o], a0));
+                                a1 = fmaf(s.lt[(r0 + i + 1) * kLB + cc], s.rzp[(i + 1) * kS1 + o],
+                                          fmaf(s.rlt[(i + 1) * kLB + cc], s.h1t[(r0 + i + 1) * kS1 + o], a1));
+                            }
+                            if (i < tr) a0 = fmaf(s.lt[(r0 + i) * kLB + cc], s.rzp[i * kS1 + o], fmaf(s.rlt[i * kLB + cc], s.h1t[(r0 + i) * kS1 + o], a0));
                         } else {
-                            for (int i = 0; i < tr; ++i) a += s.rlt[i * kLB + cc];
+                            for (int i = 0; i < tr; ++i) a0 += s.rlt[i * kLB + cc];
                         }
-                        s.rhp[idx] += a;
+                        s.rhp[idx] += a0 + a1;
                     }
                     if (tid >= NT_ - kH1) {
                         const int o = tid - (NT_ - kH1);
@@ -702,7 +741,7 @@ __global__ void __launch_bounds__(kThreads16, 1) episode_bwd_v2_kernel(EpiParams
                                 colsum[j][0] += d0;
                                 colsum[j][1] += d1;
                                 mxv = fmaxf(mxv, fmaxf(fabsf(d0), fabsf(d1)));
-                                if (r < tr) atomic_add2(&P.d_proj[s.rows[r] * kH0 + h], d0, d1);
+                                if (r < tr) atomic_add2(&P.d_proj[s.srows[r0 + r] * kH0 + h], d0, d1);
                             }
 #pragma unroll
                         for (int j = 0; j < 2; ++j)
@@ -813,7 +852,8 @@ size_t smem_w_bytes(int N) { SmemW t; return carve_w(nullptr, t, N); }
 }  // namespace
 
 int launch_episode_bwd_f16(const EpiParams& P, int grid, void* stream) {
-    const size_t smem = smem_w_bytes(P.cfg.num_ways);
+    const int nc = P.cfg.num_ways <= 5 ? 5 : (P.cfg.num_ways <= 8 ? 8 : 12);
+    const size_t smem = smem_w_bytes(nc);
     if (smem > 227 * 1024) {
         fumi_set_error("episode backward: shared-memory budget exceeded for this num_ways");
         return FUMI_ERR_UNSUPPORTED;
@@ -827,13 +867,17 @@ int launch_episode_bwd_f16(const EpiParams& P, int grid, void* stream) {
 #else
 #define FUMI_SMEM_ATTR(kern) ((void)0)
 #endif
+#define FUMI_BWD_LAUNCH(MT_, NC_)                                                   \
+    do {                                                                            \
+        FUMI_SMEM_ATTR((episode_bwd_v2_kernel<MT_, NC_>));                          \
+        FUMI_LAUNCH((episode_bwd_v2_kernel<MT_, NC_>), grid, kThreads16, smem, stream, P); \
+    } while (0)
     if (P.cfg.num_support <= 16) {
-        FUMI_SMEM_ATTR(episode_bwd_v2_kernel<1>);
-        FUMI_LAUNCH(episode_bwd_v2_kernel<1>, grid, kThreads16, smem, stream, P);
+        if (nc == 5) FUMI_BWD_LAUNCH(1, 5); else if (nc == 8) FUMI_BWD_LAUNCH(1, 8); else FUMI_BWD_LAUNCH(1, 12);
     } else {
-        FUMI_SMEM_ATTR(episode_bwd_v2_kernel<2>);
-        FUMI_LAUNCH(episode_bwd_v2_kernel<2>, grid, kThreads16, smem, stream, P);
+        if (nc == 5) FUMI_BWD_LAUNCH(2, 5); else if (nc == 8) FUMI_BWD_LAUNCH(2, 8); else FUMI_BWD_LAUNCH(2, 12);
     }
+#undef FUMI_BWD_LAUNCH
 #undef FUMI_SMEM_ATTR
     FUMI_CHECK_LAUNCH("episode_bwd_v2_kernel");
     return FUMI_OK;

@@ -25,7 +25,7 @@
 namespace fumi_epi {
 namespace {
 
-enum { FX_W1 = 0, FX_H0 = 2, FX_DZ = 4, FX_GQ = 6, FX_GS = 8, FX_HP = 9, FX_COUNT = 10 };   // x 16 floats (two parities)
+enum { FX_W1 = 0, FX_H0 = 2, FX_DZ = 4, FX_GQ = 6, FX_GS = 8, FX_HP = 9, FX_COUNT = 10 };   // FX_W1 + 1 unused   // x 16 floats (two parities)
 
 struct SmemV {
     fumi_half *w1h, *w1l, *sh, *sl, *h0h, *h0l, *dzh, *dzl, *gsh, *gsl, *gqh, *gql;
@@ -37,7 +37,7 @@ __host__ __device__ inline size_t carve_v(char* base, SmemV& s, int N) {
     auto take = [&](size_t bytes) { char* r = p; p += (bytes + 15) & ~size_t(15); return r; };
     s.ysS = reinterpret_cast<int*>(take(32 * 4));
     s.mx = reinterpret_cast<float*>(take(FX_COUNT * 16 * 4));
-    s.red = reinterpret_cast<float*>(take(2 * 16 * 4));
+    s.red = reinterpret_cast<float*>(take(3 * 16 * 4));
     // zero-filled once per kernel from here (plane pads must be finite)
     s.w1h = reinterpret_cast<fumi_half*>(take(kH0 * kHW * 2));  s.w1l = reinterpret_cast<fumi_half*>(take(kH0 * kHW * 2));
     s.sh = reinterpret_cast<fumi_half*>(take(32 * kHS * 2));    s.sl = reinterpret_cast<fumi_half*>(take(32 * kHS * 2));
@@ -55,14 +55,16 @@ __host__ __device__ inline size_t carve_v(char* base, SmemV& s, int N) {
     return size_t(p - base);
 }
 
-template <int MT>
+// MT: 16-row tiles of the support set (NK <= 16 MT); kNC: compile-time class count (>= N; the head buffer is zero-padded
+// to kNC rows so that the per-class loops carry no guards)
+template <int MT, int kNC>
 __global__ void __launch_bounds__(kThreads16, 1) episode_fwd_v2_kernel(EpiParams P) {
     constexpr int RS = 16 * MT;
     constexpr int NT_ = kThreads16;
     FUMI_DYN_SMEM(float, smem_raw);
     const fumi_episode_cfg& c = P.cfg;
     SmemV s;
-    const size_t smem_total = carve_v(reinterpret_cast<char*>(smem_raw), s, c.num_ways);
+    const size_t smem_total = carve_v(reinterpret_cast<char*>(smem_raw), s, kNC);
     const int tid = threadIdx.x, w = tid >> 5, lane = tid & 31, g = lane >> 2, t = lane & 3;
     const int n = c.num_support, m = c.num_query, N = c.num_ways, steps = c.steps;
     const float alpha = c.step_size;
@@ -87,19 +89,22 @@ __global__ void __launch_bounds__(kThreads16, 1) episode_fwd_v2_kernel(EpiParams
         float* slot = P.save ? P.stash + b * P.slot_floats : nullptr;
         bool bad = false;                                 // a lagged plane exponent overflowed fp16
         int e_w1, e_h0 = 0, e_dz, e_gs, e_gq, e_s = 0;
-        int e_h0n = 0, e_dzn = 0, e_w1n = 0, e_gqn = 0;   // exponents for the NEXT production (from the last observed max)
-        int par_h0 = 0, par_dz = 0, par_w1 = 0, par_gq = 0;
+        int e_h0n = 0, e_dzn = 0, e_gqn = 0;              // exponents for the NEXT production (from the last observed max)
+        int par_h0 = 0, par_dz = 0, par_gq = 0;
 
         // ------------------------------------------------------------------ prologue
-        float w1v[32];                                    // W1[o][h], h = tid & 255, o in [32 half, 32 half + 32)
-        const int col = tid & 255, half = tid >> 8;
+        // fp32 master of this warp's 16 rows of W1^T at the thread's accumulator positions (the layout of the W1 update
+        // GEMM), kept pre-multiplied by the plane scale 2^e_w1: the update is an FFMA and the planes are re-split from it
+        float w1m[8][4];
         {
             float mxv = 0.f;
 #pragma unroll
-            for (int q = 0; q < 32; ++q) {
-                w1v[q] = __ldg(&P.w1[(half * 32 + q) * kH0 + col]);
-                mxv = fmaxf(mxv, fabsf(w1v[q]));
-            }
+            for (int j = 0; j < 8; ++j)
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    w1m[j][q] = __ldg(&P.w1[(8 * j + 2 * t + (q & 1)) * kH0 + 16 * w + g + 8 * (q >> 1)]);
+                    mxv = fmaxf(mxv, fabsf(w1m[j][q]));
+                }
             block_max_push(s.mx + 16 * FX_W1, mxv);
         }
         float gv[2];                                      // support Gram block
@@ -115,10 +120,13 @@ __global__ void __launch_bounds__(kThreads16, 1) episode_fwd_v2_kernel(EpiParams
         }
         {
             float mxv = 0.f;
-            for (int idx = tid; idx < N * kHD; idx += NT_) {
+            for (int idx = tid; idx < kNC * kHD; idx += NT_) {
                 const int cc = idx / kHD, o = idx - cc * kHD;
-                const int64_t r = P.head_rows ? __ldg(&P.head_rows[b * N + cc]) : cc;
-                const float v = __ldg(&P.head_table[r * kHD + o]);
+                float v = 0.f;                            // rows N .. kNC-1 stay zero (inert classes)
+                if (cc < N) {
+                    const int64_t r = P.head_rows ? __ldg(&P.head_rows[b * N + cc]) : cc;
+                    v = __ldg(&P.head_table[r * kHD + o]);
+                }
                 s.hp[idx] = v;
                 if (o < kH1) mxv = fmaxf(mxv, fabsf(v));
             }
@@ -143,20 +151,30 @@ __global__ void __launch_bounds__(kThreads16, 1) episode_fwd_v2_kernel(EpiParams
 
         // projected rows at this thread's accumulator positions, straight from `proj`
         float2 ap[2][2][2];
-        auto h0_load = [&](const int64_t* rows, int tr, int mt) {
+        // (row ids travel in registers: the dependent index load is off the critical path)
+        auto h0_rows = [&](const int64_t* rows, int tr, int (&rid)[2][2]) {
+#pragma unroll
+            for (int i = 0; i < 2; ++i)
+#pragma unroll
+                for (int hq = 0; hq < 2; ++hq) {
+                    const int r = 16 * i + g + 8 * hq;
+                    rid[i][hq] = r < tr ? int(__ldg(&rows[r])) : -1;
+                }
+        };
+        auto h0_load = [&](const int (&rid)[2][2], int mt) {
 #pragma unroll
             for (int i = 0; i < 2; ++i)
                 if (i < mt)
 #pragma unroll
-                for (int hq = 0; hq < 2; ++hq) {
-                    const int r = 16 * i + g + 8 * hq;
-                    const int64_t row = r < tr ? __ldg(&rows[r]) : -1;
+                for (int hq = 0; hq < 2; ++hq)
 #pragma unroll
                     for (int j = 0; j < 2; ++j)
-                        ap[i][j][hq] = row >= 0 ? __ldg(reinterpret_cast<const float2*>(&P.proj[row * kH0 + hc + 8 * j]))
-                                                : make_float2(0.f, 0.f);
-                }
+                        ap[i][j][hq] = rid[i][hq] >= 0
+                                           ? __ldg(reinterpret_cast<const float2*>(&P.proj[int64_t(rid[i][hq]) * kH0 + hc + 8 * j]))
+                                           : make_float2(0.f, 0.f);
         };
+        int srow[2][2];
+        h0_rows(P.sup_rows + b * n, n, srow);
         // H0 epilogue shared by support steps and query tiles: acc = raw G.S product (scaled) -> activations written as
         // planes with the lagged exponent e_h0n; returns the gates.  mt: m tiles in use (support: MT, query: 2)
         auto h0_finish = [&](float (&acc)[2][2][4], int mt, int r0, int tr, float gs, int pass) -> uint32_t {
@@ -208,7 +226,7 @@ __global__ void __launch_bounds__(kThreads16, 1) episode_fwd_v2_kernel(EpiParams
 #pragma unroll
                 for (int q = 0; q < 4; ++q) hv[i][j][q] = 0.f;
         if (steps > 0) {
-            h0_load(P.sup_rows + b * n, n, MT);
+            h0_load(srow, MT);
             const uint32_t dbase = drop ? dropout_base(c, task, 0, 0) : 0u;
             float mxv = 0.f;
 #pragma unroll
@@ -235,12 +253,11 @@ __global__ void __launch_bounds__(kThreads16, 1) episode_fwd_v2_kernel(EpiParams
         __syncthreads();                                  // P1: maxes of W1, G, hp, H0(step 0)
         {
             const float mw = slot_max(s.mx + 16 * FX_W1), mg = slot_max(s.mx + 16 * FX_GS), mh = slot_max(s.mx + 16 * FX_HP);
-            e_w1 = e_w1n = fumi_plane_exp_t(__float_as_uint(mw), kTarget);
+            e_w1 = fumi_plane_exp_t(__float_as_uint(mw), kTarget);    // fixed for the task: 8 binades of headroom
             e_gs = fumi_plane_exp_t(__float_as_uint(mg), kTarget);
             e_gqn = e_gq = e_gs;                          // query Gram tiles: same magnitude class as the support block
             // |dZ1| <= dsc * sum_c |dL_c| |hp_c| <= dsc * (2 / n) * max |hp|: bound for the first production
             e_dz = e_dzn = fumi_plane_exp_t(__float_as_uint(fmaxf(mh * dsc * 2.f / float(n), 1e-30f)), kTarget);
-            par_w1 = 1;
             if (steps > 0) {
                 const float m0 = slot_max(s.mx + 16 * FX_H0);
                 e_h0 = e_h0n = fumi_plane_exp_t(__float_as_uint(m0), kTarget);
@@ -248,13 +265,13 @@ __global__ void __launch_bounds__(kThreads16, 1) episode_fwd_v2_kernel(EpiParams
             }
             const float sc = fumi_exp2i(e_w1);
 #pragma unroll
-            for (int q8 = 0; q8 < 4; ++q8) {              // 8 halves = 16 bytes per store
-                uint32_t ph[4], pl[4];
+            for (int j = 0; j < 8; ++j)
 #pragma unroll
-                for (int q = 0; q < 4; ++q) fumi_split2(w1v[8 * q8 + 2 * q] * sc, w1v[8 * q8 + 2 * q + 1] * sc, ph[q], pl[q]);
-                *reinterpret_cast<uint4*>(&s.w1h[col * kHW + half * 32 + 8 * q8]) = make_uint4(ph[0], ph[1], ph[2], ph[3]);
-                *reinterpret_cast<uint4*>(&s.w1l[col * kHW + half * 32 + 8 * q8]) = make_uint4(pl[0], pl[1], pl[2], pl[3]);
-            }
+                for (int hq = 0; hq < 2; ++hq) {
+                    w1m[j][2 * hq] *= sc;
+                    w1m[j][2 * hq + 1] *= sc;
+                    st_planes2(s.w1h, s.w1l, (16 * w + g + 8 * hq) * kHW + 8 * j + 2 * t, w1m[j][2 * hq], w1m[j][2 * hq + 1], 1.f);
+                }
             const float sg = fumi_exp2i(e_gs);
 #pragma unroll
             for (int q = 0; q < 2; ++q) {
@@ -290,15 +307,17 @@ __global__ void __launch_bounds__(kThreads16, 1) episode_fwd_v2_kernel(EpiParams
             h1a = ka ? za * dsc : 0.f;
             h1b = kb ? zb * dsc : 0.f;
         };
-        // logit of class `lane` (lanes >= N: 0)
-        auto logits_row = [&](float h1a, float h1b) -> float {
-            float lg = 0.f;
-#pragma unroll 1
-            for (int cc = 0; cc < N; ++cc) {
-                const float p = warp_sum(fmaf(h1a, s.hp[cc * kHD + lane], h1b * s.hp[cc * kHD + lane + 32]));
-                if (lane == cc) lg = p + s.hp[cc * kHD + kH1];
-            }
-            return lg;
+        // all N logits of the row in every lane's registers: N partial dot products, then ONE interleaved butterfly
+        // (independent shuffle chains; softmax / argmax / dZ1 then need no further exchange)
+        auto logits_row = [&](float h1a, float h1b, float (&lg)[kNC]) {
+#pragma unroll
+            for (int cc = 0; cc < kNC; ++cc) lg[cc] = fmaf(h1a, s.hp[cc * kHD + lane], h1b * s.hp[cc * kHD + lane + 32]);
+#pragma unroll
+            for (int off = 16; off >= 1; off >>= 1)
+#pragma unroll
+                for (int cc = 0; cc < kNC; ++cc) lg[cc] += __shfl_xor_sync(0xffffffffu, lg[cc], off);
+#pragma unroll
+            for (int cc = 0; cc < kNC; ++cc) lg[cc] = cc < N ? lg[cc] + s.hp[cc * kHD + kH1] : -3.0e38f;   // inert classes
         };
         // Z1 partial sums of the block-wide layer: warp (w >> 3, w & 7).  parts == 1: m tile w >> 3, all K;
         // parts == 2 (16 rows): m tile 0, K half w >> 3.  Stored unscaled in z1p[(16 (w >> 3) + row)][o].
@@ -319,49 +338,61 @@ __global__ void __launch_bounds__(kThreads16, 1) episode_fwd_v2_kernel(EpiParams
         for (int st = 0; st < steps; ++st) {
             float* rec = slot ? slot + L.steps + int64_t(st) * L.per_step : nullptr;
             __syncthreads();                              // B1: H0 planes, W1 planes, b1 / head of this step
-            if (st > 0) {
-                FUMI_ADOPT(e_h0, e_h0n, par_h0, FX_H0);
-                FUMI_ADOPT(e_w1, e_w1n, par_w1, FX_W1);
-            }
+            if (st > 0) FUMI_ADOPT(e_h0, e_h0n, par_h0, FX_H0);
             pc.mark(21);
             z1_gemm(MT == 1 ? 2 : 1, MT);
-            __syncthreads();                              // B2: Z1 partial sums
             pc.mark(22);
+            __syncthreads();                              // B2: Z1 partial sums
+            pc.mark(40);
             // ---- (c) one row per warp: H1, logits, softmax, dL, dZ1 (planes with the lagged exponent)
             {
                 const float invn = 1.f / float(n), sc = fumi_exp2i(e_dzn);
                 float mxv = 0.f;
-#pragma unroll 1
-                for (int i = w; i < RS; i += 16) {
-                    if (i >= n) break;                    // warp-uniform; pad rows of the planes stay zero
+                // the warp's rows (w, w + 16) are processed unconditionally and fully unrolled -- two independent
+                // instruction streams for the scheduler to interleave; pad rows (i >= n) only skip their stores
+#pragma unroll
+                for (int rr = 0; rr < MT; ++rr) {
+                    const int i = w + 16 * rr;
+                    const bool live = i < n;
                     float h1a, h1b;
                     h1_row(i, i, MT == 1 ? 2 : 1, st, h1a, h1b);
-                    s.h1t[i * kS1 + lane] = h1a;
-                    s.h1t[i * kS1 + lane + 32] = h1b;
-                    const float lg = logits_row(h1a, h1b);
-                    const float mxl = warp_max(lane < N ? lg : -3.0e38f);
-                    const float ex = lane < N ? expf(lg - mxl) : 0.f;
-                    const float sum = warp_sum(ex);
-                    const float dl = lane < N ? (ex * (1.f / sum) - (lane == s.ysS[i] ? 1.f : 0.f)) * invn : 0.f;
-                    if (lane < N) s.lt[i * kLS + lane] = dl;
-                    float da = 0.f, db = 0.f;
-#pragma unroll 1
-                    for (int cc = 0; cc < N; ++cc) {
-                        const float dlc = __shfl_sync(0xffffffffu, dl, cc);
-                        da = fmaf(dlc, s.hp[cc * kHD + lane], da);
-                        db = fmaf(dlc, s.hp[cc * kHD + lane + 32], db);
+                    if (live) {
+                        s.h1t[i * kS1 + lane] = h1a;
+                        s.h1t[i * kS1 + lane + 32] = h1b;
                     }
-                    da = h1a > 0.f ? da * dsc : 0.f;
-                    db = h1b > 0.f ? db * dsc : 0.f;
-                    s.dz1t[i * kS1 + lane] = da;
-                    s.dz1t[i * kS1 + lane + 32] = db;
-                    st_plane1(s.dzh, s.dzl, i * kHW + lane, da, sc);
-                    st_plane1(s.dzh, s.dzl, i * kHW + lane + 32, db, sc);
+                    float lg[kNC];
+                    logits_row(h1a, h1b, lg);
+                    float mxl = lg[0];
+#pragma unroll
+                    for (int cc = 1; cc < kNC; ++cc) mxl = fmaxf(mxl, lg[cc]);
+                    float sum = 0.f;
+#pragma unroll
+                    for (int cc = 0; cc < kNC; ++cc) { lg[cc] = __expf(lg[cc] - mxl); sum += lg[cc]; }   // inert: exp(-3e38) = 0
+                    const float rs = __frcp_rn(sum);
+                    const int y = s.ysS[i];               // (zero for pad rows)
+                    float da = 0.f, db = 0.f, dlw = 0.f;
+#pragma unroll
+                    for (int cc = 0; cc < kNC; ++cc) {
+                        const float dl = (lg[cc] * rs - (cc == y ? 1.f : 0.f)) * invn;
+                        if (lane == cc) dlw = dl;
+                        da = fmaf(dl, s.hp[cc * kHD + lane], da);
+                        db = fmaf(dl, s.hp[cc * kHD + lane + 32], db);
+                    }
+                    da = (live && h1a > 0.f) ? da * dsc : 0.f;
+                    db = (live && h1b > 0.f) ? db * dsc : 0.f;
+                    if (live) {
+                        if (lane < N) s.lt[i * kLS + lane] = dlw;
+                        s.dz1t[i * kS1 + lane] = da;
+                        s.dz1t[i * kS1 + lane + 32] = db;
+                        st_plane1(s.dzh, s.dzl, i * kHW + lane, da, sc);
+                        st_plane1(s.dzh, s.dzl, i * kHW + lane + 32, db, sc);
+                    }
                     mxv = fmaxf(mxv, fmaxf(fabsf(da), fabsf(db)));
                 }
                 mxv = warp_max(mxv);
                 if (lane == 0) s.mx[16 * (FX_DZ + par_dz) + w] = mxv;
             }
+            pc.mark(41);
             if (rec) {                                    // H0 planes of this step: stable between B1 and B3
                 for (int idx = tid; idx < n * 32; idx += NT_) {         // 16-byte pieces: 32 per row and plane
                     const int i = idx >> 5, q = idx & 31;
@@ -369,16 +400,24 @@ __global__ void __launch_bounds__(kThreads16, 1) episode_fwd_v2_kernel(EpiParams
                     reinterpret_cast<uint4*>(rec + L.oH0l)[idx] = *reinterpret_cast<const uint4*>(&s.h0l[i * kHS + 8 * q]);
                 }
             }
+            pc.mark(42);
             __syncthreads();                              // B3: dZ1 planes, dL, H1
             FUMI_ADOPT(e_dz, e_dzn, par_dz, FX_DZ);
             pc.mark(23);
             // ---- small updates by the first threads: head, b1 (their results are first read after the next B1)
             for (int idx = tid; idx < N * kHD; idx += NT_) {
                 const int cc = idx / kHD, o = idx - cc * kHD;
-                float a = 0.f;
-#pragma unroll 2
-                for (int i = 0; i < n; ++i) a = fmaf(s.lt[i * kLS + cc], o < kH1 ? s.h1t[i * kS1 + o] : 1.f, a);
-                s.dhp[idx] = a;
+                const float* hcol = o < kH1 ? s.h1t + o : nullptr;
+                float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;       // four independent chains over the rows
+                int i = 0;
+                for (; i + 4 <= n; i += 4) {
+                    a0 = fmaf(s.lt[i * kLS + cc], hcol ? hcol[i * kS1] : 1.f, a0);
+                    a1 = fmaf(s.lt[(i + 1) * kLS + cc], hcol ? hcol[(i + 1) * kS1] : 1.f, a1);
+                    a2 = fmaf(s.lt[(i + 2) * kLS + cc], hcol ? hcol[(i + 2) * kS1] : 1.f, a2);
+                    a3 = fmaf(s.lt[(i + 3) * kLS + cc], hcol ? hcol[(i + 3) * kS1] : 1.f, a3);
+                }
+                for (; i < n; ++i) a0 = fmaf(s.lt[i * kLS + cc], hcol ? hcol[i * kS1] : 1.f, a0);
+                s.dhp[idx] = (a0 + a1) + (a2 + a3);
             }
             // ---- (d) dZ0 = (dZ1 W1) * gate ; S += dZ0 ; b0 -= alpha colsum(dZ0): warp-local
             {
@@ -430,30 +469,28 @@ __global__ void __launch_bounds__(kThreads16, 1) episode_fwd_v2_kernel(EpiParams
                     }
             }
             pc.mark(24);
-            // ---- (e) W1 -= alpha dZ1^T H0 on this warp's rows of W1^T, in place on the planes (lagged exponent)
+            if (st + 1 < steps) h0_load(srow, MT);       // next step's projected rows (L2): the loads fly under (e)
+            // ---- (e) W1 -= alpha dZ1^T H0 on this warp's rows of W1^T: fp32 master in registers, planes re-split from it
             {
-                float acc[1][8][4];
+                // tile-outer: the A fragments (this warp's columns of H0, all rows) stay in registers; each pair of n tiles is
+                // 6 MMAs per k step followed by its own update / re-split, which overlaps the next pair's MMAs
+                uint32_t ah[MT][4], al[MT][4];
+                warp_load_a<MT, true>(s.h0h + 16 * w, s.h0l + 16 * w, kHS, ah, al);
+                const float inv = alpha * fumi_exp2i(-e_h0) * fumi_exp2i(-e_dz) * fumi_exp2i(e_w1);
 #pragma unroll
-                for (int j = 0; j < 8; ++j)
+                for (int jp = 0; jp < 4; ++jp) {
+                    float acc[2][4];
+                    warp_mma_pair<MT, false>(ah, al, s.dzh, s.dzl, kHW, 16 * jp, acc);
 #pragma unroll
-                    for (int q = 0; q < 4; ++q) acc[0][j][q] = 0.f;
-                warp_gemm_f16x3<1, 8, true, false>(s.h0h + 16 * w, s.h0l + 16 * w, kHS, s.dzh, s.dzl, kHW, RS, acc);
-                const float inv = alpha * fumi_exp2i(-e_h0) * fumi_exp2i(-e_dz);
-                const float winv = fumi_exp2i(-e_w1), wsc = fumi_exp2i(e_w1n);
-                float mxv = 0.f;
+                    for (int h = 0; h < 2; ++h)
 #pragma unroll
-                for (int j = 0; j < 8; ++j)
-#pragma unroll
-                    for (int hq = 0; hq < 2; ++hq) {
-                        const int off = (16 * w + g + 8 * hq) * kHW + 8 * j + 2 * t;
-                        float o0, o1;
-                        ld_planes2(s.w1h, s.w1l, off, winv, o0, o1);
-                        o0 -= acc[0][j][2 * hq] * inv;
-                        o1 -= acc[0][j][2 * hq + 1] * inv;
-                        mxv = fmaxf(mxv, fmaxf(fabsf(o0), fabsf(o1)));
-                        st_planes2(s.w1h, s.w1l, off, o0, o1, wsc);
-                    }
-                block_max_push(s.mx + 16 * (FX_W1 + par_w1), mxv);
+                        for (int hq = 0; hq < 2; ++hq) {
+                            const int j = 2 * jp + h;
+                            w1m[j][2 * hq] = fmaf(-inv, acc[h][2 * hq], w1m[j][2 * hq]);
+                            w1m[j][2 * hq + 1] = fmaf(-inv, acc[h][2 * hq + 1], w1m[j][2 * hq + 1]);
+                            st_planes2(s.w1h, s.w1l, (16 * w + g + 8 * hq) * kHW + 8 * j + 2 * t, w1m[j][2 * hq], w1m[j][2 * hq + 1], 1.f);
+                        }
+                }
             }
             pc.mark(25);
             // ---- step records (dZ1 planes, H1, dL, head before its update), then the head / b1 updates
@@ -523,7 +560,10 @@ __global__ void __launch_bounds__(kThreads16, 1) episode_fwd_v2_kernel(EpiParams
             block_max_push(s.mx + 16 * (FX_GQ + par_gq), fmaxf(fabsf(qg[0]), fabsf(qg[1])));
         };
         q_load(0);
-        h0_load(qrows, min(32, m), 2);
+        int qrid[2][2];
+        h0_rows(qrows, min(32, m), qrid);
+        h0_load(qrid, 2);
+        if (32 < m) h0_rows(qrows + 32, min(32, m - 32), qrid);
         if (steps == 0) {                                 // no H0 yet: bound |H0q| by dsc (max |A| + max |b0|) of tile 0
             float mxv = 0.f;
 #pragma unroll
@@ -537,14 +577,16 @@ __global__ void __launch_bounds__(kThreads16, 1) episode_fwd_v2_kernel(EpiParams
         }
         q_planes(0);
         __syncthreads();                                  // QB0: Gram planes of tile 0 (and the last step's W1 / head / b1)
-        if (steps > 0) FUMI_ADOPT(e_w1, e_w1n, par_w1, FX_W1);
-        else { e_h0n = fumi_plane_exp_t(__float_as_uint(fmaxf(slot_max(s.mx + 16 * FX_H0), 1e-30f)), kTarget); par_h0 = 1; }
+        if (steps == 0) { e_h0n = fumi_plane_exp_t(__float_as_uint(fmaxf(slot_max(s.mx + 16 * FX_H0), 1e-30f)), kTarget); par_h0 = 1; }
         FUMI_ADOPT(e_gq, e_gqn, par_gq, FX_GQ);
         if (32 < m) q_load(32);
         const float sinv = steps > 0 ? fumi_exp2i(-e_s) : 0.f;
         int qtile = 0;
         for (int r0 = 0; r0 < m; r0 += 32, ++qtile) {
             const int tr = min(32, m - r0);
+            int qy[2];                                    // labels of this warp's two rows (read at the end of the tile)
+#pragma unroll
+            for (int rr = 0; rr < 2; ++rr) qy[rr] = (w + 16 * rr) < tr ? int(__ldg(&P.qry_y[b * m + r0 + w + 16 * rr])) : 0;
             {
                 float acc[2][2][4];
 #pragma unroll
@@ -559,7 +601,8 @@ __global__ void __launch_bounds__(kThreads16, 1) episode_fwd_v2_kernel(EpiParams
                                                         s.sl + 16 * w, kHS, RS, acc);
                 h0_finish(acc, 2, r0, tr, steps > 0 ? alpha * fumi_exp2i(-e_gq) * sinv : 0.f, steps);
             }
-            if (r0 + 32 < m) h0_load(qrows + r0 + 32, min(32, m - r0 - 32), 2);      // next tile's rows, a tile ahead
+            if (r0 + 32 < m) h0_load(qrid, 2);           // next tile's projected rows, a tile ahead; row ids two tiles ahead
+            if (r0 + 64 < m) h0_rows(qrows + r0 + 64, min(32, m - r0 - 64), qrid);
             __syncthreads();                              // QB1: H0q planes
             FUMI_ADOPT(e_h0, e_h0n, par_h0, FX_H0);
             pc.mark(28);
@@ -577,43 +620,56 @@ __global__ void __launch_bounds__(kThreads16, 1) episode_fwd_v2_kernel(EpiParams
             if (r0 + 32 < m) FUMI_ADOPT(e_gq, e_gqn, par_gq, FX_GQ);
             if (r0 + 64 < m) q_load(r0 + 64);
             pc.mark(29);
-#pragma unroll 1
-            for (int i = w; i < 32; i += 16) {
-                if (i >= tr) break;
+#pragma unroll
+            for (int rr = 0; rr < 2; ++rr) {
+                const int i = w + 16 * rr;
+                const bool live = i < tr;
                 float h1a, h1b;
                 h1_row(i, r0 + i, 1, steps, h1a, h1b);
-                const float lg = logits_row(h1a, h1b);
-                const int64_t q = b * m + r0 + i;
-                const int y = int(__ldg(&P.qry_y[q]));
-                const float mxl = warp_max(lane < N ? lg : -3.0e38f);
-                const float ex = lane < N ? expf(lg - mxl) : 0.f;
-                const float sum = warp_sum(ex);
-                if (lane < N) P.logits[q * N + lane] = lg;
-                if (slot) {
+                float lg[kNC];
+                logits_row(h1a, h1b, lg);
+                const int64_t q = b * m + r0 + (live ? i : 0);
+                const int y = qy[rr];
+                float mxl = lg[0], ly = 0.f, lgw = 0.f;
+                int bi = 0;                               // argmax with ties to the lowest index (torch.max, fumi.py:180)
+#pragma unroll
+                for (int cc = 0; cc < kNC; ++cc) {
+                    if (lg[cc] > mxl) { mxl = lg[cc]; bi = cc; }
+                    if (cc == y) ly = lg[cc];
+                    if (lane == cc) lgw = lg[cc];
+                }
+                if (live && lane < N) P.logits[q * N + lane] = lgw;
+                float sum = 0.f;
+#pragma unroll
+                for (int cc = 0; cc < kNC; ++cc) { lg[cc] = __expf(lg[cc] - mxl); sum += lg[cc]; }
+                if (slot && live) {
                     slot[L.qH1 + int64_t(r0 + i) * kH1 + lane] = h1a;
                     slot[L.qH1 + int64_t(r0 + i) * kH1 + lane + 32] = h1b;
-                    if (lane < N) slot[L.qLG + int64_t(r0 + i) * N + lane] = ex * (1.f / sum) - (lane == y ? 1.f : 0.f);
-                }
-                // argmax with ties to the lowest index (torch.max, fumi.py:180)
-                float bv = lane < N ? lg : -3.0e38f;
-                int bi = lane;
+                    const float rs = __frcp_rn(sum);
+                    float pw = 0.f;
 #pragma unroll
-                for (int off = 16; off >= 1; off >>= 1) {
-                    const float ov = __shfl_xor_sync(0xffffffffu, bv, off);
-                    const int oi = __shfl_xor_sync(0xffffffffu, bi, off);
-                    if (ov > bv || (ov == bv && oi < bi)) { bv = ov; bi = oi; }
+                    for (int cc = 0; cc < kNC; ++cc)
+                        if (lane == cc) pw = lg[cc] * rs - (cc == y ? 1.f : 0.f);
+                    if (lane < N) slot[L.qLG + int64_t(r0 + i) * N + lane] = pw;
                 }
-                const float ly = __shfl_sync(0xffffffffu, lg, y);
-                if (lane == 0) {
+                if (live && lane == 0) {
                     P.preds[q] = bi;
-                    loss_sum += (logf(sum) + mxl) - ly;
+                    loss_sum += (__logf(sum) + mxl) - ly;
                     corr_sum += bi == y ? 1.f : 0.f;
                 }
             }
             pc.mark(30);
         }
         // ------------------------------------------------------------------ task epilogue
-        if (lane == 0) { s.red[w] = loss_sum; s.red[16 + w] = corr_sum; }
+        {   // W1 planes keep the exponent of the initial weights: they overflow if the adapted weights grew 250x
+            float mxv = 0.f;
+#pragma unroll
+            for (int j = 0; j < 8; ++j)
+#pragma unroll
+                for (int q = 0; q < 4; ++q) mxv = fmaxf(mxv, fabsf(w1m[j][q]));
+            mxv = warp_max(mxv);
+            if (lane == 0) { s.red[w] = loss_sum; s.red[16 + w] = corr_sum; s.red[32 + w] = mxv; }
+        }
         if (slot) {                                       // adapted state (fp32): parity dumps, backward prologue
             const float winv = fumi_exp2i(-e_w1);
             for (int idx = tid; idx < kH0 * kH1 / 2; idx += NT_) {
@@ -643,8 +699,9 @@ __global__ void __launch_bounds__(kThreads16, 1) episode_fwd_v2_kernel(EpiParams
         }
         __syncthreads();
         if (tid == 0) {
-            float ls = 0.f, cs = 0.f;
-            for (int q = 0; q < 16; ++q) { ls += s.red[q]; cs += s.red[16 + q]; }
+            float ls = 0.f, cs = 0.f, wm = 0.f;
+            for (int q = 0; q < 16; ++q) { ls += s.red[q]; cs += s.red[16 + q]; wm = fmaxf(wm, s.red[32 + q]); }
+            bad = bad || !(wm < 60000.f);
             P.task_loss[b] = bad ? __uint_as_float(0x7FC00000u) : ls / float(m);
             P.task_acc[b] = cs / float(m);
         }
@@ -654,16 +711,17 @@ __global__ void __launch_bounds__(kThreads16, 1) episode_fwd_v2_kernel(EpiParams
 }
 
 size_t smem_v_bytes(int N) { SmemV t; return carve_v(nullptr, t, N); }
+int class_bucket(int N) { return N <= 5 ? 5 : (N <= 8 ? 8 : 12); }
 
 }  // namespace
 
 bool episode_f16_supported(const fumi_episode_cfg& c) {
     // both kernels size their head buffers by N; the backward's two W1-shaped plane pairs leave room for N <= 12
-    return c.num_support <= 32 && c.num_ways <= 12 && smem_v_bytes(c.num_ways) <= 227 * 1024;
+    return c.num_support <= 32 && c.num_ways <= 12 && smem_v_bytes(class_bucket(c.num_ways)) <= 227 * 1024;
 }
 
 int launch_episode_fwd_f16(const EpiParams& P, int grid, void* stream) {
-    const size_t smem = smem_v_bytes(P.cfg.num_ways);
+    const size_t smem = smem_v_bytes(class_bucket(P.cfg.num_ways));
 #ifndef FUMI_EMU
 #define FUMI_SMEM_ATTR(kern)                                                                                       \
     do {                                                                                                            \
@@ -673,13 +731,18 @@ int launch_episode_fwd_f16(const EpiParams& P, int grid, void* stream) {
 #else
 #define FUMI_SMEM_ATTR(kern) ((void)0)
 #endif
+#define FUMI_FWD_LAUNCH(MT_, NC_)                                                   \
+    do {                                                                            \
+        FUMI_SMEM_ATTR((episode_fwd_v2_kernel<MT_, NC_>));                          \
+        FUMI_LAUNCH((episode_fwd_v2_kernel<MT_, NC_>), grid, kThreads16, smem, stream, P); \
+    } while (0)
+    const int nc = class_bucket(P.cfg.num_ways);
     if (P.cfg.num_support <= 16) {
-        FUMI_SMEM_ATTR(episode_fwd_v2_kernel<1>);
-        FUMI_LAUNCH(episode_fwd_v2_kernel<1>, grid, kThreads16, smem, stream, P);
+        if (nc == 5) FUMI_FWD_LAUNCH(1, 5); else if (nc == 8) FUMI_FWD_LAUNCH(1, 8); else FUMI_FWD_LAUNCH(1, 12);
     } else {
-        FUMI_SMEM_ATTR(episode_fwd_v2_kernel<2>);
-        FUMI_LAUNCH(episode_fwd_v2_kernel<2>, grid, kThreads16, smem, stream, P);
+        if (nc == 5) FUMI_FWD_LAUNCH(2, 5); else if (nc == 8) FUMI_FWD_LAUNCH(2, 8); else FUMI_FWD_LAUNCH(2, 12);
     }
+#undef FUMI_FWD_LAUNCH
 #undef FUMI_SMEM_ATTR
     FUMI_CHECK_LAUNCH("episode_fwd_v2_kernel");
     return FUMI_OK;

@@ -286,6 +286,48 @@ __device__ __forceinline__ void warp_gemm_f16x3(const fumi_half* Ahi, const fumi
     }
 }
 
+// ---- tile-outer building blocks: a warp holds the A fragments of its whole K range and walks the n tiles in pairs,
+// so that the epilogue of one pair (ALU) is independent of -- and gets scheduled under -- the MMAs of the next pair.
+// A fragments of a [16 x K] block, K = 16 KS.  ATRANS: A(m,k) = A[k*lda + m], else A[m*lda + k].
+template <int KS, bool ATRANS>
+__device__ __forceinline__ void warp_load_a(const fumi_half* Ahi, const fumi_half* Alo, int lda, uint32_t (&ah)[KS][4], uint32_t (&al)[KS][4]) {
+    const int lane = threadIdx.x & 31;
+    const int l7 = lane & 7, b3 = (lane >> 3) & 1, b4 = lane >> 4;
+    const int aoff = ATRANS ? (l7 + 8 * b4) * lda + 8 * b3 : (l7 + 8 * b3) * lda + 8 * b4;
+#pragma unroll
+    for (int k = 0; k < KS; ++k) {
+        const int o = ATRANS ? 16 * k * lda + aoff : 16 * k + aoff;
+        if (ATRANS) { fumi_ldsm4t(ah[k], Ahi + o); fumi_ldsm4t(al[k], Alo + o); }
+        else        { fumi_ldsm4(ah[k], Ahi + o);  fumi_ldsm4(al[k], Alo + o); }
+    }
+}
+// acc[h][0..3] = (A 2^sa) . (B 2^sb) for the n tile pair starting at column n0 (two 8-wide tiles), K = 16 KS <= 64 (one
+// accumulator restart).  B(k,n) = B[k*ldb + n]  (BTRANS: B[n*ldb + k]).
+template <int KS, bool BTRANS>
+__device__ __forceinline__ void warp_mma_pair(const uint32_t (&ah)[KS][4], const uint32_t (&al)[KS][4], const fumi_half* Bhi,
+                                              const fumi_half* Blo, int ldb, int n0, float (&acc)[2][4]) {
+    const int lane = threadIdx.x & 31;
+    const int l7 = lane & 7, b3 = (lane >> 3) & 1, b4 = lane >> 4;
+    const int boff = BTRANS ? (l7 + 8 * b4) * ldb + 8 * b3 : (l7 + 8 * b3) * ldb + 8 * b4;
+#pragma unroll
+    for (int h = 0; h < 2; ++h)
+#pragma unroll
+        for (int q = 0; q < 4; ++q) acc[h][q] = 0.f;
+#pragma unroll
+    for (int k = 0; k < KS; ++k) {
+        uint32_t bh[4], bl[4];
+        const int o = BTRANS ? n0 * ldb + 16 * k + boff : 16 * k * ldb + n0 + boff;
+        if (BTRANS) { fumi_ldsm4(bh, Bhi + o);  fumi_ldsm4(bl, Blo + o); }
+        else        { fumi_ldsm4t(bh, Bhi + o); fumi_ldsm4t(bl, Blo + o); }
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+            fumi_mma_f16(acc[h], al[k], bh[2 * h], bh[2 * h + 1]);
+            fumi_mma_f16(acc[h], ah[k], bl[2 * h], bl[2 * h + 1]);
+            fumi_mma_f16(acc[h], ah[k], bh[2 * h], bh[2 * h + 1]);
+        }
+    }
+}
+
 // power-of-two plane scale from max |x| (held as the bit pattern of a non-negative float): the largest element lands
 // in [2^13, 2^14).  Returns the exponent s (planes hold x 2^s).
 __device__ __forceinline__ int fumi_plane_exp(uint32_t absmax_bits) {

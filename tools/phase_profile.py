@@ -15,13 +15,16 @@ from fumi_b200.data.loader import EpisodeLoader  # noqa: E402
 from fumi_b200.data.synth import class_split, make_bank  # noqa: E402
 from fumi_b200.sampler import EpisodeSampler  # noqa: E402
 
-NAMES = {0: "bwd prologue", 1: "bwd q: tile loads", 2: "bwd q: a_head,dZ1q", 3: "bwd q: aW1/dZ0q gemms+atomics",
-         4: "bwd q: a_S gemm", 5: "bwd s: loads+undo W1", 6: "bwd s: tile loads", 7: "bwd s: r_dH1/r_W1/r_H0 gemms",
-         8: "bwd s: r_dL,r_head", 9: "bwd s: jacobian,r_H1", 10: "bwd s: r_Z1,r_head", 11: "bwd s: r_H0/r_W1 gemms+atomics",
-         12: "bwd s: fold+reload bZ", 13: "bwd s: a_S gemm", 14: "bwd epilogue",
-         20: "fwd prologue", 21: "fwd s: H0", 22: "fwd s: H1", 23: "fwd s: logits+softmax", 24: "fwd s: (unused)",
-         25: "fwd s: dhp,dZ1", 26: "fwd s: dZ0 gemm,S,stash", 27: "fwd s: W1 update gemm", 28: "fwd q: loads",
-         29: "fwd q: H0", 30: "fwd q: H1", 31: "fwd q: logits+softmax", 32: "fwd q: stash, tile end", 33: "fwd epilogue"}
+NAMES = {0: "bwd prologue (W1/G planes, maxes)", 1: "bwd q: tile data -> smem, wait, Q0", 2: "bwd q: dZ1q row-per-warp, Q1",
+         3: "bwd q: head sums, aW1/dZ0q/a_S gemms, atomics, Q2", 4: "bwd aW1 planes after query pass",
+         5: "bwd s: records landed (U0)", 6: "bwd s: undo W1 gemm + planes", 7: "bwd s: r_dH0 planes, T1",
+         8: "bwd s: r_dZ1 partials + r_W1/r_H0 (dZ1 parts), T2", 9: "bwd s: row chain, T3",
+         11: "bwd s: head sums, r_H0/r_W1 gemms, atomics, a_S, T4", 12: "bwd s: fold a_W1 + next records issue",
+         14: "bwd epilogue",
+         20: "fwd prologue", 21: "fwd s: wait B1", 22: "fwd s: Z1 gemm, B2", 23: "fwd s: row-per-warp c, stash H0, B3",
+         24: "fwd s: dhp sums, dZ0 gemm, S update", 25: "fwd s: W1 update gemm + planes",
+         26: "fwd s: records, head/b1 update, next H0", 28: "fwd q: Z0q gemm + H0q planes, QB1",
+         29: "fwd q: stash, Gram planes, Z1q gemm, QB2", 30: "fwd q: row-per-warp scoring", 33: "fwd epilogue"}
 
 
 def main():
@@ -38,7 +41,7 @@ def main():
     model = utils.init_model(args, {})
     opt = utils.init_optim(args, model)
     eng = model._get_engine(dev)
-    eng.precision = 1
+    eng.precision = 2
     sampler.new_iterator()
     b = loader.next_batch().to(dev)
     for _ in range(2):
@@ -51,7 +54,7 @@ def main():
     out = np.zeros(64, np.uint64)
     L.fumi_debug_read_phases(_lib.ptr(out))
     L.fumi_debug_phase_profile(0)
-    for lo, hi, name in ((20, 34, "forward"), (0, 15, "backward")):
+    for lo, hi, name in ((20, 44, "forward"), (0, 15, "backward")):
         tot = float(out[lo:hi].sum())
         print(f"== {name}: {tot / 1e6:.1f} Mcycles summed over CTAs")
         for i in range(lo, hi):
