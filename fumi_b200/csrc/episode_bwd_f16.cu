@@ -18,7 +18,7 @@
 namespace fumi_epi {
 namespace {
 
-constexpr int kLB = 16;                     // row stride of the dL / r_L tiles (N <= 12 on this path)
+constexpr int kLB = 16;                     // row stride of the dL / r_L tiles (N <= 11 on this path)
 enum { BX_W1 = 0, BX_AW = 2, BX_TT = 4, BX_RZ = 6, BX_DZ = 8, BX_GQ = 10, BX_GS = 12, BX_HP = 13, BX_COUNT = 14 };
 
 struct SmemW {
@@ -852,7 +852,7 @@ size_t smem_w_bytes(int N) { SmemW t; return carve_w(nullptr, t, N); }
 }  // namespace
 
 int launch_episode_bwd_f16(const EpiParams& P, int grid, void* stream) {
-    const int nc = P.cfg.num_ways <= 5 ? 5 : (P.cfg.num_ways <= 8 ? 8 : 12);
+    const int nc = P.cfg.num_ways <= 5 ? 5 : (P.cfg.num_ways <= 8 ? 8 : 11);
     const size_t smem = smem_w_bytes(nc);
     if (smem > 227 * 1024) {
         fumi_set_error("episode backward: shared-memory budget exceeded for this num_ways");
@@ -873,9 +873,9 @@ int launch_episode_bwd_f16(const EpiParams& P, int grid, void* stream) {
         FUMI_LAUNCH((episode_bwd_v2_kernel<MT_, NC_>), grid, kThreads16, smem, stream, P); \
     } while (0)
     if (P.cfg.num_support <= 16) {
-        if (nc == 5) FUMI_BWD_LAUNCH(1, 5); else if (nc == 8) FUMI_BWD_LAUNCH(1, 8); else FUMI_BWD_LAUNCH(1, 12);
+        if (nc == 5) FUMI_BWD_LAUNCH(1, 5); else if (nc == 8) FUMI_BWD_LAUNCH(1, 8); else FUMI_BWD_LAUNCH(1, 11);
     } else {
-        if (nc == 5) FUMI_BWD_LAUNCH(2, 5); else if (nc == 8) FUMI_BWD_LAUNCH(2, 8); else FUMI_BWD_LAUNCH(2, 12);
+        if (nc == 5) FUMI_BWD_LAUNCH(2, 5); else if (nc == 8) FUMI_BWD_LAUNCH(2, 8); else FUMI_BWD_LAUNCH(2, 11);
     }
 #undef FUMI_BWD_LAUNCH
 #undef FUMI_SMEM_ATTR

@@ -236,6 +236,7 @@ struct PhaseClock {
 int launch_episode_fwd_f16(const EpiParams& P, int grid, void* stream);
 int launch_episode_bwd_f16(const EpiParams& P, int grid, void* stream);
 bool episode_f16_supported(const fumi_episode_cfg& c);
+size_t episode_bwd_f16_smem_bytes(int class_bucket);
 unsigned long long* episode_phase_counters();      // null unless fumi_debug_phase_profile(1)
 
 }  // namespace fumi_epi

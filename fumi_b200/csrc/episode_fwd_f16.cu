@@ -711,13 +711,15 @@ __global__ void __launch_bounds__(kThreads16, 1) episode_fwd_v2_kernel(EpiParams
 }
 
 size_t smem_v_bytes(int N) { SmemV t; return carve_v(nullptr, t, N); }
-int class_bucket(int N) { return N <= 5 ? 5 : (N <= 8 ? 8 : 12); }
+int class_bucket(int N) { return N <= 5 ? 5 : (N <= 8 ? 8 : 11); }
 
 }  // namespace
 
 bool episode_f16_supported(const fumi_episode_cfg& c) {
-    // both kernels size their head buffers by N; the backward's two W1-shaped plane pairs leave room for N <= 12
-    return c.num_support <= 32 && c.num_ways <= 12 && smem_v_bytes(class_bucket(c.num_ways)) <= 227 * 1024;
+    // both kernels size their head buffers by the class bucket (5 / 8 / 11); next to the backward's two W1-shaped plane
+    // pairs 11 classes is what 227 KB of shared memory holds
+    return c.num_support <= 32 && c.num_ways <= 11 && smem_v_bytes(class_bucket(c.num_ways)) <= 227 * 1024 &&
+           episode_bwd_f16_smem_bytes(class_bucket(c.num_ways)) <= 227 * 1024;
 }
 
 int launch_episode_fwd_f16(const EpiParams& P, int grid, void* stream) {
@@ -738,9 +740,9 @@ int launch_episode_fwd_f16(const EpiParams& P, int grid, void* stream) {
     } while (0)
     const int nc = class_bucket(P.cfg.num_ways);
     if (P.cfg.num_support <= 16) {
-        if (nc == 5) FUMI_FWD_LAUNCH(1, 5); else if (nc == 8) FUMI_FWD_LAUNCH(1, 8); else FUMI_FWD_LAUNCH(1, 12);
+        if (nc == 5) FUMI_FWD_LAUNCH(1, 5); else if (nc == 8) FUMI_FWD_LAUNCH(1, 8); else FUMI_FWD_LAUNCH(1, 11);
     } else {
-        if (nc == 5) FUMI_FWD_LAUNCH(2, 5); else if (nc == 8) FUMI_FWD_LAUNCH(2, 8); else FUMI_FWD_LAUNCH(2, 12);
+        if (nc == 5) FUMI_FWD_LAUNCH(2, 5); else if (nc == 8) FUMI_FWD_LAUNCH(2, 8); else FUMI_FWD_LAUNCH(2, 11);
     }
 #undef FUMI_FWD_LAUNCH
 #undef FUMI_SMEM_ATTR

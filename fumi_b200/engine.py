@@ -477,7 +477,10 @@ class EpisodeEngine:
         else:
             eb, feats, text_rows, class_rows = self.unpack(batch, N, want_text=True)
         P = model.prototype_dim
-        if self.precision >= 1:
+        if self.precision == 2 and feats.shape[1] % 8 == 0:      # the bank's fp16 planes (split once, shared with FuMI / MAML)
+            emb = self.gemm_f16(self._feat_planes16(feats, eb.bank, False), self.split_f16(model.image_encoder.weight),
+                                bias=model.image_encoder.bias)
+        elif self.precision >= 1:
             emb = self.gemm_tc(self._feat_planes(feats, eb.bank), self.split_tf32(model.image_encoder.weight),
                                bias=model.image_encoder.bias)
         else:

@@ -6,9 +6,10 @@ second, independent check of oracle/episode_np.py: the same torch ops in the sam
                                  autograd.grad(create_graph=True), out-of-place SGD] -> query CE)
   fumi/models/maml.py:158-191
 with torchmeta's MetaLinear / gradient_update_parameters written inline (F.linear with an
-explicit parameter dict; ``p - step_size * grad``).  Dropout is not restated here (parity is
-defined at --dropout 0 / eval mode or with injected masks); the CPU baseline
-therefore does slightly *less* work per task than the reference's default train mode.
+explicit parameter dict; ``p - step_size * grad``).  ``dropout_p`` > 0 adds the reference's
+Dropout layers after both ReLUs of im_net in train mode (fumi.py:93-99: torch Bernoulli masks from the
+global generator -- used by the timing baseline; parity is defined at --dropout 0 / eval mode or
+with injected masks).
 """
 from collections import OrderedDict
 
@@ -16,15 +17,19 @@ import torch
 import torch.nn.functional as F
 
 
-def _im_forward(x, im, hp):
+def _im_forward(x, im, hp, dropout_p=0.0):
     h = F.relu(F.linear(x, im["linear0.weight"], im["linear0.bias"]))
+    if dropout_p > 0:
+        h = F.dropout(h, dropout_p, training=True)
     h = F.relu(F.linear(h, im["linear1.weight"], im["linear1.bias"]))
+    if dropout_p > 0:
+        h = F.dropout(h, dropout_p, training=True)
     out = torch.matmul(h, torch.unsqueeze(hp[:, :-1], 2))            # fumi.py:216
     out = torch.squeeze(out) + torch.unsqueeze(hp[:, -1], 1)         # fumi.py:217
     return torch.transpose(out, 0, 1)
 
 
-def fumi_batch(params, batch, alpha, steps, tanh=False, train=False):
+def fumi_batch(params, batch, alpha, steps, tanh=False, train=False, dropout_p=0.0):
     """params: OrderedDict of leaf tensors keyed by reference state_dict names.  batch tensors:
     sup_x [B,NK,D], sup_y [B,NK], qry_x [B,NQ,D], qry_y [B,NQ], class_text [B,N,T].
     If train, leaves get .grad of loss (summed over tasks / B), as fumi.py:187-192."""
@@ -39,13 +44,13 @@ def fumi_batch(params, batch, alpha, steps, tanh=False, train=False):
             hp = torch.tanh(hp)
         im = OrderedDict((k[len("im_net."):], v) for k, v in params.items() if k.startswith("im_net."))
         for _ in range(steps):
-            logit = _im_forward(batch["sup_x"][b], im, hp)
+            logit = _im_forward(batch["sup_x"][b], im, hp, dropout_p if train else 0.0)
             inner = F.cross_entropy(logit, batch["sup_y"][b])
             g_hp = torch.autograd.grad(inner, hp, create_graph=True)[0]
             g_im = torch.autograd.grad(inner, list(im.values()), create_graph=True)
             hp = hp - alpha * g_hp
             im = OrderedDict((k, p - alpha * g) for (k, p), g in zip(im.items(), g_im))
-        ql = _im_forward(batch["qry_x"][b], im, hp)
+        ql = _im_forward(batch["qry_x"][b], im, hp, dropout_p if train else 0.0)
         outer = outer + F.cross_entropy(ql, batch["qry_y"][b])
         p = ql.max(dim=-1)[1]
         preds.append(p)

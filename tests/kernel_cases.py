@@ -342,6 +342,43 @@ def maml_test_then_train_case(device, name="maml_train_n5k5_d512"):
     assert opt._is_flat(f)
 
 
+def oracle_train_case(device, N, K, Q, steps, D=2048, T=768, B=8, dropout=0.25, precision=2, tanh=False, seed=5):
+    """Meta-train step at arbitrary (benched) dimensions against oracle/episode_np in fp64, fed the same counter-based
+    dropout masks: predictions equal, logits within 1e-4, all meta-gradients within 2e-4.  No fixture: the oracle
+    is evaluated here (dW0 alone is 2 MB at D = 2048).  This is bench.py's parity probe run as a test."""
+    import random
+    import bench
+    from fumi_b200 import utils
+    from fumi_b200.data.bank import FeatureBank
+    from fumi_b200.data.loader import EpisodeLoader
+    from fumi_b200.data.synth import class_split, make_bank
+    from fumi_b200.sampler import EpisodeSampler
+    C = max(60, 3 * N)
+    bank = make_bank(num_images=C * (K + Q + 30), num_classes=C, im_dim=D, text_dim=T, min_per_class=K + Q + 8, seed=seed)
+    cats = class_split(C)[0]
+    sampler = EpisodeSampler(bank.cat_of, cats, N, K, Q)
+    fb = FeatureBank(feats=torch.from_numpy(bank.feats[sampler.ids]).to(device), text=torch.from_numpy(bank.text[cats]).to(device),
+                     ids=sampler.ids, categories=cats)
+    argv = ["--model", "fumi", "--num_ways", str(N), "--num_shots", str(K), "--num_shots_test", str(Q),
+            "--num_train_adapt_steps", str(steps), "--im_emb_dim", str(D), "--text_emb_dim", str(T),
+            "--dropout", str(dropout), "--batch_size", str(B)] + (["--norm_hypernet"] if tanh else [])
+    args = utils.parser().parse_args(argv)
+    args.device = torch.device(device)
+    args.precision = precision
+    torch.manual_seed(123); np.random.seed(123); random.seed(123)
+    model = utils.init_model(args, {})
+    FusedAdam(model.parameters(), lr=3e-5, weight_decay=5e-4)
+    eng = model._get_engine(device)
+    loader = EpisodeLoader(fb, sampler, B)
+    sampler.new_iterator()
+    batch = loader.next_batch().to(device)
+    par = bench.parity_probe(None, eng, model, args, batch, N, K, Q, steps, dropout, ntasks=B)
+    assert par["preds_equal"], par
+    assert par["logits_relerr"] < 1e-4, par
+    assert par["grad_relerr_max"] < 2e-4, par
+    return par
+
+
 def am3_case(device, name="am3_test_n10k5_d512"):
     g, bank = load_golden(name)
     m = am3_mod.AM3(im_encoder="precomputed", im_emb_dim=bank.feats.shape[1], text_encoder="BERT",

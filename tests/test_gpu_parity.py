@@ -59,12 +59,35 @@ def test_fumi_train_n5k5(via):
     kc.fumi_train_case(DEV, "fumi_train_n5k5_d512", via=via)
 
 
-def test_fumi_train_tanh():
-    kc.fumi_train_case(DEV, "fumi_train_n5k5_d512_tanh")
+@pytest.mark.parametrize("precision", [0, 2])
+def test_fumi_train_tanh(precision):
+    kc.fumi_train_case(DEV, "fumi_train_n5k5_d512_tanh", precision=precision)
 
 
-def test_fumi_train_n20k5_multitile():
-    kc.fumi_train_case(DEV, "fumi_train_n20k5_d512")
+@pytest.mark.parametrize("precision", [0, 2])
+def test_fumi_train_n20k5_multitile(precision):
+    kc.fumi_train_case(DEV, "fumi_train_n20k5_d512", precision=precision)
+
+
+def test_benched_config_gradients_vs_fp64_oracle():
+    """BASELINE configs[1] as benched: D = 2048, T = 768, NQ = 160, precision 2, dropout 0.25 -- all 8 meta-gradients
+    (dW0 included) against the fp64 oracle."""
+    par = kc.oracle_train_case(DEV, N=5, K=5, Q=32, steps=5, D=2048, T=768, B=8, dropout=0.25, precision=2)
+    print("benched-config parity:", {k: v for k, v in par.items() if k != "grad_relerr"})
+
+
+def test_config5_shape_gradients_vs_fp64_oracle():
+    """BASELINE configs[4] shape: 20-way 5-shot, NK = 100, NQ = 640, 10 inner steps, precision 2."""
+    par = kc.oracle_train_case(DEV, N=20, K=5, Q=32, steps=10, D=512, T=64, B=2, dropout=0.25, precision=2)
+    print("config-5 parity:", {k: v for k, v in par.items() if k != "grad_relerr"})
+
+
+def test_one_shot_and_ten_way_gradients_vs_fp64_oracle():
+    """The other class-count buckets / tile shapes of the tensor-core kernels: 5-way 1-shot (NK = 5, one 16-row tile),
+    10-way 3-shot (NK = 30, N = 10)."""
+    kc.oracle_train_case(DEV, N=5, K=1, Q=8, steps=5, D=512, T=64, B=3, dropout=0.25, precision=2)
+    kc.oracle_train_case(DEV, N=10, K=3, Q=6, steps=3, D=512, T=64, B=3, dropout=0.0, precision=2, tanh=True)
+    kc.oracle_train_case(DEV, N=7, K=4, Q=5, steps=2, D=512, T=64, B=2, dropout=0.1, precision=2)
 
 
 def test_fumi_evaluate_api():
@@ -74,7 +97,9 @@ def test_fumi_evaluate_api():
 @pytest.mark.parametrize("name", ["fumi_test_n5k1_full", "fumi_test_n5k5_full"])
 @pytest.mark.parametrize("via", ["dict", "bank"])
 def test_fumi_meta_test_100_steps(name, via):
-    kc.fumi_test_case(DEV, name, via=via)
+    n_ties = kc.fumi_test_case(DEV, name, via=via)
+    print(f"{name}/{via}: {n_ties} ReLU gate ties (|z| < 1e-5) over the 100-step unroll")
+    assert n_ties <= 4, "more ReLU-gate ties than rounding noise explains"
 
 
 @pytest.mark.parametrize("name", ["maml_train_n5k5_d512", "maml_train_n5k5_d512_fo", "maml_test_n5k5_d512"])
