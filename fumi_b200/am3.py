@@ -1,10 +1,12 @@
-"""AM3 baseline: host-side mirror of the reference's fumi/models/am3.py for meta-test scoring.
+"""AM3 baseline: host-side mirror of the reference's fumi/models/am3.py.
 
-In scope (SURVEY.md section 8, row A1 / BASELINE config 4): the model definition with reference
-parameter names and construction order, and ``evaluate(task != "train")`` / ``test_loop`` -- prototype
-+ text mixing, distances, argmin, CE -- on the batched kernels.  AM3 *training* is outside the
-episodic inner-loop path (section 8(f) rank 3) and raises NotImplementedError.
+The model definition with reference parameter names and construction order; ``evaluate`` for every task mode --
+prototype + text mixing, distances, argmin, CE on the batched kernels (SURVEY.md section 8 row A1 / BASELINE config 4),
+and for ``task == "train"`` the hand-written backward (fumi_am3_bwd + the dense-layer gradient kernels), the optimizer
+and scheduler steps (am3.py:154-196); ``training_run`` / ``test_loop`` (am3.py:215-367).
 """
+import os
+
 import numpy as np
 import torch
 import torch.nn as nn
@@ -72,22 +74,31 @@ class AM3(nn.Module):
 
     def evaluate(self, batch, optimizer, scheduler, num_ways, device, task="train"):
         """am3.py:128-212.  Returns the reference's 11-tuple for task == 'test', 6-tuple for 'val'."""
-        if task == "train":
-            raise NotImplementedError("AM3 meta-training is outside the accelerated episodic inner-loop path "
-                                      "(SURVEY.md section 8(f)); only meta-test scoring is built")
-        self.eval()
+        train = task == "train"
+        self.train(train)
         if self.text_encoder_type == "rand":
             raise NotImplementedError("text_encoder='rand' draws prototypes from the host RNG; not built")
-        res = self._get_engine(device).am3_batch(self, batch, num_ways)
+        if train:
+            # optimizer.zero_grad() of am3.py:189; FusedAdam keeps its flat gradient views alive
+            (optimizer if hasattr(optimizer, "_flat") else self).zero_grad()
+        res = self._get_engine(device).am3_batch(self, batch, num_ways, train=train)
+        if train:
+            optimizer.step()                      # am3.py:190-193
+            if scheduler:
+                scheduler.step()
         eb = res["batch"]
         B, NQ = eb.qry_y.shape
-        loss = (res["task_loss"].sum() / float(B * NQ)).cpu().numpy()          # mean over all queries (utils.py:402)
+        if train:
+            la = res["loss_acc"].cpu().numpy()        # (mean CE, mean lamda), summed over ranks when sharded
+            loss = la[0]
+        else:
+            loss = (res["task_loss"].sum() / float(B * NQ)).cpu().numpy()      # mean over all queries (utils.py:402)
         preds = res["preds"].cpu().numpy()
         flat_preds, flat_targets = preds.reshape(-1), eb.qry_y.cpu().numpy().reshape(-1)
         from sklearn.metrics import accuracy_score, precision_recall_fscore_support    # utils.py:16,323-326
         acc = accuracy_score(flat_targets, flat_preds)
         prec, rec, f1, _ = precision_recall_fscore_support(flat_targets, flat_preds, average="macro")
-        avg_lamda = res["sup_lamda"].mean().cpu().numpy()
+        avg_lamda = la[1] if train else res["sup_lamda"].mean().cpu().numpy()
         if task == "test":
             to_np = lambda t: t.detach().cpu().numpy() if isinstance(t, torch.Tensor) else np.asarray(t)
             return (loss, acc, f1, prec, rec, avg_lamda, preds, eb.qry_y, to_np(eb.qry_ids), to_np(eb.sup_ids),
@@ -96,7 +107,46 @@ class AM3(nn.Module):
 
 
 def training_run(args, model, optimizer, train_loader, val_loader, max_test_batches):
-    raise NotImplementedError("AM3 meta-training is outside the accelerated path (SURVEY.md section 8(f))")
+    """am3.py:215-305: initial validation, train step per batch, validation + checkpoint every eval_freq batches (batch 0
+    included, unlike FuMI's loop), patience, best-checkpoint reload."""
+    from . import utils
+    best_loss, best_acc = test_loop(args, model, val_loader, max_test_batches)[:2]
+    print(f"\ninitial loss: {best_loss}, acc: {best_acc}")
+    best_batch_idx = 0
+    if type(optimizer) == tuple:
+        opt, scheduler = optimizer
+    else:
+        opt, scheduler = optimizer, None
+    saved_best = False
+    try:
+        for batch_idx, batch in enumerate(train_loader):
+            train_loss, train_acc, train_f1, train_prec, train_rec, train_lamda = model.evaluate(
+                batch=batch, optimizer=opt, scheduler=scheduler, num_ways=args.num_ways, device=args.device, task="train")
+            utils.log({"train/acc": train_acc, "train/f1": train_f1, "train/prec": train_prec, "train/rec": train_rec,
+                       "train/loss": train_loss, "train/avg_lamda": train_lamda,
+                       "num_episodes": (batch_idx + 1) * args.batch_size}, step=batch_idx)
+            if batch_idx % args.eval_freq == 0:
+                val = test_loop(args, model, val_loader, max_test_batches)
+                val_loss, val_acc, val_f1, val_prec, val_rec, val_lamda = val[:6]
+                is_best = val_loss < best_loss
+                if is_best:
+                    best_loss = val_loss
+                    best_batch_idx = batch_idx
+                utils.log({"val/acc": val_acc, "val/f1": val_f1, "val/prec": val_prec, "val/rec": val_rec,
+                           "val/loss": val_loss, "val/avg_lamda": val_lamda}, step=batch_idx)
+                utils.save_checkpoint({"batch_idx": batch_idx, "state_dict": model.state_dict(), "best_loss": best_loss,
+                                       "optimizer": opt.state_dict(), "args": utils.args_dict(args)}, is_best, args)
+                saved_best |= is_best
+                print(f"\nBatch {batch_idx+1}/{args.epochs}: \ntrain/loss: {train_loss}, train/acc: {train_acc}, "
+                      f"train/avg_lamda: {train_lamda}\nval/loss: {val_loss}, val/acc: {val_acc}, val/avg_lamda: {val_lamda}")
+            if (batch_idx > args.epochs - 1) or (args.patience > 0 and batch_idx - best_batch_idx > args.patience):
+                break
+    except KeyboardInterrupt:
+        pass
+    best_file = os.path.join(utils.run_dir(args), "best.pth.tar")
+    if saved_best and os.path.exists(best_file):                   # am3.py:302-303 (only a checkpoint of THIS run)
+        model, _ = utils.load_checkpoint(model, opt, args.device, best_file)
+    return model
 
 
 def test_loop(args, model, test_dataloader, max_num_batches):

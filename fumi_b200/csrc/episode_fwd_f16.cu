@@ -337,6 +337,7 @@ __global__ void __launch_bounds__(kThreads16, 1) episode_fwd_v2_kernel(EpiParams
         // ------------------------------------------------------------------ inner steps
         for (int st = 0; st < steps; ++st) {
             float* rec = slot ? slot + L.steps + int64_t(st) * L.per_step : nullptr;
+            pc.mark(45);
             __syncthreads();                              // B1: H0 planes, W1 planes, b1 / head of this step
             if (st > 0) FUMI_ADOPT(e_h0, e_h0n, par_h0, FX_H0);
             pc.mark(21);
@@ -367,8 +368,8 @@ __global__ void __launch_bounds__(kThreads16, 1) episode_fwd_v2_kernel(EpiParams
                     for (int cc = 1; cc < kNC; ++cc) mxl = fmaxf(mxl, lg[cc]);
                     float sum = 0.f;
 #pragma unroll
-                    for (int cc = 0; cc < kNC; ++cc) { lg[cc] = __expf(lg[cc] - mxl); sum += lg[cc]; }   // inert: exp(-3e38) = 0
-                    const float rs = __frcp_rn(sum);
+                    for (int cc = 0; cc < kNC; ++cc) { lg[cc] = fumi_fast_exp(lg[cc] - mxl); sum += lg[cc]; }   // inert: exp(-3e38) = 0
+                    const float rs = fumi_fast_rcp(sum);
                     const int y = s.ysS[i];               // (zero for pad rows)
                     float da = 0.f, db = 0.f, dlw = 0.f;
 #pragma unroll
@@ -603,6 +604,7 @@ __global__ void __launch_bounds__(kThreads16, 1) episode_fwd_v2_kernel(EpiParams
             }
             if (r0 + 32 < m) h0_load(qrid, 2);           // next tile's projected rows, a tile ahead; row ids two tiles ahead
             if (r0 + 64 < m) h0_rows(qrows + r0 + 64, min(32, m - r0 - 64), qrid);
+            pc.mark(43);
             __syncthreads();                              // QB1: H0q planes
             FUMI_ADOPT(e_h0, e_h0n, par_h0, FX_H0);
             pc.mark(28);
@@ -616,6 +618,7 @@ __global__ void __launch_bounds__(kThreads16, 1) episode_fwd_v2_kernel(EpiParams
                 }
             }
             z1_gemm(1, 2);
+            pc.mark(44);
             __syncthreads();                              // QB2: Z1q partial sums, next Gram planes
             if (r0 + 32 < m) FUMI_ADOPT(e_gq, e_gqn, par_gq, FX_GQ);
             if (r0 + 64 < m) q_load(r0 + 64);
@@ -641,11 +644,11 @@ __global__ void __launch_bounds__(kThreads16, 1) episode_fwd_v2_kernel(EpiParams
                 if (live && lane < N) P.logits[q * N + lane] = lgw;
                 float sum = 0.f;
 #pragma unroll
-                for (int cc = 0; cc < kNC; ++cc) { lg[cc] = __expf(lg[cc] - mxl); sum += lg[cc]; }
+                for (int cc = 0; cc < kNC; ++cc) { lg[cc] = fumi_fast_exp(lg[cc] - mxl); sum += lg[cc]; }
                 if (slot && live) {
                     slot[L.qH1 + int64_t(r0 + i) * kH1 + lane] = h1a;
                     slot[L.qH1 + int64_t(r0 + i) * kH1 + lane + 32] = h1b;
-                    const float rs = __frcp_rn(sum);
+                    const float rs = fumi_fast_rcp(sum);
                     float pw = 0.f;
 #pragma unroll
                     for (int cc = 0; cc < kNC; ++cc)
@@ -654,7 +657,7 @@ __global__ void __launch_bounds__(kThreads16, 1) episode_fwd_v2_kernel(EpiParams
                 }
                 if (live && lane == 0) {
                     P.preds[q] = bi;
-                    loss_sum += (__logf(sum) + mxl) - ly;
+                    loss_sum += (fumi_fast_log(sum) + mxl) - ly;
                     corr_sum += bi == y ? 1.f : 0.f;
                 }
             }

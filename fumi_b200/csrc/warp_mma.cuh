@@ -27,6 +27,9 @@ static inline void fumi_join2(uint32_t hi, uint32_t lo, float& a, float& b) {
     a = fumi_h2f(fumi_half{uint16_t(hi & 0xFFFFu)}) + fumi_h2f(fumi_half{uint16_t(lo & 0xFFFFu)});
     b = fumi_h2f(fumi_half{uint16_t(hi >> 16)}) + fumi_h2f(fumi_half{uint16_t(lo >> 16)});
 }
+static inline float fumi_fast_exp(float x) { return std::exp(x); }
+static inline float fumi_fast_log(float x) { return std::log(x); }
+static inline float fumi_fast_rcp(float x) { return 1.f / x; }
 static inline void fumi_cp_async16(void* smem_dst, const void* gmem_src) { std::memcpy(smem_dst, gmem_src, 16); }
 static inline void fumi_cp_async_wait() {}
 #else
@@ -66,6 +69,11 @@ __device__ __forceinline__ uint32_t fumi_tf32_hi(float x) {
     asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(h) : "f"(x));
     return h;
 }
+// MUFU-based exp / log / reciprocal (softmax probabilities and the CE loss: ~1e-6 relative, far inside the 1e-4 bar;
+// the argmax that decides the predictions is taken on the logits themselves)
+__device__ __forceinline__ float fumi_fast_exp(float x) { return __expf(x); }
+__device__ __forceinline__ float fumi_fast_log(float x) { return __logf(x); }
+__device__ __forceinline__ float fumi_fast_rcp(float x) { return __frcp_rn(x); }
 // 16-byte asynchronous global -> shared copy (LDGSTS) and the wait for all copies of this thread
 __device__ __forceinline__ void fumi_cp_async16(void* smem_dst, const void* gmem_src) {
     const uint32_t d = static_cast<uint32_t>(__cvta_generic_to_shared(smem_dst));

@@ -466,17 +466,33 @@ class EpisodeEngine:
         self._allreduce_finish(params, la, pending)
         return res
 
-    # ------------------------------------------------------------------ AM3 (meta-test scoring)
-    def am3_batch(self, model, batch, num_ways):
-        """AM3.evaluate in eval mode (am3.py:159-200): prototypes, distances, argmin, CE."""
+    # ------------------------------------------------------------------ AM3
+    def _dropout(self, x, seed, layer, p):
+        if p > 0:
+            self._call("fumi_dropout_apply", self.L.fumi_dropout_apply, _lib.ptr(x), x.shape[0], x.shape[1], C.c_uint64(seed),
+                       C.c_uint32(layer), float(p), self._stream())
+            self.launches += 1
+        return x
+
+    def am3_batch(self, model, batch, num_ways, train=False):
+        """AM3.evaluate (am3.py:128-212): prototypes, distances, argmin, CE; with train=True also the gradients of
+        the mean query CE wrt every parameter (loss.backward(), am3.py:188-190), left in p.grad.
+
+        The text path is evaluated once per class description (one row of bank.text), as the support samples of a class
+        share their text (am3.py:123 maps the same description K times).  In train mode the Dropout layers inside g / h
+        (am3.py:66-88) use the counter-based masks of the episode kernels, one mask per class description and meta-batch
+        (the reference draws one per support sample from the torch generator; parity is defined at --dropout 0)."""
         N = num_ways
         if isinstance(batch, EpisodeBatch):
             eb = batch.to(self.device)
             feats, text_rows, class_rows = eb.bank.feats, eb.bank.text, eb.head_class
-            sup_text_row = None
         else:
             eb, feats, text_rows, class_rows = self.unpack(batch, N, want_text=True)
         P = model.prototype_dim
+        p_drop = float(model.dropout) if train else 0.0
+        if train:
+            model.dropout_seed = getattr(model, "dropout_seed", 0) + 1
+        seed = (int(getattr(model, "dropout_base_seed", 0)) << 20) + getattr(model, "dropout_seed", 0)
         if self.precision == 2 and feats.shape[1] % 8 == 0:      # the bank's fp16 planes (split once, shared with FuMI / MAML)
             emb = self.gemm_f16(self._feat_planes16(feats, eb.bank, False), self.split_f16(model.image_encoder.weight),
                                 bias=model.image_encoder.bias)
@@ -486,16 +502,16 @@ class EpisodeEngine:
         else:
             emb = self.linear_fwd(feats, model.image_encoder.weight, model.image_encoder.bias, precision=0)
         g0, g3, h0, h3 = model.g[0], model.g[3], model.h[0], model.h[3]
-        t = self.linear_fwd(self.linear_fwd(text_rows, g0.weight, g0.bias, act=1, precision=0), g3.weight, g3.bias,
-                            precision=0)
-        lam = self.linear_fwd(self.linear_fwd(t, h0.weight, h0.bias, act=1, precision=0), h3.weight, h3.bias, act=3,
-                              precision=0)
+        u = self._dropout(self.linear_fwd(text_rows, g0.weight, g0.bias, act=1, precision=0), seed, 0, p_drop)
+        t = self.linear_fwd(u, g3.weight, g3.bias, precision=0)
+        z = self._dropout(self.linear_fwd(t, h0.weight, h0.bias, act=1, precision=0), seed, 1, p_drop)
+        lam = self.linear_fwd(z, h3.weight, h3.bias, act=3, precision=0)
         B, NK = eb.sup_rows.shape
         NQ = eb.qry_rows.shape[1]
         protos, dist_, preds = self._new(B, N, P), self._new(B, NQ, N), self._new(B, NQ, dtype=torch.int64)
         task_loss = self._new(B)
         fixed = -1 if model.lamda_fixed is None else int(model.lamda_fixed)
-        self._call("fumi_am3_score", self.L.fumi_am3_score, 
+        self._call("fumi_am3_score", self.L.fumi_am3_score,
             _lib.ptr(emb), _lib.ptr(t), _lib.ptr(lam.reshape(-1)), _lib.ptr(eb.sup_rows), _lib.ptr(eb.qry_rows),
             _lib.ptr(eb.sup_y), _lib.ptr(eb.qry_y), _lib.ptr(class_rows), B, N, NK, NQ, P, fixed, _lib.ptr(protos),
             _lib.ptr(dist_), _lib.ptr(preds), _lib.ptr(task_loss), self._stream())
@@ -506,4 +522,47 @@ class EpisodeEngine:
             label_lam = torch.zeros_like(label_lam)
         elif fixed == 1:
             label_lam = torch.ones_like(label_lam)
-        return dict(task_loss=task_loss, preds=preds, dist=dist_, protos=protos, sup_lamda=label_lam, batch=eb)
+        res = dict(task_loss=task_loss, preds=preds, dist=dist_, protos=protos, sup_lamda=label_lam, batch=eb)
+        if not train:
+            return res
+        # ---- backward (am3.py:188-190): gradients of sum_b sum_q CE / (B_global * NQ)
+        world = self._world()
+        Cn = text_rows.shape[0]
+        d_emb = torch.zeros_like(emb)
+        d_tp, d_lam = self._new(B, N, P), self._new(B, N)
+        self._call("fumi_am3_bwd", self.L.fumi_am3_bwd,
+            _lib.ptr(emb), _lib.ptr(t), _lib.ptr(lam.reshape(-1)), _lib.ptr(eb.sup_rows), _lib.ptr(eb.qry_rows),
+            _lib.ptr(eb.sup_y), _lib.ptr(eb.qry_y), _lib.ptr(class_rows), B, N, NK, NQ, P, fixed, _lib.ptr(protos),
+            _lib.ptr(dist_), 1.0 / float(B * world * NQ), _lib.ptr(d_emb), _lib.ptr(d_tp), _lib.ptr(d_lam), self._stream())
+        self.launches += 1
+        rows_flat = class_rows.reshape(-1).contiguous()
+        d_t2 = torch.zeros(2, Cn, P, dtype=torch.float32, device=self.device)          # [from prototypes | through h]
+        d_lt = torch.zeros(Cn, 1, dtype=torch.float32, device=self.device)
+        self._call("fumi_scatter_add_rows", self.L.fumi_scatter_add_rows, _lib.ptr(d_tp), _lib.ptr(rows_flat), B * N, P,
+                   _lib.ptr(d_t2[0]), self._stream())
+        self._call("fumi_scatter_add_rows", self.L.fumi_scatter_add_rows, _lib.ptr(d_lam), _lib.ptr(rows_flat), B * N, 1,
+                   _lib.ptr(d_lt), self._stream())
+        self.launches += 2
+        # lamda = sigmoid(h(t)):  h = Linear(P, Th) - ReLU - Dropout - Linear(Th, 1)
+        self._call("fumi_sigmoid_bwd", self.L.fumi_sigmoid_bwd, _lib.ptr(lam), _lib.ptr(d_lt), Cn, self._stream())
+        self.launches += 1
+        self.linear_wgrad(d_lt, z, self._grad(h3.weight), self._grad(h3.bias), precision=0)
+        d_z = self._dropout(self.linear_dgrad(d_lt, h3.weight, gate=z), seed, 1, p_drop)   # z > 0 <=> ReLU gate and mask kept
+        self.linear_wgrad(d_z, t, self._grad(h0.weight), self._grad(h0.bias), precision=0)
+        self._call("fumi_linear_dgrad", self.L.fumi_linear_dgrad, _lib.ptr(d_z), _lib.ptr(h0.weight), None,
+                   _lib.ptr(d_t2[1]), Cn, h0.weight.shape[0], P, self._stream())
+        self.launches += 1
+        d_t = self._new(Cn, P)
+        self.reduce_parts(d_t2.reshape(2, Cn * P), 2, d_t.reshape(-1))
+        # t = g(text):  g = Linear(T, Th) - ReLU - Dropout - Linear(Th, P)
+        self.linear_wgrad(d_t, u, self._grad(g3.weight), self._grad(g3.bias), precision=0)
+        d_u = self._dropout(self.linear_dgrad(d_t, g3.weight, gate=u), seed, 0, p_drop)
+        self.linear_wgrad(d_u, text_rows, self._grad(g0.weight), self._grad(g0.bias), precision=0)
+        # image encoder: dW = d_emb^T X over the bank, db = column sums
+        self.wgrad_rows(d_emb, feats, eb.bank, self._grad(model.image_encoder.weight))
+        self.reduce_parts(d_emb, d_emb.shape[0], self._grad(model.image_encoder.bias))
+        params = [p for p in model.parameters() if p.requires_grad]
+        la = torch.stack([task_loss.sum() / float(B * NQ), label_lam.mean()])
+        self._allreduce_finish(params, la, None)
+        res["loss_acc"] = la
+        return res

@@ -129,7 +129,7 @@ def init_model(args, dictionary, watch=True):
     model = build_model(args, dictionary)
     model.to(args.device)
     model._get_engine(args.device).precision = int(getattr(args, "precision", 2))
-    if hasattr(model, "dropout_base_seed") or args.model == "fumi":
+    if hasattr(model, "dropout_base_seed") or args.model in ("fumi", "am3"):
         model.dropout_base_seed = int(getattr(args, "seed", 0))
     return model
 

@@ -246,6 +246,23 @@ int fumi_am3_score(const float* emb, const float* text_proto, const float* lamda
                    int64_t B, int32_t N, int32_t NK, int32_t NQ, int32_t P, int32_t lamda_fixed,
                    float* protos, float* dist, int64_t* preds, float* task_loss, void* stream);
 
+/* AM3 meta-training (am3.py:154-196, 215-305): backward of fumi_am3_score's loss = loss_scale * sum of the query CEs.
+ *   protos / dist  outputs of fumi_am3_score for the same batch
+ *   d_emb [R,P]    += d loss / d image embedding rows (atomic scatter-add; zero it first)
+ *   d_tproto [B,N,P], d_lamda [B,N]  gradients wrt the class text prototype / lamda of label i of task b
+ *                  (scatter them into the class tables with fumi_scatter_add_rows by class_rows)
+ * fumi_dropout_apply: x[r,c] *= keep(seed, layer, r, c) / (1 - p), the counter-based mask of the episode kernels (also
+ *   its own backward when applied to the gradient) -- AM3's Dropout inside g / h (am3.py:66-88) in train mode.
+ * fumi_sigmoid_bwd: dy *= y (1 - y)   (lamda = sigmoid(h(.)), am3.py:125). */
+int fumi_am3_bwd(const float* emb, const float* text_proto, const float* lamda,
+                 const int64_t* sup_rows, const int64_t* qry_rows,
+                 const int64_t* sup_y, const int64_t* qry_y, const int64_t* class_rows,
+                 int64_t B, int32_t N, int32_t NK, int32_t NQ, int32_t P, int32_t lamda_fixed,
+                 const float* protos, const float* dist, float loss_scale,
+                 float* d_emb, float* d_tproto, float* d_lamda, void* stream);
+int fumi_dropout_apply(float* x, int64_t rows, int64_t cols, uint64_t seed, uint32_t layer, float p, void* stream);
+int fumi_sigmoid_bwd(const float* y, float* dy, int64_t n, void* stream);
+
 /* ------------------------------------------------------------------------------------------
  * Episodic task sampler (HOST side, native): bit-exact restatement of
  * BatchMetaDataLoader(ClassSplitter(InatAnim(...), shuffle=True, K, Q).seed(0)) --

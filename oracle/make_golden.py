@@ -208,8 +208,37 @@ def golden_am3(tag, bank_kw, argv):
     print(tag, "loss", loss, "acc", acc, "size", os.path.getsize(os.path.join(GOLD, f"{tag}.npz")) >> 10, "KiB")
 
 
+def golden_am3_train(tag, bank_kw, argv):
+    """One AM3 meta-train step (am3.py:154-196) at --dropout 0: loss, metrics, all gradients, post-Adam parameters."""
+    ref, bank, args, (tl, vl, te, _), model, optim = setup(bank_kw, ["--model", "am3", *argv])
+    out = meta(bank_kw, bank, argv)
+    batch = next(iter(tl))
+    out.update(flat(batch))
+    for k, v in model.state_dict().items():
+        out["param:" + k] = v.detach().clone().numpy()
+    r = model.evaluate(batch=batch, optimizer=optim, scheduler=None, num_ways=args.num_ways, device=args.device,
+                       task="train")
+    loss, acc, f1, prec, rec, lam = r
+    out.update(loss=np.asarray(loss), acc=np.asarray(acc), f1=np.asarray(f1), prec=np.asarray(prec), rec=np.asarray(rec),
+               avg_lamda=np.asarray(lam))
+    for k, p in model.named_parameters():
+        if p.grad is not None:
+            out["grad:" + k] = p.grad.detach().numpy()
+    for k, v in model.state_dict().items():
+        out["post:" + k] = v.detach().numpy()
+    out["lr"], out["wd"] = np.asarray(args.lr), np.asarray(args.weight_decay)
+    np.savez_compressed(os.path.join(GOLD, f"{tag}.npz"), **out)
+    print(tag, "loss", loss, "acc", acc, "size", os.path.getsize(os.path.join(GOLD, f"{tag}.npz")) >> 10, "KiB")
+
+
 def main():
     os.makedirs(GOLD, exist_ok=True)
+    if len(sys.argv) > 1 and sys.argv[1] == "am3_train":       # only the fixture added in round 2
+        small = dict(num_images=120 * 70, num_classes=120, im_dim=512, text_dim=64, min_per_class=60, seed=11)
+        golden_am3_train("am3_train_n10k5_d512", small,
+                         ["--num_ways", "10", "--num_shots", "5", "--num_shots_test", "6", "--batch_size", "3",
+                          "--dropout", "0"])
+        return
     golden_sampler()
     small = dict(num_images=120 * 70, num_classes=120, im_dim=512, text_dim=64, min_per_class=60, seed=11)
     full = dict(num_images=60 * 70, num_classes=60, im_dim=2048, text_dim=768, min_per_class=60, seed=2022)
@@ -245,6 +274,9 @@ def main():
     # config 4 (AM3 10-way 5-shot meta-test)
     golden_am3("am3_test_n10k5_d512", small,
                ["--num_ways", "10", "--num_shots", "5", "--batch_size", "3"])
+    golden_am3_train("am3_train_n10k5_d512", small,
+                     ["--num_ways", "10", "--num_shots", "5", "--num_shots_test", "6", "--batch_size", "3",
+                      "--dropout", "0"])
 
 
 if __name__ == "__main__":

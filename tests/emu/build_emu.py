@@ -7,13 +7,13 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(os.path.dirname(HERE))
 CSRC = os.path.join(ROOT, "fumi_b200", "csrc")
 OUT = os.path.join(HERE, "libfumi_emu.so")
-SRCS = ["episode.cu", "gram.cu", "dense.cu", "optim.cu", "am3.cu", "sampler.cpp", "sampler_expand.cu"]
+SRCS = ["episode.cu", "episode_fwd_f16.cu", "episode_bwd_f16.cu", "gram.cu", "dense.cu", "optim.cu", "am3.cu", "sampler.cpp", "sampler_expand.cu"]
 TEST_SRCS = [os.path.join(ROOT, "tests", "csrc", "debug_gemm.cu")]
 
 
 def build(force=False):
     srcs = [os.path.join(CSRC, f) for f in SRCS] + TEST_SRCS + [os.path.join(HERE, "cuda_emu.cpp")]
-    deps = srcs + [os.path.join(HERE, "cuda_emu.h"), os.path.join(CSRC, "common.cuh"), os.path.join(CSRC, "launch.cuh"), os.path.join(CSRC, "warp_mma.cuh"),
+    deps = srcs + [os.path.join(HERE, "cuda_emu.h"), os.path.join(CSRC, "common.cuh"), os.path.join(CSRC, "launch.cuh"), os.path.join(CSRC, "warp_mma.cuh"), os.path.join(CSRC, "episode_common.cuh"),
                    os.path.join(ROOT, "include", "fumi_b200.h")]
     if not force and os.path.exists(OUT) and os.path.getmtime(OUT) > max(os.path.getmtime(d) for d in deps):
         return OUT

@@ -79,9 +79,6 @@ static inline float atomicAdd(float* addr, float v) {
 static inline float __uint_as_float(uint32_t u) { float f; std::memcpy(&f, &u, 4); return f; }
 static inline uint32_t __float_as_uint(float f) { uint32_t u; std::memcpy(&u, &f, 4); return u; }
 #define __forceinline__ inline
-static inline float __expf(float x) { return std::exp(x); }
-static inline float __logf(float x) { return std::log(x); }
-static inline float __frcp_rn(float x) { return 1.f / x; }
 template <typename T> static inline T __ldg(const T* p) { return *p; }
 
 // ---- warp-collective emulation: tf32 rounding and mma.sync.m16n8k8 (TF32 inputs, fp32 accumulate)

@@ -396,6 +396,35 @@ def am3_case(device, name="am3_test_n10k5_d512"):
     assert np.array_equal(qidx, g["qry_ids"]) and np.array_equal(sidx, g["sup_ids"])
 
 
+def am3_train_case(device, name="am3_train_n10k5_d512"):
+    """One AM3 meta-train step through AM3.evaluate(task='train') (am3.py:154-196) against the reference's gradients and
+    post-Adam parameters (--dropout 0 golden)."""
+    g, bank = load_golden(name)
+    m = am3_mod.AM3(im_encoder="precomputed", im_emb_dim=bank.feats.shape[1], text_encoder="BERT",
+                    text_emb_dim=bank.text.shape[1], text_hid_dim=256, prototype_dim=64, dropout=0.0)
+    model = _load(m, params_of(g), device)
+    opt = FusedAdam(model.parameters(), lr=float(g["lr"]), weight_decay=float(g["wd"]))
+    out = model.evaluate(batch=_torchmeta_batch(g, bank), optimizer=opt, scheduler=None, num_ways=10, device=device,
+                         task="train")
+    loss, acc, f1, prec, rec, lam = out
+    assert abs(float(loss) - float(g["loss"])) < TOL * abs(float(g["loss"]))
+    for a, k in ((acc, "acc"), (f1, "f1"), (prec, "prec"), (rec, "rec")):
+        assert abs(float(a) - float(g[k])) < 1e-9, k
+    assert abs(float(lam) - float(g["avg_lamda"])) < 1e-6
+    f = opt._flat[0]
+    off = 0
+    for k, p in model.named_parameters():
+        if not p.requires_grad:
+            continue
+        got = f["g"][off:off + p.numel()].view(p.shape).cpu().numpy()
+        assert relerr(got, g["grad:" + k]) < 2e-4, (k, relerr(got, g["grad:" + k]))
+        off += p.numel()
+        ref, pre = g["post:" + k], g["param:" + k]
+        big = np.abs(g["grad:" + k] + float(g["wd"]) * pre) > 1e-5
+        assert np.abs(p.detach().cpu().numpy() - ref)[big].max() <= 1e-6, k
+        assert np.abs(p.detach().cpu().numpy() - pre).max() <= 1.01 * float(g["lr"]) + 1e-7
+
+
 def dropout_case(device, name="fumi_train_n5k5_d512", p=0.25, seed=77):
     """Counter-based dropout masks: the device path must equal the oracle fed the same masks."""
     from fumi_b200.dropout import mask_array

@@ -95,3 +95,8 @@ def test_device_sampler_equals_host_sampler():
 
 def test_device_loader_prefetch():
     kc.device_loader_case("cpu")
+
+
+def test_am3_train_step():
+    kc.am3_train_case("cpu")
+

@@ -111,6 +111,10 @@ def test_am3():
     kc.am3_case(DEV)
 
 
+def test_am3_train_step():
+    kc.am3_train_case(DEV)
+
+
 def test_dropout_masks():
     kc.dropout_case(DEV)
 

@@ -23,8 +23,8 @@ NAMES = {0: "bwd prologue (W1/G planes, maxes)", 1: "bwd q: tile data -> smem, w
          14: "bwd epilogue",
          20: "fwd prologue", 21: "fwd s: wait B1", 22: "fwd s: Z1 gemm, B2", 23: "fwd s: row-per-warp c, stash H0, B3",
          24: "fwd s: dhp sums, dZ0 gemm, S update", 25: "fwd s: W1 update gemm + planes",
-         26: "fwd s: records, head/b1 update, next H0", 28: "fwd q: Z0q gemm + H0q planes, QB1",
-         29: "fwd q: stash, Gram planes, Z1q gemm, QB2", 30: "fwd q: row-per-warp scoring", 33: "fwd epilogue"}
+         26: "fwd s: records, head/b1 update, next H0", 28: "fwd q: wait QB1",
+         29: "fwd q: wait QB2", 30: "fwd q: row-per-warp scoring", 33: "fwd epilogue"}
 
 
 def main():
@@ -54,7 +54,7 @@ def main():
     out = np.zeros(64, np.uint64)
     L.fumi_debug_read_phases(_lib.ptr(out))
     L.fumi_debug_phase_profile(0)
-    for lo, hi, name in ((20, 44, "forward"), (0, 15, "backward")):
+    for lo, hi, name in ((20, 48, "forward"), (0, 15, "backward")):
         tot = float(out[lo:hi].sum())
         print(f"== {name}: {tot / 1e6:.1f} Mcycles summed over CTAs")
         for i in range(lo, hi):
