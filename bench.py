@@ -322,7 +322,7 @@ class Context:
         return float(t.item())
 
 
-def run_workload(ctx, wl, n_steps, n_warmup, kernel_pass, cpu_budget_s, parity):
+def run_workload(ctx, wl, n_steps, n_warmup, kernel_pass, cpu_budget_s, parity, tasks_override=0):
     """One workload on this rank's GPU: device-resident leg (value), end-to-end leg through the public API (e2e),
     per-kernel pass, CPU baseline (rank 0, N=1)."""
     import random
@@ -335,7 +335,7 @@ def run_workload(ctx, wl, n_steps, n_warmup, kernel_pass, cpu_budget_s, parity):
     a, device, rank, world = ctx.a, ctx.device, ctx.rank, ctx.world
     w = WORKLOADS[wl]
     model_name, N, K, Q, steps, train = w["model"], w["N"], w["K"], w["Q"], w["steps"], w["train"]
-    tasks = a.tasks if (a.tasks and wl == a.workload) else w["tasks"]
+    tasks = tasks_override or (a.tasks if (a.tasks and wl == a.workload) else w["tasks"])
     split = 0 if train else 2
     cats = class_split(a.bank_classes)[split]
     sampler = EpisodeSampler(ctx.bank.cat_of, cats, N, K, Q, num_threads=max(2, (os.cpu_count() or 8) // max(1, world)))
@@ -622,6 +622,13 @@ def main():
                                          "by_kernel": r["roofline"].get("by_kernel")}
             if "ranks_in_sync" in r:
                 secondary[wl]["ranks_in_sync"] = r["ranks_in_sync"]
+    strong = None
+    if ctx.world > 1 and not solo and not a.no_secondary:
+        # strong scaling: the single-GPU meta-batch (4096 tasks) split over the ranks, same all-reduce per step
+        per = max(1, WORKLOADS[PRIMARY]["tasks"] // ctx.world)
+        r = run_workload(ctx, PRIMARY, a.steps, a.warmup, False, 0.0, False, tasks_override=per)
+        strong = {"scaling": "strong", "global_tasks_per_step": per * ctx.world, "tasks_per_gpu": per, "value": r["value"],
+                  "unit": r["unit"], "ms_per_step": r["ms_per_step"], "e2e": r["e2e"], "ranks_in_sync": r.get("ranks_in_sync")}
     if ctx.rank == 0:
         line = {"metric": main_r["metric"], "value": main_r["value"], "unit": main_r["unit"], "n_gpus": ctx.world,
                 "steps": a.steps, "warmup": a.warmup, "ms_per_step": main_r["ms_per_step"], "higher_is_better": True,
@@ -635,6 +642,8 @@ def main():
                 line[key] = main_r[key]
         if secondary:
             line["secondary"] = secondary
+        if strong:
+            line["strong_scaling"] = strong
         print(json.dumps(line))
     if ctx.world > 1:
         import torch.distributed as dist

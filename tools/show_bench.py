@@ -1,5 +1,5 @@
 import json,sys
-d=json.load(open(sys.argv[1]))
+d=json.loads([l for l in open(sys.argv[1]) if l.startswith("{")][-1])
 print("primary", round(d["value"]), round(d["ms_per_step"],3), "e2e", round(d["e2e"]["value"]), "frac", round(d["roofline"]["frac"],4), "parity", {k:v for k,v in (d.get("parity") or {}).items() if k not in("grad_relerr","checker","tolerance")})
 print("cpu", d["cpu_baseline"])
 for k,v in (d.get("secondary") or {}).items():
