@@ -20,31 +20,40 @@
 //
 // In train mode the step records are stashed as the planes themselves (LayoutF): the backward copies them into its
 // operand tiles with no conversion.
+//
+// Query scoring (fumi.py:178-185) has no such coupling -- S, W1, b0, b1 and the head are final -- so it runs with NO
+// block barrier: a warp owns 16 query rows, walks the 256 hidden units in 16-column slabs, and the activations of a slab
+// (accumulator layout of the Z0 MMAs) are used directly as the A fragments of one k step of Z1q = H0q W1^T.  The
+// projected rows arrive through a per-warp cp.async ring three slabs ahead.
 #include "episode_common.cuh"
 
 namespace fumi_epi {
 namespace {
 
-enum { FX_W1 = 0, FX_H0 = 2, FX_DZ = 4, FX_GQ = 6, FX_GS = 8, FX_HP = 9, FX_COUNT = 10 };   // FX_W1 + 1 unused   // x 16 floats (two parities)
+enum { FX_W1 = 0, FX_H0 = 2, FX_DZ = 4, FX_GS = 6, FX_HP = 7, FX_COUNT = 8 };   // x 16 floats (H0 / dZ1: two parities)
+
+constexpr int kRingRow = 24;                 // words per row of a ring slab (64 data bytes + pad: conflict-free LDS.64)
+constexpr int kRingSlab = 16 * kRingRow;     // one slab: 16 rows
 
 struct SmemV {
-    fumi_half *w1h, *w1l, *sh, *sl, *h0h, *h0l, *dzh, *dzl, *gsh, *gsl, *gqh, *gql;
-    float *z1p, *h1t, *dz1t, *lt, *hp, *dhp, *b1s, *mx, *red;
-    int* ysS;
+    fumi_half *w1h, *w1l, *sh, *sl, *h0h, *h0l, *dzh, *dzl, *gsh, *gsl;
+    float *z1p, *h1t, *dz1t, *lt, *hp, *dhp, *b1s, *b0s, *mx, *red;
+    int *ysS, *es;
 };
 __host__ __device__ inline size_t carve_v(char* base, SmemV& s, int N) {
     char* p = base;
     auto take = [&](size_t bytes) { char* r = p; p += (bytes + 15) & ~size_t(15); return r; };
     s.ysS = reinterpret_cast<int*>(take(32 * 4));
     s.mx = reinterpret_cast<float*>(take(FX_COUNT * 16 * 4));
-    s.red = reinterpret_cast<float*>(take(3 * 16 * 4));
+    s.red = reinterpret_cast<float*>(take(4 * 16 * 4));
+    s.es = reinterpret_cast<int*>(take(16 * 4));
+    s.b0s = reinterpret_cast<float*>(take(kH0 * 4));
     // zero-filled once per kernel from here (plane pads must be finite)
     s.w1h = reinterpret_cast<fumi_half*>(take(kH0 * kHW * 2));  s.w1l = reinterpret_cast<fumi_half*>(take(kH0 * kHW * 2));
     s.sh = reinterpret_cast<fumi_half*>(take(32 * kHS * 2));    s.sl = reinterpret_cast<fumi_half*>(take(32 * kHS * 2));
     s.h0h = reinterpret_cast<fumi_half*>(take(32 * kHS * 2));   s.h0l = reinterpret_cast<fumi_half*>(take(32 * kHS * 2));
     s.dzh = reinterpret_cast<fumi_half*>(take(32 * kHW * 2));   s.dzl = reinterpret_cast<fumi_half*>(take(32 * kHW * 2));
     s.gsh = reinterpret_cast<fumi_half*>(take(32 * kHG * 2));   s.gsl = reinterpret_cast<fumi_half*>(take(32 * kHG * 2));
-    s.gqh = reinterpret_cast<fumi_half*>(take(2 * 32 * kHG * 2)); s.gql = reinterpret_cast<fumi_half*>(take(2 * 32 * kHG * 2));
     s.z1p = reinterpret_cast<float*>(take(32 * kS1 * 4));
     s.h1t = reinterpret_cast<float*>(take(32 * kS1 * 4));
     s.dz1t = reinterpret_cast<float*>(take(32 * kS1 * 4));
@@ -88,9 +97,9 @@ __global__ void __launch_bounds__(kThreads16, 1) episode_fwd_v2_kernel(EpiParams
         const int64_t task = c.task_offset + b;
         float* slot = P.save ? P.stash + b * P.slot_floats : nullptr;
         bool bad = false;                                 // a lagged plane exponent overflowed fp16
-        int e_w1, e_h0 = 0, e_dz, e_gs, e_gq, e_s = 0;
-        int e_h0n = 0, e_dzn = 0, e_gqn = 0;              // exponents for the NEXT production (from the last observed max)
-        int par_h0 = 0, par_dz = 0, par_gq = 0;
+        int e_w1, e_h0 = 0, e_dz, e_gs, e_s = 0;
+        int e_h0n = 0, e_dzn = 0;                         // exponents for the NEXT production (from the last observed max)
+        int par_h0 = 0, par_dz = 0;
 
         // ------------------------------------------------------------------ prologue
         // fp32 master of this warp's 16 rows of W1^T at the thread's accumulator positions (the layout of the W1 update
@@ -134,6 +143,8 @@ __global__ void __launch_bounds__(kThreads16, 1) episode_fwd_v2_kernel(EpiParams
         }
         if (tid < kH1) s.b1s[tid] = __ldg(&P.b1[tid]);
         if (tid < 32) s.ysS[tid] = tid < n ? int(P.sup_y[b * n + tid]) : 0;
+        // the previous task's query pass used [h0 planes, hp) as its ring: planes whose pad rows no phase writes start as zeros
+        for (int idx = tid; idx < 2 * 32 * kHW * 2 / 16; idx += NT_) reinterpret_cast<uint4*>(s.dzh)[idx] = make_uint4(0u, 0u, 0u, 0u);
         float b0r[2][2];                                  // adapted linear0.bias at this thread's columns (warp-private)
 #pragma unroll
         for (int j = 0; j < 2; ++j) {
@@ -255,7 +266,6 @@ __global__ void __launch_bounds__(kThreads16, 1) episode_fwd_v2_kernel(EpiParams
             const float mw = slot_max(s.mx + 16 * FX_W1), mg = slot_max(s.mx + 16 * FX_GS), mh = slot_max(s.mx + 16 * FX_HP);
             e_w1 = fumi_plane_exp_t(__float_as_uint(mw), kTarget);    // fixed for the task: 8 binades of headroom
             e_gs = fumi_plane_exp_t(__float_as_uint(mg), kTarget);
-            e_gqn = e_gq = e_gs;                          // query Gram tiles: same magnitude class as the support block
             // |dZ1| <= dsc * sum_c |dL_c| |hp_c| <= dsc * (2 / n) * max |hp|: bound for the first production
             e_dz = e_dzn = fumi_plane_exp_t(__float_as_uint(fmaxf(mh * dsc * 2.f / float(n), 1e-30f)), kTarget);
             if (steps > 0) {
@@ -537,35 +547,57 @@ __global__ void __launch_bounds__(kThreads16, 1) episode_fwd_v2_kernel(EpiParams
             pc.mark(26);
         }
 
-        // ------------------------------------------------------------------ query scoring, 32 rows per tile
-        // Tile t: [Z0q GEMM on this warp's columns -> H0q planes] B [Z1q partial sums; Gram planes of tile t+1] B
-        // [one row per warp: H1q, logits, softmax, loss, argmax].  The Gram rows of tile t+1 / t+2 and the projected
-        // rows of tile t+1 travel in registers.
-        const int64_t* qrows = P.qry_rows + b * m;
-        float qg[2];
-        auto q_load = [&](int r0) {
-            const int tr = min(32, m - r0);
+        // ------------------------------------------------------------------ adapted state is final
+        // The query pass below is barrier-free and owns ROWS, not hidden units, so what was warp-private goes public
+        // here: b0 and the exponents of the S planes of each 16-column slab; the fp32 masters leave the registers.
+        {
+            float mxv = 0.f;        // W1 planes keep the exponent of the initial weights: they overflow if the weights grew 250x
 #pragma unroll
-            for (int q = 0; q < 2; ++q) {
-                const int idx = tid + q * NT_, i = idx >> 5, j = idx & 31;
-                qg[q] = (i < tr && j < n) ? __ldg(&P.gram[(b * int64_t(n + m) + n + r0 + i) * n + j]) : 0.f;
-            }
-        };
-        auto q_planes = [&](int buf) {                    // qg -> Gram planes of buffer `buf` (lagged exponent e_gqn)
-            const float sg = fumi_exp2i(e_gqn);
+            for (int j = 0; j < 8; ++j)
 #pragma unroll
-            for (int q = 0; q < 2; ++q) {
-                const int idx = tid + q * NT_, i = idx >> 5, j = idx & 31;
-                st_plane1(s.gqh + buf * 32 * kHG, s.gql + buf * 32 * kHG, i * kHG + j, qg[q], sg);
+                for (int q = 0; q < 4; ++q) mxv = fmaxf(mxv, fabsf(w1m[j][q]));
+            mxv = warp_max(mxv);
+            if (lane == 0) { s.red[32 + w] = mxv; s.es[w] = e_s; }
+            if (g == 0) {
+#pragma unroll
+                for (int j = 0; j < 2; ++j)
+                    *reinterpret_cast<float2*>(&s.b0s[hc + 8 * j]) = make_float2(b0r[j][0], b0r[j][1]);
             }
-            block_max_push(s.mx + 16 * (FX_GQ + par_gq), fmaxf(fabsf(qg[0]), fabsf(qg[1])));
-        };
-        q_load(0);
-        int qrid[2][2];
-        h0_rows(qrows, min(32, m), qrid);
-        h0_load(qrid, 2);
-        if (32 < m) h0_rows(qrows + 32, min(32, m - 32), qrid);
-        if (steps == 0) {                                 // no H0 yet: bound |H0q| by dsc (max |A| + max |b0|) of tile 0
+        }
+        if (slot) {                                       // adapted state (fp32): parity dumps, backward prologue
+            float* sl = const_cast<float*>(slot);
+            const float winv = fumi_exp2i(-e_w1);
+#pragma unroll
+            for (int j = 0; j < 8; ++j)
+#pragma unroll
+                for (int hq = 0; hq < 2; ++hq)
+                    *reinterpret_cast<float2*>(&sl[L.w1t + (16 * w + g + 8 * hq) * kH1 + 8 * j + 2 * t]) =
+                        make_float2(w1m[j][2 * hq] * winv, w1m[j][2 * hq + 1] * winv);
+            if (g == 0) {
+#pragma unroll
+                for (int j = 0; j < 2; ++j)
+                    *reinterpret_cast<float2*>(&sl[L.b0 + hc + 8 * j]) = make_float2(b0r[j][0], b0r[j][1]);
+            }
+            if (tid < kH1) sl[L.b1 + tid] = s.b1s[tid];                          // (the thread that updated it)
+            for (int idx = tid; idx < N * kHD; idx += NT_) sl[L.head + idx] = s.hp[idx];
+#pragma unroll
+            for (int i = 0; i < MT; ++i)
+#pragma unroll
+                for (int j = 0; j < 2; ++j)
+#pragma unroll
+                    for (int hq = 0; hq < 2; ++hq) {
+                        const int r = 16 * i + g + 8 * hq;
+                        if (r < n)
+                            *reinterpret_cast<float2*>(&sl[L.S + int64_t(r) * kH0 + hc + 8 * j]) =
+                                make_float2(Sr[i][j][2 * hq], Sr[i][j][2 * hq + 1]);
+                    }
+        }
+        // plane exponent of the query activations: the one derived from the last support H0 (8 binades of headroom);
+        // without inner steps, from a bound on the first rows' pre-activations
+        if (steps == 0) {
+            int rid0[2][2];
+            h0_rows(P.qry_rows + b * m, min(32, m), rid0);
+            h0_load(rid0, 2);
             float mxv = 0.f;
 #pragma unroll
             for (int i = 0; i < 2; ++i)
@@ -576,135 +608,270 @@ __global__ void __launch_bounds__(kThreads16, 1) episode_fwd_v2_kernel(EpiParams
                         mxv = fmaxf(mxv, fmaxf(fabsf(ap[i][j][hq].x + b0r[j][0]), fabsf(ap[i][j][hq].y + b0r[j][1])) * dsc);
             block_max_push(s.mx + 16 * FX_H0, mxv);
         }
-        q_planes(0);
-        __syncthreads();                                  // QB0: Gram planes of tile 0 (and the last step's W1 / head / b1)
-        if (steps == 0) { e_h0n = fumi_plane_exp_t(__float_as_uint(fmaxf(slot_max(s.mx + 16 * FX_H0), 1e-30f)), kTarget); par_h0 = 1; }
-        FUMI_ADOPT(e_gq, e_gqn, par_gq, FX_GQ);
-        if (32 < m) q_load(32);
-        const float sinv = steps > 0 ? fumi_exp2i(-e_s) : 0.f;
-        int qtile = 0;
-        for (int r0 = 0; r0 < m; r0 += 32, ++qtile) {
-            const int tr = min(32, m - r0);
-            int qy[2];                                    // labels of this warp's two rows (read at the end of the tile)
+        int rid_first[2] = {-1, -1};                      // row ids of this warp's first query tile: loaded ahead of the barrier
 #pragma unroll
-            for (int rr = 0; rr < 2; ++rr) qy[rr] = (w + 16 * rr) < tr ? int(__ldg(&P.qry_y[b * m + r0 + w + 16 * rr])) : 0;
-            {
-                float acc[2][2][4];
+        for (int hq = 0; hq < 2; ++hq)
+            if (16 * w + g + 8 * hq < m) rid_first[hq] = int(__ldg(&P.qry_rows[b * m + 16 * w + g + 8 * hq]));
+        pc.mark(43);
+        __syncthreads();                                  // QB: S / W1 planes, head, b1, b0, exponents of the adapted model
+        if (steps == 0) e_h0n = fumi_plane_exp_t(__float_as_uint(fmaxf(slot_max(s.mx + 16 * FX_H0), 1e-30f)), kTarget);
+        pc.mark(28);
+
+        // ------------------------------------------------------------------ query scoring: one warp per 16 query rows
+        // Z0q = Aq + b0 - alpha Gq S goes through in 16-column slabs; the activations of a slab ARE the A fragments of one
+        // k step of Z1q = H0q W1^T (accumulator layout == A layout of m16n8k16), so H0q never touches shared memory and the
+        // whole pass needs no block barrier: per slab 12 MMAs (Gram fragments held in registers x S planes) + 24 MMAs
+        // (H0q fragments x W1^T planes).  The Z0 MMAs of slab c+1 are issued ahead of the Z1 MMAs of slab c.
+        {
+            const int64_t* qrows = P.qry_rows + b * m;
+            const int e_hq = e_h0n;
+            const float hsc = fumi_exp2i(e_hq);
+            const uint32_t db0 = drop ? dropout_base(c, task, steps, 0) : 0u;
+            const uint32_t db1 = drop ? dropout_base(c, task, steps, 1) : 0u;
+            float* sl = const_cast<float*>(slot);
+            if (slot && tid < (m + 31) / 32) reinterpret_cast<int*>(sl + L.qEXP)[tid] = e_hq;
+            const int l7 = lane & 7, b3 = (lane >> 3) & 1, b4 = lane >> 4;
+            const int boffw = (l7 + 8 * b3) * kHW + 8 * b4;          // ldmatrix row of this lane within a W1^T slab
+            float hmax = 0.f;
+            for (int mtile = w; 16 * mtile < m; mtile += 16) {
+                const int r0 = 16 * mtile, tr = min(16, m - r0);
+                int rid[2];
+                bool live[2];
 #pragma unroll
-                for (int i = 0; i < 2; ++i)
-#pragma unroll
-                    for (int j = 0; j < 2; ++j)
-#pragma unroll
-                        for (int q = 0; q < 4; ++q) acc[i][j][q] = 0.f;
-                const int buf = qtile & 1;
-                if (steps > 0)
-                    warp_gemm_f16x3<2, 2, false, false>(s.gqh + buf * 32 * kHG, s.gql + buf * 32 * kHG, kHG, s.sh + 16 * w,
-                                                        s.sl + 16 * w, kHS, RS, acc);
-                h0_finish(acc, 2, r0, tr, steps > 0 ? alpha * fumi_exp2i(-e_gq) * sinv : 0.f, steps);
-            }
-            if (r0 + 32 < m) h0_load(qrid, 2);           // next tile's projected rows, a tile ahead; row ids two tiles ahead
-            if (r0 + 64 < m) h0_rows(qrows + r0 + 64, min(32, m - r0 - 64), qrid);
-            pc.mark(43);
-            __syncthreads();                              // QB1: H0q planes
-            FUMI_ADOPT(e_h0, e_h0n, par_h0, FX_H0);
-            pc.mark(28);
-            if (r0 + 32 < m) q_planes((qtile + 1) & 1);   // Gram planes of the next tile into the other buffer
-            if (slot) {
-                if (tid == 0) reinterpret_cast<int*>(slot + L.qEXP)[qtile] = e_h0;
-                for (int idx = tid; idx < tr * 32; idx += NT_) {
-                    const int i = idx >> 5, q = idx & 31;
-                    reinterpret_cast<uint4*>(slot + L.qH0h)[int64_t(r0) * 32 + idx] = *reinterpret_cast<const uint4*>(&s.h0h[i * kHS + 8 * q]);
-                    reinterpret_cast<uint4*>(slot + L.qH0l)[int64_t(r0) * 32 + idx] = *reinterpret_cast<const uint4*>(&s.h0l[i * kHS + 8 * q]);
+                for (int hq = 0; hq < 2; ++hq) {
+                    live[hq] = g + 8 * hq < tr;
+                    rid[hq] = mtile == w ? rid_first[hq] : (live[hq] ? int(__ldg(&qrows[r0 + g + 8 * hq])) : -1);
                 }
-            }
-            z1_gemm(1, 2);
-            pc.mark(44);
-            __syncthreads();                              // QB2: Z1q partial sums, next Gram planes
-            if (r0 + 32 < m) FUMI_ADOPT(e_gq, e_gqn, par_gq, FX_GQ);
-            if (r0 + 64 < m) q_load(r0 + 64);
-            pc.mark(29);
+                // Gram rows of the tile as A fragments (exact per-warp exponent)
+                uint32_t gah[MT][4], gal[MT][4];
+                int e_g = 0;
+                if (steps > 0) {
+                    float gvv[MT][4][2];
+                    float mxv = 0.f;
 #pragma unroll
-            for (int rr = 0; rr < 2; ++rr) {
-                const int i = w + 16 * rr;
-                const bool live = i < tr;
-                float h1a, h1b;
-                h1_row(i, r0 + i, 1, steps, h1a, h1b);
-                float lg[kNC];
-                logits_row(h1a, h1b, lg);
-                const int64_t q = b * m + r0 + (live ? i : 0);
-                const int y = qy[rr];
-                float mxl = lg[0], ly = 0.f, lgw = 0.f;
-                int bi = 0;                               // argmax with ties to the lowest index (torch.max, fumi.py:180)
+                    for (int ks = 0; ks < MT; ++ks)
 #pragma unroll
-                for (int cc = 0; cc < kNC; ++cc) {
-                    if (lg[cc] > mxl) { mxl = lg[cc]; bi = cc; }
-                    if (cc == y) ly = lg[cc];
-                    if (lane == cc) lgw = lg[cc];
+                        for (int q = 0; q < 4; ++q)
+#pragma unroll
+                            for (int e = 0; e < 2; ++e) {
+                                const int k = 16 * ks + 8 * (q >> 1) + 2 * t + e;
+                                const bool ok = live[q & 1] && k < n;
+                                gvv[ks][q][e] = ok ? __ldg(&P.gram[(b * int64_t(n + m) + n + r0 + g + 8 * (q & 1)) * n + k]) : 0.f;
+                                mxv = fmaxf(mxv, fabsf(gvv[ks][q][e]));
+                            }
+                    mxv = warp_max(mxv);
+                    e_g = fumi_plane_exp(__float_as_uint(mxv));
+                    const float gsc = fumi_exp2i(e_g);
+#pragma unroll
+                    for (int ks = 0; ks < MT; ++ks)
+#pragma unroll
+                        for (int q = 0; q < 4; ++q) fumi_split2(gvv[ks][q][0] * gsc, gvv[ks][q][1] * gsc, gah[ks][q], gal[ks][q]);
+                } else {
+#pragma unroll
+                    for (int ks = 0; ks < MT; ++ks)
+#pragma unroll
+                        for (int q = 0; q < 4; ++q) gah[ks][q] = gal[ks][q] = 0u;
                 }
-                if (live && lane < N) P.logits[q * N + lane] = lgw;
-                float sum = 0.f;
+                const float ginv = steps > 0 ? alpha * fumi_exp2i(-e_g) : 0.f;
+                // projected rows of the tile: 64-byte pieces (one slab of one row) travel through a per-warp ring of three
+                // slabs in the shared memory the support steps no longer need (cp.async, three slabs ahead: the rows are
+                // random 1 KB lines of a 119 MB matrix, i.e. DRAM latency); lane (g, t) copies piece t of rows g and g + 8
+                float* ring = reinterpret_cast<float*>(s.h0h) + w * (3 * kRingSlab);
+                auto a_issue = [&](int slab) {
+                    if (slab < 16) {
+                        float* dst = ring + (slab % 3) * kRingSlab;
 #pragma unroll
-                for (int cc = 0; cc < kNC; ++cc) { lg[cc] = fumi_fast_exp(lg[cc] - mxl); sum += lg[cc]; }
-                if (slot && live) {
-                    slot[L.qH1 + int64_t(r0 + i) * kH1 + lane] = h1a;
-                    slot[L.qH1 + int64_t(r0 + i) * kH1 + lane + 32] = h1b;
-                    const float rs = fumi_fast_rcp(sum);
-                    float pw = 0.f;
+                        for (int hq = 0; hq < 2; ++hq)
+                            fumi_cp_async16(dst + (g + 8 * hq) * kRingRow + 4 * t,
+                                            &P.proj[int64_t(rid[hq] >= 0 ? rid[hq] : 0) * kH0 + 16 * slab + 4 * t]);
+                    }
+                    fumi_cp_async_commit();
+                };
+                float2 apq[2][2];                         // ... at this thread's positions [n tile][row half]
+                auto a_load = [&](int slab, float2 (&dst)[2][2]) {
+                    const float* src = ring + (slab % 3) * kRingSlab;
 #pragma unroll
-                    for (int cc = 0; cc < kNC; ++cc)
-                        if (lane == cc) pw = lg[cc] * rs - (cc == y ? 1.f : 0.f);
-                    if (lane < N) slot[L.qLG + int64_t(r0 + i) * N + lane] = pw;
+                    for (int h = 0; h < 2; ++h)
+#pragma unroll
+                        for (int hq = 0; hq < 2; ++hq) dst[h][hq] = *reinterpret_cast<const float2*>(src + (g + 8 * hq) * kRingRow + 8 * h + 2 * t);
+                };
+                uint32_t ah[4], al[4];                    // H0q fragments of the current slab
+                uint32_t rb0[2];                          // row part of the dropout counter
+                uint32_t *sth[2], *stl[2];                // stash rows of the H0q planes
+#pragma unroll
+                for (int hq = 0; hq < 2; ++hq) {
+                    rb0[hq] = db0 + uint32_t(r0 + g + 8 * hq) * 0xC2B2AE35u;
+                    sth[hq] = slot ? reinterpret_cast<uint32_t*>(sl + L.qH0h) + int64_t(r0 + g + 8 * hq) * (kH0 / 2) + t : nullptr;
+                    stl[hq] = slot ? reinterpret_cast<uint32_t*>(sl + L.qH0l) + int64_t(r0 + g + 8 * hq) * (kH0 / 2) + t : nullptr;
                 }
-                if (live && lane == 0) {
-                    P.preds[q] = bi;
-                    loss_sum += (fumi_fast_log(sum) + mxl) - ly;
-                    corr_sum += bi == y ? 1.f : 0.f;
+                auto h0_slab = [&](int slab, const float (&acc)[2][4], const float2 (&a)[2][2]) {
+                    const float gs = steps > 0 ? ginv * fumi_exp2i(-s.es[slab]) : 0.f;
+#pragma unroll
+                    for (int h = 0; h < 2; ++h) {
+                        const int col = 16 * slab + 8 * h + 2 * t;
+                        const float2 bb = *reinterpret_cast<const float2*>(&s.b0s[col]);
+#pragma unroll
+                        for (int hq = 0; hq < 2; ++hq) {
+                            const float z0 = a[h][hq].x + bb.x - gs * acc[h][2 * hq];
+                            const float z1 = a[h][hq].y + bb.y - gs * acc[h][2 * hq + 1];
+                            bool k0 = live[hq] && z0 > 0.f, k1 = live[hq] && z1 > 0.f;
+                            if (drop) {
+                                const uint32_t bits = fumi_lowbias32(rb0[hq] + uint32_t(col >> 1) * 0x27D4EB2Fu);   // == dropout_bits
+                                k0 = k0 && (bits & 0xFFFFu) >= thr;
+                                k1 = k1 && (bits >> 16) >= thr;
+                            }
+                            const float v0 = k0 ? z0 * dsc : 0.f, v1 = k1 ? z1 * dsc : 0.f;
+                            hmax = fmaxf(hmax, fmaxf(v0, v1));
+                            fumi_split2(v0 * hsc, v1 * hsc, ah[2 * h + hq], al[2 * h + hq]);
+                            if (slot && live[hq]) {
+                                sth[hq][8 * slab + 4 * h] = ah[2 * h + hq];
+                                stl[hq][8 * slab + 4 * h] = al[2 * h + hq];
+                            }
+                        }
+                    }
+                };
+                auto z0_slab = [&](int slab, float (&acc)[2][4]) {
+                    if (steps > 0) {
+                        warp_mma_pair<MT, false>(gah, gal, s.sh, s.sl, kHS, 16 * slab, acc);
+                    } else {
+#pragma unroll
+                        for (int h = 0; h < 2; ++h)
+#pragma unroll
+                            for (int q = 0; q < 4; ++q) acc[h][q] = 0.f;
+                    }
+                };
+                float tot[8][4];
+#pragma unroll
+                for (int j = 0; j < 8; ++j)
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) tot[j][q] = 0.f;
+                float acc[2][4];
+                __syncwarp();                             // every lane is done with the ring (previous tile)
+                a_issue(0);
+                a_issue(1);
+                a_issue(2);
+                z0_slab(0, acc);
+                fumi_cp_async_wait_n<2>();
+                __syncwarp();
+                a_load(0, apq);
+                __syncwarp();
+                a_issue(3);
+                h0_slab(0, acc, apq);
+                // one accumulator over all 256 hidden units (48 accumulations: ~3e-6 relative from the tensor core's
+                // truncating adds, and nothing compounds on the query side)
+#pragma unroll 1
+                for (int slab = 0; slab < 16; ++slab) {
+                    if (slab + 1 < 16) z0_slab(slab + 1, acc);                     // next slab's Z0 MMAs fly under this slab's Z1 MMAs
+#pragma unroll
+                    for (int jp = 0; jp < 4; ++jp) {
+                        uint32_t bh[4], bl[4];
+                        const int o = 16 * slab * kHW + 16 * jp + boffw;
+                        fumi_ldsm4t(bh, s.w1h + o);
+                        fumi_ldsm4t(bl, s.w1l + o);
+#pragma unroll
+                        for (int h = 0; h < 2; ++h) {
+                            fumi_mma_f16(tot[2 * jp + h], al, bh[2 * h], bh[2 * h + 1]);
+                            fumi_mma_f16(tot[2 * jp + h], ah, bl[2 * h], bl[2 * h + 1]);
+                            fumi_mma_f16(tot[2 * jp + h], ah, bh[2 * h], bh[2 * h + 1]);
+                        }
+                    }
+                    if (slab + 1 < 16) {
+                        fumi_cp_async_wait_n<2>();        // the copies of slab + 1 have landed (two younger groups may be in flight)
+                        __syncwarp();
+                        a_load(slab + 1, apq);
+                        __syncwarp();
+                        a_issue(slab + 4);                // into the ring slot just read
+                        h0_slab(slab + 1, acc, apq);
+                    }
                 }
-            }
-            pc.mark(30);
-        }
-        // ------------------------------------------------------------------ task epilogue
-        {   // W1 planes keep the exponent of the initial weights: they overflow if the adapted weights grew 250x
-            float mxv = 0.f;
+                fumi_cp_async_wait_n<0>();
+                // ---- H1q at the accumulator positions (rows g / g + 8, units 8 j + 2 t + {0, 1}), then the N logits of both
+                // rows: per-lane partial dot products over its 16 units, summed over the 4 lanes of the quad
+                const float zinv = fumi_exp2i(-e_hq) * fumi_exp2i(-e_w1);
 #pragma unroll
-            for (int j = 0; j < 8; ++j)
-#pragma unroll
-                for (int q = 0; q < 4; ++q) mxv = fmaxf(mxv, fabsf(w1m[j][q]));
-            mxv = warp_max(mxv);
-            if (lane == 0) { s.red[w] = loss_sum; s.red[16 + w] = corr_sum; s.red[32 + w] = mxv; }
-        }
-        if (slot) {                                       // adapted state (fp32): parity dumps, backward prologue
-            const float winv = fumi_exp2i(-e_w1);
-            for (int idx = tid; idx < kH0 * kH1 / 2; idx += NT_) {
-                const int k = idx >> 5, o = (idx & 31) * 2;
-                float a0, a1;
-                ld_planes2(s.w1h, s.w1l, k * kHW + o, winv, a0, a1);
-                *reinterpret_cast<float2*>(&slot[L.w1t + k * kH1 + o]) = make_float2(a0, a1);
-            }
-            if (g == 0) {
-#pragma unroll
-                for (int j = 0; j < 2; ++j)
-                    *reinterpret_cast<float2*>(&slot[L.b0 + hc + 8 * j]) = make_float2(b0r[j][0], b0r[j][1]);
-            }
-            if (tid < kH1) slot[L.b1 + tid] = s.b1s[tid];
-            for (int idx = tid; idx < N * kHD; idx += NT_) slot[L.head + idx] = s.hp[idx];
-#pragma unroll
-            for (int i = 0; i < MT; ++i)
-#pragma unroll
-                for (int j = 0; j < 2; ++j)
+                for (int j = 0; j < 8; ++j) {
+                    const float2 bb = *reinterpret_cast<const float2*>(&s.b1s[8 * j + 2 * t]);
 #pragma unroll
                     for (int hq = 0; hq < 2; ++hq) {
-                        const int r = 16 * i + g + 8 * hq;
-                        if (r < n)
-                            *reinterpret_cast<float2*>(&slot[L.S + int64_t(r) * kH0 + hc + 8 * j]) =
-                                make_float2(Sr[i][j][2 * hq], Sr[i][j][2 * hq + 1]);
+                        const float z0 = fmaf(tot[j][2 * hq], zinv, bb.x), z1 = fmaf(tot[j][2 * hq + 1], zinv, bb.y);
+                        bool k0 = z0 > 0.f, k1 = z1 > 0.f;
+                        if (drop) {
+                            const uint32_t bits = dropout_bits(db1, r0 + g + 8 * hq, 8 * j + 2 * t);
+                            k0 = k0 && (bits & 0xFFFFu) >= thr;
+                            k1 = k1 && (bits >> 16) >= thr;
+                        }
+                        tot[j][2 * hq] = k0 ? z0 * dsc : 0.f;
+                        tot[j][2 * hq + 1] = k1 ? z1 * dsc : 0.f;
+                        if (slot && live[hq])
+                            *reinterpret_cast<float2*>(&sl[L.qH1 + int64_t(r0 + g + 8 * hq) * kH1 + 8 * j + 2 * t]) =
+                                make_float2(tot[j][2 * hq], tot[j][2 * hq + 1]);
                     }
+                }
+                float lg[2][kNC];
+#pragma unroll
+                for (int cc = 0; cc < kNC; ++cc) {
+                    float s0 = 0.f, s1 = 0.f;
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) {
+                        const float h0 = s.hp[cc * kHD + 8 * j + 2 * t], h1 = s.hp[cc * kHD + 8 * j + 2 * t + 1];
+                        s0 = fmaf(tot[j][0], h0, fmaf(tot[j][1], h1, s0));
+                        s1 = fmaf(tot[j][2], h0, fmaf(tot[j][3], h1, s1));
+                    }
+                    lg[0][cc] = s0;
+                    lg[1][cc] = s1;
+                }
+#pragma unroll
+                for (int off = 1; off <= 2; off <<= 1)
+#pragma unroll
+                    for (int cc = 0; cc < kNC; ++cc) {
+                        lg[0][cc] += __shfl_xor_sync(0xffffffffu, lg[0][cc], off);
+                        lg[1][cc] += __shfl_xor_sync(0xffffffffu, lg[1][cc], off);
+                    }
+#pragma unroll
+                for (int hq = 0; hq < 2; ++hq) {
+                    const int64_t q = b * m + r0 + g + 8 * hq;
+                    const int y = live[hq] ? int(__ldg(&P.qry_y[q])) : 0;
+#pragma unroll
+                    for (int cc = 0; cc < kNC; ++cc) lg[hq][cc] = cc < N ? lg[hq][cc] + s.hp[cc * kHD + kH1] : -3.0e38f;   // inert classes
+                    float mxl = lg[hq][0], ly = 0.f;
+                    int bi = 0;                           // argmax with ties to the lowest index (torch.max, fumi.py:180)
+#pragma unroll
+                    for (int cc = 0; cc < kNC; ++cc) {
+                        if (lg[hq][cc] > mxl) { mxl = lg[hq][cc]; bi = cc; }
+                        if (cc == y) ly = lg[hq][cc];
+                        if (live[hq] && cc < N && (cc & 3) == t) P.logits[q * N + cc] = lg[hq][cc];
+                    }
+                    float sum = 0.f;
+#pragma unroll
+                    for (int cc = 0; cc < kNC; ++cc) { lg[hq][cc] = fumi_fast_exp(lg[hq][cc] - mxl); sum += lg[hq][cc]; }
+                    if (slot && live[hq]) {
+                        const float rs = fumi_fast_rcp(sum);
+#pragma unroll
+                        for (int cc = 0; cc < kNC; ++cc)
+                            if (cc < N && (cc & 3) == t) sl[L.qLG + int64_t(r0 + g + 8 * hq) * N + cc] = lg[hq][cc] * rs - (cc == y ? 1.f : 0.f);
+                    }
+                    if (live[hq] && t == 0) {
+                        P.preds[q] = bi;
+                        loss_sum += (fumi_fast_log(sum) + mxl) - ly;
+                        corr_sum += bi == y ? 1.f : 0.f;
+                    }
+                }
+            }
+            loss_sum = warp_sum(loss_sum);
+            corr_sum = warp_sum(corr_sum);
+            hmax = warp_max(hmax);
+            if (lane == 0) {
+                s.red[w] = loss_sum;
+                s.red[16 + w] = corr_sum;
+                s.red[48 + w] = plane_overflow(hmax, e_hq) ? 1.f : 0.f;
+            }
         }
+        pc.mark(30);
         __syncthreads();
         if (tid == 0) {
-            float ls = 0.f, cs = 0.f, wm = 0.f;
-            for (int q = 0; q < 16; ++q) { ls += s.red[q]; cs += s.red[16 + q]; wm = fmaxf(wm, s.red[32 + q]); }
-            bad = bad || !(wm < 60000.f);
+            float ls = 0.f, cs = 0.f, wm = 0.f, ov = 0.f;
+            for (int q = 0; q < 16; ++q) { ls += s.red[q]; cs += s.red[16 + q]; wm = fmaxf(wm, s.red[32 + q]); ov += s.red[48 + q]; }
+            bad = bad || !(wm < 60000.f) || ov > 0.f;
             P.task_loss[b] = bad ? __uint_as_float(0x7FC00000u) : ls / float(m);
             P.task_acc[b] = cs / float(m);
         }

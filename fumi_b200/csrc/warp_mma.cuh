@@ -32,6 +32,8 @@ static inline float fumi_fast_log(float x) { return std::log(x); }
 static inline float fumi_fast_rcp(float x) { return 1.f / x; }
 static inline void fumi_cp_async16(void* smem_dst, const void* gmem_src) { std::memcpy(smem_dst, gmem_src, 16); }
 static inline void fumi_cp_async_wait() {}
+static inline void fumi_cp_async_commit() {}
+template <int N> static inline void fumi_cp_async_wait_n() {}
 #else
 #include <cuda_fp16.h>
 // ---- fp16 plane primitives (see warp_gemm_f16x3 below) ------------------------------------------------------
@@ -82,6 +84,8 @@ __device__ __forceinline__ void fumi_cp_async16(void* smem_dst, const void* gmem
 __device__ __forceinline__ void fumi_cp_async_wait() {
     asm volatile("cp.async.commit_group;\ncp.async.wait_group 0;" ::: "memory");
 }
+__device__ __forceinline__ void fumi_cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N> __device__ __forceinline__ void fumi_cp_async_wait_n() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
 // (a, b) -> packed fp16 pairs hi = (fp16(a), fp16(b)) and lo = (fp16(a - hi.x), fp16(b - hi.y)): one F2FP per pair
 __device__ __forceinline__ void fumi_split2(float a, float b, uint32_t& hi, uint32_t& lo) {
     const __half2 h = __floats2half2_rn(a, b);
