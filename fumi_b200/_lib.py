@@ -57,6 +57,7 @@ _SIGS = {
     "fumi_reduce_loss_acc": (C.c_int, [_P, _P, _I64, _P, _P]),
     "fumi_adam_step": (C.c_int, [_P, _P, _P, _P, _I64, _F, _F, _F, _F, _F, _I64, _I32, _P]),
     "fumi_am3_score": (C.c_int, [_P] * 8 + [_I64, _I32, _I32, _I32, _I32, _I32] + [_P] * 5),
+    "fumi_confusion_counts": (C.c_int, [_P, _P, _I64, _I32, _P, _P]),
     "fumi_am3_bwd": (C.c_int, [_P] * 8 + [_I64, _I32, _I32, _I32, _I32, _I32] + [_P, _P, _F] + [_P] * 4),
     "fumi_dropout_apply": (C.c_int, [_P, _I64, _I64, C.c_uint64, C.c_uint32, _F, _P]),
     "fumi_sigmoid_bwd": (C.c_int, [_P, _P, _I64, _P]),

@@ -93,17 +93,34 @@ class AM3(nn.Module):
             loss = la[0]
         else:
             loss = (res["task_loss"].sum() / float(B * NQ)).cpu().numpy()      # mean over all queries (utils.py:402)
-        preds = res["preds"].cpu().numpy()
-        flat_preds, flat_targets = preds.reshape(-1), eb.qry_y.cpu().numpy().reshape(-1)
-        from sklearn.metrics import accuracy_score, precision_recall_fscore_support    # utils.py:16,323-326
-        acc = accuracy_score(flat_targets, flat_preds)
-        prec, rec, f1, _ = precision_recall_fscore_support(flat_targets, flat_preds, average="macro")
+        acc, prec, rec, f1 = macro_scores(res["confusion"].cpu().numpy())                 # utils.py:323-326
         avg_lamda = la[1] if train else res["sup_lamda"].mean().cpu().numpy()
         if task == "test":
             to_np = lambda t: t.detach().cpu().numpy() if isinstance(t, torch.Tensor) else np.asarray(t)
+            preds = res["preds"].cpu().numpy()
             return (loss, acc, f1, prec, rec, avg_lamda, preds, eb.qry_y, to_np(eb.qry_ids), to_np(eb.sup_ids),
                     res["sup_lamda"].cpu().numpy())
         return loss, acc, f1, prec, rec, avg_lamda
+
+
+def macro_scores(counts):
+    """accuracy_score and precision_recall_fscore_support(average="macro") of sklearn (utils/utils.py:16,323-326) from
+    the confusion counts [target, prediction] the device produced (fumi_confusion_counts): same labels (those present
+    in the targets or the predictions), same divisions with zero_division -> 0, same unweighted means."""
+    counts = np.asarray(counts, dtype=np.int64)
+    tp, pred_sum, true_sum = np.diag(counts), counts.sum(0), counts.sum(1)
+    present = (pred_sum + true_sum) > 0
+    tp, pred_sum, true_sum = tp[present], pred_sum[present], true_sum[present]
+
+    def div(a, b):
+        out = np.zeros(len(a), dtype=np.float64)
+        np.divide(a, b, out=out, where=b != 0)
+        return out
+
+    acc = float(np.diag(counts).sum() / counts.sum())
+    prec, rec = div(tp.astype(np.float64), pred_sum.astype(np.float64)), div(tp.astype(np.float64), true_sum.astype(np.float64))
+    f1 = div(2.0 * tp.astype(np.float64), true_sum.astype(np.float64) + pred_sum.astype(np.float64))
+    return acc, float(np.average(prec)), float(np.average(rec)), float(np.average(f1))
 
 
 def training_run(args, model, optimizer, train_loader, val_loader, max_test_batches):

@@ -202,6 +202,34 @@ extern "C" int fumi_dropout_apply(float* x, int64_t rows, int64_t cols, uint64_t
     return FUMI_OK;
 }
 
+// counts[t * N + p] += 1 per (target t, prediction p): the sufficient statistics of sklearn's accuracy_score and
+// precision_recall_fscore_support(average="macro") that AM3.evaluate / get_preds report (utils.py:302-328,
+// am3.py:196-204) -- 8 N^2 bytes leave the device instead of a host pass over every prediction.
+__global__ void __launch_bounds__(256) confusion_kernel(const int64_t* __restrict__ y, const int64_t* __restrict__ pred,
+                                                        int64_t n, int N, unsigned long long* __restrict__ counts) {
+    __shared__ int h[kMaxWays * kMaxWays];
+    for (int i = threadIdx.x; i < N * N; i += 256) h[i] = 0;
+    __syncthreads();
+    for (int64_t i = int64_t(blockIdx.x) * 256 + threadIdx.x; i < n; i += int64_t(gridDim.x) * 256) {
+        const int64_t t = y[i], p = pred[i];
+        if (t >= 0 && t < N && p >= 0 && p < N) atomicAdd(&h[int(t) * N + int(p)], 1);
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < N * N; i += 256)
+        if (h[i]) atomicAdd(&counts[i], (unsigned long long)h[i]);
+}
+
+extern "C" int fumi_confusion_counts(const int64_t* y, const int64_t* pred, int64_t n, int32_t N, int64_t* counts,
+                                     void* stream) {
+    FUMI_CHECK_ARG(n >= 0 && N >= 1 && N <= kMaxWays, "bad shape");
+    if (n == 0) return FUMI_OK;
+    FUMI_CHECK_ARG(y && pred && counts, "null pointer");
+    const unsigned grid = unsigned((n + 256 * 16 - 1) / (256 * 16) < 592 ? (n + 256 * 16 - 1) / (256 * 16) : 592);
+    FUMI_LAUNCH(confusion_kernel, grid, 256, 0, stream, y, pred, n, int(N), reinterpret_cast<unsigned long long*>(counts));
+    FUMI_CHECK_LAUNCH("confusion_kernel");
+    return FUMI_OK;
+}
+
 extern "C" int fumi_sigmoid_bwd(const float* y, float* dy, int64_t n, void* stream) {
     FUMI_CHECK_ARG(y && dy && n >= 0, "bad argument");
     if (n == 0) return FUMI_OK;

@@ -522,7 +522,11 @@ class EpisodeEngine:
             label_lam = torch.zeros_like(label_lam)
         elif fixed == 1:
             label_lam = torch.ones_like(label_lam)
-        res = dict(task_loss=task_loss, preds=preds, dist=dist_, protos=protos, sup_lamda=label_lam, batch=eb)
+        counts = torch.zeros(N, N, dtype=torch.int64, device=self.device)      # confusion counts (utils.py:323-326)
+        self._call("fumi_confusion_counts", self.L.fumi_confusion_counts, _lib.ptr(eb.qry_y), _lib.ptr(preds),
+                   B * NQ, N, _lib.ptr(counts), self._stream())
+        self.launches += 1
+        res = dict(task_loss=task_loss, preds=preds, dist=dist_, protos=protos, sup_lamda=label_lam, batch=eb, confusion=counts)
         if not train:
             return res
         # ---- backward (am3.py:188-190): gradients of sum_b sum_q CE / (B_global * NQ)

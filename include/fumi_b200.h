@@ -246,6 +246,11 @@ int fumi_am3_score(const float* emb, const float* text_proto, const float* lamda
                    int64_t B, int32_t N, int32_t NK, int32_t NQ, int32_t P, int32_t lamda_fixed,
                    float* protos, float* dist, int64_t* preds, float* task_loss, void* stream);
 
+/* Confusion counts of a flat prediction array: counts[t * N + p] += #(y == t, pred == p)  (int64 [N, N], zero it first).
+ * Replaces the host pass of utils.get_preds / AM3.evaluate (utils/utils.py:323-326: sklearn accuracy_score and
+ * precision_recall_fscore_support over every query prediction) by its sufficient statistics. */
+int fumi_confusion_counts(const int64_t* y, const int64_t* pred, int64_t n, int32_t N, int64_t* counts, void* stream);
+
 /* AM3 meta-training (am3.py:154-196, 215-305): backward of fumi_am3_score's loss = loss_scale * sum of the query CEs.
  *   protos / dist  outputs of fumi_am3_score for the same batch
  *   d_emb [R,P]    += d loss / d image embedding rows (atomic scatter-add; zero it first)

@@ -76,6 +76,9 @@ static inline float atomicAdd(float* addr, float v) {
     return f;
 }
 
+static inline int atomicAdd(int* addr, int v) { return __atomic_fetch_add(addr, v, __ATOMIC_RELAXED); }
+static inline unsigned long long atomicAdd(unsigned long long* addr, unsigned long long v) { return __atomic_fetch_add(addr, v, __ATOMIC_RELAXED); }
+
 static inline float __uint_as_float(uint32_t u) { float f; std::memcpy(&f, &u, 4); return f; }
 static inline uint32_t __float_as_uint(float f) { uint32_t u; std::memcpy(&u, &f, 4); return u; }
 #define __forceinline__ inline

@@ -132,3 +132,19 @@ def test_flat_sampler_matches_reference_loader(name, N, K, Qtrain):
         assert np.array_equal(b["qry_ids"], g[f"b{i}_qry_ids"]), (i, split)
         assert np.array_equal(b["sup_targets"], g[f"b{i}_sup_y"]), (i, split)
         assert np.array_equal(b["qry_targets"], g[f"b{i}_qry_y"]), (i, split)
+
+
+def test_macro_scores_equal_sklearn():
+    """AM3.evaluate's metrics come from device confusion counts (fumi_confusion_counts); the host formulas must equal
+    sklearn's accuracy_score / precision_recall_fscore_support(average='macro') (utils/utils.py:323-326) exactly."""
+    import warnings
+    from sklearn.metrics import accuracy_score, precision_recall_fscore_support
+    from fumi_b200.am3 import macro_scores
+    rng = np.random.default_rng(5)
+    for N, n, hi in ((10, 4096, 10), (5, 64, 3), (20, 500, 20)):
+        y, p = rng.integers(0, N, n), rng.integers(0, hi, n)
+        cm = np.bincount(y * N + p, minlength=N * N).reshape(N, N)
+        with warnings.catch_warnings():
+            warnings.simplefilter("ignore")
+            ref = (accuracy_score(y, p),) + precision_recall_fscore_support(y, p, average="macro")[:3]
+        assert macro_scores(cm) == ref

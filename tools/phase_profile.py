@@ -29,11 +29,13 @@ NAMES = {0: "bwd prologue (W1/G planes, maxes)", 1: "bwd q: tile data -> smem, w
 
 def main():
     tasks = int(sys.argv[1]) if len(sys.argv) > 1 else 1184
+    test = len(sys.argv) > 2 and sys.argv[2] == "test"          # meta-test: 100 steps, no stash, no dropout
+    K = int(sys.argv[3]) if len(sys.argv) > 3 else 5
     dev = torch.device("cuda", 0)
-    args = bench.make_args("fumi", 5, 5, 32, 5, True, dev, 2048, 768, tasks, 0.25)
+    args = bench.make_args("fumi", 5, K, 20 if test else 32, 100 if test else 5, not test, dev, 2048, 768, tasks, 0.0 if test else 0.25)
     bank = make_bank(num_images=673 * 62, num_classes=673)
     cats = class_split(673)[0]
-    sampler = EpisodeSampler(bank.cat_of, cats, 5, 5, 32)
+    sampler = EpisodeSampler(bank.cat_of, cats, 5, K, 20 if test else 32)
     fb = FeatureBank(feats=torch.from_numpy(bank.feats[sampler.ids]).to(dev), text=torch.from_numpy(bank.text[cats]).to(dev),
                      ids=sampler.ids, categories=cats)
     loader = EpisodeLoader(fb, sampler, tasks)
@@ -44,12 +46,13 @@ def main():
     eng.precision = 2
     sampler.new_iterator()
     b = loader.next_batch().to(dev)
+    nst = 100 if test else 5
     for _ in range(2):
-        eng.fumi_batch(model, b, steps=5, step_size=0.01, train=True)
+        eng.fumi_batch(model, b, steps=nst, step_size=0.01, train=not test)
     torch.cuda.synchronize()
     L = _lib.lib()
     L.fumi_debug_phase_profile(1)
-    eng.fumi_batch(model, b, steps=5, step_size=0.01, train=True)
+    eng.fumi_batch(model, b, steps=nst, step_size=0.01, train=not test)
     torch.cuda.synchronize()
     out = np.zeros(64, np.uint64)
     L.fumi_debug_read_phases(_lib.ptr(out))
