@@ -456,7 +456,9 @@ def run_workload(ctx, wl, n_steps, n_warmup, kernel_pass, cpu_budget_s, parity, 
         torch.cuda.synchronize()
         for name, evs in eng.profile.items():
             ts = [x.elapsed_time(y) for x, y in evs]
-            kernels[name] = {"ms_per_step": sum(ts) / nprof, "calls_per_step": len(ts) / nprof}
+            cps = max(1, len(ts) // nprof)                  # calls per step; per-step totals, median over the steps
+            per_step = sorted(sum(ts[i * cps:(i + 1) * cps]) for i in range(len(ts) // cps))
+            kernels[name] = {"ms_per_step": per_step[len(per_step) // 2], "calls_per_step": len(ts) / nprof}
         eng.profile = None
         top = max(kernels, key=lambda k: kernels[k]["ms_per_step"])
         dur = kernels[top]["ms_per_step"] / kernels[top]["calls_per_step"] * 1e-3

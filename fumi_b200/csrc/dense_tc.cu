@@ -19,7 +19,8 @@
 //              tcgen05.commit releases the smem stage and publishes the TMEM buffer
 //   warps 2-9: accumulate + epilogue -- every stage: tcgen05.ld 32x32b.x32 TMEM -> registers and add into
 //              128 fp32 register accumulators per thread with round-to-nearest; at the end bias +
-//              activation and float4 stores (or fp32 atomics for split-K partial tiles).
+//              activation and float4 stores (split-K: the split's partial tile goes to a workspace that
+//              splitk_reduce_kernel sums in split order -- no floating-point atomics, run-to-run reproducible).
 // Why two levels: the tensor core adds into its accumulator with truncation, a bias that grows linearly
 // with the number of accumulated MMAs (measured 5.6e-6 relative at K=768 in a single accumulator, 10x
 // plain fp32); restarting the accumulator every stage keeps <= 4 significant truncations per partial sum.
@@ -37,23 +38,33 @@
 
 namespace {
 
-constexpr int BM = 128, BN = 256, BK = 32;          // BK fp32 = 128 bytes = one swizzle row
-constexpr int kStages = 2;
+// Stage rows are 64 bytes (SWIZZLE_64B): 16 tf32 / 32 fp16 k per stage, 48 KB per stage, FOUR stages.  Both bank-sized
+// contractions are bound by operand arrival, not by MMA rate: with two 96 KB stages of 128-byte rows a CTA had one
+// stage in flight and measured ~4.5k cycles per stage against 1.5k cycles of MMAs; three 48 KB stages in flight keep
+// 1.5x the bytes outstanding at half the granularity.
+constexpr int BM = 128, BN = 256, BK = 16;          // BK fp32 = 64 bytes = one swizzle row
+constexpr int kRowBytes = BK * 4;
+constexpr int kStages = 4;
 constexpr int kThreadsTc = 320;
-constexpr uint32_t kABytes = BM * BK * 4;           // 16 KB per plane
-constexpr uint32_t kBBytes = BN * BK * 4;           // 32 KB per plane
-constexpr uint32_t kStageBytes = 2 * kABytes + 2 * kBBytes;   // 96 KB
+constexpr uint32_t kABytes = BM * kRowBytes;        // 8 KB per plane
+constexpr uint32_t kBBytes = BN * kRowBytes;        // 16 KB per plane
+constexpr uint32_t kStageBytes = 2 * kABytes + 2 * kBBytes;   // 48 KB
 constexpr uint32_t kSmemBytes = kStages * kStageBytes + 1024 /*align*/ + 256 /*barriers*/;
 
 struct TcParams {
-    CUtensorMap a_hi, a_lo, b_hi, b_lo;
+    CUtensorMap a_hi, a_lo, b_hi, b_lo;      // b_*: box of BN rows, or of BN / 2 rows when mcast
+    int mcast;              // 1: CTA pairs (cluster 2x1x1 along M) share every B stage: each CTA loads half of it and
+                            //    multicasts it into both CTAs' shared memory (half the L2 reads of the re-streamed operand)
     float* C;
     const float* bias;
     int64_t M, N, ldc;
+    int m_tiles;            // M tiles (even when mcast); a CTA walks tiles blockIdx.x, blockIdx.x + gridDim.x, ... (persistent:
+                            // the operand ring and the TMEM ping-pong run on across tiles, so prologue / epilogue overlap)
     int k_tiles;            // total BK tiles along K
     int k_tiles_per_split;
     int act;
-    int atomic;             // 1: atomicAdd partial tiles (split-K / accumulate); bias & act must be off
+    int atomic;             // 0: store (bias / act fused); 1: C += tile (single writer); 2: split-K partial tile -> parts
+    float* parts;           // split-K workspace [splits][M][N] (dense), summed in split order by splitk_reduce_kernel
     int drain;              // k stages accumulated in one TMEM buffer before it is drained into registers
     const float* a_absmax;  // f16x3 only: device scalars max|A|, max|B| that fixed the power-of-two plane scales
     const float* b_absmax;
@@ -95,11 +106,26 @@ __device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map
         ::"r"(dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(bar), "r"(c0), "r"(c1)
         : "memory");
 }
-// K-major, SWIZZLE_128B shared-memory matrix descriptor (cute::UMMA::SmemDescriptor bit layout):
-// start>>4 [0,14) | LBO>>4 [16,30) | SBO>>4 [32,46) | version=1 [46,48) | layout SWIZZLE_128B=2 [61,64)
+__device__ __forceinline__ void tma_load_2d_mcast(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, uint16_t mask) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1, {%4, %5}], [%2], %3;"
+        ::"r"(dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(bar), "h"(mask), "r"(c0), "r"(c1)
+        : "memory");
+}
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+    uint32_t r;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+    return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+    asm volatile("barrier.cluster.arrive.release.aligned;\nbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// K-major, SWIZZLE_64B shared-memory matrix descriptor (cute::UMMA::SmemDescriptor bit layout):
+// start>>4 [0,14) | LBO>>4 [16,30) | SBO>>4 [32,46) | version=1 [46,48) | layout [61,64): SWIZZLE_128B = 2, SWIZZLE_64B = 4
+// SBO = bytes between 8-row groups = 8 x 64
 __device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t saddr) {
-    return uint64_t((saddr & 0x3FFFF) >> 4) | (uint64_t(1) << 16) | (uint64_t(1024 >> 4) << 32) | (uint64_t(1) << 46) |
-           (uint64_t(2) << 61);
+    return uint64_t((saddr & 0x3FFFF) >> 4) | (uint64_t(1) << 16) | (uint64_t((8 * kRowBytes) >> 4) << 32) | (uint64_t(1) << 46) |
+           (uint64_t(4) << 61);
 }
 __device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t da, uint64_t db, uint32_t idesc, uint32_t accum) {
     asm volatile(
@@ -122,6 +148,11 @@ __device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t da, uint64_t 
 __device__ __forceinline__ void umma_commit(uint32_t bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
 }
+// same, arriving on the barrier at this offset in every CTA of `mask` (a stage is free when BOTH CTAs of a pair have read it)
+__device__ __forceinline__ void umma_commit_mcast(uint32_t bar, uint16_t mask) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(bar), "h"(mask)
+                 : "memory");
+}
 __device__ __forceinline__ float act_f(float v, int act) {
     if (act == 1) return fmaxf(v, 0.f);
     if (act == 2) return tanhf(v);
@@ -136,18 +167,19 @@ template <bool F16>
 __global__ void __launch_bounds__(kThreadsTc, 1) gemm_x3_kernel(const __grid_constant__ TcParams p) {
     extern __shared__ uint8_t smem_dyn[];
     const uint32_t base = (smem_u32(smem_dyn) + 1023u) & ~1023u;          // SWIZZLE_128B atoms: 1024 B aligned
-    const uint32_t bars = base + kStages * kStageBytes;     // full[2], empty[2], tmem_full[2], tmem_empty[2], tmem_ptr
+    const uint32_t bars = base + kStages * kStageBytes;     // full[kStages], empty[kStages], tmem_full[2], tmem_empty[2], tmem_ptr
     const uint32_t full_bar = bars, empty_bar = bars + 8 * kStages, tmem_full_bar = bars + 16 * kStages;
     const uint32_t tmem_empty_bar = tmem_full_bar + 16;
     const uint32_t tmem_slot = tmem_empty_bar + 16;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int m0 = blockIdx.x * BM, n0 = blockIdx.y * BN;
+    const int n0 = blockIdx.y * BN;
     const int kt0 = blockIdx.z * p.k_tiles_per_split;
     const int kt1 = min(p.k_tiles, kt0 + p.k_tiles_per_split);
     const int nk = kt1 - kt0;
 
+    const uint32_t crank = p.mcast ? cluster_ctarank() : 0u;
     if (threadIdx.x == 0) {
-        for (int s = 0; s < kStages; ++s) { mbar_init(full_bar + 8 * s, 1); mbar_init(empty_bar + 8 * s, 1); }
+        for (int s = 0; s < kStages; ++s) { mbar_init(full_bar + 8 * s, 1); mbar_init(empty_bar + 8 * s, p.mcast ? 2 : 1); }
         for (int b = 0; b < 2; ++b) { mbar_init(tmem_full_bar + 8 * b, 1); mbar_init(tmem_empty_bar + 8 * b, 8); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
@@ -157,6 +189,7 @@ __global__ void __launch_bounds__(kThreadsTc, 1) gemm_x3_kernel(const __grid_con
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
+    if (p.mcast) cluster_sync_all();          // the peer's barriers are initialised before anything is multicast into them
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     uint32_t tmem_base;
     asm volatile("ld.shared.b32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
@@ -164,17 +197,28 @@ __global__ void __launch_bounds__(kThreadsTc, 1) gemm_x3_kernel(const __grid_con
     if (warp == 0) {
         // ===== TMA producer =====
         if (lane == 0 && nk > 0) {
-            for (int it = 0; it < nk; ++it) {
-                const int s = it % kStages;
-                const uint32_t ph = (it / kStages) & 1;
+            int git = 0;                                   // stage counter across this CTA's tiles
+            for (int mt = blockIdx.x; mt < p.m_tiles; mt += gridDim.x) {
+            const int m0 = mt * BM;
+            for (int it = 0; it < nk; ++it, ++git) {
+                const int s = git % kStages;
+                const uint32_t ph = (git / kStages) & 1;
                 mbar_wait(empty_bar + 8 * s, ph ^ 1);
                 const uint32_t st = base + s * kStageBytes;
                 mbar_expect_tx(full_bar + 8 * s, kStageBytes);
                 const int kc = (kt0 + it) * (F16 ? 2 * BK : BK);              // element coordinate of the stage
                 tma_load_2d(st, &p.a_hi, full_bar + 8 * s, kc, m0);
                 tma_load_2d(st + kABytes, &p.a_lo, full_bar + 8 * s, kc, m0);
-                tma_load_2d(st + 2 * kABytes, &p.b_hi, full_bar + 8 * s, kc, n0);
-                tma_load_2d(st + 2 * kABytes + kBBytes, &p.b_lo, full_bar + 8 * s, kc, n0);
+                if (p.mcast) {                 // my half of the B rows, into both CTAs of the pair
+                    const uint32_t off = crank * (kBBytes / 2);
+                    const int nr = n0 + int(crank) * (BN / 2);
+                    tma_load_2d_mcast(st + 2 * kABytes + off, &p.b_hi, full_bar + 8 * s, kc, nr, uint16_t(3));
+                    tma_load_2d_mcast(st + 2 * kABytes + kBBytes + off, &p.b_lo, full_bar + 8 * s, kc, nr, uint16_t(3));
+                } else {
+                    tma_load_2d(st + 2 * kABytes, &p.b_hi, full_bar + 8 * s, kc, n0);
+                    tma_load_2d(st + 2 * kABytes + kBBytes, &p.b_lo, full_bar + 8 * s, kc, n0);
+                }
+            }
             }
         }
     } else if (warp == 1) {
@@ -187,10 +231,14 @@ __global__ void __launch_bounds__(kThreadsTc, 1) gemm_x3_kernel(const __grid_con
             auto mma = [&](uint32_t td, uint64_t da, uint64_t db, uint32_t accum) {
                 if (F16) umma_f16(td, da, db, idesc, accum); else umma_tf32(td, da, db, idesc, accum);
             };
-            for (int it = 0; it < nk; ++it) {
-                const int s = it % kStages;
-                const uint32_t ph = (it / kStages) & 1;
-                const int grp = it / p.drain, sub = it - grp * p.drain;
+            int git = 0, gg = 0;                          // stage / TMEM-group counters across this CTA's tiles
+            const int ngroups_t = (nk + p.drain - 1) / p.drain;
+            for (int mt = blockIdx.x; mt < p.m_tiles; mt += gridDim.x, gg += ngroups_t)
+            for (int it = 0; it < nk; ++it, ++git) {
+                const int s = git % kStages;
+                const uint32_t ph = (git / kStages) & 1;
+                const int grp_t = it / p.drain, sub = it - grp_t * p.drain;
+                const int grp = gg + grp_t;
                 const int tb = grp & 1;                                  // TMEM ping-pong buffer of this group of stages
                 if (sub == 0) mbar_wait(tmem_empty_bar + 8 * tb, ((grp >> 1) & 1) ^ 1);   // accumulate warps drained it
                 mbar_wait(full_bar + 8 * s, ph);
@@ -211,21 +259,24 @@ __global__ void __launch_bounds__(kThreadsTc, 1) gemm_x3_kernel(const __grid_con
                     const uint64_t bhi = umma_desc_sw128(st + 2 * kABytes + k * 32);
                     mma(td, ahi, bhi, 1);
                 }
-                umma_commit(empty_bar + 8 * s);        // frees the smem stage once these MMAs retire
+                if (p.mcast) umma_commit_mcast(empty_bar + 8 * s, uint16_t(3));
+                else umma_commit(empty_bar + 8 * s);   // frees the smem stage once these MMAs retire
                 if (sub == p.drain - 1 || it == nk - 1) umma_commit(tmem_full_bar + 8 * tb);   // partial sums complete
             }
         }
     } else {
         // ===== accumulate + epilogue: warps 2..9; lane quarter = warp % 4, column half = (warp - 2) / 4 =====
         const int q = warp & 3, half = (warp - 2) >> 2;
-        const int row = m0 + q * 32 + lane;
+        const int ngroups = (nk + p.drain - 1) / p.drain;
+        int gg = 0;
+        for (int mt = blockIdx.x; mt < p.m_tiles; mt += gridDim.x, gg += ngroups) {
+        const int row = mt * BM + q * 32 + lane;
         float acc[128];
 #pragma unroll
         for (int j = 0; j < 128; ++j) acc[j] = 0.f;
-        const int ngroups = (nk + p.drain - 1) / p.drain;
-        for (int it = 0; it < ngroups; ++it) {
-            const int tb = it & 1;
-            mbar_wait(tmem_full_bar + 8 * tb, (it >> 1) & 1);
+        for (int git = gg; git < gg + ngroups; ++git) {
+            const int tb = git & 1;
+            mbar_wait(tmem_full_bar + 8 * tb, (git >> 1) & 1);
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
 #pragma unroll
             for (int c = 0; c < 4; ++c) {
@@ -254,17 +305,22 @@ __global__ void __launch_bounds__(kThreadsTc, 1) gemm_x3_kernel(const __grid_con
 #pragma unroll
             for (int j = 0; j < 128; ++j) acc[j] = (acc[j] * ia) * ib;
         }
-        if (nk > 0 && row < p.M) {
+        if ((nk > 0 || p.atomic == 2) && row < p.M) {       // (an empty split still owns -- and zeroes -- its partial tile)
 #pragma unroll
             for (int c = 0; c < 4; ++c) {
                 const int col0 = n0 + half * 128 + c * 32;
                 if (col0 >= p.N) break;
-                float* crow = p.C + int64_t(row) * p.ldc + col0;
+                float* crow = p.atomic == 2 ? p.parts + (int64_t(blockIdx.z) * p.M + row) * p.N + col0
+                                            : p.C + int64_t(row) * p.ldc + col0;
                 const int ncols = min(32, int(p.N) - col0);
-                if (p.atomic) {
+                if (p.atomic == 2) {                  // deterministic split-K: every split owns its partial tile
 #pragma unroll
                     for (int j = 0; j < 32; ++j)
-                        if (j < ncols) atomicAdd(crow + j, acc[c * 32 + j]);
+                        if (j < ncols) crow[j] = acc[c * 32 + j];
+                } else if (p.atomic == 1) {           // accumulate, one writer per element
+#pragma unroll
+                    for (int j = 0; j < 32; ++j)
+                        if (j < ncols) crow[j] += acc[c * 32 + j];
                 } else if (ncols == 32 && (p.ldc & 3) == 0) {
 #pragma unroll
                     for (int j = 0; j < 32; j += 4) {
@@ -282,11 +338,26 @@ __global__ void __launch_bounds__(kThreadsTc, 1) gemm_x3_kernel(const __grid_con
                 }
             }
         }
+        }
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
+    if (p.mcast) cluster_sync_all();          // no CTA leaves while its peer may still arrive on its barriers
     if (warp == 1) {
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(2 * BN) : "memory");
+    }
+}
+
+// C[m][n] (=|+=) sum over splits of parts[s][m][n], in split order (deterministic: no floating-point atomics)
+__global__ void splitk_reduce_kernel(const float* __restrict__ parts, int splits, int64_t M, int64_t N, float* __restrict__ C,
+                                     int64_t ldc, int accumulate) {
+    const int64_t total = M * N;
+    for (int64_t i = int64_t(blockIdx.x) * blockDim.x + threadIdx.x; i < total; i += int64_t(gridDim.x) * blockDim.x) {
+        float v = 0.f;
+        for (int sidx = 0; sidx < splits; ++sidx) v += parts[int64_t(sidx) * total + i];
+        const int64_t m = i / N, n = i - m * N;
+        float* dst = C + m * ldc + n;
+        *dst = accumulate ? *dst + v : v;
     }
 }
 
@@ -341,17 +412,17 @@ EncodeTiledFn get_encode() {
     return fn;
 }
 
-// 2D row-major [rows, cols] with leading dimension ld (elements); box = [128 bytes of columns x box_rows]
+// 2D row-major [rows, cols] with leading dimension ld (elements); box = [64 bytes of columns x box_rows]
 int make_map(CUtensorMap* m, const void* ptr, int64_t rows, int64_t cols, int64_t ld, int box_rows, bool f16) {
     EncodeTiledFn enc = get_encode();
     if (!enc) { fumi_set_error("cuTensorMapEncodeTiled is not available from the driver"); return FUMI_ERR_CUDA; }
     const int esz = f16 ? 2 : 4;
     cuuint64_t dims[2] = {cuuint64_t(cols), cuuint64_t(rows)};
     cuuint64_t strides[1] = {cuuint64_t(ld) * esz};
-    cuuint32_t box[2] = {cuuint32_t(128 / esz), cuuint32_t(box_rows)};
+    cuuint32_t box[2] = {cuuint32_t(kRowBytes / esz), cuuint32_t(box_rows)};
     cuuint32_t estr[2] = {1, 1};
     CUresult r = enc(m, f16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<void*>(ptr), dims,
-                     strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                     strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_64B,
                      CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) {
         fumi_set_error("cuTensorMapEncodeTiled failed with CUresult " + std::to_string(int(r)));
@@ -441,8 +512,12 @@ int launch_gemm_x3(bool f16, const void* a_hi, const void* a_lo, const void* b_h
     int rc;
     if ((rc = make_map(&p.a_hi, a_hi, M, K, lda, BM, f16)) != FUMI_OK) return rc;
     if ((rc = make_map(&p.a_lo, a_lo, M, K, lda, BM, f16)) != FUMI_OK) return rc;
-    if ((rc = make_map(&p.b_hi, b_hi, N, K, ldb, BN, f16)) != FUMI_OK) return rc;
-    if ((rc = make_map(&p.b_lo, b_lo, N, K, ldb, BN, f16)) != FUMI_OK) return rc;
+    // CTA pairs along M share the B stages (TMA multicast) whenever there are at least two M tiles
+    static int mcast_on = -1;
+    if (mcast_on < 0) { const char* e = getenv("FUMI_GEMM_MCAST"); mcast_on = (e && atoi(e) == 0) ? 0 : 1; }
+    p.mcast = (mcast_on && M > BM) ? 1 : 0;
+    if ((rc = make_map(&p.b_hi, b_hi, N, K, ldb, p.mcast ? BN / 2 : BN, f16)) != FUMI_OK) return rc;
+    if ((rc = make_map(&p.b_lo, b_lo, N, K, ldb, p.mcast ? BN / 2 : BN, f16)) != FUMI_OK) return rc;
     p.C = c; p.bias = bias; p.M = M; p.N = N; p.ldc = ldc; p.act = act;
     p.a_absmax = a_absmax; p.b_absmax = b_absmax;
     {   // stages per TMEM drain: 1 = best accuracy (<= 4 truncating adds per partial sum), more = fewer drains
@@ -453,7 +528,8 @@ int launch_gemm_x3(bool f16, const void* a_hi, const void* a_lo, const void* b_h
             if (drain < 1) drain = 1;
             if (drain > 8) drain = 8;
         }
-        p.drain = f16 ? (drain + 1) / 2 : drain;         // an f16 stage holds twice the k
+        // `drain` counts 32-k tf32 slices; a stage is 16 tf32 k or 32 fp16 k
+        p.drain = f16 ? 2 * ((drain + 1) / 2) : 2 * drain;
     }
     const int kstage = f16 ? 2 * BK : BK;
     p.k_tiles = int((K + kstage - 1) / kstage);
@@ -463,19 +539,26 @@ int launch_gemm_x3(bool f16, const void* a_hi, const void* a_lo, const void* b_h
     if (splits <= 0) {                                   // auto: fill the SMs when there are few output tiles
         int sms = fumi_device_sm_count();
         if (sms <= 0) return sms;
-        splits = tiles >= sms ? 1 : int((sms + tiles - 1) / tiles);
+        splits = tiles >= sms ? 1 : int(sms / tiles);    // one wave: tiles * splits <= #SMs (one CTA per SM)
         if (splits > p.k_tiles / 4) splits = p.k_tiles / 4 > 0 ? p.k_tiles / 4 : 1;
     }
     if (splits > p.k_tiles) splits = p.k_tiles;
     p.k_tiles_per_split = (p.k_tiles + splits - 1) / splits;
     splits = (p.k_tiles + p.k_tiles_per_split - 1) / p.k_tiles_per_split;
-    p.atomic = (splits > 1 || accumulate) ? 1 : 0;
-    if (p.atomic) {
-        FUMI_CHECK_ARG(bias == nullptr && act == 0, "bias / activation cannot be fused into a split-K or accumulating GEMM");
-        if (!accumulate) {
-            cudaError_t e = cudaMemset2DAsync(c, ldc * 4, 0, N * 4, M, (cudaStream_t)stream);
-            if (e != cudaSuccess) return fumi_cuda_fail(e, "cudaMemset2DAsync");
+    p.atomic = splits > 1 ? 2 : (accumulate ? 1 : 0);
+    if (p.atomic) FUMI_CHECK_ARG(bias == nullptr && act == 0, "bias / activation cannot be fused into a split-K or accumulating GEMM");
+    if (p.atomic == 2) {                                 // workspace of the partial tiles (grown on demand, kept per process)
+        static float* ws = nullptr;
+        static size_t ws_bytes = 0;
+        const size_t need = size_t(splits) * size_t(M) * size_t(N) * sizeof(float);
+        if (need > ws_bytes) {
+            if (ws) cudaFree(ws);
+            ws = nullptr; ws_bytes = 0;
+            cudaError_t e = cudaMalloc(&ws, need);
+            if (e != cudaSuccess) return fumi_cuda_fail(e, "cudaMalloc(split-K workspace)");
+            ws_bytes = need;
         }
+        p.parts = ws;
     }
     static bool attr_done = false;
     if (!attr_done) {
@@ -487,9 +570,33 @@ int launch_gemm_x3(bool f16, const void* a_hi, const void* a_lo, const void* b_h
     }
     dim3 grid((unsigned)((M + BM - 1) / BM), (unsigned)((N + BN - 1) / BN), (unsigned)splits);
     FUMI_CHECK_ARG(grid.y <= 65535 && grid.z <= 65535, "grid too large");
-    if (f16) gemm_x3_kernel<true><<<grid, kThreadsTc, kSmemBytes, (cudaStream_t)stream>>>(p);
+    if (p.mcast) grid.x = (grid.x + 1) & ~1u;  // whole pairs: an odd last M tile gets an idle partner (all its rows out of range)
+    p.m_tiles = int(grid.x);
+    {   // persistent over M: at most one CTA per SM; a CTA walks M tiles with its ring / TMEM ping-pong running on
+        const int sms = fumi_device_sm_count();
+        if (sms <= 0) return sms;
+        unsigned budget = unsigned(sms) / (grid.y * grid.z);
+        if (p.mcast) budget &= ~1u;
+        if (budget >= (p.mcast ? 2u : 1u) && grid.x > budget) grid.x = budget;
+    }
+    if (p.mcast) {
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = grid; cfg.blockDim = dim3(kThreadsTc); cfg.dynamicSmemBytes = kSmemBytes; cfg.stream = (cudaStream_t)stream;
+        cudaLaunchAttribute attr;
+        attr.id = cudaLaunchAttributeClusterDimension;
+        attr.val.clusterDim.x = 2; attr.val.clusterDim.y = 1; attr.val.clusterDim.z = 1;
+        cfg.attrs = &attr; cfg.numAttrs = 1;
+        cudaError_t e = f16 ? cudaLaunchKernelEx(&cfg, gemm_x3_kernel<true>, p) : cudaLaunchKernelEx(&cfg, gemm_x3_kernel<false>, p);
+        if (e != cudaSuccess) return fumi_cuda_fail(e, "cudaLaunchKernelEx(gemm_x3_kernel, cluster 2x1x1)");
+    } else if (f16) gemm_x3_kernel<true><<<grid, kThreadsTc, kSmemBytes, (cudaStream_t)stream>>>(p);
     else gemm_x3_kernel<false><<<grid, kThreadsTc, kSmemBytes, (cudaStream_t)stream>>>(p);
     FUMI_CHECK_LAUNCH("gemm_x3_kernel");
+    if (p.atomic == 2) {
+        const int64_t total = M * N;
+        const unsigned rgrid = unsigned((total + 255) / 256 < 148 * 8 ? (total + 255) / 256 : 148 * 8);
+        splitk_reduce_kernel<<<rgrid, 256, 0, (cudaStream_t)stream>>>(p.parts, splits, M, N, c, ldc, accumulate);
+        FUMI_CHECK_LAUNCH("splitk_reduce_kernel");
+    }
     return FUMI_OK;
 }
 }  // namespace

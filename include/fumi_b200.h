@@ -98,7 +98,8 @@ int fumi_tanh_bwd(const float* y, float* dy, int64_t n, void* stream);
  * fumi_gemm_tf32x3: C[M,N] (=|+=) act(A[M,K] . B[N,K]^T + bias[N]); both operands K-contiguous with
  *   leading dimensions lda/ldb (floats, multiples of 4, planes 16-byte aligned).  TMA-fed tcgen05.mma
  *   (kind::tf32, M128 N256 K8) with the accumulator in TMEM.  split_k: 0 = auto, n = split K into n
- *   slices (partial tiles are combined with fp32 atomics; bias/act must then be off, as with accumulate).
+ *   slices (each slice writes its partial tile to an internal workspace and a second pass sums them in slice order:
+ *   deterministic, no floating-point atomics; bias/act must then be off, as with accumulate).
  * Replaces: F.linear of the hypernetwork (fumi.py:70-107,109-113) and of im_net.linear0 over the bank
  * (fumi.py:215), and the linear0.weight gradient of outer_loss.backward() (fumi.py:192).
  * ---------------------------------------------------------------------------------------- */
