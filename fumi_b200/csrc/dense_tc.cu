@@ -153,7 +153,9 @@ __device__ __forceinline__ void umma_commit_mcast(uint32_t bar, uint16_t mask) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(bar), "h"(mask)
                  : "memory");
 }
-__device__ __forceinline__ float act_f(float v, int act) {
+// (not inlined: 128 expansions of tanhf / expf per thread made the kernel 300 KB of SASS, and the once-per-tile epilogue
+// then ran out of the instruction cache -- 38 % of all stall samples were no_instruction)
+__device__ __noinline__ float act_f(float v, int act) {
     if (act == 1) return fmaxf(v, 0.f);
     if (act == 2) return tanhf(v);
     if (act == 3) return 1.f / (1.f + expf(-v));
@@ -321,6 +323,10 @@ __global__ void __launch_bounds__(kThreadsTc, 1) gemm_x3_kernel(const __grid_con
 #pragma unroll
                     for (int j = 0; j < 32; ++j)
                         if (j < ncols) crow[j] += acc[c * 32 + j];
+                } else if (ncols == 32 && (p.ldc & 3) == 0 && p.bias == nullptr && p.act == 0) {
+#pragma unroll
+                    for (int j = 0; j < 32; j += 4)       // the bank-sized contractions: plain stores
+                        *reinterpret_cast<float4*>(crow + j) = make_float4(acc[c * 32 + j], acc[c * 32 + j + 1], acc[c * 32 + j + 2], acc[c * 32 + j + 3]);
                 } else if (ncols == 32 && (p.ldc & 3) == 0) {
 #pragma unroll
                     for (int j = 0; j < 32; j += 4) {
