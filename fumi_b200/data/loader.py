@@ -153,7 +153,7 @@ class EpisodeLoader:
                 if isinstance(item, Exception):
                     raise item
                 ts, arrs, py_after, st_after = item
-                random.setstate((ver, tuple(int(x) for x in py_after), gauss))
+                random.setstate((ver, tuple(py_after.tolist()), gauss))       # (tolist: C speed; 625 words every batch)
                 _torch_state_set(st_after, raw)
                 if isinstance(ts, EpisodeBatch):                 # expanded on the loader stream
                     cur = torch.cuda.current_stream(dev)

@@ -16,6 +16,7 @@ PyTorch supplies device memory, streams and torch.distributed only; every arithm
 kernel of libfumi_b200.so.  There is no CPU path: a non-CUDA device raises.
 """
 import ctypes as C
+import os
 
 import numpy as np
 import torch
@@ -278,6 +279,44 @@ class EpisodeEngine:
         self.launches += 1
         return out
 
+    def loss_acc_early(self, la):
+        """Start the device -> host copy of [loss, acc] as soon as the forward has produced them (they do not depend on
+        the backward or the optimizer step), into a pinned buffer with an event behind it.  `read_loss_acc` then waits for
+        that event only, so the caller gets the step's loss (fumi.py:195-196) while the device is still in the backward,
+        and enqueues the next step without ever letting the stream run dry.  With more than one rank the two scalars are
+        averaged over ranks first, by a 2-float all-reduce on a side stream (the compute stream never waits for it)."""
+        if self.device.type != "cuda" or os.environ.get("FUMI_EARLY_LOSS", "1") == "0":
+            return None
+        world = self._world()
+        main = torch.cuda.current_stream(self.device)
+        if getattr(self, "_la_host", None) is None:
+            self._la_host = torch.empty(2, dtype=torch.float32, pin_memory=True)
+            self._la_event = torch.cuda.Event()
+            self._la_tmp = torch.empty(2, dtype=torch.float32, device=self.device)
+            self._la_stream = torch.cuda.Stream(self.device)
+        if world == 1:
+            self._la_host.copy_(la, non_blocking=True)
+            self._la_event.record(main)
+            return self._la_event
+        side = self._la_stream
+        side.wait_stream(main)
+        la.record_stream(side)
+        with torch.cuda.stream(side):
+            self._la_tmp.copy_(la)
+            dist.all_reduce(self._la_tmp)
+            self._la_tmp /= world
+            self._la_host.copy_(self._la_tmp, non_blocking=True)
+            self._la_event.record(side)
+        return self._la_event
+
+    def read_loss_acc(self, res):
+        """[loss, acc] of a batch as a host array (the one device sync per batch of the reference API)."""
+        ev = res.get("loss_acc_event")
+        if ev is None:
+            return res["loss_acc"].cpu().numpy()
+        ev.synchronize()
+        return self._la_host.numpy().copy()
+
     # ------------------------------------------------------------------ batch plumbing
     def _to_dev(self, t, dtype=None):
         if isinstance(t, np.ndarray):
@@ -364,11 +403,18 @@ class EpisodeEngine:
         loss_acc /= world
 
     # ------------------------------------------------------------------ FuMI
-    def hypernet(self, model, text_rows, keep=False):
-        """hyper_net(text): Linear-ReLU-Linear(-Tanh)  (fumi.py:70-107,109-113)."""
+    def hypernet(self, model, text_rows, keep=False, bank=None):
+        """hyper_net(text): Linear-ReLU-Linear(-Tanh)  (fumi.py:70-107,109-113).  `bank`: the FeatureBank whose static
+        description rows `text_rows` are (their operand planes are split once and cached on it)."""
         l0, l2 = model.hyper_net[0], model.hyper_net[2]
         if self.precision >= 1 and text_rows.shape[1] % 4 == 0:
-            u = self.gemm_tc(self.split_tf32(text_rows), self.split_tf32(l0.weight), bias=l0.bias, act=1)
+            if bank is not None and text_rows is bank.text:
+                if getattr(bank, "_text_tf32", None) is None:
+                    bank._text_tf32 = self.split_tf32(text_rows)
+                tplanes = bank._text_tf32
+            else:
+                tplanes = self.split_tf32(text_rows)
+            u = self.gemm_tc(tplanes, self.split_tf32(l0.weight), bias=l0.bias, act=1)
         else:
             u = self.linear_fwd(text_rows, l0.weight, l0.bias, act=1, precision=0)
         hp = self.linear_fwd(u, l2.weight, l2.bias, act=2 if model.norm_hypernet else 0, precision=0)
@@ -398,12 +444,14 @@ class EpisodeEngine:
         cfg = self.make_cfg(N, NK, NQ, steps, step_size, dropout_p=p_drop,
                             dropout_seed=(int(getattr(model, "dropout_base_seed", 0)) << 20) + model.dropout_seed,
                             task_offset=rank * B, save=train or return_state)
-        hp_table, u = self.hypernet(model, text_rows, keep=True)
+        # the bank-sized projection goes first: after the host sync that ends every step (loss / accuracy come back,
+        # fumi.py:195-196) it gives the device 0.4 ms of work while the host enqueues the small hypernetwork launches
         proj = self.project_rows(feats, eb.bank, lin0.weight)
+        hp_table, u = self.hypernet(model, text_rows, keep=True, bank=eb.bank)
         gram = self.gram(feats, eb.sup_rows, eb.qry_rows, bank=eb.bank)
         out = self.episode_fwd(cfg, proj, eb, gram, lin0.bias, lin1.weight, lin1.bias, hp_table, head_rows)
         la = self.loss_acc(out["task_loss"], out["task_acc"])
-        res = dict(loss_acc=la, preds=out["preds"], logits=out["logits"], qry_y=eb.qry_y, task_loss=out["task_loss"],
+        res = dict(loss_acc=la, loss_acc_event=self.loss_acc_early(la), preds=out["preds"], logits=out["logits"], qry_y=eb.qry_y, task_loss=out["task_loss"],
                    task_acc=out["task_acc"], cfg=cfg, stash=out["stash"] if (train or return_state) else None,
                    hp_table=hp_table, head_rows=head_rows, batch=eb)
         if not train:
@@ -446,7 +494,7 @@ class EpisodeEngine:
         gram = self.gram(feats, eb.sup_rows, eb.qry_rows, bank=eb.bank)
         out = self.episode_fwd(cfg, proj, eb, gram, lin0.bias, lin1.weight, lin1.bias, head_table, None)
         la = self.loss_acc(out["task_loss"], out["task_acc"])
-        res = dict(loss_acc=la, preds=out["preds"], logits=out["logits"], qry_y=eb.qry_y, cfg=cfg,
+        res = dict(loss_acc=la, loss_acc_event=self.loss_acc_early(la), preds=out["preds"], logits=out["logits"], qry_y=eb.qry_y, cfg=cfg,
                    stash=out["stash"] if (train or return_state) else None, batch=eb)
         if not train:
             return res

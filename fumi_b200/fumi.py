@@ -141,8 +141,9 @@ class FUMI(nn.Module):
         if task == "train":
             # optimizer.zero_grad(); outer_loss.backward(); optimizer.step()   (fumi.py:190-193)
             optimizer.step()
-        # the single device sync per batch, as the reference's .cpu().numpy() (fumi.py:195-196)
-        la = res["loss_acc"].cpu().numpy()
+        # the single device sync per batch, as the reference's .cpu().numpy() (fumi.py:195-196); on one GPU it waits
+        # for the forward's loss only (engine.loss_acc_early), the backward and the Adam step keep running behind it
+        la = eng.read_loss_acc(res)
         return la[0], la[1], res["preds"].to(torch.float32), res["qry_y"]
 
 

@@ -65,7 +65,7 @@ def evaluate(args, model, batch, optimizer, task="train"):
                          first_order=bool(args.first_order))
     if task == "train":
         optimizer.step()          # maml.py:188-191
-    la = res["loss_acc"].cpu().numpy()
+    la = eng.read_loss_acc(res)  # (one GPU: waits for the forward's loss only, engine.loss_acc_early)
     evaluate.last = res           # logits / preds of the last call, for inspection and tests
     return la[0], la[1]
 
