@@ -87,9 +87,14 @@ class EpisodeLoader:
                             head_class=ts["head_class"], host=arrs)
 
     def close(self):
+        """Stop the prefetch thread and wait for it (a thread still inside a CUDA call at interpreter exit aborts the
+        process)."""
         if self._stop is not None:
             self._stop.set()
             self._stop = None
+        th, self._thread = getattr(self, "_thread", None), None
+        if th is not None and th.is_alive() and th is not threading.current_thread():
+            th.join(timeout=5.0)
 
     def __iter__(self):
         self.sampler.new_iterator()
@@ -146,7 +151,8 @@ class EpisodeLoader:
             except Exception as e:          # surfaced on the consumer side
                 q.put(e)
 
-        threading.Thread(target=worker, daemon=True).start()
+        self._thread = threading.Thread(target=worker, daemon=True)
+        self._thread.start()
         try:
             while True:
                 item = q.get()

@@ -9,7 +9,7 @@ def f(r, k):
         return float(r[idx[k]].replace(",", ""))
     except (KeyError, ValueError):
         return None
-names = {"gram_tc_kernel": "fumi_gram", "gram_kernel": "fumi_gram", "episode_fwd_mma16": "fumi_episode_fwd", "episode_fwd_f16": "fumi_episode_fwd",
+names = {"episode_fwd_v2": "fumi_episode_fwd", "episode_bwd_v2": "fumi_episode_bwd", "gram_tc_kernel": "fumi_gram", "gram_kernel": "fumi_gram", "episode_fwd_mma16": "fumi_episode_fwd", "episode_fwd_f16": "fumi_episode_fwd",
          "episode_bwd_mma16": "fumi_episode_bwd", "gemm_x3_kernel<1>": "fumi_gemm_f16x3",
          "gemm_x3_kernel<0>": "fumi_gemm_tf32x3", "gemm_tf32x3": "fumi_gemm_tf32x3", "sampler_expand": "fumi_sampler_expand"}
 out = {"source": sys.argv[3], "workload": sys.argv[4], "tasks": int(sys.argv[5]), "kernels": {}}
