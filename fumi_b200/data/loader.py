@@ -112,13 +112,30 @@ class EpisodeLoader:
         # device sampler on a CUDA bank: the plan upload and fumi_sampler_expand run on the loader's own stream from
         # the prefetch thread, so they overlap the previous batch's kernels; the consumer's stream waits on an event.
         dev = self.bank.feats.device
-        side = torch.cuda.Stream(dev) if (self.device_sampler and dev.type == "cuda") else None
+        side = None
+        if self.device_sampler and dev.type == "cuda":       # one loader stream (and allocator pool) per loader, not per epoch
+            if getattr(self, "_side", None) is None:
+                self._side = torch.cuda.Stream(dev)
+            side = self._side
 
         # pinned plan buffers are allocated once and reused round-robin: a pinned allocation in steady state
         # (cudaHostAlloc) stalls every CUDA call of the process for milliseconds.  A buffer is rewritten prefetch + 2
         # batches after its upload was enqueued, long after the consumer waited on that batch's event.
         ring = [self.sampler.empty_plan(self._draw, pin_memory=self.pin) for _ in range(self.prefetch + 2)] \
             if self.device_sampler else []
+        if side is not None:
+            # Same for device memory: a batch's index arrays are allocated on the loader stream and return to its pool
+            # only when the consumer's stream has passed them, so the pool keeps growing (cudaMalloc from this thread,
+            # which stalls the consumer's launches for tens of milliseconds while the device is busy) until it holds
+            # every batch in flight.  Fill it once, up front: prefetch + 6 sets of exactly the tensors of a batch.
+            N, K, Q, B = self.sampler.N, self.sampler.K, self.sampler.Q, self.batch_size
+            with torch.cuda.stream(side):
+                warm = []
+                for _ in range(self.prefetch + 6):
+                    warm.append([t.to(dev, non_blocking=True) for t in self.sampler.empty_plan(B, pin_memory=False).values()])
+                    warm.append([torch.empty((B, N * w_), dtype=torch.int64, device=dev) for w_ in (K, Q, K, Q, K, Q)])
+                del warm
+            side.synchronize()
 
         def worker():
             try:
