@@ -152,7 +152,7 @@ __global__ void __launch_bounds__(kThreads16, 1) episode_bwd_v2_kernel(EpiParams
             s.sys[tid] = tid < n ? int(P.sup_y[b * n + tid]) : 0;
         }
         float aS[2][2][4];                                // adjoint of S at this thread's positions (rows x own columns)
-        float wacc[8][4];                                 // adjoint of W1^T rows [16w, 16w+16): query pass sum, then per step
+        float wacc[8][4];                                 // adjoint of W1^T rows [16w, 16w+16): fp32 master (planes are re-split from it)
         float ab0r[2][2] = {{0.f, 0.f}, {0.f, 0.f}};      // adjoint of b0 at this thread's columns
 #pragma unroll
         for (int i = 0; i < 2; ++i)
@@ -502,10 +502,8 @@ __global__ void __launch_bounds__(kThreads16, 1) episode_bwd_v2_kernel(EpiParams
                 float gb0[2][2], rb0r[2][2] = {{0.f, 0.f}, {0.f, 0.f}};
 #pragma unroll
                 for (int j = 0; j < 2; ++j) { gb0[j][0] = -alpha * ab0r[j][0]; gb0[j][1] = -alpha * ab0r[j][1]; }
-#pragma unroll
-                for (int j = 0; j < 8; ++j)
-#pragma unroll
-                    for (int q = 0; q < 4; ++q) wacc[j][q] = 0.f;
+                // (wacc is the fp32 master of this warp's rows of a_W1^T and runs on across the steps: the planes keep the
+                // value from before the step until they are re-split from it at the end of the step)
                 fumi_cp_async_wait();
                 __syncthreads();                          // U0: records of the step in shared memory; a_W1 planes folded
                 if (st < steps - 1) FUMI_ADOPT(e_aw, e_awn, par_aw, BX_AW);
@@ -786,19 +784,15 @@ __global__ void __launch_bounds__(kThreads16, 1) episode_bwd_v2_kernel(EpiParams
                 // ---- end of the reversed step: next step's records start travelling, then the adjoints are folded
                 if (st > 0) s_issue(st - 1);
                 {
-                    const float ainv = fumi_exp2i(-e_aw), asc = fumi_exp2i(e_awn);
+                    const float asc = fumi_exp2i(e_awn);
                     float mxv = 0.f;
 #pragma unroll
                     for (int j = 0; j < 8; ++j)
 #pragma unroll
                         for (int hq = 0; hq < 2; ++hq) {
                             const int off = (16 * w + g + 8 * hq) * kHW + 8 * j + 2 * t;
-                            float o0, o1;
-                            ld_planes2(s.awh, s.awl, off, ainv, o0, o1);
-                            o0 += wacc[j][2 * hq];
-                            o1 += wacc[j][2 * hq + 1];
-                            mxv = fmaxf(mxv, fmaxf(fabsf(o0), fabsf(o1)));
-                            st_planes2(s.awh, s.awl, off, o0, o1, asc);
+                            mxv = fmaxf(mxv, fmaxf(fabsf(wacc[j][2 * hq]), fabsf(wacc[j][2 * hq + 1])));
+                            st_planes2(s.awh, s.awl, off, wacc[j][2 * hq], wacc[j][2 * hq + 1], asc);
                         }
                     block_max_push(s.mx + 16 * (BX_AW + par_aw), mxv);
                 }
