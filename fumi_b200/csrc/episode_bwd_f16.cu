@@ -318,7 +318,7 @@ __global__ void __launch_bounds__(kThreads16, 1) episode_bwd_v2_kernel(EpiParams
                 for (int j = 0; j < 8; ++j)
 #pragma unroll
                     for (int q = 0; q < 4; ++q) acc[0][j][q] = 0.f;
-                warp_gemm_f16x3<1, 8, true, false>(qh + 16 * w, ql + 16 * w, kHS, s.dzh, s.dzl, kHW, 32, acc);
+                warp_gemm_f16x3<1, 8, true, false, true>(qh + 16 * w, ql + 16 * w, kHS, s.dzh, s.dzl, kHW, 32, acc);
                 const float inv = fumi_exp2i(-e_h0) * fumi_exp2i(-e_dz);
 #pragma unroll
                 for (int j = 0; j < 8; ++j)
@@ -334,7 +334,7 @@ __global__ void __launch_bounds__(kThreads16, 1) episode_bwd_v2_kernel(EpiParams
                     for (int j = 0; j < 2; ++j)
 #pragma unroll
                         for (int q = 0; q < 4; ++q) acc[i][j][q] = 0.f;
-                warp_gemm_f16x3<2, 2, false, true>(s.dzh, s.dzl, kHW, s.w1h + 16 * w * kHW, s.w1l + 16 * w * kHW, kHW, kH1, acc);
+                warp_gemm_f16x3<2, 2, false, true, true>(s.dzh, s.dzl, kHW, s.w1h + 16 * w * kHW, s.w1l + 16 * w * kHW, kHW, kH1, acc);
                 const float inv = fumi_exp2i(-e_dz) * fumi_exp2i(-e_w1) * sc;
                 float colsum[2][2] = {{0.f, 0.f}, {0.f, 0.f}};
                 float mxv = 0.f;
@@ -385,7 +385,7 @@ __global__ void __launch_bounds__(kThreads16, 1) episode_bwd_v2_kernel(EpiParams
                         for (int j = 0; j < 2; ++j)
 #pragma unroll
                             for (int q = 0; q < 4; ++q) as[i][j][q] = 0.f;
-                    warp_gemm_f16x3<MT, 2, true, false>(s.gqh, s.gql, kHG, s.bzh + 16 * w, s.bzl + 16 * w, kHS, 32, as);
+                    warp_gemm_f16x3<MT, 2, true, false, true>(s.gqh, s.gql, kHG, s.bzh + 16 * w, s.bzl + 16 * w, kHS, 32, as);
                     const float ainv = -alpha * fumi_exp2i(-e_gq) * fumi_exp2i(-e_bz);
 #pragma unroll
                     for (int i = 0; i < MT; ++i)
@@ -515,7 +515,7 @@ __global__ void __launch_bounds__(kThreads16, 1) episode_bwd_v2_kernel(EpiParams
                     for (int j = 0; j < 8; ++j)
 #pragma unroll
                         for (int q = 0; q < 4; ++q) acc[0][j][q] = 0.f;
-                    warp_gemm_f16x3<1, 8, true, false>(s.h0h + 16 * w, s.h0l + 16 * w, kHS, s.dzh, s.dzl, kHW, RS, acc);
+                    warp_gemm_f16x3<1, 8, true, false, true>(s.h0h + 16 * w, s.h0l + 16 * w, kHS, s.dzh, s.dzl, kHW, RS, acc);
                     const float inv = alpha * fumi_exp2i(-e_h0) * fumi_exp2i(-e_dzs);
                     const float winv = fumi_exp2i(-e_w1), wsc = fumi_exp2i(e_w1n);
                     float mxv = 0.f;
@@ -599,7 +599,7 @@ __global__ void __launch_bounds__(kThreads16, 1) episode_bwd_v2_kernel(EpiParams
                         for (int j = 0; j < 8; ++j)
 #pragma unroll
                             for (int q = 0; q < 4; ++q) acc[0][j][q] = 0.f;
-                        warp_gemm_f16x3<1, 8, true, false>(s.h0h + 16 * kHS + 16 * w, s.h0l + 16 * kHS + 16 * w, kHS, s.dzh + r0 * kHW,
+                        warp_gemm_f16x3<1, 8, true, false, true>(s.h0h + 16 * kHS + 16 * w, s.h0l + 16 * kHS + 16 * w, kHS, s.dzh + r0 * kHW,
                                                             s.dzl + r0 * kHW, kHW, 16, acc);
                         const float inv = fumi_exp2i(-e_tt) * fumi_exp2i(-e_dzs);
 #pragma unroll
@@ -611,7 +611,7 @@ __global__ void __launch_bounds__(kThreads16, 1) episode_bwd_v2_kernel(EpiParams
                         for (int j = 0; j < 2; ++j)
 #pragma unroll
                             for (int q = 0; q < 4; ++q) a2[0][j][q] = 0.f;
-                        warp_gemm_f16x3<1, 2, false, true>(s.dzh + r0 * kHW, s.dzl + r0 * kHW, kHW, s.awh + 16 * w * kHW, s.awl + 16 * w * kHW, kHW, kH1, a2);
+                        warp_gemm_f16x3<1, 2, false, true, true>(s.dzh + r0 * kHW, s.dzl + r0 * kHW, kHW, s.awh + 16 * w * kHW, s.awl + 16 * w * kHW, kHW, kH1, a2);
                         const float i2 = -alpha * fumi_exp2i(-e_dzs) * fumi_exp2i(-e_aw);
 #pragma unroll
                         for (int j = 0; j < 2; ++j)
@@ -711,14 +711,14 @@ __global__ void __launch_bounds__(kThreads16, 1) episode_bwd_v2_kernel(EpiParams
                         for (int j = 0; j < 2; ++j)
 #pragma unroll
                             for (int q = 0; q < 4; ++q) a2[0][j][q] = 0.f;
-                        warp_gemm_f16x3<1, 2, false, true>(s.rzh, s.rzl, kHW, s.w1h + 16 * w * kHW, s.w1l + 16 * w * kHW, kHW, kH1, a2);
+                        warp_gemm_f16x3<1, 2, false, true, true>(s.rzh, s.rzl, kHW, s.w1h + 16 * w * kHW, s.w1l + 16 * w * kHW, kHW, kH1, a2);
                         const float i2 = fumi_exp2i(-e_rz) * fumi_exp2i(-e_w1);
                         float acc[1][8][4];
 #pragma unroll
                         for (int j = 0; j < 8; ++j)
 #pragma unroll
                             for (int q = 0; q < 4; ++q) acc[0][j][q] = 0.f;
-                        warp_gemm_f16x3<1, 8, true, false>(s.h0h + 16 * w, s.h0l + 16 * w, kHS, s.rzh, s.rzl, kHW, 16, acc);
+                        warp_gemm_f16x3<1, 8, true, false, true>(s.h0h + 16 * w, s.h0l + 16 * w, kHS, s.rzh, s.rzl, kHW, 16, acc);
                         const float inv = fumi_exp2i(-e_h0) * fumi_exp2i(-e_rz);
 #pragma unroll
                         for (int j = 0; j < 8; ++j)
@@ -768,7 +768,7 @@ __global__ void __launch_bounds__(kThreads16, 1) episode_bwd_v2_kernel(EpiParams
                             for (int j = 0; j < 2; ++j)
 #pragma unroll
                                 for (int q = 0; q < 4; ++q) as[i][j][q] = 0.f;
-                        warp_gemm_f16x3<MT, 2, false, false>(s.gsh + r0, s.gsl + r0, kHG, s.h0h + 16 * kHS + 16 * w, s.h0l + 16 * kHS + 16 * w,
+                        warp_gemm_f16x3<MT, 2, false, false, true>(s.gsh + r0, s.gsl + r0, kHG, s.h0h + 16 * kHS + 16 * w, s.h0l + 16 * kHS + 16 * w,
                                                              kHS, 16, as);
                         const float ainv = -alpha * fumi_exp2i(-e_gs) * fumi_exp2i(-e_bz);
 #pragma unroll

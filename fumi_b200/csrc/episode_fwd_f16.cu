@@ -415,21 +415,6 @@ __global__ void __launch_bounds__(kThreads16, 1) episode_fwd_v2_kernel(EpiParams
             __syncthreads();                              // B3: dZ1 planes, dL, H1
             FUMI_ADOPT(e_dz, e_dzn, par_dz, FX_DZ);
             pc.mark(23);
-            // ---- small updates by the first threads: head, b1 (their results are first read after the next B1)
-            for (int idx = tid; idx < N * kHD; idx += NT_) {
-                const int cc = idx / kHD, o = idx - cc * kHD;
-                const float* hcol = o < kH1 ? s.h1t + o : nullptr;
-                float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;       // four independent chains over the rows
-                int i = 0;
-                for (; i + 4 <= n; i += 4) {
-                    a0 = fmaf(s.lt[i * kLS + cc], hcol ? hcol[i * kS1] : 1.f, a0);
-                    a1 = fmaf(s.lt[(i + 1) * kLS + cc], hcol ? hcol[(i + 1) * kS1] : 1.f, a1);
-                    a2 = fmaf(s.lt[(i + 2) * kLS + cc], hcol ? hcol[(i + 2) * kS1] : 1.f, a2);
-                    a3 = fmaf(s.lt[(i + 3) * kLS + cc], hcol ? hcol[(i + 3) * kS1] : 1.f, a3);
-                }
-                for (; i < n; ++i) a0 = fmaf(s.lt[i * kLS + cc], hcol ? hcol[i * kS1] : 1.f, a0);
-                s.dhp[idx] = (a0 + a1) + (a2 + a3);
-            }
             // ---- (d) dZ0 = (dZ1 W1) * gate ; S += dZ0 ; b0 -= alpha colsum(dZ0): warp-local
             {
                 float acc[MT][2][4];
@@ -439,7 +424,23 @@ __global__ void __launch_bounds__(kThreads16, 1) episode_fwd_v2_kernel(EpiParams
                     for (int j = 0; j < 2; ++j)
 #pragma unroll
                         for (int q = 0; q < 4; ++q) acc[i][j][q] = 0.f;
-                warp_gemm_f16x3<MT, 2, false, true>(s.dzh, s.dzl, kHW, s.w1h + 16 * w * kHW, s.w1l + 16 * w * kHW, kHW, kH1, acc);
+                warp_gemm_f16x3<MT, 2, false, true, true>(s.dzh, s.dzl, kHW, s.w1h + 16 * w * kHW, s.w1l + 16 * w * kHW, kHW, kH1, acc);
+                // (the MMAs above are in flight: the head-gradient sums of the first threads run under them)
+                // ---- small updates by the first threads: head, b1 (their results are first read after the next B1)
+                for (int idx = tid; idx < N * kHD; idx += NT_) {
+                    const int cc = idx / kHD, o = idx - cc * kHD;
+                    const float* hcol = o < kH1 ? s.h1t + o : nullptr;
+                    float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;       // four independent chains over the rows
+                    int i = 0;
+                    for (; i + 4 <= n; i += 4) {
+                        a0 = fmaf(s.lt[i * kLS + cc], hcol ? hcol[i * kS1] : 1.f, a0);
+                        a1 = fmaf(s.lt[(i + 1) * kLS + cc], hcol ? hcol[(i + 1) * kS1] : 1.f, a1);
+                        a2 = fmaf(s.lt[(i + 2) * kLS + cc], hcol ? hcol[(i + 2) * kS1] : 1.f, a2);
+                        a3 = fmaf(s.lt[(i + 3) * kLS + cc], hcol ? hcol[(i + 3) * kS1] : 1.f, a3);
+                    }
+                    for (; i < n; ++i) a0 = fmaf(s.lt[i * kLS + cc], hcol ? hcol[i * kS1] : 1.f, a0);
+                    s.dhp[idx] = (a0 + a1) + (a2 + a3);
+                }
                 const float inv = fumi_exp2i(-e_dz) * fumi_exp2i(-e_w1) * dsc;
                 float colsum[2][2] = {{0.f, 0.f}, {0.f, 0.f}};
                 float mxv = 0.f;
@@ -540,7 +541,7 @@ __global__ void __launch_bounds__(kThreads16, 1) episode_fwd_v2_kernel(EpiParams
 #pragma unroll
                         for (int q = 0; q < 4; ++q) acc[i][j][q] = 0.f;
                 __syncwarp();                             // this warp's S planes are complete
-                warp_gemm_f16x3<MT, 2, false, false>(s.gsh, s.gsl, kHG, s.sh + 16 * w, s.sl + 16 * w, kHS, RS,
+                warp_gemm_f16x3<MT, 2, false, false, true>(s.gsh, s.gsl, kHG, s.sh + 16 * w, s.sl + 16 * w, kHS, RS,
                                                      reinterpret_cast<float(&)[MT][2][4]>(acc));
                 gate0 = h0_finish(acc, MT, 0, n, alpha * fumi_exp2i(-e_gs) * fumi_exp2i(-e_s), st + 1);
             }

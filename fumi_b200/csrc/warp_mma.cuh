@@ -221,7 +221,10 @@ __device__ __forceinline__ void warp_tile_foreach(float (&acc)[MT][NT][4], F f) 
 //   A(m,k) = A[m*lda + k]  (ATRANS: A[k*lda + m]);   B(k,n) = B[k*ldb + n]  (BTRANS: B[n*ldb + k]);  lda / ldb in
 //   halves, rows 16-byte aligned and 16 bytes apart mod 128 (ld = cols + 8 for cols % 64 == 0) -> conflict-free.
 //   K % 16 == 0; the accumulator restarts every 64 k (the tensor core adds with truncation).
-template <int MT, int NT, bool ATRANS, bool BTRANS>
+//   SINGLE: K <= 64 and acc holds zeros on entry (every warp-local product of the episode kernels: K = 16 / 32 / 64) --
+//   the one 64-wide slice accumulates straight into acc, without the zeroed partial tile and the add that fold a
+//   slice into a running sum (5-7 % of the episode kernels' instructions were those moves and adds).
+template <int MT, int NT, bool ATRANS, bool BTRANS, bool SINGLE = false>
 __device__ __forceinline__ void warp_gemm_f16x3(const fumi_half* Ahi, const fumi_half* Alo, int lda, const fumi_half* Bhi,
                                                 const fumi_half* Blo, int ldb, int K, float (&acc)[MT][NT][4]) {
     static_assert(NT == 1 || NT % 2 == 0, "n tiles come in pairs (ldmatrix.x4) or alone");
@@ -235,8 +238,11 @@ __device__ __forceinline__ void warp_gemm_f16x3(const fumi_half* Ahi, const fumi
     // instead of one dependent chain of 3 K/16 MMAs -- the 64-wide layer has one tile per warp and was latency-bound)
     constexpr bool kSplitAcc = MT * NT <= 2;
 #pragma unroll 1
-    for (int k0 = 0; k0 < K; k0 += 64) {
-        float part[MT][NT][4];
+    for (int k0 = 0; k0 < (SINGLE ? 1 : K); k0 += 64) {
+        float part_[SINGLE ? 1 : MT][SINGLE ? 1 : NT][4];
+        auto part = [&](int i, int j) -> float (&)[4] {
+            if constexpr (SINGLE) return acc[i][j]; else return part_[i][j];
+        };
         float c1[kSplitAcc ? MT : 1][kSplitAcc ? NT : 1][4], c2[kSplitAcc ? MT : 1][kSplitAcc ? NT : 1][4];
 #pragma unroll
         for (int i = 0; i < MT; ++i)
@@ -244,7 +250,7 @@ __device__ __forceinline__ void warp_gemm_f16x3(const fumi_half* Ahi, const fumi
             for (int j = 0; j < NT; ++j)
 #pragma unroll
                 for (int q = 0; q < 4; ++q) {
-                    part[i][j][q] = 0.f;
+                    if (!SINGLE) part(i, j)[q] = 0.f;
                     if (kSplitAcc) { c1[i][j][q] = 0.f; c2[i][j][q] = 0.f; }
                 }
 #pragma unroll
@@ -265,9 +271,9 @@ __device__ __forceinline__ void warp_gemm_f16x3(const fumi_half* Ahi, const fumi
                 else        { fumi_ldsm2t(bh, Bhi + o); fumi_ldsm2t(bl, Blo + o); }
 #pragma unroll
                 for (int i = 0; i < MT; ++i) {
-                    fumi_mma_f16(kSplitAcc ? c1[i][0] : part[i][0], al[i], bh[0], bh[1]);
-                    fumi_mma_f16(kSplitAcc ? c2[i][0] : part[i][0], ah[i], bl[0], bl[1]);
-                    fumi_mma_f16(part[i][0], ah[i], bh[0], bh[1]);
+                    fumi_mma_f16(kSplitAcc ? c1[i][0] : part(i, 0), al[i], bh[0], bh[1]);
+                    fumi_mma_f16(kSplitAcc ? c2[i][0] : part(i, 0), ah[i], bl[0], bl[1]);
+                    fumi_mma_f16(part(i, 0), ah[i], bh[0], bh[1]);
                 }
             } else {
 #pragma unroll
@@ -280,9 +286,9 @@ __device__ __forceinline__ void warp_gemm_f16x3(const fumi_half* Ahi, const fumi
                     for (int i = 0; i < MT; ++i) {
 #pragma unroll
                         for (int h = 0; h < 2; ++h) {
-                            fumi_mma_f16(kSplitAcc ? c1[i][2 * jp + h] : part[i][2 * jp + h], al[i], bh[2 * h], bh[2 * h + 1]);
-                            fumi_mma_f16(kSplitAcc ? c2[i][2 * jp + h] : part[i][2 * jp + h], ah[i], bl[2 * h], bl[2 * h + 1]);
-                            fumi_mma_f16(part[i][2 * jp + h], ah[i], bh[2 * h], bh[2 * h + 1]);
+                            fumi_mma_f16(kSplitAcc ? c1[i][2 * jp + h] : part(i, 2 * jp + h), al[i], bh[2 * h], bh[2 * h + 1]);
+                            fumi_mma_f16(kSplitAcc ? c2[i][2 * jp + h] : part(i, 2 * jp + h), ah[i], bl[2 * h], bl[2 * h + 1]);
+                            fumi_mma_f16(part(i, 2 * jp + h), ah[i], bh[2 * h], bh[2 * h + 1]);
                         }
                     }
                 }
@@ -293,8 +299,10 @@ __device__ __forceinline__ void warp_gemm_f16x3(const fumi_half* Ahi, const fumi
 #pragma unroll
             for (int j = 0; j < NT; ++j)
 #pragma unroll
-                for (int q = 0; q < 4; ++q)
-                    acc[i][j][q] += kSplitAcc ? part[i][j][q] + (c1[i][j][q] + c2[i][j][q]) : part[i][j][q];
+                for (int q = 0; q < 4; ++q) {
+                    if (SINGLE) { if (kSplitAcc) acc[i][j][q] += c1[i][j][q] + c2[i][j][q]; }
+                    else acc[i][j][q] += kSplitAcc ? part(i, j)[q] + (c1[i][j][q] + c2[i][j][q]) : part(i, j)[q];
+                }
     }
 }
 
