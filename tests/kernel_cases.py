@@ -154,6 +154,16 @@ def gemm_f16_case(device):
     x1[rs.rand(R) < 0.5] = 0.0                                    # like d_proj: many untouched rows
     got = eng.gemm_f16(eng.transpose_split_f16(t(x1)), eng.transpose_split_f16(t(x2)), K=R).cpu().numpy()
     assert relerr(got, x1.astype(np.float64).T @ x2.astype(np.float64)) < 2e-6
+    # more M tiles than SMs (a CTA walks several tiles: ring / TMEM ping-pong run on across them; odd tile count -> idle
+    # partner in the last multicast pair), and split-K summed in slice order: two runs are bit-identical
+    a = rs.randn(148 * 128 * 2 + 77, 192).astype(np.float32)
+    b = (rs.randn(256, 192) / np.sqrt(192)).astype(np.float32)
+    got = eng.gemm_f16(eng.split_f16(t(a)), eng.split_f16(t(b))).cpu().numpy()
+    assert relerr(got, a.astype(np.float64) @ b.astype(np.float64).T) < 2e-6
+    xa, xb = eng.transpose_split_f16(t(x1)), eng.transpose_split_f16(t(x2))
+    r1 = eng.gemm_f16(xa, xb, K=R, split_k=5).cpu().numpy()
+    r2 = eng.gemm_f16(xa, xb, K=R, split_k=5).cpu().numpy()
+    assert np.array_equal(r1, r2), "split-K must be reproducible run to run"
     z = eng.split_f16(torch.zeros(8, 64, device=device))          # all-zero operand: scale 1, no NaN
     assert float(eng.gemm_f16(z, eng.split_f16(t(rs.randn(16, 64).astype(np.float32)))).abs().max()) == 0.0
 
