@@ -66,7 +66,8 @@ __host__ __device__ inline size_t carve_v(char* base, SmemV& s, int N) {
 
 // MT: 16-row tiles of the support set (NK <= 16 MT); kNC: compile-time class count (>= N; the head buffer is zero-padded
 // to kNC rows so that the per-class loops carry no guards)
-template <int MT, int kNC>
+// SAVE = false: meta-test (no stash, no dropout): the record / mask code is compiled out
+template <int MT, int kNC, bool SAVE>
 __global__ void __launch_bounds__(kThreads16, 1) episode_fwd_v2_kernel(EpiParams P) {
     constexpr int RS = 16 * MT;
     constexpr int NT_ = kThreads16;
@@ -79,7 +80,7 @@ __global__ void __launch_bounds__(kThreads16, 1) episode_fwd_v2_kernel(EpiParams
     const float alpha = c.step_size;
     const LayoutF L = make_layout_f(c);
     const float dsc = dropout_scale(c);
-    const bool drop = c.dropout_p > 0.f;
+    const bool drop = SAVE && c.dropout_p > 0.f;
     const uint32_t thr = dropout_thr(c);
     const int hc = 16 * w + 2 * t;                       // this thread's column pairs: hc + 8 j + {0, 1}
     PhaseClock pc;
@@ -95,7 +96,7 @@ __global__ void __launch_bounds__(kThreads16, 1) episode_fwd_v2_kernel(EpiParams
 
     for (int64_t b = blockIdx.x; b < P.B; b += gridDim.x) {
         const int64_t task = c.task_offset + b;
-        float* slot = P.save ? P.stash + b * P.slot_floats : nullptr;
+        float* slot = (SAVE && P.save) ? P.stash + b * P.slot_floats : nullptr;
         bool bad = false;                                 // a lagged plane exponent overflowed fp16
         int e_w1, e_h0 = 0, e_dz, e_gs, e_s = 0;
         int e_h0n = 0, e_dzn = 0;                         // exponents for the NEXT production (from the last observed max)
@@ -906,8 +907,13 @@ int launch_episode_fwd_f16(const EpiParams& P, int grid, void* stream) {
 #endif
 #define FUMI_FWD_LAUNCH(MT_, NC_)                                                   \
     do {                                                                            \
-        FUMI_SMEM_ATTR((episode_fwd_v2_kernel<MT_, NC_>));                          \
-        FUMI_LAUNCH((episode_fwd_v2_kernel<MT_, NC_>), grid, kThreads16, smem, stream, P); \
+        if (P.save || P.cfg.dropout_p > 0.f) {                                      \
+            FUMI_SMEM_ATTR((episode_fwd_v2_kernel<MT_, NC_, true>));                \
+            FUMI_LAUNCH((episode_fwd_v2_kernel<MT_, NC_, true>), grid, kThreads16, smem, stream, P); \
+        } else {                                                                    \
+            FUMI_SMEM_ATTR((episode_fwd_v2_kernel<MT_, NC_, false>));               \
+            FUMI_LAUNCH((episode_fwd_v2_kernel<MT_, NC_, false>), grid, kThreads16, smem, stream, P); \
+        }                                                                           \
     } while (0)
     const int nc = class_bucket(P.cfg.num_ways);
     if (P.cfg.num_support <= 16) {
