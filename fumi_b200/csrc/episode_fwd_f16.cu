@@ -66,8 +66,8 @@ __host__ __device__ inline size_t carve_v(char* base, SmemV& s, int N) {
 
 // MT: 16-row tiles of the support set (NK <= 16 MT); kNC: compile-time class count (>= N; the head buffer is zero-padded
 // to kNC rows so that the per-class loops carry no guards)
-// SAVE = false: meta-test (no stash, no dropout): the record / mask code is compiled out
-template <int MT, int kNC, bool SAVE>
+// SAVE = false: meta-test (no stash): the record code is compiled out; DROP = false (meta-test, MAML): the mask code too
+template <int MT, int kNC, bool SAVE, bool DROP>
 __global__ void __launch_bounds__(kThreads16, 1) episode_fwd_v2_kernel(EpiParams P) {
     constexpr int RS = 16 * MT;
     constexpr int NT_ = kThreads16;
@@ -80,7 +80,7 @@ __global__ void __launch_bounds__(kThreads16, 1) episode_fwd_v2_kernel(EpiParams
     const float alpha = c.step_size;
     const LayoutF L = make_layout_f(c);
     const float dsc = dropout_scale(c);
-    const bool drop = SAVE && c.dropout_p > 0.f;
+    constexpr bool drop = DROP;
     const uint32_t thr = dropout_thr(c);
     const int hc = 16 * w + 2 * t;                       // this thread's column pairs: hc + 8 j + {0, 1}
     PhaseClock pc;
@@ -907,12 +907,15 @@ int launch_episode_fwd_f16(const EpiParams& P, int grid, void* stream) {
 #endif
 #define FUMI_FWD_LAUNCH(MT_, NC_)                                                   \
     do {                                                                            \
-        if (P.save || P.cfg.dropout_p > 0.f) {                                      \
-            FUMI_SMEM_ATTR((episode_fwd_v2_kernel<MT_, NC_, true>));                \
-            FUMI_LAUNCH((episode_fwd_v2_kernel<MT_, NC_, true>), grid, kThreads16, smem, stream, P); \
+        if (P.cfg.dropout_p > 0.f) {                                                \
+            FUMI_SMEM_ATTR((episode_fwd_v2_kernel<MT_, NC_, true, true>));          \
+            FUMI_LAUNCH((episode_fwd_v2_kernel<MT_, NC_, true, true>), grid, kThreads16, smem, stream, P); \
+        } else if (P.save) {                                                        \
+            FUMI_SMEM_ATTR((episode_fwd_v2_kernel<MT_, NC_, true, false>));         \
+            FUMI_LAUNCH((episode_fwd_v2_kernel<MT_, NC_, true, false>), grid, kThreads16, smem, stream, P); \
         } else {                                                                    \
-            FUMI_SMEM_ATTR((episode_fwd_v2_kernel<MT_, NC_, false>));               \
-            FUMI_LAUNCH((episode_fwd_v2_kernel<MT_, NC_, false>), grid, kThreads16, smem, stream, P); \
+            FUMI_SMEM_ATTR((episode_fwd_v2_kernel<MT_, NC_, false, false>));        \
+            FUMI_LAUNCH((episode_fwd_v2_kernel<MT_, NC_, false, false>), grid, kThreads16, smem, stream, P); \
         }                                                                           \
     } while (0)
     const int nc = class_bucket(P.cfg.num_ways);
