@@ -90,6 +90,13 @@ def test_one_shot_and_ten_way_gradients_vs_fp64_oracle():
     kc.oracle_train_case(DEV, N=7, K=4, Q=5, steps=2, D=512, T=64, B=2, dropout=0.1, precision=2)
 
 
+def test_fumi_train_many_classes_few_rows():
+    """NK <= 32 with more than 11 classes (16-way 2-shot: NK = 32): outside the fp16-plane kernels' class buckets, this
+    lands on round 1's tensor-core kernels in normal operation (episode.cu, path 1) -- same oracle, same bar."""
+    kc.oracle_train_case(DEV, N=16, K=2, Q=4, steps=3, D=512, T=64, B=3, dropout=0.25, precision=2)
+    kc.oracle_train_case(DEV, N=12, K=1, Q=3, steps=2, D=512, T=64, B=2, dropout=0.0, precision=2)
+
+
 def test_fumi_evaluate_api():
     kc.fumi_evaluate_api_case(DEV, "fumi_train_n5k5_d512")
 
