@@ -279,15 +279,17 @@ class EpisodeEngine:
         self.launches += 1
         return out
 
-    def loss_acc_early(self, la):
+    def loss_acc_early(self, la, reduce=True):
         """Start the device -> host copy of [loss, acc] as soon as the forward has produced them (they do not depend on
         the backward or the optimizer step), into a pinned buffer with an event behind it.  `read_loss_acc` then waits for
         that event only, so the caller gets the step's loss (fumi.py:195-196) while the device is still in the backward,
-        and enqueues the next step without ever letting the stream run dry.  With more than one rank the two scalars are
-        averaged over ranks first, by a 2-float all-reduce on a side stream (the compute stream never waits for it)."""
+        and enqueues the next step without ever letting the stream run dry.  With more than one rank and `reduce` (a
+        training step: every rank is in the gradient all-reduce anyway) the two scalars are averaged over ranks first,
+        by a 2-float all-reduce on a side stream (the compute stream never waits for it); evaluation passes stay local,
+        as before -- no collective is added where only some ranks may be evaluating."""
         if self.device.type != "cuda" or os.environ.get("FUMI_EARLY_LOSS", "1") == "0":
             return None
-        world = self._world()
+        world = self._world() if reduce else 1
         main = torch.cuda.current_stream(self.device)
         if getattr(self, "_la_host", None) is None:
             self._la_host = torch.empty(2, dtype=torch.float32, pin_memory=True)
@@ -451,7 +453,7 @@ class EpisodeEngine:
         gram = self.gram(feats, eb.sup_rows, eb.qry_rows, bank=eb.bank)
         out = self.episode_fwd(cfg, proj, eb, gram, lin0.bias, lin1.weight, lin1.bias, hp_table, head_rows)
         la = self.loss_acc(out["task_loss"], out["task_acc"])
-        res = dict(loss_acc=la, loss_acc_event=self.loss_acc_early(la), preds=out["preds"], logits=out["logits"], qry_y=eb.qry_y, task_loss=out["task_loss"],
+        res = dict(loss_acc=la, loss_acc_event=self.loss_acc_early(la, reduce=train), preds=out["preds"], logits=out["logits"], qry_y=eb.qry_y, task_loss=out["task_loss"],
                    task_acc=out["task_acc"], cfg=cfg, stash=out["stash"] if (train or return_state) else None,
                    hp_table=hp_table, head_rows=head_rows, batch=eb)
         if not train:
@@ -494,7 +496,7 @@ class EpisodeEngine:
         gram = self.gram(feats, eb.sup_rows, eb.qry_rows, bank=eb.bank)
         out = self.episode_fwd(cfg, proj, eb, gram, lin0.bias, lin1.weight, lin1.bias, head_table, None)
         la = self.loss_acc(out["task_loss"], out["task_acc"])
-        res = dict(loss_acc=la, loss_acc_event=self.loss_acc_early(la), preds=out["preds"], logits=out["logits"], qry_y=eb.qry_y, cfg=cfg,
+        res = dict(loss_acc=la, loss_acc_event=self.loss_acc_early(la, reduce=train), preds=out["preds"], logits=out["logits"], qry_y=eb.qry_y, cfg=cfg,
                    stash=out["stash"] if (train or return_state) else None, batch=eb)
         if not train:
             return res
