@@ -25,7 +25,11 @@ namespace {
 
 struct MT19937 {                       // reference mt19937ar; shared by CPython, numpy and torch
     uint32_t key[624];
+    uint32_t out[624];                 // tempered words of the current block (one vectorisable pass per 624 draws)
     int pos;                           // 624 => regenerate before the next draw
+    void retemper() {                  // after key[] was written from outside (state import)
+        for (int i = 0; i < 624; ++i) out[i] = temper(key[i]);
+    }
     void seed(uint32_t s) {            // init_genrand
         for (int i = 0; i < 624; ++i) {
             key[i] = s;
@@ -47,6 +51,7 @@ struct MT19937 {                       // reference mt19937ar; shared by CPython
         uint32_t y = (key[623] & UP) | (key[0] & LO);
         key[623] = key[396] ^ (y >> 1) ^ ((y & 1u) ? A : 0u);
         pos = 0;
+        retemper();
     }
     static inline uint32_t temper(uint32_t y) {
         y ^= (y >> 11);
@@ -57,15 +62,14 @@ struct MT19937 {                       // reference mt19937ar; shared by CPython
     }
     inline uint32_t next() {
         if (pos >= 624) twist();
-        return temper(key[pos++]);
+        return out[pos++];
     }
 };
 
 // numpy legacy random_interval(max): masked rejection sampling on 32-bit draws.
 inline uint32_t np_interval(MT19937& g, uint32_t max) {
     if (max == 0) return 0;
-    uint32_t mask = max;
-    mask |= mask >> 1; mask |= mask >> 2; mask |= mask >> 4; mask |= mask >> 8; mask |= mask >> 16;
+    const uint32_t mask = 0xFFFFFFFFu >> __builtin_clz(max);       // smallest 2^k - 1 >= max  (max >= 1 here)
     uint32_t v;
     do { v = g.next() & mask; } while (v > max);
     return v;
@@ -196,6 +200,7 @@ extern "C" int fumi_sampler_next(fumi_sampler* s, int64_t B, uint32_t* py_state,
     MT19937 py;
     std::memcpy(py.key, py_state, sizeof(py.key));
     py.pos = int(py_state[624]);
+    py.retemper();
     for (int64_t b = 0; b < B; ++b) py_sample_range(py, s->C, N, classes + b * N);
     std::memcpy(py_state, py.key, sizeof(py.key));
     py_state[624] = uint32_t(py.pos);
@@ -289,6 +294,7 @@ extern "C" int fumi_sampler_plan(fumi_sampler* s, int64_t B, uint32_t* py_state,
     MT19937 py;                                        // stream 1: all B class tuples first
     std::memcpy(py.key, py_state, sizeof(py.key));
     py.pos = int(py_state[624]);
+    py.retemper();
     for (int64_t b = 0; b < B; ++b) py_sample_range(py, s->C, N, classes + b * N);
     std::memcpy(py_state, py.key, sizeof(py.key));
     py_state[624] = uint32_t(py.pos);
