@@ -204,11 +204,11 @@ __global__ void __launch_bounds__(kThreads16, 1) episode_fwd_v2_kernel(EpiParams
                         const int r = 16 * i + g + 8 * hq, h = hc + 8 * j;
                         const float z0 = ap[i][j][hq].x + b0r[j][0] - gs * acc[i][j][2 * hq];
                         const float z1 = ap[i][j][hq].y + b0r[j][1] - gs * acc[i][j][2 * hq + 1];
-                        bool k0 = r < tr && z0 > 0.f, k1 = r < tr && z1 > 0.f;
+                        bool k0 = (r < tr) & (z0 > 0.f), k1 = (r < tr) & (z1 > 0.f);      // (&, not &&: no divergent branches)
                         if (drop) {
                             const uint32_t bits = dropout_bits(dbase, r0 + r, h);
-                            k0 = k0 && (bits & 0xFFFFu) >= thr;
-                            k1 = k1 && (bits >> 16) >= thr;
+                            k0 = k0 & ((bits & 0xFFFFu) >= thr);
+                            k1 = k1 & ((bits >> 16) >= thr);
                         }
                         const float v0 = k0 ? z0 * dsc : 0.f, v1 = k1 ? z1 * dsc : 0.f;
                         gates |= (uint32_t(k0) | (uint32_t(k1) << 1)) << (2 * (4 * i + 2 * j + hq));
@@ -249,11 +249,11 @@ __global__ void __launch_bounds__(kThreads16, 1) episode_fwd_v2_kernel(EpiParams
                     for (int hq = 0; hq < 2; ++hq) {
                         const int r = 16 * i + g + 8 * hq, h = hc + 8 * j;
                         const float z0 = ap[i][j][hq].x + b0r[j][0], z1 = ap[i][j][hq].y + b0r[j][1];
-                        bool k0 = r < n && z0 > 0.f, k1 = r < n && z1 > 0.f;
+                        bool k0 = (r < n) & (z0 > 0.f), k1 = (r < n) & (z1 > 0.f);
                         if (drop) {
                             const uint32_t bits = dropout_bits(dbase, r, h);
-                            k0 = k0 && (bits & 0xFFFFu) >= thr;
-                            k1 = k1 && (bits >> 16) >= thr;
+                            k0 = k0 & ((bits & 0xFFFFu) >= thr);
+                            k1 = k1 & ((bits >> 16) >= thr);
                         }
                         hv[i][j][2 * hq] = k0 ? z0 * dsc : 0.f;
                         hv[i][j][2 * hq + 1] = k1 ? z1 * dsc : 0.f;
@@ -312,8 +312,8 @@ __global__ void __launch_bounds__(kThreads16, 1) episode_fwd_v2_kernel(EpiParams
             bool ka = za > 0.f, kb = zb > 0.f;
             if (drop) {
                 const uint32_t dbase = dropout_base(c, task, pass, 1);
-                ka = ka && dropout_keep_bits(dropout_bits(dbase, grow, lane), lane, thr);
-                kb = kb && dropout_keep_bits(dropout_bits(dbase, grow, lane + 32), lane + 32, thr);
+                ka = ka & dropout_keep_bits(dropout_bits(dbase, grow, lane), lane, thr);
+                kb = kb & dropout_keep_bits(dropout_bits(dbase, grow, lane + 32), lane + 32, thr);
             }
             h1a = ka ? za * dsc : 0.f;
             h1b = kb ? zb * dsc : 0.f;
@@ -390,8 +390,8 @@ __global__ void __launch_bounds__(kThreads16, 1) episode_fwd_v2_kernel(EpiParams
                         da = fmaf(dl, s.hp[cc * kHD + lane], da);
                         db = fmaf(dl, s.hp[cc * kHD + lane + 32], db);
                     }
-                    da = (live && h1a > 0.f) ? da * dsc : 0.f;
-                    db = (live && h1b > 0.f) ? db * dsc : 0.f;
+                    da = (live & (h1a > 0.f)) ? da * dsc : 0.f;
+                    db = (live & (h1b > 0.f)) ? db * dsc : 0.f;
                     if (live) {
                         if (lane < N) s.lt[i * kLS + lane] = dlw;
                         s.dz1t[i * kS1 + lane] = da;
@@ -716,11 +716,11 @@ __global__ void __launch_bounds__(kThreads16, 1) episode_fwd_v2_kernel(EpiParams
                         for (int hq = 0; hq < 2; ++hq) {
                             const float z0 = a[h][hq].x + bb.x - gs * acc[h][2 * hq];
                             const float z1 = a[h][hq].y + bb.y - gs * acc[h][2 * hq + 1];
-                            bool k0 = live[hq] && z0 > 0.f, k1 = live[hq] && z1 > 0.f;
+                            bool k0 = live[hq] & (z0 > 0.f), k1 = live[hq] & (z1 > 0.f);
                             if (drop) {
                                 const uint32_t bits = fumi_lowbias32(rb0[hq] + uint32_t(col >> 1) * 0x27D4EB2Fu);   // == dropout_bits
-                                k0 = k0 && (bits & 0xFFFFu) >= thr;
-                                k1 = k1 && (bits >> 16) >= thr;
+                                k0 = k0 & ((bits & 0xFFFFu) >= thr);
+                                k1 = k1 & ((bits >> 16) >= thr);
                             }
                             const float v0 = k0 ? z0 * dsc : 0.f, v1 = k1 ? z1 * dsc : 0.f;
                             hmax = fmaxf(hmax, fmaxf(v0, v1));
@@ -799,8 +799,8 @@ __global__ void __launch_bounds__(kThreads16, 1) episode_fwd_v2_kernel(EpiParams
                         bool k0 = z0 > 0.f, k1 = z1 > 0.f;
                         if (drop) {
                             const uint32_t bits = dropout_bits(db1, r0 + g + 8 * hq, 8 * j + 2 * t);
-                            k0 = k0 && (bits & 0xFFFFu) >= thr;
-                            k1 = k1 && (bits >> 16) >= thr;
+                            k0 = k0 & ((bits & 0xFFFFu) >= thr);
+                            k1 = k1 & ((bits >> 16) >= thr);
                         }
                         tot[j][2 * hq] = k0 ? z0 * dsc : 0.f;
                         tot[j][2 * hq + 1] = k1 ? z1 * dsc : 0.f;

@@ -57,7 +57,7 @@ def main():
     out = np.zeros(64, np.uint64)
     L.fumi_debug_read_phases(_lib.ptr(out))
     L.fumi_debug_phase_profile(0)
-    for lo, hi, name in ((20, 48, "forward"), (0, 15, "backward")):
+    for lo, hi, name in ((20, 60, "forward"), (0, 15, "backward")):
         tot = float(out[lo:hi].sum())
         print(f"== {name}: {tot / 1e6:.1f} Mcycles summed over CTAs")
         for i in range(lo, hi):
