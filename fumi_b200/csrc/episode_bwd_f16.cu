@@ -345,7 +345,7 @@ __global__ void __launch_bounds__(kThreads16, 1) episode_bwd_v2_kernel(EpiParams
 #pragma unroll
                         for (int hq = 0; hq < 2; ++hq) {
                             const int r = 16 * i + g + 8 * hq, h = hc + 8 * j;
-                            const uint32_t gt = r < tr ? plane_gates2(qh, ql, r * kHS + h) : 0u;
+                            const uint32_t gt = plane_gates2(qh, ql, r * kHS + h);          // (pad rows hold zeros: gates 0)
                             const float d0 = (gt & 1u) ? acc[i][j][2 * hq] * inv : 0.f;
                             const float d1 = (gt & 2u) ? acc[i][j][2 * hq + 1] * inv : 0.f;
                             acc[i][j][2 * hq] = d0;
@@ -551,7 +551,7 @@ __global__ void __launch_bounds__(kThreads16, 1) episode_bwd_v2_kernel(EpiParams
 #pragma unroll
                             for (int hq = 0; hq < 2; ++hq) {
                                 const int r = g + 8 * hq, h = hc + 8 * j;
-                                const uint32_t gt = r < tr ? plane_gates2(s.h0h, s.h0l, r * kHS + h) : 0u;
+                                const uint32_t gt = plane_gates2(s.h0h, s.h0l, r * kHS + h);    // (pad rows hold zeros: gates 0)
                                 gate0 |= gt << (2 * (2 * j + hq));
                                 const float a0 = ti == 0 ? aS[0][j][2 * hq] : aS1[j][2 * hq];
                                 const float a1 = ti == 0 ? aS[0][j][2 * hq + 1] : aS1[j][2 * hq + 1];
@@ -627,8 +627,8 @@ __global__ void __launch_bounds__(kThreads16, 1) episode_bwd_v2_kernel(EpiParams
                         const float h10 = s.h1t[(r0 + i) * kS1 + lane], h11 = s.h1t[(r0 + i) * kS1 + lane + 32];
                         float rd0 = s.rzp[i * kS1 + lane] + s.rzp[(16 + i) * kS1 + lane] - alpha * s.ab1[lane];
                         float rd1 = s.rzp[i * kS1 + lane + 32] + s.rzp[(16 + i) * kS1 + lane + 32] - alpha * s.ab1[lane + 32];
-                        rd0 = (arow && h10 > 0.f) ? rd0 * sc : 0.f;           // r_dH1
-                        rd1 = (arow && h11 > 0.f) ? rd1 * sc : 0.f;
+                        rd0 = (arow & (h10 > 0.f)) ? rd0 * sc : 0.f;           // r_dH1  (&, not &&: selects, no divergent branches)
+                        rd1 = (arow & (h11 > 0.f)) ? rd1 * sc : 0.f;
                         // r_dL of every class in every lane: N partial sums, one interleaved butterfly
                         float rdl[kNC];
 #pragma unroll
@@ -664,7 +664,7 @@ __global__ void __launch_bounds__(kThreads16, 1) episode_bwd_v2_kernel(EpiParams
                         if (lane < N) s.rlt[i * kLB + lane] = arow ? rl : 0.f;
                         s.rzp[i * kS1 + lane] = rd0;                           // r_dH1 for the head sums
                         s.rzp[i * kS1 + lane + 32] = rd1;
-                        const float z0 = (arow && h10 > 0.f) ? ra0 * sc : 0.f, z1 = (arow && h11 > 0.f) ? ra1 * sc : 0.f;
+                        const float z0 = (arow & (h10 > 0.f)) ? ra0 * sc : 0.f, z1 = (arow & (h11 > 0.f)) ? ra1 * sc : 0.f;
                         const float mxv = warp_max(fmaxf(fabsf(z0), fabsf(z1)));
                         if (lane == 0) s.mx[16 * (BX_RZ + par_rz) + w] = mxv;
                         if (rz_first) {
