@@ -166,7 +166,9 @@ __device__ inline void tile_h0(const EpiParams& P, const Smem& s, int64_t task, 
         if (i < tr) {
             const float a = CACHED ? s.sA[i * kH0 + h] : P.proj[s.rows[i] * kH0 + h];
             const float z = a + b0h - alpha * acc[i];
-            if (z > 0.f && (!drop || dropout_keep_bits(dropout_bits(dbase, r0 + i, h), h, thr))) v = z * sc;
+            // (no short-circuit: a mask hashed under a data-dependent branch is a divergent branch per element)
+            const bool keep = !drop | dropout_keep_bits(dropout_bits(dbase, r0 + i, h), h, thr);
+            v = ((z > 0.f) & keep) ? z * sc : 0.f;
         }
         s.h0t[i * kH0 + h] = v;
     }
@@ -203,8 +205,8 @@ __device__ inline void tile_h1(const EpiParams& P, const Smem& s, int64_t task, 
         float v = 0.f;
         if (i < tr) {
             const float z = acc[ii] + b;
-            if (z > 0.f && (!drop || dropout_keep_bits(dropout_bits(dbase, r0 + i, o), o, thr)))
-                v = z * sc;
+            const bool keep = !drop | dropout_keep_bits(dropout_bits(dbase, r0 + i, o), o, thr);
+            v = ((z > 0.f) & keep) ? z * sc : 0.f;
         }
         s.h1t[i * kH1 + o] = v;
     }
