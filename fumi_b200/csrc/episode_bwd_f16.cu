@@ -353,7 +353,7 @@ __global__ void __launch_bounds__(kThreads16, 1) episode_bwd_v2_kernel(EpiParams
                             colsum[j][0] += d0;
                             colsum[j][1] += d1;
                             mxv = fmaxf(mxv, fmaxf(fabsf(d0), fabsf(d1)));
-                            if (r < tr) atomic_add2(&P.d_proj[s.rows[r] * kH0 + h], d0, d1);
+                            atomic_add2_if(r < tr, &P.d_proj[s.rows[r] * kH0 + h], d0, d1);
                         }
 #pragma unroll
                 for (int j = 0; j < 2; ++j)
@@ -739,7 +739,7 @@ __global__ void __launch_bounds__(kThreads16, 1) episode_bwd_v2_kernel(EpiParams
                                 colsum[j][0] += d0;
                                 colsum[j][1] += d1;
                                 mxv = fmaxf(mxv, fmaxf(fabsf(d0), fabsf(d1)));
-                                if (r < tr) atomic_add2(&P.d_proj[s.srows[r0 + r] * kH0 + h], d0, d1);
+                                atomic_add2_if(r < tr, &P.d_proj[s.srows[min(r0 + r, 31)] * kH0 + h], d0, d1);
                             }
 #pragma unroll
                         for (int j = 0; j < 2; ++j)

@@ -199,6 +199,16 @@ __device__ __forceinline__ void ld_planes2(const fumi_half* hi, const fumi_half*
 // does max * 2^e fit fp16 with margin?  (uniform across the block: every thread evaluates the same values)
 __device__ __forceinline__ bool plane_overflow(float mx, int e) { return mx * fumi_exp2i(e) >= 60000.f; }
 
+// predicated form: the row test lives inside the instruction (@p red...) instead of a divergent branch around an
+// opaque asm statement (one BSSY / BRA / BSYNC region per call otherwise)
+__device__ __forceinline__ void atomic_add2_if(bool pred, float* addr, float a, float b) {
+#ifdef FUMI_EMU
+    if (pred) { atomicAdd(addr, a); atomicAdd(addr + 1, b); }
+#else
+    asm volatile("{\n.reg .pred p;\nsetp.ne.b32 p, %3, 0;\n@p red.global.add.v2.f32 [%0], {%1, %2};\n}" ::"l"(addr), "f"(a), "f"(b),
+                 "r"(int(pred)) : "memory");
+#endif
+}
 __device__ __forceinline__ void atomic_add2(float* addr, float a, float b) {
 #ifdef FUMI_EMU
     atomicAdd(addr, a);
