@@ -684,16 +684,20 @@ __global__ void __launch_bounds__(kThreads16, 1) episode_bwd_v2_kernel(EpiParams
                     for (int idx = tid; idx < N * kHD; idx += NT_) {
                         const int cc = idx / kHD, o = idx - cc * kHD;
                         float a0 = 0.f, a1 = 0.f;          // two independent chains over the rows
-                        if (o < kH1) {
-                            int i = 0;
-                            for (; i + 2 <= tr; i += 2) {
-                                a0 = fmaf(s.lt[(r0 + i) * kLB + cc], s.rzp[i * kS1 + o], fmaf(s.rlt[i * kLB + cc], s.h1t[(r0 + i) * kS1 + o], a0));
-                                a1 = fmaf(s.lt[(r0 + i + 1) * kLB + cc], s.rzp[(i + 1) * kS1 + o],
-                                          fmaf(s.rlt[(i + 1) * kLB + cc], s.h1t[(r0 + i + 1) * kS1 + o], a1));
-                            }
-                            if (i < tr) a0 = fmaf(s.lt[(r0 + i) * kLB + cc], s.rzp[i * kS1 + o], fmaf(s.rlt[i * kLB + cc], s.h1t[(r0 + i) * kS1 + o], a0));
-                        } else {
-                            for (int i = 0; i < tr; ++i) a0 += s.rlt[i * kLB + cc];
+                        // one loop for weight and bias columns (the bias column reads r_dH1 = 0, H1 = 1): a warp that holds
+                        // both kinds would otherwise run two loops one after the other
+                        const bool wcol = o < kH1;
+                        const int oc = wcol ? o : 0;
+                        int i = 0;
+                        for (; i + 2 <= tr; i += 2) {
+                            const float z0 = wcol ? s.rzp[i * kS1 + oc] : 0.f, z1 = wcol ? s.rzp[(i + 1) * kS1 + oc] : 0.f;
+                            const float u0 = wcol ? s.h1t[(r0 + i) * kS1 + oc] : 1.f, u1 = wcol ? s.h1t[(r0 + i + 1) * kS1 + oc] : 1.f;
+                            a0 = fmaf(s.lt[(r0 + i) * kLB + cc], z0, fmaf(s.rlt[i * kLB + cc], u0, a0));
+                            a1 = fmaf(s.lt[(r0 + i + 1) * kLB + cc], z1, fmaf(s.rlt[(i + 1) * kLB + cc], u1, a1));
+                        }
+                        if (i < tr) {
+                            const float z0 = wcol ? s.rzp[i * kS1 + oc] : 0.f, u0 = wcol ? s.h1t[(r0 + i) * kS1 + oc] : 1.f;
+                            a0 = fmaf(s.lt[(r0 + i) * kLB + cc], z0, fmaf(s.rlt[i * kLB + cc], u0, a0));
                         }
                         s.rhp[idx] += a0 + a1;
                     }
