@@ -527,10 +527,18 @@ __global__ void __launch_bounds__(kThreads16, 1) episode_fwd_v2_kernel(EpiParams
                 if (rec) rec[L.oHP + idx] = s.hp[idx];
                 s.hp[idx] -= alpha * s.dhp[idx];
             }
-            if (tid < kH1) {
-                float db1 = 0.f;
-                for (int i = 0; i < n; ++i) db1 += s.dz1t[i * kS1 + tid];
-                s.b1s[tid] -= alpha * db1;
+            if (tid >= NT_ - kH1) {                       // the last two warps: the first eleven carry the head update
+                const int o = tid - (NT_ - kH1);
+                float d0 = 0.f, d1 = 0.f, d2 = 0.f, d3 = 0.f;           // four independent chains over the rows
+                int i = 0;
+                for (; i + 4 <= n; i += 4) {
+                    d0 += s.dz1t[i * kS1 + o];
+                    d1 += s.dz1t[(i + 1) * kS1 + o];
+                    d2 += s.dz1t[(i + 2) * kS1 + o];
+                    d3 += s.dz1t[(i + 3) * kS1 + o];
+                }
+                for (; i < n; ++i) d0 += s.dz1t[i * kS1 + o];
+                s.b1s[o] -= alpha * ((d0 + d1) + (d2 + d3));
             }
             // ---- (a) of the next step: H0 = act(A + b0 - alpha G S), warp-local (S, b0 are this warp's own)
             if (st + 1 < steps) {
@@ -580,7 +588,7 @@ __global__ void __launch_bounds__(kThreads16, 1) episode_fwd_v2_kernel(EpiParams
                 for (int j = 0; j < 2; ++j)
                     *reinterpret_cast<float2*>(&sl[L.b0 + hc + 8 * j]) = make_float2(b0r[j][0], b0r[j][1]);
             }
-            if (tid < kH1) sl[L.b1 + tid] = s.b1s[tid];                          // (the thread that updated it)
+            if (tid >= NT_ - kH1) sl[L.b1 + tid - (NT_ - kH1)] = s.b1s[tid - (NT_ - kH1)];       // (the thread that updated it)
             for (int idx = tid; idx < N * kHD; idx += NT_) sl[L.head + idx] = s.hp[idx];
 #pragma unroll
             for (int i = 0; i < MT; ++i)
