@@ -673,8 +673,8 @@ __global__ void __launch_bounds__(kThreads16, 1) episode_fwd_f16_kernel(EpiParam
                     bool k0 = r < tr && z0 > 0.f, k1 = r < tr && z1 > 0.f;
                     if (drop) {
                         const uint32_t bits = dropout_bits(dbase, r0 + r, h);
-                        k0 = k0 && (bits & 0xFFFFu) >= thr;
-                        k1 = k1 && (bits >> 16) >= thr;
+                        k0 = k0 & ((bits & 0xFFFFu) >= thr);
+                        k1 = k1 & ((bits >> 16) >= thr);
                     }
                     const float v0 = k0 ? z0 * dsc : 0.f, v1 = k1 ? z1 * dsc : 0.f;
                     acc[i][j][2 * hq] = v0;
@@ -712,7 +712,7 @@ __global__ void __launch_bounds__(kThreads16, 1) episode_fwd_f16_kernel(EpiParam
             if (i < tr) {
                 const float z = cv * inv + s.b1s[o];
                 if (drop && (oo & 1) == 0) bits = dropout_bits(dbase, r0 + i, o);
-                if (z > 0.f && (!drop || dropout_keep_bits(bits, o, thr))) v = z * dsc;
+                v = ((z > 0.f) & (!drop | dropout_keep_bits(bits, o, thr))) ? z * dsc : 0.f;
             }
             s.h1t[i * kS1 + o] = v;
         });
